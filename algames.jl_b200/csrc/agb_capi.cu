@@ -1,0 +1,753 @@
+// agb_capi.cu — kernels + C ABI of libalgames_b200.so (see include/algames_b200.h for the contract).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include "agb_solver.cuh"
+
+using namespace agb;
+
+// Kernel launch / dynamic shared memory go through two macros so that the test-only CTA emulator under tests/emu/
+// can compile this very file with g++ (AGB_EMULATE); the shipped library is always the nvcc build.
+#ifndef AGB_EMULATE
+#define AGB_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+#define AGB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+// =============================================================================================================
+// Kernels
+// =============================================================================================================
+// newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
+template <int P>
+__global__ void __launch_bounds__(kThreads) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int batch) {
+  AGB_DYN_SMEM(sm);
+  Inst<P> I;
+  I.bind(dd, sm);
+  constexpr int n = Inst<P>::n;
+  const int K = I.K;
+  const double S = (double)(K * Inst<P>::b);
+  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+    __syncthreads();
+    I.load_params(g, inst);
+    I.load_iterate(g.Z0, g.L0, inst);
+    I.load_duals(g, inst);
+    __syncthreads();
+    for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];     // x_1 ← x0 (primal_dual_traj.jl:42)
+    __syncthreads();
+    I.rollout();                                                                        // :17
+    if (o.dual_reset) I.reset_duals_penalties(o);                                       // :25
+    int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0;
+    double delta = 0.0;
+    Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int kout = 1; kout <= o.outer_iter; kout++) {                                  // :30
+      outer_done = kout;
+      int ls_count = 0;
+      for (int l = 1; l <= o.inner_iter; l++) {                                         // :38
+        const double l2 = (double)l * (double)l;
+        const double reg = o.reg_0 * (l2 * l2);                                         // :39
+        // ---- inner_iteration (:67-103)
+        rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                           // :73-75 (the reg terms vanish at Z)
+        n_eval++;
+        const double res_norm = rec.sum / S;                                            // :76
+        delta = 0.0;
+        if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
+        if (rec.opt < o.eps_opt) break;                                                 // :80-82
+        if (!I.kkt_solve(reg, reg)) failed = 1;                                         // :84-88
+        n_newton++;
+        double alpha; int j;
+        I.line_search(o, reg, res_norm, alpha, j, n_eval);                              // :91
+        ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;                                 // :92-93
+        delta = I.update_traj(alpha);                                                   // :94-95 (taken even when the search failed)
+        if (delta < o.delta_min) break;                                                 // :96-98
+        if (ls_count >= 1) break;                                                       // :43
+        if (!(delta == delta)) { failed = 1; break; }
+      }
+      if (failed) break;
+      if (kout == o.outer_iter || (rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt))
+        break;                                                                          // :49-55
+      I.dual_update(o);                                                                 // :57-58
+      I.penalty_update(o);                                                              // :61
+    }
+    rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                               // :63 final record
+    n_eval++;
+    const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
+    const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
+    I.store_iterate(g.Z, g.L, inst);
+    I.store_duals(g, inst);
+    if (I.tid == 0) {
+      double* st = g.stats + (size_t)inst * AGB_NSTATS;
+      st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;
+      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)outer_done; st[8] = (double)n_eval; st[9] = (double)failed;
+      g.status[inst] = conv ? AGB_CONVERGED : ((failed || !finite) ? AGB_NUMERICAL_FAILURE : AGB_NOT_CONVERGED);
+    }
+  }
+}
+
+// Per-function entry points on the resident batch (parity tests and stand-alone use of the exported reference API).
+template <int P>
+__global__ void __launch_bounds__(kThreads) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
+  AGB_DYN_SMEM(sm);
+  Inst<P> I;
+  I.bind(dd, sm);
+  constexpr int n = Inst<P>::n, m = Inst<P>::m, b = Inst<P>::b;
+  const int K = I.K, Sz = K * b, nrow = I.nrow;
+  const double S = (double)Sz;
+  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+    __syncthreads();
+    I.load_params(g, inst);
+    I.load_iterate(g.Z, g.L, inst);
+    I.load_duals(g, inst);
+    __syncthreads();
+    for (int q = I.tid; q < n; q += kThreads) I.X[q] = g.x0[(size_t)inst * n + q];
+    __syncthreads();
+    double* D = g.D + (size_t)inst * Sz;
+    switch (a.op) {
+      case OP_ROLLOUT: {
+        I.rollout();
+        I.store_iterate(g.Z, g.L, inst);
+      } break;
+      case OP_RESIDUAL: {
+        Acc r;
+        double* out = a.out0 ? a.out0 + (size_t)inst * Sz : nullptr;
+        if (a.alpha == 0.0) {
+          r = I.template residual<false>(0.0, 0.0, 0.0, I.R);
+          if (out) for (int q = I.tid; q < Sz; q += kThreads) out[q] = I.R[q];
+        } else {
+          for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
+          __syncthreads();
+          r = I.template residual<true>(a.alpha, a.reg_x, a.reg_u, out);
+        }
+        if (a.out1 && I.tid == 0) {
+          double* nr = a.out1 + (size_t)inst * 5;
+          nr[0] = r.sum / S; nr[1] = r.dyn; nr[2] = r.con; nr[3] = r.sta; nr[4] = r.opt;
+        }
+      } break;
+      case OP_JAC_DENSE: {
+        // residual_jacobian! + regularize_residual_jacobian! written block by block in the reference's
+        // (vertical, horizontal) order (core/newton_core.jl:40-89); J_out must be zeroed by the caller.
+        I.template residual<false>(0.0, 0.0, 0.0, I.R);
+        __syncthreads();
+        double* J = a.out0 + (size_t)inst * Sz * Sz;
+        const int vdyn = P * K * (n + 2);
+        for (int item = I.tid; item < P * K; item += kThreads) {
+          const int s = item % K, i = item / K, k = s + 1;
+          const size_t vx = (size_t)(i * K + s) * (n + 2), vu = vx + n;
+          for (int r = 0; r < n; r++) {
+            double* row = J + (vx + r) * Sz;
+            for (int c = 0; c < n; c++) {
+              double v = (r == c) ? I.hd_entry(i, k, r, a.reg_x) : 0.0;
+              if (r < 2 * P && c < 2 * P) v += I.hpos_entry(i, k, r, c);
+              row[s * b + c] = v;                                               // (opt_i x_k, x_k)
+            }
+            row[s * b + n + m + i * n + r] = -1.0;                               // (opt_i x_k, λ_{i,k-1}) = −I
+            if (k < K) {
+              const int cr = r / P, ir = r % P;
+              for (int q = 0; q < 4; q++) row[k * b + n + m + i * n + q * P + ir] = I.Ael(k, ir, q, cr);   // A_kᵀ
+            }
+          }
+          for (int j = 0; j < 2; j++) {
+            double* row = J + (vu + j) * Sz;
+            row[s * b + n + i * 2 + j] = I.hu_entry(s, j * P + i, a.reg_u);       // (opt_i u_ik, u_ik)
+            for (int q = 0; q < 4; q++) row[s * b + n + m + i * n + q * P + i] = I.Bel(s, i, q, j);          // B_iᵀ
+          }
+        }
+        for (int item = I.tid; item < K * n; item += kThreads) {
+          const int r = item % n, s = item / n;
+          const int cr = r / P, ir = r % P;
+          double* row = J + (size_t)(vdyn + s * n + r) * Sz;
+          if (s > 0) for (int q = 0; q < 4; q++) row[(s - 1) * b + q * P + ir] = I.Ael(s, ir, cr, q);        // A_s
+          for (int j = 0; j < 2; j++) row[s * b + n + ir * 2 + j] = I.Bel(s, ir, cr, j);                    // B_i
+          row[s * b + r] = -1.0;                                                                            // −I
+        }
+      } break;
+      case OP_KKT_SOLVE: {
+        I.template residual<false>(0.0, 0.0, 0.0, I.R);
+        __syncthreads();
+        const bool ok = I.kkt_solve(a.reg_x, a.reg_u);
+        for (int q = I.tid; q < Sz; q += kThreads) D[q] = I.R[q];
+        if (a.iout && I.tid == 0) a.iout[inst] = ok ? 0 : 1;
+      } break;
+      case OP_LINE_SEARCH: {
+        for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
+        __syncthreads();
+        Acc r0 = I.template residual<true>(0.0, 0.0, 0.0, nullptr);
+        double alpha; int j, ne = 0;
+        const double reg = a.reg_x;
+        I.line_search(o, reg, r0.sum / S, alpha, j, ne);
+        if (I.tid == 0) { a.out0[inst] = alpha; a.iout[inst] = j; }
+      } break;
+      case OP_UPDATE: {
+        for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
+        __syncthreads();
+        const double delta = I.update_traj(a.in0[inst]);
+        __syncthreads();
+        I.store_iterate(g.Z, g.L, inst);
+        if (a.out0 && I.tid == 0) a.out0[inst] = delta;
+      } break;
+      case OP_DUAL_UPDATE: { I.dual_update(o); I.store_duals(g, inst); } break;
+      case OP_PENALTY_UPDATE: { I.penalty_update(o); I.store_duals(g, inst); } break;
+      case OP_RESET: { I.reset_duals_penalties(o); I.store_duals(g, inst); } break;
+      case OP_EVAL_CON: {
+        for (int q = I.tid; q < K * nrow; q += kThreads) a.out0[(size_t)inst * K * nrow + q] = I.con_value(q / nrow, q % nrow);
+      } break;
+      case OP_ACTIVE_SET: {
+        for (int q = I.tid; q < K * nrow; q += kThreads) {
+          const double c = I.con_value(q / nrow, q % nrow);
+          a.bout[(size_t)inst * K * nrow + q] = ((c >= -a.tol) || (I.CL[q] > 0.0)) ? 1 : 0;
+        }
+      } break;
+      default: break;
+    }
+  }
+}
+
+// internal stage-major layout → reference row ("vertical", mode 0) or column ("horizontal", mode 1) order
+__global__ void agb_export_kernel(const double* __restrict__ in, double* __restrict__ out, int batch, int P, int K, int mode) {
+  const int n = 4 * P, m = 2 * P, b = P * n + m + n, Sz = K * b;
+  const size_t total = (size_t)batch * Sz;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(t % Sz);
+    const size_t inst = t / Sz;
+    const int s = q / b, e = q - s * b;
+    int dst;
+    if (e < P * n) {                 // rx(i,s,a): row (opt_i x_{s+2}) / column λ_{i,s+1}
+      const int i = e / n, a = e - i * n;
+      dst = (mode == 0) ? (i * K + s) * (n + 2) + a : s * b + n + m + i * n + a;
+    } else if (e < P * n + m) {      // ru(s, idx=(j,i))
+      const int idx = e - P * n, j = idx / P, i = idx - j * P;
+      dst = (mode == 0) ? (i * K + s) * (n + 2) + n + j : s * b + n + i * 2 + j;
+    } else {                         // rd(s,a): row dyn_s / column x_{s+2}
+      const int a = e - P * n - m;
+      dst = (mode == 0) ? P * K * (n + 2) + s * n + a : s * b + a;
+    }
+    out[inst * Sz + dst] = in[t];
+  }
+}
+
+// init_traj! with shift s (primal_dual_traj.jl:29-44) on device: the resident solution moves s knots earlier,
+// the tail comes from the fresh arrays (zeros if null).
+__global__ void agb_shift_kernel(const double* __restrict__ Z, const double* __restrict__ L, const double* __restrict__ Zf,
+                                 const double* __restrict__ Lf, double* __restrict__ Z0, double* __restrict__ L0,
+                                 int batch, int P, int N, int shift) {
+  const int n = 4 * P, m = 2 * P, K = N - 1, zs = N * (n + m), ls = P * K * n;
+  const size_t total = (size_t)batch * (zs + ls);
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t inst = t / (zs + ls);
+    const int q = (int)(t % (zs + ls));
+    if (q < zs) {
+      const int k = q / (n + m), e = q - k * (n + m);
+      const size_t o = inst * zs;
+      Z0[o + q] = (k + shift < N) ? Z[o + (size_t)(k + shift) * (n + m) + e] : (Zf ? Zf[o + q] : 0.0);
+    } else {
+      const int r = q - zs, i = r / (K * n), rem = r - i * K * n, k = rem / n, e = rem - k * n;
+      const size_t o = inst * ls;
+      L0[o + r] = (k + shift < K) ? L[o + (size_t)(i * K + k + shift) * n + e] : (Lf ? Lf[o + r] : 0.0);
+    }
+  }
+}
+
+__global__ void agb_broadcast_kernel(double* dst, const double* src, int batch, int len) {
+  const size_t total = (size_t)batch * len;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) dst[t] = src[t % len];
+}
+__global__ void agb_fill_kernel(double* dst, double v, size_t total) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) dst[t] = v;
+}
+
+// =============================================================================================================
+// Host side
+// =============================================================================================================
+struct agb_handle {
+  int device = 0, batch = 0;
+  agb_problem_desc desc;
+  DevDesc hd;
+  DevDesc* dd = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  // device buffers
+  double *x0 = nullptr, *xf = nullptr, *Q = nullptr, *R = nullptr, *uf = nullptr;
+  double *Z0 = nullptr, *L0 = nullptr, *Z = nullptr, *L = nullptr, *conlam = nullptr, *conmu = nullptr, *D = nullptr, *stats = nullptr;
+  int* status = nullptr;
+  double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
+  double* stage2 = nullptr; size_t stage2_bytes = 0;
+  long long launches = 0;
+  size_t smem_bytes = 0;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(agb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+#define AGB_CUDA(h, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(h, AGB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* why) {
+  memset(o, 0, sizeof(*o));
+  if (d->p < 1 || d->p > AGB_MAX_P) { *why = "p must be in 1..4"; return AGB_EINVAL; }
+  if (d->model < 0 || d->model > 2) { *why = "unknown model"; return AGB_EINVAL; }
+  if (d->model == AGB_MODEL_DOUBLE_INTEGRATOR && d->d != 2) { *why = "DoubleIntegratorGame: only d = 2 is supported"; return AGB_EUNSUPPORTED; }
+  if (d->N < 2) { *why = "N must be >= 2"; return AGB_EINVAL; }
+  if (!(d->dt > 0)) { *why = "dt must be positive"; return AGB_EINVAL; }
+  const int p = d->p, n = 4 * p, m = 2 * p;
+  o->model = d->model; o->p = p; o->n = n; o->m = m; o->N = d->N; o->K = d->N - 1;
+  o->b = p * n + m + n; o->S = o->K * o->b;
+  o->dt = d->dt; o->lf = d->lf; o->lr = d->lr;
+  if (d->model == AGB_MODEL_BICYCLE && !(d->lr > 0)) { *why = "BicycleGame: lr must be positive"; return AGB_EINVAL; }
+  o->has_cc = d->has_collision_cost ? 1 : 0;
+  o->npairs = p * (p - 1);
+  for (int i = 0; i < p; i++) { o->cc_radius[i] = d->cc_radius[i]; o->cc_mu[i] = d->cc_mu[i]; }
+  int row = 0;
+  for (int i = 0; i < AGB_MAX_P; i++) {
+    for (int j = 0; j < AGB_MAX_P; j++) o->col_row[i][j] = -1;
+    for (int a = 0; a < AGB_MAX_N; a++) { o->sbmax_row[i][a] = -1; o->sbmin_row[i][a] = -1; }
+  }
+  for (int i = 0; i < p; i++) {
+    o->srow_off[i] = row;
+    for (int j = 0; j < p; j++) {
+      if (j != i && d->col_radius[i][j] > 0) { o->col_radius[i][j] = d->col_radius[i][j]; o->col_row[i][j] = row++; }
+    }
+    if (d->has_state_bound[i]) {
+      for (int a = 0; a < n; a++) {
+        if (!(d->x_max[i][a] >= d->x_min[i][a])) { *why = "Upper bounds must be greater than or equal to lower bounds"; return AGB_EINVAL; }
+      }
+      for (int a = 0; a < n; a++) if (isfinite(d->x_max[i][a])) { o->x_max[i][a] = d->x_max[i][a]; o->sbmax_row[i][a] = row++; }
+      for (int a = 0; a < n; a++) if (isfinite(d->x_min[i][a])) { o->x_min[i][a] = d->x_min[i][a]; o->sbmin_row[i][a] = row++; }
+    }
+    if (d->n_walls[i] < 0 || d->n_walls[i] > AGB_MAX_WALLS || d->n_circles[i] < 0 || d->n_circles[i] > AGB_MAX_CIRCLES) {
+      *why = "too many walls / circles"; return AGB_EINVAL;
+    }
+    o->n_walls[i] = d->n_walls[i]; o->wall_row[i] = row; row += d->n_walls[i];
+    for (int q = 0; q < d->n_walls[i]; q++) for (int e = 0; e < 6; e++) o->walls[i][q][e] = d->walls[i][q][e];
+    o->n_circles[i] = d->n_circles[i]; o->circle_row[i] = row; row += d->n_circles[i];
+    for (int q = 0; q < d->n_circles[i]; q++) for (int e = 0; e < 3; e++) o->circles[i][q][e] = d->circles[i][q][e];
+  }
+  for (int i = p; i <= AGB_MAX_P; i++) o->srow_off[i] = row;
+  o->nrow_state = row;
+  for (int idx = 0; idx < AGB_MAX_M; idx++) { o->ub_row[idx] = -1; o->lb_row[idx] = -1; }
+  if (d->has_control_bound) {
+    for (int idx = 0; idx < m; idx++) {
+      if (!(d->u_max[idx] >= d->u_min[idx])) { *why = "Upper bounds must be greater than or equal to lower bounds"; return AGB_EINVAL; }
+    }
+    for (int idx = 0; idx < m; idx++) if (isfinite(d->u_max[idx])) { o->u_max[idx] = d->u_max[idx]; o->ub_row[idx] = row++; }
+    for (int idx = 0; idx < m; idx++) if (isfinite(d->u_min[idx])) { o->u_min[idx] = d->u_min[idx]; o->lb_row[idx] = row++; }
+  }
+  o->nrow = row;
+  o->nrow_control = row - o->nrow_state;
+  // shared-memory layout
+  const int N = o->N, K = o->K, W = m + n + 1;
+  int off = 0;
+  auto take = [&](int cnt) { int r = off; off += (cnt + 1) & ~1; return r; };
+  o->o_X = take(N * n); o->o_U = take(N * m); o->o_L = take(p * K * n); o->o_R = take(K * o->b);
+  o->o_KU = take(K * m * (n + 1));
+  o->o_AB = take(d->model == AGB_MODEL_DOUBLE_INTEGRATOR ? 0 : K * p * 24);
+  o->o_CL = take(K * o->nrow); o->o_CM = take(K * o->nrow); o->o_CW = take(K * o->nrow);
+  o->o_CC = take(o->has_cc ? N * o->npairs * 3 : 0);
+  o->o_P = take(2 * p * n * n); o->o_Sv = take(2 * p * n); o->o_Aug = take(m * W); o->o_Acl = take(n * (n + 1));
+  o->o_Hpos = take(p * 4 * p * p); o->o_Hd = take(p * n); o->o_par = take(2 * n + 2 * m); o->o_red = take(5 * (kThreads / 32));
+  o->smem_doubles = off;
+  return AGB_OK;
+}
+
+extern "C" {
+
+void agb_default_options(agb_options* o) {   // src/struct/options.jl:5-116
+  memset(o, 0, sizeof(*o));
+  o->reg_0 = 1e-3; o->regularize = 1; o->alpha_decrease = 0.5; o->beta = 0.01; o->ls_iter = 25; o->delta_min = 1e-9;
+  o->rho_0 = 1.0; o->rho_increase = 10.0; o->rho_max = 1e7; o->lambda_max = 1e7; o->alpha_dual = 1.0;
+  for (int i = 0; i < AGB_MAX_P; i++) o->alphax_dual[i] = 1.0;
+  o->active_set_tolerance = 1e-4;
+  o->eps_dyn = o->eps_sta = o->eps_con = o->eps_opt = 1e-3;
+  o->outer_iter = 7; o->inner_iter = 20; o->dual_reset = 1;
+}
+
+int agb_sizes_of(const agb_problem_desc* d, agb_sizes* out) {
+  if (!d || !out) return fail(nullptr, AGB_EINVAL, "null argument");
+  DevDesc t; std::string why;
+  int rc = build_dev_desc(d, &t, &why);
+  if (rc) return fail(nullptr, rc, why);
+  out->n = t.n; out->m = t.m; out->p = t.p; out->N = t.N; out->S = t.S;
+  out->nrow = t.nrow; out->nrow_state = t.nrow_state; out->nrow_control = t.nrow_control;
+  return AGB_OK;
+}
+
+const char* agb_last_error(const agb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+static void* kernel_ptr(int p, bool solve) {
+  switch (p) {
+    case 1: return solve ? (void*)agb_newton_solve_kernel<1> : (void*)agb_op_kernel<1>;
+    case 2: return solve ? (void*)agb_newton_solve_kernel<2> : (void*)agb_op_kernel<2>;
+    case 3: return solve ? (void*)agb_newton_solve_kernel<3> : (void*)agb_op_kernel<3>;
+    default: return solve ? (void*)agb_newton_solve_kernel<4> : (void*)agb_op_kernel<4>;
+  }
+}
+
+void agb_destroy(agb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->Z, h->L, h->conlam, h->conmu, h->D, h->stats, h->status, h->stage, h->stage2};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int alloc_d(agb_handle* h, double** p, size_t count) {
+  AGB_CUDA(h, cudaMalloc((void**)p, (count ? count : 1) * sizeof(double)));
+  AGB_CUDA(h, cudaMemsetAsync(*p, 0, (count ? count : 1) * sizeof(double), h->stream));
+  return AGB_OK;
+}
+
+static inline int grid_for(size_t total) { size_t g = (total + 255) / 256; return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g)); }
+
+int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle** out) {
+  if (!desc || !out) return fail(nullptr, AGB_EINVAL, "null argument");
+  *out = nullptr;
+  if (batch < 1) return fail(nullptr, AGB_EINVAL, "batch must be >= 1");
+  DevDesc t; std::string why;
+  int rc = build_dev_desc(desc, &t, &why);
+  if (rc) return fail(nullptr, rc, why);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, AGB_ECUDA, "no CUDA device: libalgames_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, AGB_EINVAL, "bad device ordinal");
+  agb_handle* h = new (std::nothrow) agb_handle();
+  if (!h) return fail(nullptr, AGB_ENOMEM, "out of host memory");
+  h->device = device; h->batch = batch; h->desc = *desc; h->hd = t;
+  h->smem_bytes = (size_t)t.smem_doubles * sizeof(double);
+#define CK(call) do { int rc_ = (call); if (rc_) { g_create_err = h->err; agb_destroy(h); return rc_; } } while (0)
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e_); agb_destroy(h); return AGB_ECUDA; } } while (0)
+  CKC(cudaSetDevice(device));
+  int max_smem = 0;
+  CKC(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if ((int)h->smem_bytes > max_smem) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "instance needs %zu B of shared memory per CTA, device allows %d B", h->smem_bytes, max_smem);
+    g_create_err = buf; agb_destroy(h); return AGB_EUNSUPPORTED;
+  }
+  CKC(cudaFuncSetAttribute(kernel_ptr(t.p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CKC(cudaFuncSetAttribute(kernel_ptr(t.p, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&h->ev0));
+  CKC(cudaEventCreate(&h->ev1));
+  CKC(cudaMalloc((void**)&h->dd, sizeof(DevDesc)));
+  CKC(cudaMemcpyAsync(h->dd, &h->hd, sizeof(DevDesc), cudaMemcpyHostToDevice, h->stream));
+  const size_t B = batch, n = t.n, m = t.m, N = t.N, K = t.K, p = t.p;
+  CK(alloc_d(h, &h->x0, B * n)); CK(alloc_d(h, &h->xf, B * n)); CK(alloc_d(h, &h->Q, B * n));
+  CK(alloc_d(h, &h->R, B * m)); CK(alloc_d(h, &h->uf, B * m));
+  CK(alloc_d(h, &h->Z0, B * N * (n + m))); CK(alloc_d(h, &h->L0, B * p * K * n));
+  CK(alloc_d(h, &h->Z, B * N * (n + m))); CK(alloc_d(h, &h->L, B * p * K * n));
+  CK(alloc_d(h, &h->conlam, B * K * t.nrow)); CK(alloc_d(h, &h->conmu, B * K * t.nrow));
+  CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->stats, B * AGB_NSTATS));
+  CKC(cudaMalloc((void**)&h->status, B * sizeof(int)));
+  CKC(cudaMemsetAsync(h->status, 0, B * sizeof(int), h->stream));
+  // descriptor defaults broadcast to every instance; μ starts at 1 (Altro ALConVal default)
+  double tmp[2 * AGB_MAX_N + 2 * AGB_MAX_M];
+  double* dtmp = nullptr;
+  CKC(cudaMalloc((void**)&dtmp, sizeof tmp));
+  memcpy(tmp, desc->xf, n * sizeof(double)); memcpy(tmp + n, desc->Q, n * sizeof(double));
+  memcpy(tmp + 2 * n, desc->R, m * sizeof(double)); memcpy(tmp + 2 * n + m, desc->uf, m * sizeof(double));
+  CKC(cudaMemcpyAsync(dtmp, tmp, sizeof tmp, cudaMemcpyHostToDevice, h->stream));
+  AGB_LAUNCH(agb_broadcast_kernel, grid_for(B * n), 256, 0, h->stream, h->xf, dtmp, batch, (int)n);
+  AGB_LAUNCH(agb_broadcast_kernel, grid_for(B * n), 256, 0, h->stream, h->Q, dtmp + n, batch, (int)n);
+  AGB_LAUNCH(agb_broadcast_kernel, grid_for(B * m), 256, 0, h->stream, h->R, dtmp + 2 * n, batch, (int)m);
+  AGB_LAUNCH(agb_broadcast_kernel, grid_for(B * m), 256, 0, h->stream, h->uf, dtmp + 2 * n + m, batch, (int)m);
+  if (t.nrow) AGB_LAUNCH(agb_fill_kernel, grid_for(B * K * t.nrow), 256, 0, h->stream, h->conmu, 1.0, B * K * t.nrow);
+  h->launches += 5;
+  CKC(cudaStreamSynchronize(h->stream));
+  cudaFree(dtmp);
+  CKC(cudaGetLastError());
+#undef CK
+#undef CKC
+  *out = h;
+  return AGB_OK;
+}
+
+int agb_get_sizes(const agb_handle* h, agb_sizes* out) {
+  if (!h || !out) return AGB_EINVAL;
+  out->n = h->hd.n; out->m = h->hd.m; out->p = h->hd.p; out->N = h->hd.N; out->S = h->hd.S;
+  out->nrow = h->hd.nrow; out->nrow_state = h->hd.nrow_state; out->nrow_control = h->hd.nrow_control;
+  return AGB_OK;
+}
+
+static Buffers buffers_of(agb_handle* h) {
+  Buffers g;
+  g.x0 = h->x0; g.xf = h->xf; g.Q = h->Q; g.R = h->R; g.uf = h->uf; g.Z0 = h->Z0; g.L0 = h->L0; g.Z = h->Z; g.L = h->L;
+  g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.stats = h->stats; g.status = h->status;
+  return g;
+}
+
+static int h2d(agb_handle* h, double* dst, const double* src, size_t count) {
+  if (!src || !count) return AGB_OK;
+  AGB_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return AGB_OK;
+}
+static int d2h(agb_handle* h, double* dst, const double* src, size_t count) {
+  if (!dst || !count) return AGB_OK;
+  AGB_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return AGB_OK;
+}
+#define AGB_TRY(call) do { int rc_ = (call); if (rc_) return rc_; } while (0)
+
+int agb_set_instance_params(agb_handle* h, const double* x0, const double* xf, const double* Q, const double* R, const double* uf) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, n = h->hd.n, m = h->hd.m;
+  AGB_TRY(h2d(h, h->x0, x0, B * n)); AGB_TRY(h2d(h, h->xf, xf, B * n)); AGB_TRY(h2d(h, h->Q, Q, B * n));
+  AGB_TRY(h2d(h, h->R, R, B * m)); AGB_TRY(h2d(h, h->uf, uf, B * m));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return AGB_OK;
+}
+
+int agb_set_initial(agb_handle* h, const double* Z0, const double* L0, const double* conlam, const double* conmu) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n, cs = (size_t)h->hd.K * h->hd.nrow;
+  AGB_TRY(h2d(h, h->Z0, Z0, B * zs)); AGB_TRY(h2d(h, h->L0, L0, B * ls));
+  if (Z0) AGB_CUDA(h, cudaMemcpyAsync(h->Z, h->Z0, B * zs * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (L0) AGB_CUDA(h, cudaMemcpyAsync(h->L, h->L0, B * ls * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  AGB_TRY(h2d(h, h->conlam, conlam, B * cs)); AGB_TRY(h2d(h, h->conmu, conmu, B * cs));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return AGB_OK;
+}
+
+int agb_get_state(agb_handle* h, double* Z, double* L, double* conlam, double* conmu) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n, cs = (size_t)h->hd.K * h->hd.nrow;
+  AGB_TRY(d2h(h, Z, h->Z, B * zs)); AGB_TRY(d2h(h, L, h->L, B * ls));
+  AGB_TRY(d2h(h, conlam, h->conlam, B * cs)); AGB_TRY(d2h(h, conmu, h->conmu, B * cs));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return AGB_OK;
+}
+
+static int ensure_stage(agb_handle* h, double** buf, size_t* cur, size_t bytes) {
+  if (*cur >= bytes) return AGB_OK;
+  if (*buf) { cudaFree(*buf); *buf = nullptr; *cur = 0; }
+  cudaError_t e = cudaMalloc((void**)buf, bytes);
+  if (e != cudaSuccess) return fail(h, AGB_ENOMEM, std::string("cudaMalloc staging: ") + cudaGetErrorString(e));
+  *cur = bytes;
+  return AGB_OK;
+}
+
+int agb_shift_initial(agb_handle* h, int s, const double* Zfresh, const double* Lfresh) {
+  if (!h || s < 0) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n;
+  double *zf = nullptr, *lf = nullptr;
+  if (Zfresh) { AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, B * zs * sizeof(double))); zf = h->stage; AGB_TRY(h2d(h, zf, Zfresh, B * zs)); }
+  if (Lfresh) { AGB_TRY(ensure_stage(h, &h->stage2, &h->stage2_bytes, B * ls * sizeof(double))); lf = h->stage2; AGB_TRY(h2d(h, lf, Lfresh, B * ls)); }
+  AGB_LAUNCH(agb_shift_kernel, grid_for(B * (zs + ls)), 256, 0, h->stream, h->Z, h->L, zf, lf, h->Z0, h->L0, h->batch, h->hd.p, h->hd.N, s);
+  h->launches++;
+  AGB_CUDA(h, cudaMemcpyAsync(h->Z, h->Z0, B * zs * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  AGB_CUDA(h, cudaMemcpyAsync(h->L, h->L0, B * ls * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  AGB_CUDA(h, cudaGetLastError());
+  return AGB_OK;
+}
+
+static int launch_op(agb_handle* h, const agb_options* o, const OpArgs& a) {
+  agb_options od;
+  if (o) od = *o; else agb_default_options(&od);
+  Buffers g = buffers_of(h);
+  const int grid = h->batch;
+  switch (h->hd.p) {
+    case 1: AGB_LAUNCH(agb_op_kernel<1>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
+    case 2: AGB_LAUNCH(agb_op_kernel<2>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
+    case 3: AGB_LAUNCH(agb_op_kernel<3>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
+    default: AGB_LAUNCH(agb_op_kernel<4>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
+  }
+  h->launches++;
+  AGB_CUDA(h, cudaGetLastError());
+  return AGB_OK;
+}
+static int finish(agb_handle* h) {
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  AGB_CUDA(h, cudaGetLastError());
+  return AGB_OK;
+}
+static OpArgs op_args(int op) { OpArgs a; memset(&a, 0, sizeof a); a.op = op; return a; }
+
+int agb_rollout(agb_handle* h) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  AGB_TRY(launch_op(h, nullptr, op_args(OP_ROLLOUT)));
+  return finish(h);
+}
+
+static int export_to_host(agb_handle* h, const double* internal, double* host_out, int mode) {
+  const size_t B = h->batch, S = h->hd.S;
+  AGB_TRY(ensure_stage(h, &h->stage2, &h->stage2_bytes, B * S * sizeof(double)));
+  AGB_LAUNCH(agb_export_kernel, grid_for(B * S), 256, 0, h->stream, internal, h->stage2, h->batch, h->hd.p, h->hd.K, mode);
+  h->launches++;
+  return d2h(h, host_out, h->stage2, B * S);
+}
+
+int agb_residual(agb_handle* h, double reg_x, double reg_u, double alpha, double* res_out, double* norms_out) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, S = h->hd.S;
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, (B * S + B * 5) * sizeof(double)));
+  OpArgs a = op_args(OP_RESIDUAL);
+  a.reg_x = reg_x; a.reg_u = reg_u; a.alpha = alpha; a.out0 = h->stage; a.out1 = h->stage + B * S;
+  AGB_TRY(launch_op(h, nullptr, a));
+  if (res_out) AGB_TRY(export_to_host(h, h->stage, res_out, 0));
+  AGB_TRY(d2h(h, norms_out, h->stage + B * S, B * 5));
+  return finish(h);
+}
+
+int agb_residual_jacobian_dense(agb_handle* h, double reg_x, double reg_u, double* J_out) {
+  if (!h || !J_out) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, S = h->hd.S;
+  const size_t bytes = B * S * S * sizeof(double);
+  if (bytes > ((size_t)8 << 30)) return fail(h, AGB_EUNSUPPORTED, "dense Jacobian export is for small cases only (> 8 GiB requested)");
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, bytes));
+  AGB_CUDA(h, cudaMemsetAsync(h->stage, 0, bytes, h->stream));
+  OpArgs a = op_args(OP_JAC_DENSE);
+  a.reg_x = reg_x; a.reg_u = reg_u; a.out0 = h->stage;
+  AGB_TRY(launch_op(h, nullptr, a));
+  AGB_TRY(d2h(h, J_out, h->stage, B * S * S));
+  return finish(h);
+}
+
+int agb_kkt_solve(agb_handle* h, double reg_x, double reg_u, double* dtraj_out) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  OpArgs a = op_args(OP_KKT_SOLVE);
+  a.reg_x = reg_x; a.reg_u = reg_u;
+  AGB_TRY(launch_op(h, nullptr, a));
+  if (dtraj_out) AGB_TRY(export_to_host(h, h->D, dtraj_out, 1));
+  return finish(h);
+}
+
+int agb_line_search(agb_handle* h, const agb_options* o, double reg_x, double reg_u, double* alpha_out, int* j_out) {
+  if (!h || !o) return AGB_EINVAL;
+  (void)reg_u;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch;
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, B * (sizeof(double) + sizeof(int))));
+  OpArgs a = op_args(OP_LINE_SEARCH);
+  a.reg_x = reg_x; a.reg_u = reg_u; a.out0 = h->stage; a.iout = (int*)(h->stage + B);
+  AGB_TRY(launch_op(h, o, a));
+  AGB_TRY(d2h(h, alpha_out, h->stage, B));
+  if (j_out) AGB_CUDA(h, cudaMemcpyAsync(j_out, a.iout, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+int agb_update_traj(agb_handle* h, const double* alpha, double* delta_step_out) {
+  if (!h || !alpha) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch;
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, 2 * B * sizeof(double)));
+  AGB_TRY(h2d(h, h->stage, alpha, B));
+  OpArgs a = op_args(OP_UPDATE);
+  a.in0 = h->stage; a.out0 = h->stage + B;
+  AGB_TRY(launch_op(h, nullptr, a));
+  AGB_TRY(d2h(h, delta_step_out, h->stage + B, B));
+  return finish(h);
+}
+
+static int simple_op(agb_handle* h, const agb_options* o, int op) {
+  if (!h || !o) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  AGB_TRY(launch_op(h, o, op_args(op)));
+  return finish(h);
+}
+int agb_dual_update(agb_handle* h, const agb_options* o) { return simple_op(h, o, OP_DUAL_UPDATE); }
+int agb_penalty_update(agb_handle* h, const agb_options* o) { return simple_op(h, o, OP_PENALTY_UPDATE); }
+int agb_reset_duals_penalties(agb_handle* h, const agb_options* o) { return simple_op(h, o, OP_RESET); }
+
+int agb_evaluate_constraints(agb_handle* h, double* c_out) {
+  if (!h || !c_out) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->batch * h->hd.K * h->hd.nrow;
+  if (!cnt) return AGB_OK;
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, cnt * sizeof(double)));
+  OpArgs a = op_args(OP_EVAL_CON);
+  a.out0 = h->stage;
+  AGB_TRY(launch_op(h, nullptr, a));
+  AGB_TRY(d2h(h, c_out, h->stage, cnt));
+  return finish(h);
+}
+
+int agb_active_set(agb_handle* h, double tol, unsigned char* active_out) {
+  if (!h || !active_out) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->batch * h->hd.K * h->hd.nrow;
+  if (!cnt) return AGB_OK;
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, cnt));
+  OpArgs a = op_args(OP_ACTIVE_SET);
+  a.tol = tol; a.bout = (unsigned char*)h->stage;
+  AGB_TRY(launch_op(h, nullptr, a));
+  AGB_CUDA(h, cudaMemcpyAsync(active_out, h->stage, cnt, cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
+  Buffers g = buffers_of(h);
+  const int grid = h->batch;
+  switch (h->hd.p) {
+    case 1: AGB_LAUNCH(agb_newton_solve_kernel<1>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
+    case 2: AGB_LAUNCH(agb_newton_solve_kernel<2>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
+    case 3: AGB_LAUNCH(agb_newton_solve_kernel<3>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
+    default: AGB_LAUNCH(agb_newton_solve_kernel<4>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
+  }
+  h->launches++;
+  AGB_CUDA(h, cudaGetLastError());
+  return AGB_OK;
+}
+
+int agb_newton_solve_async(agb_handle* h, const agb_options* o, void* stream) {
+  if (!h || !o) return AGB_EINVAL;
+  if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1) return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter must be >= 1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  return launch_solve(h, o, (cudaStream_t)stream);
+}
+
+int agb_newton_solve_batch(agb_handle* h, const agb_options* o, double* Z_out, double* L_out, double* conlam_out,
+                           double* conmu_out, double* stats_out, int* status_out) {
+  if (!h || !o) return AGB_EINVAL;
+  if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1) return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter must be >= 1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  AGB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  AGB_TRY(launch_solve(h, o, h->stream));
+  AGB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  const size_t B = h->batch, zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n, cs = (size_t)h->hd.K * h->hd.nrow;
+  AGB_TRY(d2h(h, Z_out, h->Z, B * zs)); AGB_TRY(d2h(h, L_out, h->L, B * ls));
+  AGB_TRY(d2h(h, conlam_out, h->conlam, B * cs)); AGB_TRY(d2h(h, conmu_out, h->conmu, B * cs));
+  AGB_TRY(d2h(h, stats_out, h->stats, B * AGB_NSTATS));
+  if (status_out) AGB_CUDA(h, cudaMemcpyAsync(status_out, h->status, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+int agb_get_device_view(agb_handle* h, agb_device_view* out) {
+  if (!h || !out) return AGB_EINVAL;
+  out->Z_dev = h->Z; out->L_dev = h->L; out->conlam_dev = h->conlam; out->conmu_dev = h->conmu; out->stats_dev = h->stats;
+  out->status_dev = h->status; out->x0_dev = h->x0; out->Z0_dev = h->Z0; out->L0_dev = h->L0;
+  return AGB_OK;
+}
+
+long long agb_launch_count(const agb_handle* h) { return h ? h->launches : 0; }
+
+float agb_last_solve_ms(agb_handle* h) {
+  if (!h || !h->timed) return -1.0f;
+  cudaSetDevice(h->device);
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// agb_internal.h — device-side problem descriptor shared by the kernels and the C-ABI layer.
+// Not part of the public ABI (include/algames_b200.h is).
+#pragma once
+#include "../../include/algames_b200.h"
+
+namespace agb {
+
+constexpr int kThreads = 128;      // one CTA (4 warps) owns one game instance
+constexpr int kMaxRows = 96;       // AL constraint rows per stage (state rows of knot k+1 + control rows of knot k)
+
+// Flattened, index-resolved form of agb_problem_desc, lives in device global memory (read through L1).
+// Index conventions follow the reference's component-major joint layout (src/dynamics/unicycle.jl:18-20):
+// state comp c of player i -> c*p+i, control comp j of player i -> j*p+i.
+struct DevDesc {
+  int model, p, n, m, N, K, b, S;      // K = N-1 stages, b = p*n+m+n rows per stage, S = K*b (problem_size.jl:22)
+  double dt, lf, lr;
+  // objective (objective.jl:84-100)
+  int has_cc, npairs;
+  double cc_radius[AGB_MAX_P], cc_mu[AGB_MAX_P];
+  // state-constraint rows of player i at one knot, canonical order:
+  // [collision j!=i ascending | state bound max rows | min rows | walls | circles]
+  double col_radius[AGB_MAX_P][AGB_MAX_P];
+  int col_row[AGB_MAX_P][AGB_MAX_P];       // row inside the stage row block, -1 = no constraint
+  int sbmax_row[AGB_MAX_P][AGB_MAX_N];     // row of the x_max bound on joint comp a owned by player i, -1 = none
+  int sbmin_row[AGB_MAX_P][AGB_MAX_N];
+  double x_max[AGB_MAX_P][AGB_MAX_N], x_min[AGB_MAX_P][AGB_MAX_N];
+  int n_walls[AGB_MAX_P], wall_row[AGB_MAX_P];
+  double walls[AGB_MAX_P][AGB_MAX_WALLS][6];
+  int n_circles[AGB_MAX_P], circle_row[AGB_MAX_P];
+  double circles[AGB_MAX_P][AGB_MAX_CIRCLES][3];
+  int srow_off[AGB_MAX_P + 1];             // first state row of player i; srow_off[p] = nrow_state
+  // control-bound rows (control_bound_constraint.jl:33-35): finite u_max rows then finite u_min rows
+  int ub_row[AGB_MAX_M], lb_row[AGB_MAX_M];   // row inside the stage row block, -1 = none
+  double u_max[AGB_MAX_M], u_min[AGB_MAX_M];
+  int nrow_state, nrow_control, nrow;
+  // shared-memory layout (offsets in doubles)
+  int o_X, o_U, o_L, o_R, o_KU, o_AB, o_CL, o_CM, o_CW, o_CC, o_P, o_Sv, o_Aug, o_Acl, o_Hpos, o_Hd, o_par, o_red;
+  int smem_doubles;
+};
+
+// Per-batch device buffers (all FP64 unless noted); layouts as in include/algames_b200.h.
+struct Buffers {
+  const double* x0;   // [B][n]
+  const double* xf;   // [B][n]
+  const double* Q;    // [B][n]
+  const double* R;    // [B][m]
+  const double* uf;   // [B][m]
+  const double* Z0;   // [B][N][n+m]  initial iterate as init_traj! leaves it
+  const double* L0;   // [B][p][K][n]
+  double* Z;          // resident iterate / result
+  double* L;
+  double* conlam;     // [B][K][nrow]
+  double* conmu;
+  double* D;          // [B][S] Newton step, internal stage-major layout
+  double* stats;      // [B][AGB_NSTATS]
+  int* status;        // [B]
+};
+
+enum Op {
+  OP_ROLLOUT = 0, OP_RESIDUAL, OP_JAC_DENSE, OP_KKT_SOLVE, OP_LINE_SEARCH, OP_UPDATE,
+  OP_DUAL_UPDATE, OP_PENALTY_UPDATE, OP_RESET, OP_EVAL_CON, OP_ACTIVE_SET
+};
+
+struct OpArgs {
+  int op;
+  double reg_x, reg_u, alpha;
+  double tol;
+  double* out0;          // device staging, meaning depends on op
+  double* out1;
+  int* iout;
+  unsigned char* bout;
+  const double* in0;     // e.g. per-instance alpha for OP_UPDATE
+};
+
+}  // namespace agb

@@ -1,0 +1,690 @@
+"""Host-side mirror of the reference's exported API for the hot path (src/Algames.jl:124-143).
+
+Same names, argument meaning and error behaviour as the Julia package — `DoubleIntegratorGame/UnicycleGame/BicycleGame`,
+`ProblemSize`, `GameObjective` + `add_collision_cost`, `GameConstraintValues` + `add_*`, `Options`, `GameProblem`,
+`newton_solve` (Julia: `newton_solve!`) — with the work done by libalgames_b200.so on the GPU.  Julia's `!` suffix is
+dropped and Unicode option names are spelled out (ρ_0 → rho_0, ϵ_dyn → eps_dyn, Δ_min → delta_min, ...).
+
+Host arithmetic here is limited to packing descriptors and drawing the tiny random initial iterate
+(primal_dual_traj.jl:29-44); everything numerical runs in the CUDA library.  Nothing in this package imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field, fields
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+
+__all__ = [
+    "DoubleIntegratorGame", "UnicycleGame", "BicycleGame", "ProblemSize", "Options", "GameObjective",
+    "add_collision_cost", "GameConstraintValues", "add_collision_avoidance", "add_control_bound", "add_state_bound",
+    "add_circle_constraint", "add_wall_constraint", "Wall", "GameProblem", "GameBatch", "newton_solve",
+    "residual", "residual_jacobian", "kkt_solve", "line_search", "update_traj", "rollout", "dual_update",
+    "penalty_update", "reset", "evaluate", "active_set", "Statistics", "spec_of",
+]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Models (src/dynamics/*.jl): component-major joint layout, pu[i] = [i, i+p], px[i] = [i, i+p], pz[i] = [i, i+p, ...]
+# ------------------------------------------------------------------------------------------------------------
+class _GameModel:
+    name = "abstract"
+
+    def __init__(self, p: int):
+        if not 1 <= p <= _capi.MAX_P:
+            raise ValueError(f"p must be in 1..{_capi.MAX_P}")
+        self.p, self.n, self.m = p, 4 * p, 2 * p
+        self.ni, self.mi = [4] * p, [2] * p
+        self.pu = [[i + j * p for j in range(2)] for i in range(p)]       # 0-based
+        self.px = [[i + j * p for j in range(2)] for i in range(p)]
+        self.pz = [[i + j * p for j in range(4)] for i in range(p)]
+
+
+class DoubleIntegratorGame(_GameModel):
+    """dynamics/double_integrator.jl:2-33 (only d = 2 is supported by the CUDA path)."""
+    name = "double_integrator"
+
+    def __init__(self, p: int = 2, d: int = 2):
+        if d != 2:
+            raise NotImplementedError("DoubleIntegratorGame: only d = 2 is supported")
+        super().__init__(p)
+        self.d = d
+
+
+class UnicycleGame(_GameModel):
+    """dynamics/unicycle.jl:2-34."""
+    name = "unicycle"
+
+    def __init__(self, p: int = 2):
+        super().__init__(p)
+
+
+class BicycleGame(_GameModel):
+    """dynamics/bicycle.jl:2-43."""
+    name = "bicycle"
+
+    def __init__(self, p: int = 2, lf: float = 0.05, lr: float = 0.05):
+        super().__init__(p)
+        self.lf, self.lr = lf, lr
+
+
+class ProblemSize:
+    """struct/problem_size.jl:5-35."""
+
+    def __init__(self, N: int, model: _GameModel):
+        self.N, self.n, self.m, self.p = N, model.n, model.m, model.p
+        self.ni, self.mi, self.pu, self.px, self.pz = model.ni, model.mi, model.pu, model.px, model.pz
+        self.S = self.n * self.p * (N - 1) + self.m * (N - 1) + self.n * (N - 1)
+        self.b = self.n * self.p + self.m + self.n
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Options (struct/options.jl:5-116) — live fields only; dead ones (θ, α_0, γ, ...) are accepted and ignored
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class Options:
+    amplitude_init: float = 1e-8
+    shift: int = 2 ** 10
+    regularize: bool = True
+    reg_0: float = 1e-3
+    alpha_decrease: float = 0.5
+    beta: float = 0.01
+    ls_iter: int = 25
+    delta_min: float = 1e-9
+    rho_0: float = 1.0
+    rho_increase: float = 10.0
+    rho_max: float = 1e7
+    lambda_max: float = 1e7
+    alpha_dual: float = 1.0
+    alphax_dual: List[float] = field(default_factory=lambda: [1.0] * 10)
+    active_set_tolerance: float = 1e-4
+    eps_dyn: float = 1e-3
+    eps_sta: float = 1e-3
+    eps_con: float = 1e-3
+    eps_opt: float = 1e-3
+    outer_iter: int = 7
+    inner_iter: int = 20
+    seed: int = 100
+    dual_reset: bool = True
+    inner_print: bool = False
+    outer_print: bool = False
+
+    def to_c(self) -> _capi.OptionsC:
+        o = _capi.OptionsC()
+        for name in ("reg_0", "alpha_decrease", "beta", "delta_min", "rho_0", "rho_increase", "rho_max", "lambda_max",
+                     "alpha_dual", "active_set_tolerance", "eps_dyn", "eps_sta", "eps_con", "eps_opt"):
+            setattr(o, name, float(getattr(self, name)))
+        for name in ("ls_iter", "outer_iter", "inner_iter"):
+            setattr(o, name, int(getattr(self, name)))
+        o.regularize, o.dual_reset = int(self.regularize), int(self.dual_reset)
+        ax = list(self.alphax_dual) + [1.0] * _capi.MAX_P
+        for i in range(_capi.MAX_P):
+            o.alphax_dual[i] = float(ax[i])
+        return o
+
+    def to_dict(self) -> dict:
+        return {f.name: (list(getattr(self, f.name)) if f.name == "alphax_dual" else getattr(self, f.name))
+                for f in fields(self)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Objective (objective/objective.jl:6-35, :84-100)
+# ------------------------------------------------------------------------------------------------------------
+def _diag(v, k):
+    v = np.asarray(v, float)
+    if v.ndim == 2:
+        if not np.allclose(v, np.diag(np.diag(v))):
+            raise NotImplementedError("only diagonal Q / R are supported (the reference builds Diagonal LQR costs)")
+        v = np.diag(v)
+    if v.shape != (k,):
+        raise ValueError(f"expected {k} weights, got shape {v.shape}")
+    return v.copy()
+
+
+class GameObjective:
+    """Per-player LQR cost (+ optional soft collision cost).  Q[i] (4,), R[i] (2,), xf[i] (4,), uf[i] (2,)."""
+
+    def __init__(self, Q, R, xf, uf, N: int, model: _GameModel):
+        p = model.p
+        if not (len(Q) == len(R) == len(xf) == len(uf) == p):
+            raise ValueError("Q, R, xf, uf must have one entry per player")
+        self.p, self.N, self.model = p, N, model
+        self.Q = [_diag(Q[i], 4) for i in range(p)]
+        self.R = [_diag(R[i], 2) for i in range(p)]
+        self.xf = [np.asarray(xf[i], float).reshape(4).copy() for i in range(p)]
+        self.uf = [np.asarray(uf[i], float).reshape(2).copy() for i in range(p)]
+        self.collision_cost = None     # (radius[p], mu[p])
+
+
+def add_collision_cost(game_obj: GameObjective, radius, mu):
+    """add_collision_cost!(game_obj, radius, μ) (objective.jl:84-100): every ordered pair (i, j≠i), all knots."""
+    radius = np.broadcast_to(np.asarray(radius, float), (game_obj.p,)).copy()
+    mu = np.broadcast_to(np.asarray(mu, float), (game_obj.p,)).copy()
+    game_obj.collision_cost = (radius, mu)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Constraints (constraints/game_constraints.jl, constraints_methods.jl:5-195)
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class Wall:
+    """constraints_methods.jl:155-159."""
+    p1: Sequence[float]
+    p2: Sequence[float]
+    v: Sequence[float]
+
+
+class GameConstraintValues:
+    """Constraint schema of a game.  Row order of the AL multipliers is canonical (see include/algames_b200.h)."""
+
+    def __init__(self, probsize: ProblemSize):
+        self.probsize = probsize
+        p = probsize.p
+        self.col_radius = np.zeros((p, p))
+        self.control_bound = None                  # (u_max[m], u_min[m])
+        self.state_bound = [None] * p              # (x_max[n], x_min[n]) owned by player i
+        self.walls: List[List[Wall]] = [[] for _ in range(p)]
+        self.circles: List[List[tuple]] = [[] for _ in range(p)]
+
+
+def add_collision_avoidance(game_con: GameConstraintValues, radius, i: Optional[int] = None, j: Optional[int] = None):
+    """add_collision_avoidance!(game_con, radius) / (game_con, i, j, radius) — players 0-based here.
+    A scalar or per-player radius gives the pair radius r_i + r_j (constraints_methods.jl:21-39)."""
+    p = game_con.probsize.p
+    if i is not None:
+        game_con.col_radius[i, j] = float(radius)
+        return
+    r = np.broadcast_to(np.asarray(radius, float), (p,))
+    for a in range(p):
+        for b in range(p):
+            if a != b:
+                game_con.col_radius[a, b] = r[a] + r[b]
+
+
+def _check_bounds(hi, lo, k):
+    hi = np.broadcast_to(np.asarray(hi, float), (k,)).copy()
+    lo = np.broadcast_to(np.asarray(lo, float), (k,)).copy()
+    if not np.all(hi >= lo):
+        raise ValueError("Upper bounds must be greater than or equal to lower bounds")   # control_bound_constraint.jl:62-68
+    return hi, lo
+
+
+def add_control_bound(game_con: GameConstraintValues, u_max, u_min):
+    if game_con.control_bound is not None:
+        raise NotImplementedError("one control bound per game")
+    game_con.control_bound = _check_bounds(u_max, u_min, game_con.probsize.m)
+
+
+def add_state_bound(game_con: GameConstraintValues, i: int, x_max, x_min):
+    if game_con.state_bound[i] is not None:
+        raise NotImplementedError("one state bound per player")
+    game_con.state_bound[i] = _check_bounds(x_max, x_min, game_con.probsize.n)
+
+
+def add_circle_constraint(game_con: GameConstraintValues, xc, yc, radius, i: Optional[int] = None):
+    for a in (range(game_con.probsize.p) if i is None else [i]):
+        for t in zip(xc, yc, radius):
+            game_con.circles[a].append(tuple(float(v) for v in t))
+        if len(game_con.circles[a]) > _capi.MAX_CIRCLES:
+            raise ValueError(f"at most {_capi.MAX_CIRCLES} circles per player")
+
+
+def add_wall_constraint(game_con: GameConstraintValues, walls: Sequence[Wall], i: Optional[int] = None):
+    for a in (range(game_con.probsize.p) if i is None else [i]):
+        game_con.walls[a].extend(walls)
+        if len(game_con.walls[a]) > _capi.MAX_WALLS:
+            raise ValueError(f"at most {_capi.MAX_WALLS} walls per player")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Descriptor packing
+# ------------------------------------------------------------------------------------------------------------
+def _joint(per_player, p, k):
+    """per-player (k,) vectors -> component-major joint vector (objective.jl:24-28 expand_vector)."""
+    out = np.zeros(k * p)
+    for i in range(p):
+        out[[i + c * p for c in range(k)]] = per_player[i]
+    return out
+
+
+def _make_desc(model, N, dt, game_obj: GameObjective, game_con: GameConstraintValues) -> _capi.ProblemDesc:
+    d = _capi.ProblemDesc()
+    p, n, m = model.p, model.n, model.m
+    d.model, d.p, d.d, d.N, d.dt = _capi.MODEL_IDS[model.name], p, getattr(model, "d", 2), N, dt
+    d.lf, d.lr = getattr(model, "lf", 0.05), getattr(model, "lr", 0.05)
+    for name, vec in (("Q", _joint(game_obj.Q, p, 4)), ("xf", _joint(game_obj.xf, p, 4)),
+                      ("R", _joint(game_obj.R, p, 2)), ("uf", _joint(game_obj.uf, p, 2))):
+        arr = getattr(d, name)
+        for a, v in enumerate(vec):
+            arr[a] = v
+    if game_obj.collision_cost is not None:
+        d.has_collision_cost = 1
+        for i in range(p):
+            d.cc_radius[i], d.cc_mu[i] = game_obj.collision_cost[0][i], game_obj.collision_cost[1][i]
+    for i in range(p):
+        for j in range(p):
+            d.col_radius[i][j] = game_con.col_radius[i, j]
+        if game_con.state_bound[i] is not None:
+            d.has_state_bound[i] = 1
+            for a in range(n):
+                d.x_max[i][a], d.x_min[i][a] = game_con.state_bound[i][0][a], game_con.state_bound[i][1][a]
+        d.n_walls[i] = len(game_con.walls[i])
+        for q, w in enumerate(game_con.walls[i]):
+            for e, v in enumerate([w.p1[0], w.p1[1], w.p2[0], w.p2[1], w.v[0], w.v[1]]):
+                d.walls[i][q][e] = float(v)
+        d.n_circles[i] = len(game_con.circles[i])
+        for q, c in enumerate(game_con.circles[i]):
+            for e in range(3):
+                d.circles[i][q][e] = c[e]
+    if game_con.control_bound is not None:
+        d.has_control_bound = 1
+        for a in range(m):
+            d.u_max[a], d.u_min[a] = game_con.control_bound[0][a], game_con.control_bound[1][a]
+    return d
+
+
+def spec_of(prob: "GameProblem") -> dict:
+    """Neutral plain-dict description of a problem (what the tests hand to the oracle's problem_from_spec)."""
+    model, obj, con = prob.model, prob.game_obj, prob.game_con
+    p = model.p
+    return {
+        "model": model.name, "p": p, "d": getattr(model, "d", 2), "lf": getattr(model, "lf", 0.05),
+        "lr": getattr(model, "lr", 0.05), "N": prob.probsize.N, "dt": prob.dt, "x0": np.asarray(prob.x0, float).tolist(),
+        "Q": [q.tolist() for q in obj.Q], "R": [r.tolist() for r in obj.R],
+        "xf": [x.tolist() for x in obj.xf], "uf": [u.tolist() for u in obj.uf],
+        "collision_cost": None if obj.collision_cost is None else
+        {"radius": obj.collision_cost[0].tolist(), "mu": obj.collision_cost[1].tolist()},
+        "collision_radius": con.col_radius.tolist() if con.col_radius.any() else None,
+        "state_bounds": [None if sb is None else {"x_max": sb[0].tolist(), "x_min": sb[1].tolist()} for sb in con.state_bound],
+        "walls": [[[w.p1[0], w.p1[1], w.p2[0], w.p2[1], w.v[0], w.v[1]] for w in con.walls[i]] for i in range(p)],
+        "circles": [[list(c) for c in con.circles[i]] for i in range(p)],
+        "control_bounds": None if con.control_bound is None else
+        {"u_max": con.control_bound[0].tolist(), "u_min": con.control_bound[1].tolist()},
+        "opts": prob.opts.to_dict(),
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Batch of games sharing one schema: thin object wrapper over an agb_handle
+# ------------------------------------------------------------------------------------------------------------
+class AlgamesError(RuntimeError):
+    pass
+
+
+class GameBatch:
+    """`batch` independent GameProblems with one schema (model, players, horizon, constraint lists) resident on one GPU.
+
+    Arrays use the ABI layouts: x0 [B,n], Z [B,N,n+m], L [B,p,N-1,n], conlam/conmu [B,N-1,nrow], res/dtraj [B,S].
+    """
+
+    def __init__(self, model, N, dt, game_obj, game_con, batch: int, device: int = 0, lib_path: Optional[str] = None):
+        self.lib = _capi.load(lib_path)
+        self.model, self.N, self.dt, self.batch, self.device = model, N, dt, batch, device
+        self.probsize = ProblemSize(N, model)
+        self.desc = _make_desc(model, N, dt, game_obj, game_con)
+        h = C.c_void_p()
+        rc = self.lib.agb_create(C.byref(self.desc), batch, device, C.byref(h))
+        if rc != 0:
+            raise AlgamesError(f"agb_create failed ({rc}): {self.lib.agb_last_error(None).decode()}")
+        self.h = h
+        sz = _capi.Sizes()
+        self._ck(self.lib.agb_get_sizes(self.h, C.byref(sz)))
+        self.sizes = sz
+        self.n, self.m, self.p, self.S, self.nrow = sz.n, sz.m, sz.p, sz.S, sz.nrow
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AlgamesError(f"libalgames_b200 error {rc}: {self.lib.agb_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.agb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- shapes
+    def _z(self):
+        return (self.batch, self.N, self.n + self.m)
+
+    def _l(self):
+        return (self.batch, self.p, self.N - 1, self.n)
+
+    def _c(self):
+        return (self.batch, self.N - 1, self.nrow)
+
+    @staticmethod
+    def _arr(a, shape):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+        return a
+
+    # ---- state
+    def set_instance_params(self, x0=None, xf=None, Q=None, R=None, uf=None):
+        B, n, m = self.batch, self.n, self.m
+        a = [self._arr(x0, (B, n)), self._arr(xf, (B, n)), self._arr(Q, (B, n)), self._arr(R, (B, m)), self._arr(uf, (B, m))]
+        self._ck(self.lib.agb_set_instance_params(self.h, *[_capi.dptr(v) for v in a]))
+
+    def set_initial(self, Z0, L0, conlam=None, conmu=None):
+        a = [self._arr(Z0, self._z()), self._arr(L0, self._l()), self._arr(conlam, self._c()), self._arr(conmu, self._c())]
+        self._ck(self.lib.agb_set_initial(self.h, *[_capi.dptr(v) for v in a]))
+
+    def random_initial(self, amplitude=1e-8, seed=100):
+        """init_traj!(…; f=rand, amplitude) for every instance (primal_dual_traj.jl:29-44).  The reference draws from
+        Julia's MersenneTwister(seed); that stream is not reproducible here, numpy's default_rng(seed) is used instead."""
+        rng = np.random.default_rng(seed)
+        Z0 = amplitude * rng.random(self._z())
+        L0 = amplitude * rng.random(self._l())
+        self.set_initial(Z0, L0)
+        return Z0, L0
+
+    def shift_initial(self, s: int, Zfresh=None, Lfresh=None):
+        a = [self._arr(Zfresh, self._z()), self._arr(Lfresh, self._l())]
+        self._ck(self.lib.agb_shift_initial(self.h, int(s), *[_capi.dptr(v) for v in a]))
+
+    def get_state(self):
+        Z, L = np.empty(self._z()), np.empty(self._l())
+        cl, cm = np.empty(self._c()), np.empty(self._c())
+        self._ck(self.lib.agb_get_state(self.h, _capi.dptr(Z), _capi.dptr(L), _capi.dptr(cl), _capi.dptr(cm)))
+        return Z, L, cl, cm
+
+    # ---- per-function entry points
+    def rollout(self):
+        self._ck(self.lib.agb_rollout(self.h))
+
+    def residual(self, reg_x=0.0, reg_u=0.0, alpha=0.0, want_res=True):
+        res = np.empty((self.batch, self.S)) if want_res else None
+        norms = np.empty((self.batch, 5))
+        self._ck(self.lib.agb_residual(self.h, reg_x, reg_u, alpha, _capi.dptr(res), _capi.dptr(norms)))
+        return res, norms
+
+    def residual_jacobian_dense(self, reg_x=0.0, reg_u=0.0):
+        J = np.empty((self.batch, self.S, self.S))
+        self._ck(self.lib.agb_residual_jacobian_dense(self.h, reg_x, reg_u, _capi.dptr(J)))
+        return J
+
+    def kkt_solve(self, reg_x=0.0, reg_u=0.0):
+        d = np.empty((self.batch, self.S))
+        self._ck(self.lib.agb_kkt_solve(self.h, reg_x, reg_u, _capi.dptr(d)))
+        return d
+
+    def line_search(self, opts: Options, reg: float):
+        alpha = np.empty(self.batch)
+        j = np.empty(self.batch, dtype=np.int32)
+        oc = opts.to_c()
+        self._ck(self.lib.agb_line_search(self.h, C.byref(oc), reg, reg, _capi.dptr(alpha), _capi.iptr(j)))
+        return alpha, j
+
+    def update_traj(self, alpha):
+        alpha = self._arr(np.broadcast_to(np.asarray(alpha, float), (self.batch,)), (self.batch,))
+        d = np.empty(self.batch)
+        self._ck(self.lib.agb_update_traj(self.h, _capi.dptr(alpha), _capi.dptr(d)))
+        return d
+
+    def dual_update(self, opts: Options):
+        oc = opts.to_c()
+        self._ck(self.lib.agb_dual_update(self.h, C.byref(oc)))
+
+    def penalty_update(self, opts: Options):
+        oc = opts.to_c()
+        self._ck(self.lib.agb_penalty_update(self.h, C.byref(oc)))
+
+    def reset(self, opts: Options):
+        oc = opts.to_c()
+        self._ck(self.lib.agb_reset_duals_penalties(self.h, C.byref(oc)))
+
+    def evaluate(self):
+        c = np.empty(self._c())
+        self._ck(self.lib.agb_evaluate_constraints(self.h, _capi.dptr(c)))
+        return c
+
+    def active_set(self, tol):
+        a = np.empty(self._c(), dtype=np.uint8)
+        self._ck(self.lib.agb_active_set(self.h, float(tol), a.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return a.astype(bool)
+
+    # ---- the hot path
+    def newton_solve(self, opts: Options, want=("Z", "L", "conlam", "conmu", "stats", "status")):
+        out = {}
+        if "Z" in want: out["Z"] = np.empty(self._z())
+        if "L" in want: out["L"] = np.empty(self._l())
+        if "conlam" in want: out["conlam"] = np.empty(self._c())
+        if "conmu" in want: out["conmu"] = np.empty(self._c())
+        if "stats" in want: out["stats"] = np.empty((self.batch, _capi.NSTATS))
+        if "status" in want: out["status"] = np.empty(self.batch, dtype=np.int32)
+        oc = opts.to_c()
+        self._ck(self.lib.agb_newton_solve_batch(
+            self.h, C.byref(oc), _capi.dptr(out.get("Z")), _capi.dptr(out.get("L")), _capi.dptr(out.get("conlam")),
+            _capi.dptr(out.get("conmu")), _capi.dptr(out.get("stats")), _capi.iptr(out.get("status"))))
+        return out
+
+    def newton_solve_async(self, opts: Options, stream: int = 0):
+        oc = opts.to_c()
+        self._ck(self.lib.agb_newton_solve_async(self.h, C.byref(oc), C.c_void_p(stream)))
+
+    def device_view(self) -> _capi.DeviceView:
+        v = _capi.DeviceView()
+        self._ck(self.lib.agb_get_device_view(self.h, C.byref(v)))
+        return v
+
+    def launch_count(self) -> int:
+        return int(self.lib.agb_launch_count(self.h))
+
+    def last_solve_ms(self) -> float:
+        return float(self.lib.agb_last_solve_ms(self.h))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GameProblem: the reference's single-problem object (problem/problem.jl:19-53)
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class Violation:
+    max: float
+
+
+class Statistics:
+    """Final-record subset of struct/statistics.jl:5-57 (the device keeps the last record only)."""
+
+    def __init__(self):
+        self.iter = 0
+        self.outer_iter: List[int] = []
+        self.res: List[float] = []
+        self.delta: List[float] = []
+        self.dyn_vio: List[Violation] = []
+        self.con_vio: List[Violation] = []
+        self.sta_vio: List[Violation] = []
+        self.opt_vio: List[Violation] = []
+        self.newton_steps = 0
+        self.residual_evals = 0
+
+    def record(self, st):
+        self.iter += 1
+        self.res.append(float(st[0])); self.dyn_vio.append(Violation(float(st[1]))); self.con_vio.append(Violation(float(st[2])))
+        self.sta_vio.append(Violation(float(st[3]))); self.opt_vio.append(Violation(float(st[4])))
+        self.delta.append(float(st[5])); self.newton_steps = int(st[6]); self.outer_iter.append(int(st[7]))
+        self.residual_evals = int(st[8])
+
+
+class _Core:
+    def __init__(self, S):
+        self.res = np.zeros(S)
+        self.jac = None
+
+
+class _PrimalDualTraj:
+    """X [N,n], U [N,m] (last row = the unused terminal control), du [p,N-1,n] (struct/primal_dual_traj.jl:5-20)."""
+
+    def __init__(self, ps: ProblemSize):
+        self.X, self.U, self.du = np.zeros((ps.N, ps.n)), np.zeros((ps.N, ps.m)), np.zeros((ps.p, ps.N - 1, ps.n))
+
+
+class GameProblem:
+    """GameProblem(N, dt, x0, model, opts, game_obj, game_con)."""
+
+    def __init__(self, N, dt, x0, model, opts: Options, game_obj: GameObjective, game_con: GameConstraintValues,
+                 device: int = 0, lib_path: Optional[str] = None):
+        self.probsize = ProblemSize(N, model)
+        self.N, self.dt, self.model, self.opts = N, dt, model, opts
+        self.x0 = np.asarray(x0, float).reshape(model.n).copy()
+        self.game_obj, self.game_con = game_obj, game_con
+        self.core = _Core(self.probsize.S)
+        self.pdtraj = _PrimalDualTraj(self.probsize)
+        self.stats = Statistics()
+        self.status = None
+        self.conlam = self.conmu = None
+        self._device, self._lib_path, self._batch = device, lib_path, None
+
+    def batch(self) -> GameBatch:
+        if self._batch is None:
+            self._batch = GameBatch(self.model, self.N, self.dt, self.game_obj, self.game_con, 1, self._device, self._lib_path)
+        self._batch.set_instance_params(x0=self.x0[None, :])
+        return self._batch
+
+    def _push(self):
+        b = self.batch()
+        Z = np.concatenate([self.pdtraj.X, self.pdtraj.U], axis=1)[None]
+        b.set_initial(Z, self.pdtraj.du[None], None if self.conlam is None else self.conlam[None],
+                      None if self.conmu is None else self.conmu[None])
+        return b
+
+    def _pull(self, b: GameBatch):
+        Z, L, cl, cm = b.get_state()
+        n = self.probsize.n
+        self.pdtraj.X[:], self.pdtraj.U[:], self.pdtraj.du[:] = Z[0, :, :n], Z[0, :, n:], L[0]
+        self.conlam, self.conmu = cl[0], cm[0]
+
+
+def _same_schema(a: GameProblem, b: GameProblem) -> bool:
+    sa, sb = spec_of(a), spec_of(b)
+    for k in ("x0", "xf", "Q", "R", "uf", "opts"):
+        sa.pop(k); sb.pop(k)
+    return sa == sb
+
+
+def init_traj(prob: GameProblem, rng=None):
+    """init_traj!(pdtraj; x0, f=rand, amplitude, s=shift) (primal_dual_traj.jl:29-44), on the host arrays."""
+    o, ps, pd = prob.opts, prob.probsize, prob.pdtraj
+    rng = rng or np.random.default_rng(o.seed)
+    s, N = o.shift, ps.N
+    for k in range(1, N + 1):
+        if k + s <= N:
+            pd.X[k - 1], pd.U[k - 1] = pd.X[k + s - 1], pd.U[k + s - 1]
+        else:
+            z = o.amplitude_init * rng.random(ps.n + ps.m)
+            pd.X[k - 1], pd.U[k - 1] = z[:ps.n], z[ps.n:]
+    for i in range(ps.p):
+        for k in range(1, N):
+            pd.du[i, k - 1] = pd.du[i, k + s - 1] if k + s <= N - 1 else o.amplitude_init * rng.random(ps.n)
+    pd.X[0] = prob.x0
+
+
+def newton_solve(probs, init: bool = True):
+    """newton_solve!(prob) for one GameProblem or a list sharing one schema (solver_methods.jl:5-65).
+    Mutates prob.pdtraj, prob.stats, prob.core.res, prob.conlam/conmu, prob.status like the reference mutates prob."""
+    single = isinstance(probs, GameProblem)
+    plist = [probs] if single else list(probs)
+    if not plist:
+        return None
+    p0 = plist[0]
+    for q in plist[1:]:
+        if not _same_schema(p0, q):
+            raise ValueError("all problems of a batch must share model, sizes and constraint schema")
+    B, ps = len(plist), p0.probsize
+    batch = p0.batch() if B == 1 else GameBatch(p0.model, p0.N, p0.dt, p0.game_obj, p0.game_con, B, p0._device, p0._lib_path)
+    try:
+        if init:
+            for q in plist:
+                init_traj(q)
+        obj = [q.game_obj for q in plist]
+        batch.set_instance_params(
+            x0=np.stack([q.x0 for q in plist]),
+            xf=np.stack([_joint(o.xf, ps.p, 4) for o in obj]), Q=np.stack([_joint(o.Q, ps.p, 4) for o in obj]),
+            R=np.stack([_joint(o.R, ps.p, 2) for o in obj]), uf=np.stack([_joint(o.uf, ps.p, 2) for o in obj]))
+        Z0 = np.stack([np.concatenate([q.pdtraj.X, q.pdtraj.U], axis=1) for q in plist])
+        L0 = np.stack([q.pdtraj.du for q in plist])
+        have_duals = all(q.conlam is not None for q in plist)
+        batch.set_initial(Z0, L0, np.stack([q.conlam for q in plist]) if have_duals else None,
+                          np.stack([q.conmu for q in plist]) if have_duals else None)
+        out = batch.newton_solve(p0.opts)
+        res, _ = batch.residual()
+        for b, q in enumerate(plist):
+            q.pdtraj.X[:], q.pdtraj.U[:], q.pdtraj.du[:] = out["Z"][b, :, :ps.n], out["Z"][b, :, ps.n:], out["L"][b]
+            q.conlam, q.conmu = out["conlam"][b], out["conmu"][b]
+            q.stats = Statistics(); q.stats.record(out["stats"][b])
+            q.status = _capi.STATUS_NAMES[int(out["status"][b])]
+            q.core.res[:] = res[b]
+    finally:
+        if B > 1:
+            batch.close()
+    return None
+
+
+# ---- stand-alone exported functions of the reference, single-problem form ----------------------------------------
+def residual(prob: GameProblem):
+    """residual!(prob): fills prob.core.res (reference row order)."""
+    b = prob._push()
+    res, _ = b.residual()
+    prob.core.res[:] = res[0]
+    return prob.core.res
+
+
+def residual_jacobian(prob: GameProblem, reg: float = 0.0):
+    """residual_jacobian!(prob) + regularize_residual_jacobian!(prob): dense S×S prob.core.jac."""
+    b = prob._push()
+    prob.core.jac = b.residual_jacobian_dense(reg, reg)[0]
+    return prob.core.jac
+
+
+def kkt_solve(prob: GameProblem, reg: float = 0.0):
+    """Δtraj = −(lu(jac) \\ res) (solver_methods.jl:87), reference column order."""
+    return prob._push().kkt_solve(reg, reg)[0]
+
+
+def line_search(prob: GameProblem, reg: float = 0.0):
+    b = prob._push()
+    b.kkt_solve(reg, reg)
+    a, j = b.line_search(prob.opts, reg)
+    return float(a[0]), int(j[0])
+
+
+def update_traj(prob: GameProblem, alpha: float, reg: float = 0.0):
+    b = prob._push()
+    b.kkt_solve(reg, reg)
+    d = b.update_traj(alpha)
+    prob._pull(b)
+    return float(d[0])
+
+
+def rollout(prob: GameProblem):
+    b = prob._push(); b.rollout(); prob._pull(b)
+
+
+def dual_update(prob: GameProblem):
+    b = prob._push(); b.dual_update(prob.opts); prob._pull(b)
+
+
+def penalty_update(prob: GameProblem):
+    b = prob._push(); b.penalty_update(prob.opts); prob._pull(b)
+
+
+def reset(prob: GameProblem):
+    b = prob._push(); b.reset(prob.opts); prob._pull(b)
+
+
+def evaluate(prob: GameProblem):
+    return prob._push().evaluate()[0]
+
+
+def active_set(prob: GameProblem, tol: Optional[float] = None):
+    return prob._push().active_set(prob.opts.active_set_tolerance if tol is None else tol)[0]

@@ -1,0 +1,135 @@
+"""Synthetic inputs of the BASELINE.json configurations.  Each builder returns
+(model, N, dt, game_obj, game_con, opts, x0[B,n], xf[B,n] or None)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .problem import (BicycleGame, DoubleIntegratorGame, GameConstraintValues, GameObjective, Options, ProblemSize,
+                      UnicycleGame, Wall, add_circle_constraint, add_collision_avoidance, add_collision_cost,
+                      add_control_bound, add_state_bound, add_wall_constraint)
+
+
+def config_a():
+    """2-player UnicycleGame, N=20: test/problem/solver_methods.jl:132-182 verbatim (runs with the previous
+    block's opts, :108-126 — see SURVEY §8d)."""
+    p, N, dt = 2, 20, 0.1
+    model = UnicycleGame(p=p)
+    ps = ProblemSize(N, model)
+    obj = GameObjective([np.ones(4)] * p, [0.5 * np.ones(2)] * p, [np.zeros(4)] * p, [-np.ones(2)] * p, N, model)
+    con = GameConstraintValues(ps)
+    add_collision_avoidance(con, 0.05)
+    add_control_bound(con, np.ones(model.m), -np.ones(model.m))
+    add_circle_constraint(con, [1.5, 0.2, 0.3], [1.25, 0.2, 0.3], [0.2, 0.2, 0.3])
+    opts = Options(outer_iter=7, inner_iter=20, ls_iter=25, reg_0=1e-7, eps_dyn=1e-10, eps_opt=1e-10)
+    x0 = np.array([[1.0, 2.0, 1.1, 2.0, 0.0, 0.0, 0.9, 0.9]])
+    return model, N, dt, obj, con, opts, x0, None
+
+
+def config_a_prime():
+    """examples/intro_example.jl:11-72 verbatim: 3-player BicycleGame, N=20."""
+    p, N, dt = 3, 20, 0.1
+    model = BicycleGame(p=p)
+    ps = ProblemSize(N, model)
+    xf = [np.array([2, 0.4, 0, 0.0]), np.array([2, 0.0, 0, 0]), np.array([3, -0.4, 0, 0])]
+    obj = GameObjective([10 * np.ones(4)] * p, [0.1 * np.ones(2)] * p, xf, [np.zeros(2)] * p, N, model)
+    add_collision_cost(obj, np.ones(p), 5.0 * np.ones(p))
+    con = GameConstraintValues(ps)
+    add_collision_avoidance(con, 0.08)
+    add_control_bound(con, 5 * np.ones(model.m), -5 * np.ones(model.m))
+    add_state_bound(con, 0, 5 * np.ones(model.n), -5 * np.ones(model.n))
+    add_wall_constraint(con, [Wall([0.0, -0.4], [1.0, -0.4], [0.0, -1.0])])
+    add_circle_constraint(con, [1.0, 2.0, 3.0], [1.0, 2.0, 3.0], [0.1, 0.2, 0.3])
+    x0 = np.array([[0.1, 0.0, 0.5, -0.4, 0.0, 0.7, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]])
+    return model, N, dt, obj, con, Options(), x0, None
+
+
+def config_b(batch=1024, seed=1234, N=40):
+    """3-player DoubleIntegratorGame(d=2), N=40 — shape of examples/ibr_example.jl:12-74, jittered x0."""
+    p, dt = 3, 0.1
+    model = DoubleIntegratorGame(p=p, d=2)
+    ps = ProblemSize(N, model)
+    obj = GameObjective([50 * np.ones(4)] * p, [0.01 * np.ones(2)] * p, [np.zeros(4)] * p, [np.zeros(2)] * p, N, model)
+    add_collision_cost(obj, 3.0 * np.ones(p), 2.0 * np.ones(p))
+    con = GameConstraintValues(ps)
+    add_collision_avoidance(con, 0.25)
+    th = np.array([2 * math.pi * (1 - 1 / p) * i / (p - 1) for i in range(p)])
+    base = np.zeros(model.n)
+    base[0:p] = (0.5 + th / 10) * np.cos(th)
+    base[p:2 * p] = (0.5 + th / 10) * np.sin(th)
+    rng = np.random.default_rng(seed)
+    x0 = np.tile(base, (batch, 1))
+    x0[:, :2 * p] += rng.uniform(-0.1, 0.1, (batch, 2 * p))
+    x0[:, 2 * p:] += rng.uniform(-0.05, 0.05, (batch, 2 * p))
+    return model, N, dt, obj, con, Options(), x0, None
+
+
+def config_c(batch=8192, seed=2345, N=50):
+    """4-player UnicycleGame with collision constraints + control bounds, N=50."""
+    p, dt = 4, 0.1
+    model = UnicycleGame(p=p)
+    ps = ProblemSize(N, model)
+    obj = GameObjective([np.ones(4)] * p, [0.5 * np.ones(2)] * p, [np.zeros(4)] * p, [np.zeros(2)] * p, N, model)
+    con = GameConstraintValues(ps)
+    add_collision_avoidance(con, 0.15)
+    add_control_bound(con, 2 * np.ones(model.m), -2 * np.ones(model.m))
+    ang = np.array([2 * math.pi * i / p for i in range(p)])
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((batch, model.n))
+    x0[:, 0:p] = 2 * np.cos(ang) + rng.uniform(-0.1, 0.1, (batch, p))
+    x0[:, p:2 * p] = 2 * np.sin(ang) + rng.uniform(-0.1, 0.1, (batch, p))
+    x0[:, 2 * p:3 * p] = ang + math.pi                   # heading to the centre
+    x0[:, 3 * p:4 * p] = 0.5
+    xf = np.zeros((batch, model.n))
+    xf[:, 0:p] = -2 * np.cos(ang)                        # antipodal point
+    xf[:, p:2 * p] = -2 * np.sin(ang)
+    xf[:, 2 * p:3 * p] = ang + math.pi
+    return model, N, dt, obj, con, Options(), x0, xf
+
+
+def _lane_game(batch, seed, N, ramp):
+    """Synthetic 3-player Unicycle lane scenario used by configs D (ramp merge) and E (highway)."""
+    p, dt = 3, 0.1
+    model = UnicycleGame(p=p)
+    ps = ProblemSize(N, model)
+    obj = GameObjective([np.array([0.0, 1.0, 1.0, 1.0])] * p, [0.5 * np.ones(2)] * p, [np.zeros(4)] * p, [np.zeros(2)] * p, N, model)
+    con = GameConstraintValues(ps)
+    add_collision_avoidance(con, 0.08)
+    add_control_bound(con, 5 * np.ones(model.m), -5 * np.ones(model.m))
+    half = 0.4 if ramp else 0.5
+    lane = [Wall([-50.0, half], [50.0, half], [0.0, 1.0]), Wall([-50.0, -half], [50.0, -half], [0.0, -1.0])]
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((batch, model.n)); xf = np.zeros((batch, model.n))
+    if ramp:
+        add_wall_constraint(con, lane, 0); add_wall_constraint(con, lane, 1)
+        add_wall_constraint(con, [lane[0], Wall([-50.0, -0.9], [50.0, -0.9], [0.0, -1.0])], 2)
+        x0[:, 0:p] = np.array([0.0, 0.6, 0.3]) + rng.uniform(-0.05, 0.05, (batch, p))
+        x0[:, p:2 * p] = np.array([0.15, -0.15, -0.6])
+        x0[:, 3 * p:4 * p] = 1.0
+        xf[:, p:2 * p] = np.array([0.15, -0.15, -0.15])
+        xf[:, 3 * p:4 * p] = 1.0
+    else:
+        add_wall_constraint(con, lane)
+        x0[:, 0:p] = np.sort(rng.uniform(0, 3, (batch, p)), axis=1)
+        lanes = rng.choice([-0.25, 0.25], (batch, p))
+        x0[:, p:2 * p] = lanes
+        x0[:, 3 * p:4 * p] = rng.uniform(0.5, 1.5, (batch, p))
+        xf[:, p:2 * p] = lanes
+        xf[:, 3 * p:4 * p] = rng.uniform(0.8, 1.2, (batch, p))
+    return model, N, dt, obj, con, Options(), x0, xf
+
+
+def config_d(batch=4096, seed=3456, N=40):
+    """MPC ramp merge (synthetic; AlgamesDriving.jl is not in the reference tree): shift=1, dual_reset=False."""
+    model, N, dt, obj, con, opts, x0, xf = _lane_game(batch, seed, N, ramp=True)
+    opts.shift, opts.dual_reset = 1, False
+    return model, N, dt, obj, con, opts, x0, xf
+
+
+def config_e(batch=65536, seed=4567, N=60):
+    """Monte-Carlo highway sweep (synthetic)."""
+    return _lane_game(batch, seed, N, ramp=False)
+
+
+CONFIGS = {"A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}

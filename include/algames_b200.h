@@ -1,0 +1,206 @@
+/*
+ * algames_b200.h — C ABI of libalgames_b200.so: the batched ALGAMES Newton/KKT +
+ * augmented-Lagrangian solve on NVIDIA B200 (sm_100a).
+ *
+ * The reference (RoboticExplorationLab/Algames.jl) has no FFI boundary of its own
+ * (SURVEY.md F8): the drop-in boundary is its exported Julia API.  Every entry point
+ * below replaces one exported reference function on a *batch* of independent
+ * GameProblems that share one schema (model, players, horizon, constraint lists) and
+ * differ in x0 / targets / weights.  The Julia-side binding (`ccall`) is shown in
+ * INTEGRATION.md and shipped in julia/AlgamesB200.jl.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all arrays are C row-major, FP64, caller-owned host
+ *    memory unless the name says `_dev`.  A Julia Array{Float64} with reversed dims has
+ *    exactly this layout.
+ *  - every function returns 0 on success, <0 on error (agb_last_error() gives the text);
+ *    nothing throws across the boundary; one bad instance never aborts the batch
+ *    (per-instance `status`).
+ *  - calls on one handle must be serialised by the caller; host-buffer calls are
+ *    synchronous (return after the stream has drained).
+ *  - state / control / multiplier vectors use the REFERENCE layouts:
+ *      x, xf, Q   [n]  component-major joint state   (src/dynamics/unicycle.jl:18-20)
+ *      u, uf, R   [m]  component-major joint control
+ *      Z     [B][N][n+m]      knot-major primal trajectory, z_k = [x_k; u_k]       (struct/primal_dual_traj.jl:5-20)
+ *      L     [B][p][N-1][n]   dynamics multipliers λ_{i,k}                          (primal_dual_traj.jl:9)
+ *      res   [B][S]           KKT residual, reference row ("vertical") order        (core/newton_core.jl:40-63)
+ *      dtraj [B][S]           Newton step, reference column ("horizontal") order    (core/newton_core.jl:65-89)
+ *      conlam/conmu [B][N-1][nrow]  AL multipliers/penalties: stage k holds the state-constraint
+ *                 rows of knot k+1 — per player [collision j≠i ascending | state bound max rows, min rows |
+ *                 walls | circles] — followed by the control-bound rows of knot k [u_max rows, u_min rows]
+ *                 (finite bounds only, reference component order; control_bound_constraint.jl:33-35).
+ */
+#ifndef ALGAMES_B200_H
+#define ALGAMES_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGB_MAX_P 4      /* players                       */
+#define AGB_MAX_N 16     /* joint state dim  n = 4p       */
+#define AGB_MAX_M 8      /* joint control dim m = 2p      */
+#define AGB_MAX_WALLS 8  /* walls per player              */
+#define AGB_MAX_CIRCLES 8
+#define AGB_NSTATS 10
+
+enum { AGB_MODEL_DOUBLE_INTEGRATOR = 0, AGB_MODEL_UNICYCLE = 1, AGB_MODEL_BICYCLE = 2 };
+
+/* per-instance status written by agb_newton_solve_batch */
+enum {
+  AGB_CONVERGED = 0,      /* final record: dyn, con, sta, opt maxima all below their ϵ (solver_methods.jl:49-53) */
+  AGB_NOT_CONVERGED = 1,  /* outer_iter exhausted / line search failed / Δ<Δ_min with tolerances unmet       */
+  AGB_NUMERICAL_FAILURE = 2 /* singular pivot or non-finite residual                                       */
+};
+
+/* error codes */
+enum { AGB_OK = 0, AGB_EINVAL = -1, AGB_ECUDA = -2, AGB_ENOMEM = -3, AGB_EUNSUPPORTED = -4 };
+
+/* Problem schema shared by the whole batch.
+ * Mirrors GameProblem's constructor arguments (src/problem/problem.jl:35-53):
+ * model (dynamics/*.jl), GameObjective (objective/objective.jl:12-35, :84-100),
+ * GameConstraintValues + adders (constraints/constraints_methods.jl:5-195).           */
+typedef struct agb_problem_desc {
+  int model;                 /* AGB_MODEL_*                                              */
+  int p;                     /* players (1..4); n = 4p, m = 2p                           */
+  int d;                     /* DoubleIntegratorGame dimension — only d = 2 is supported */
+  int N;                     /* knots                                                    */
+  double dt;
+  double lf, lr;             /* BicycleGame (dynamics/bicycle.jl:15)                     */
+  /* LQR defaults, joint component-major (objective.jl:24-28 expand_vector); may be
+   * overridden per instance with agb_set_instance_params                              */
+  double Q[AGB_MAX_N], R[AGB_MAX_M], xf[AGB_MAX_N], uf[AGB_MAX_M];
+  /* add_collision_cost!(game_obj, radius, μ)  (objective.jl:84-100)                   */
+  int has_collision_cost;
+  double cc_radius[AGB_MAX_P], cc_mu[AGB_MAX_P];
+  /* add_collision_avoidance!: pair radius r_i+r_j for the ordered pair (i,j); 0 = none */
+  double col_radius[AGB_MAX_P][AGB_MAX_P];
+  /* add_control_bound!: ±INFINITY = no bound                                          */
+  int has_control_bound;
+  double u_max[AGB_MAX_M], u_min[AGB_MAX_M];
+  /* add_state_bound!(game_con, i, x_max, x_min): bound on the JOINT state, owned by player i */
+  int has_state_bound[AGB_MAX_P];
+  double x_max[AGB_MAX_P][AGB_MAX_N], x_min[AGB_MAX_P][AGB_MAX_N];
+  /* add_wall_constraint!: (x1,y1,x2,y2,xv,yv) per wall per player                      */
+  int n_walls[AGB_MAX_P];
+  double walls[AGB_MAX_P][AGB_MAX_WALLS][6];
+  /* add_circle_constraint!: (xc,yc,r)                                                  */
+  int n_circles[AGB_MAX_P];
+  double circles[AGB_MAX_P][AGB_MAX_CIRCLES][3];
+} agb_problem_desc;
+
+/* Live fields of Options (src/struct/options.jl:5-116; dead fields omitted). */
+typedef struct agb_options {
+  double reg_0;                 /* :27  */
+  int regularize;               /* :21  */
+  double alpha_decrease;        /* :37  */
+  double beta;                  /* :40  */
+  int ls_iter;                  /* :43  */
+  double delta_min;             /* :46  */
+  double rho_0;                 /* :50  initial penalty μ0 */
+  double rho_increase;          /* :56  ϕ  */
+  double rho_max;               /* :59  μ_max */
+  double lambda_max;            /* :62  */
+  double alpha_dual;            /* :65  */
+  double alphax_dual[AGB_MAX_P];/* :68  */
+  double active_set_tolerance;  /* :71 (only used by agb_active_set) */
+  double eps_dyn, eps_sta, eps_con, eps_opt; /* :75-84 */
+  int outer_iter, inner_iter;   /* :88, :91 */
+  int dual_reset;               /* :115 */
+} agb_options;
+
+typedef struct agb_handle agb_handle;
+
+/* Fills *o with the reference defaults (options.jl). */
+void agb_default_options(agb_options* o);
+
+/* Sizes derived from a descriptor (problem_size.jl:22 and the row schema above). */
+typedef struct agb_sizes { int n, m, p, N, S, nrow, nrow_state, nrow_control; } agb_sizes;
+int agb_sizes_of(const agb_problem_desc* d, agb_sizes* out);
+
+/* GameProblem(...) for a batch: allocates all device state.  device = CUDA ordinal.   */
+int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle** out);
+void agb_destroy(agb_handle* h);
+const char* agb_last_error(const agb_handle* h);   /* h may be NULL (creation errors)  */
+int agb_get_sizes(const agb_handle* h, agb_sizes* out);
+
+/* Per-instance x0 [B][n] and optional overrides (NULL keeps the descriptor default):
+ * xf [B][n], Q [B][n], R [B][m], uf [B][m].                                            */
+int agb_set_instance_params(agb_handle* h, const double* x0, const double* xf,
+                            const double* Q, const double* R, const double* uf);
+
+/* Initial iterate as init_traj! leaves it (primal_dual_traj.jl:29-44; x_1 is overwritten
+ * with x0 by the solver): Z0 [B][N][n+m], L0 [B][p][N-1][n].  conlam/conmu [B][N-1][nrow]
+ * may be NULL (zeros / rho_0 are used when dual_reset, else the resident values).      */
+int agb_set_initial(agb_handle* h, const double* Z0, const double* L0,
+                    const double* conlam, const double* conmu);
+int agb_get_state(agb_handle* h, double* Z, double* L, double* conlam, double* conmu);
+
+/* MPC warm start = init_traj! with shift s (primal_dual_traj.jl:34-41): the resident
+ * solution is shifted by s knots; the tail is filled from Zfresh/Lfresh (same shapes
+ * as Z0/L0; only the last s knots are read).  New x0 comes from agb_set_instance_params. */
+int agb_shift_initial(agb_handle* h, int s, const double* Zfresh, const double* Lfresh);
+
+/* ---- per-function entry points (operate on the resident batch; parity tests) -------- */
+/* rollout!(RK3, model, traj)                                  solver_methods.jl:17     */
+int agb_rollout(agb_handle* h);
+/* residual! + regularize_residual! at (Z + alpha·Δ) relative to Z, Δ = last agb_kkt_solve
+ * step (alpha = 0 ⇒ residual!(prob, pdtraj)).  res_out [B][S] or NULL.
+ * norms_out [B][5] or NULL: ‖res‖₁/S, dyn, con, sta, opt maxima (violations.jl:18-168). */
+int agb_residual(agb_handle* h, double reg_x, double reg_u, double alpha,
+                 double* res_out, double* norms_out);
+/* residual_jacobian! + regularize_residual_jacobian!, dense [B][S][S] (small cases).    */
+int agb_residual_jacobian_dense(agb_handle* h, double reg_x, double reg_u, double* J_out);
+/* Δtraj = −(lu(jac) \ res)                                    solver_methods.jl:87-88  */
+int agb_kkt_solve(agb_handle* h, double reg_x, double reg_u, double* dtraj_out);
+/* line_search(prob, res_norm)                                 solver_methods.jl:105-125 */
+int agb_line_search(agb_handle* h, const agb_options* o, double reg_x, double reg_u,
+                    double* alpha_out, int* j_out);
+/* update_traj!(pdtraj, pdtraj, α, Δpdtraj) + Δ_step           primal_dual_traj.jl:109-147 */
+int agb_update_traj(agb_handle* h, const double* alpha, double* delta_step_out);
+/* evaluate! + dual_update!, penalty_update!, reset!           constraints_methods.jl:295-440 */
+int agb_dual_update(agb_handle* h, const agb_options* o);
+int agb_penalty_update(agb_handle* h, const agb_options* o);
+int agb_reset_duals_penalties(agb_handle* h, const agb_options* o);
+/* constraint values c [B][N-1][nrow] at the resident iterate (evaluate!), and the active-set
+ * predicate (c >= -tol) | (λ > 0) as 0/1 bytes (update_active_set!, constraints_methods.jl:396-415) */
+int agb_evaluate_constraints(agb_handle* h, double* c_out);
+int agb_active_set(agb_handle* h, double tol, unsigned char* active_out);
+
+/* ---- the hot path: newton_solve!(prob) for every instance ---------------------------- */
+/* Host-buffer form.  All outputs may be NULL.  Z_out [B][N][n+m], L_out [B][p][N-1][n],
+ * conlam_out/conmu_out [B][N-1][nrow], stats_out [B][AGB_NSTATS] =
+ *   {‖res‖₁/S, dyn, con, sta, opt (final record), last Δ, Newton steps, outer iterations,
+ *    residual evaluations, spare}, status_out [B].                                      */
+int agb_newton_solve_batch(agb_handle* h, const agb_options* o,
+                           double* Z_out, double* L_out, double* conlam_out, double* conmu_out,
+                           double* stats_out, int* status_out);
+
+/* Device-resident form: enqueue the solve on `stream` (a cudaStream_t, 0 = legacy default)
+ * with no host copies and no synchronisation; results stay in the handle's device buffers. */
+int agb_newton_solve_async(agb_handle* h, const agb_options* o, void* stream);
+
+/* Raw device pointers of the resident results (for NCCL all-gather / zero-copy consumers). */
+typedef struct agb_device_view {
+  double* Z_dev;      /* [B][N][n+m]    */
+  double* L_dev;      /* [B][p][N-1][n] */
+  double* conlam_dev; /* [B][N-1][nrow] */
+  double* conmu_dev;
+  double* stats_dev;  /* [B][AGB_NSTATS] */
+  int* status_dev;    /* [B] */
+  double* x0_dev;     /* [B][n] */
+  double* Z0_dev;     /* initial iterate [B][N][n+m] */
+  double* L0_dev;
+} agb_device_view;
+int agb_get_device_view(agb_handle* h, agb_device_view* out);
+
+/* Number of kernels this library has launched on the handle since creation. */
+long long agb_launch_count(const agb_handle* h);
+/* Device time of the last agb_newton_solve_* kernel (CUDA events on its own stream), ms;
+ * synchronises.                                                                         */
+float agb_last_solve_ms(agb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
