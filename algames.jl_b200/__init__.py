@@ -7,5 +7,6 @@ from . import _capi
 from .problem import *          # noqa: F401,F403
 from .problem import AlgamesError, init_traj
 from . import workloads
+from . import distributed
 
 __version__ = "0.1.0"

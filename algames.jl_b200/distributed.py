@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: instances are independent, so a batch is split contiguously across ranks with no
+data-path collective; one all-gather collects converged trajectories, duals, stats and status at the end."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(total: int, world: int, rank: int):
+    """Contiguous split of `total` instances: ranks < total % world get one extra."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
+
+
+def device_tensor(ptr, shape, dtype="f8", device=0):
+    """Zero-copy torch view of a device buffer owned by an agb_handle (agb_get_device_view)."""
+    import torch
+    return torch.as_tensor(_CudaArray(ptr, shape, "<" + dtype), device=f"cuda:{device}")
+
+
+def result_views(batch):
+    """torch views (no copy) of the resident results of a GameBatch."""
+    v, B = batch.device_view(), batch.batch
+    dev = batch.device
+    out = {
+        "Z": device_tensor(v.Z_dev, (B, batch.N * (batch.n + batch.m)), "f8", dev),
+        "L": device_tensor(v.L_dev, (B, batch.p * (batch.N - 1) * batch.n), "f8", dev),
+        "stats": device_tensor(v.stats_dev, (B, 10), "f8", dev),
+        "status": device_tensor(v.status_dev, (B,), "i4", dev),
+    }
+    return out
+
+
+def pack_results(views, out=None):
+    """[B, zs+ls+10+1] FP64 slab (status widened to FP64) — one buffer, so one collective."""
+    import torch
+    parts = [views["Z"], views["L"], views["stats"], views["status"].to(torch.float64)[:, None]]
+    if out is None:
+        return torch.cat(parts, dim=1)
+    torch.cat(parts, dim=1, out=out)
+    return out
+
+
+def all_gather_results(local_slab, group=None):
+    """The single collective of the path: all-gather of the per-rank result slabs (equal shard sizes)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local_slab.shape[0], local_slab.shape[1]), dtype=local_slab.dtype, device=local_slab.device)
+    dist.all_gather_into_tensor(out, local_slab.contiguous(), group=group)
+    return out
+
+
+def unpack_results(slab, N, n, m, p):
+    zs, ls = N * (n + m), p * (N - 1) * n
+    a = slab.cpu().numpy() if hasattr(slab, "cpu") else np.asarray(slab)
+    B = a.shape[0]
+    return {"Z": a[:, :zs].reshape(B, N, n + m), "L": a[:, zs:zs + ls].reshape(B, p, N - 1, n),
+            "stats": a[:, zs + ls:zs + ls + 10], "status": a[:, -1].astype(np.int32)}

@@ -455,7 +455,15 @@ class GameBatch:
         return a.astype(bool)
 
     # ---- the hot path
-    def newton_solve(self, opts: Options, want=("Z", "L", "conlam", "conmu", "stats", "status")):
+    def newton_solve(self, opts: Options, want=("Z", "L", "conlam", "conmu", "stats", "status"), out=None):
+        """agb_newton_solve_batch: solve every instance and copy the requested results to host arrays (`out` may hold
+        preallocated, e.g. pinned, arrays of the right shapes)."""
+        if out is not None:
+            oc = opts.to_c()
+            self._ck(self.lib.agb_newton_solve_batch(
+                self.h, C.byref(oc), _capi.dptr(out.get("Z")), _capi.dptr(out.get("L")), _capi.dptr(out.get("conlam")),
+                _capi.dptr(out.get("conmu")), _capi.dptr(out.get("stats")), _capi.iptr(out.get("status"))))
+            return out
         out = {}
         if "Z" in want: out["Z"] = np.empty(self._z())
         if "L" in want: out["L"] = np.empty(self._l())

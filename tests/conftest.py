@@ -6,6 +6,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def pytest_configure(config):
@@ -13,6 +15,8 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    if os.environ.get("AGB_GPU_TESTS_ON_EMULATOR"):      # developer aid, see tests/test_gpu_parity.py
+        return
     try:
         import torch
         has_gpu = torch.cuda.is_available()

@@ -1,0 +1,226 @@
+"""Parity checks shared by the CPU tier (CTA emulator, tests/emu) and the GPU tier (real libalgames_b200.so).
+Every check drives the library through the C ABI (ctypes) and compares with the NumPy oracle on the same inputs."""
+import numpy as np
+
+import algames_b200 as ab
+import oracle.algames_oracle as O
+
+# tolerances (floating point, FP64): per-function results on identical inputs, and converged solutions
+TOL_FUNC = 1e-10       # relative, residual / Jacobian / Newton step vs the oracle
+TOL_SOLVE = 1e-6       # absolute, primal/dual trajectories and violations of a full newton_solve (north_star bound)
+
+
+def small_config(name, batch=1, N=None):
+    W = ab.workloads
+    if name == "A":
+        return W.config_a()
+    if name == "A'":
+        return W.config_a_prime()
+    kw = {"batch": batch}
+    if N is not None:
+        kw["N"] = N
+    return W.CONFIGS[name](**kw)
+
+
+def oracle_problem(model, N, dt, obj, con, opts, x0, xf_joint=None):
+    prob = ab.GameProblem(N, dt, x0, model, opts, obj, con, lib_path="unused")
+    xfb = None
+    if xf_joint is not None:
+        p = model.p
+        xfb = np.stack([np.asarray(xf_joint)[[i + c * p for c in range(4)]] for i in range(p)])
+    return O.problem_from_spec(ab.spec_of(prob), xf=xfb)
+
+
+def random_state(oprob, x0, rng, mu_exp=(0, 3)):
+    pd = oprob.pdtraj
+    pd.X[:] = rng.normal(size=pd.X.shape); pd.U[:] = rng.normal(size=pd.U.shape); pd.du[:] = rng.normal(size=pd.du.shape)
+    pd.X[0] = x0
+    for _, _, cv in oprob.game_con.all_convals():
+        cv.mu[:] = 10 ** rng.uniform(mu_exp[0], mu_exp[1], cv.mu.shape)
+        cv.lam[:] = rng.random(cv.lam.shape) * (rng.random(cv.lam.shape) > 0.5)
+    lam, mu = O.pack_multipliers(oprob)
+    Z = np.concatenate([pd.X, pd.U], axis=1)
+    return Z, pd.du.copy(), lam, mu
+
+
+def check_per_function(lib_path, name, seed=0, reg=1e-3, N=None):
+    """residual!, residual_jacobian!, Δtraj solve, line search, update_traj!, Δ_step, evaluate!, dual/penalty update,
+    active set — one random (far from converged) iterate with random multipliers and penalties up to 1e3."""
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, 2, N)
+    B = 2
+    x0 = np.tile(x0[:1], (B, 1)) if x0.shape[0] < B else x0[:B]
+    xf = None if xf is None else xf[:B]
+    rng = np.random.default_rng(seed)
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path)
+    gb.set_instance_params(x0=x0, xf=xf)
+    oprobs, Zs, Ls, lams, mus = [], [], [], [], []
+    for b in range(B):
+        op = oracle_problem(model, N, dt, obj, con, opts, x0[b], None if xf is None else xf[b])
+        Z, L, lam, mu = random_state(op, x0[b], rng)
+        oprobs.append(op); Zs.append(Z); Ls.append(L); lams.append(lam); mus.append(mu)
+    has_con = lams[0].size > 0
+    gb.set_initial(np.stack(Zs), np.stack(Ls), np.stack(lams) if has_con else None, np.stack(mus) if has_con else None)
+    res, norms = gb.residual()
+    J = gb.residual_jacobian_dense(reg, reg)
+    d = gb.kkt_solve(reg, reg)
+    alpha, j = gb.line_search(opts, reg)
+    c = gb.evaluate()
+    act = gb.active_set(opts.active_set_tolerance)
+    for b, op in enumerate(oprobs):
+        pd = op.pdtraj
+        ores = O.residual(op, pd).copy()
+        scale = np.abs(ores).max()
+        assert np.abs(res[b] - ores).max() <= TOL_FUNC * scale
+        rec = O.record(op, pd, 0.0, 1)
+        assert np.allclose(norms[b], [rec.res, rec.dyn, rec.con, rec.sta, rec.opt], rtol=1e-12, atol=1e-12)
+        op.opts.reg.set(reg)
+        O.residual(op, pd)
+        Jo = O.residual_jacobian(op, pd)
+        assert np.abs(J[b] - Jo).max() <= TOL_FUNC * np.abs(Jo).max()
+        ref = -np.linalg.solve(Jo, ores)
+        assert np.abs(d[b] - ref).max() <= 1e-9 * np.abs(ref).max()
+        # the step solves the reference's linear system at least as well as dense LU does
+        assert np.abs(Jo @ d[b] + ores).max() <= 10 * max(np.abs(Jo @ ref + ores).max(), 1e-12 * scale)
+        # line search from the same step
+        O.set_traj(op.core, op.dpdtraj, d[b])
+        op.pdtraj_trial = op.pdtraj.copy()          # x_1 = x0 on the trial trajectory (solver_methods.jl:14)
+        res_norm = np.abs(ores).sum() / len(ores)
+        op.core.res[:] = ores
+        a_o, j_o = O.line_search(op, res_norm)
+        assert j[b] == j_o and alpha[b] == a_o
+        # constraint values / active set
+        if has_con:
+            op.game_con.evaluate(pd.X, pd.U)
+            vals, _ = pack_vals(op)
+            assert np.allclose(c[b], vals, rtol=1e-13, atol=1e-13)
+            lam_o, _ = O.pack_multipliers(op)
+            assert np.array_equal(act[b], (vals >= -opts.active_set_tolerance) | (lam_o > 0))
+    # trial residual (regularize_residual!) at alpha = 0.25
+    rt, _ = gb.residual(reg, reg, 0.25)
+    for b, op in enumerate(oprobs):
+        O.update_traj(op.pdtraj_trial, op.pdtraj, 0.25, op.dpdtraj)
+        O.residual(op, op.pdtraj_trial)
+        O.regularize_residual(op, op.pdtraj_trial, op.pdtraj)
+        assert np.abs(rt[b] - op.core.res).max() <= TOL_FUNC * np.abs(op.core.res).max()
+    # update_traj! + Δ_step
+    dstep = gb.update_traj(alpha)
+    Z, L, _, _ = gb.get_state()
+    n = model.n
+    for b, op in enumerate(oprobs):
+        O.update_traj(op.pdtraj, op.pdtraj, alpha[b], op.dpdtraj)
+        assert abs(dstep[b] - O.delta_step(op.dpdtraj, alpha[b])) <= 1e-12 * max(1.0, abs(dstep[b]))
+        assert np.abs(Z[b, :, :n] - op.pdtraj.X).max() <= 1e-12 * max(1.0, np.abs(op.pdtraj.X).max())
+        assert np.abs(Z[b, :-1, n:] - op.pdtraj.U[:-1]).max() <= 1e-12 * max(1.0, np.abs(op.pdtraj.U).max())
+        assert np.abs(L[b] - op.pdtraj.du).max() <= 1e-12 * max(1.0, np.abs(op.pdtraj.du).max())
+    # dual ascent + penalty schedule at the new iterate
+    if has_con:
+        gb.dual_update(opts); gb.penalty_update(opts)
+        _, _, cl, cm = gb.get_state()
+        for b, op in enumerate(oprobs):
+            op.game_con.evaluate(op.pdtraj.X, op.pdtraj.U)
+            op.game_con.dual_update(); op.game_con.penalty_update()
+            lam_o, mu_o = O.pack_multipliers(op)
+            assert np.allclose(cl[b], lam_o, rtol=1e-13, atol=1e-13) and np.allclose(cm[b], mu_o, rtol=1e-13)
+        gb.reset(opts)
+        _, _, cl, cm = gb.get_state()
+        assert (cl == 0).all() and (cm == opts.rho_0).all()
+    gb.close()
+
+
+def pack_vals(op):
+    ps, gc = op.probsize, op.game_con
+    out = []
+    for k in range(1, ps.N):
+        row = []
+        for i in range(ps.p):
+            for cv in gc.state_conval[i]:
+                row.append(cv.vals[k - 1])
+        for cv in gc.control_conval:
+            row.append(cv.vals[k - 1])
+        out.append(np.concatenate(row) if row else np.zeros(0))
+    return np.array(out), None
+
+
+def check_rollout(lib_path, name):
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, 1)
+    gb = ab.GameBatch(model, N, dt, obj, con, 1, lib_path=lib_path)
+    gb.set_instance_params(x0=x0[:1])
+    rng = np.random.default_rng(3)
+    Z0 = rng.normal(size=(1, N, model.n + model.m)); L0 = np.zeros((1, model.p, N - 1, model.n))
+    gb.set_initial(Z0, L0)
+    gb.rollout()
+    Z, _, _, _ = gb.get_state()
+    op = oracle_problem(model, N, dt, obj, con, opts, x0[0])
+    op.pdtraj.X[:] = Z0[0, :, :model.n]; op.pdtraj.U[:] = Z0[0, :, model.n:]; op.pdtraj.X[0] = x0[0]
+    O.rollout_rk3(op.model, op.pdtraj)
+    assert np.abs(Z[0, :, :model.n] - op.pdtraj.X).max() <= 1e-12 * max(1.0, np.abs(op.pdtraj.X).max())
+    gb.close()
+
+
+def solve_batch(lib_path, name, B, N=None, opts_override=None):
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, B, N)
+    if x0.shape[0] < B:
+        x0 = np.tile(x0[:1], (B, 1)); x0[:, :2 * model.p] += 0.01 * np.arange(B)[:, None]
+    if opts_override:
+        for k, v in opts_override.items():
+            setattr(opts, k, v)
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path)
+    gb.set_instance_params(x0=x0, xf=xf)
+    Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+    out = gb.newton_solve(opts)
+    return (model, N, dt, obj, con, opts, x0, xf), gb, Z0, L0, out
+
+
+def check_solve_vs_oracle(lib_path, name, B=2, N=None, which=None):
+    """Full newton_solve! on the same initial iterate: converged trajectories, duals, AL multipliers, final record."""
+    cfg, gb, Z0, L0, out = solve_batch(lib_path, name, B, N)
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    for b in (range(B) if which is None else which):
+        op = oracle_problem(model, N, dt, obj, con, opts, x0[b], None if xf is None else xf[b])
+        O.newton_solve(op, Z0=Z0[b], L0=L0[b])
+        last, st = op.stats[-1], out["stats"][b]
+        Zo = np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1)
+        assert np.abs(out["Z"][b] - Zo).max() < TOL_SOLVE
+        assert np.abs(out["L"][b] - op.pdtraj.du).max() < TOL_SOLVE * max(1.0, np.abs(op.pdtraj.du).max())
+        assert np.allclose(st[:5], [last.res, last.dyn, last.con, last.sta, last.opt], atol=TOL_SOLVE)
+        assert (out["status"][b] == 0) == op.converged
+        lam_o, mu_o = O.pack_multipliers(op)
+        if lam_o.size:
+            assert np.allclose(out["conlam"][b], lam_o, atol=TOL_SOLVE * max(1.0, np.abs(lam_o).max()))
+            assert np.allclose(out["conmu"][b], mu_o, rtol=1e-12)
+    gb.close()
+    return out
+
+
+def check_solution_properties(cfg, out, gb_factory):
+    """Size-independent properties of a solved batch: the reported record is reproduced by re-evaluating the residual
+    at the returned iterate, converged instances meet every tolerance, and a solve restarted from the solution with the
+    returned multipliers stops immediately."""
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    gb = gb_factory()
+    gb.set_instance_params(x0=x0, xf=xf)
+    gb.set_initial(out["Z"], out["L"], out["conlam"] if out["conlam"].size else None, out["conmu"] if out["conmu"].size else None)
+    _, norms = gb.residual(want_res=False)
+    assert np.allclose(norms, out["stats"][:, :5], rtol=1e-9, atol=1e-12)
+    conv = out["status"] == 0
+    eps = np.array([opts.eps_dyn, opts.eps_con, opts.eps_sta, opts.eps_opt])
+    assert (out["stats"][conv][:, 1:5] < eps).all()
+    assert np.isfinite(out["Z"]).all() and np.isfinite(out["L"]).all()
+    return gb, conv
+
+
+def check_golden(lib_path, path):
+    """Committed golden vector (tests/golden/make_golden.py): same inputs -> same converged solution and Newton count."""
+    g = np.load(path)
+    name, B = str(g["config"]), int(g["x0"].shape[0])
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, B, int(g["N"]))
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path)
+    gb.set_instance_params(x0=g["x0"], xf=(g["xf"] if "xf" in g.files else None))
+    gb.set_initial(g["Z0"], g["L0"])
+    out = gb.newton_solve(opts)
+    assert np.abs(out["Z"] - g["Z"]).max() < TOL_SOLVE, path
+    assert np.abs(out["L"] - g["L"]).max() < TOL_SOLVE * max(1.0, np.abs(g["L"]).max()), path
+    assert np.allclose(out["stats"][:, :5], g["stats"], atol=TOL_SOLVE), path
+    assert np.array_equal(out["status"] == 0, g["converged"]), path
+    assert np.array_equal(out["stats"][:, 6].astype(int), g["n_newton"]), path
+    gb.close()

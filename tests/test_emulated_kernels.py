@@ -1,0 +1,79 @@
+"""CPU tier: the CUDA library's sources compiled by g++ against the test-only CTA emulator (tests/emu) and driven
+through the same C ABI, compared with the oracle.  Checks kernel *logic* without a GPU; the real parity tests are
+tests/test_gpu_parity.py."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu", "libagb_emu.so")
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    src = [os.path.join(HERE, "emu", f) for f in ("emu.cpp", "cuda_runtime.h")]
+    csrc = os.path.join(HERE, "..", "algames.jl_b200", "csrc")
+    src += [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in src):
+        subprocess.run([os.path.join(HERE, "emu", "build.sh")], check=True)
+    return EMU
+
+
+@pytest.mark.parametrize("name,N", [("A", None), ("A'", None), ("B", 12), ("C", 10), ("D", 10), ("E", 12)])
+def test_per_function_parity_emulated(emu_lib, name, N):
+    parity.check_per_function(emu_lib, name, seed=1, N=N)
+
+
+@pytest.mark.parametrize("name", ["A'", "B"])
+def test_rollout_emulated(emu_lib, name):
+    parity.check_rollout(emu_lib, name)
+
+
+def test_solve_config_a_emulated(emu_lib):
+    # test/problem/solver_methods.jl:132-182 through the device control flow
+    out = parity.check_solve_vs_oracle(emu_lib, "A", B=1)
+    assert out["status"][0] == 0 and (out["stats"][0, 1:5] < 1e-3).all()
+
+
+def test_solve_config_b_short_horizon_emulated(emu_lib):
+    parity.check_solve_vs_oracle(emu_lib, "B", B=2, N=12)
+
+
+def test_unconstrained_lq_game_one_newton_step_emulated(emu_lib):
+    # test/problem/solver_methods.jl:68-97: 2-player LQ game solved by exactly one Newton step
+    import algames_b200 as ab
+    p, N, dt = 2, 20, 0.1
+    model = ab.DoubleIntegratorGame(p=p)
+    obj = ab.GameObjective([np.ones(4)] * p, [0.5 * np.ones(2)] * p, [np.zeros(4)] * p, [-np.ones(2)] * p, N, model)
+    con = ab.GameConstraintValues(ab.ProblemSize(N, model))
+    opts = ab.Options(outer_iter=1, inner_iter=1, ls_iter=25, reg_0=1e-7, eps_dyn=1e-10, eps_opt=1e-10)
+    prob = ab.GameProblem(N, dt, [1.0, 2.0, 1.0, 2.0, 0, 0, 0.9, 0.9], model, opts, obj, con, lib_path=emu_lib)
+    ab.newton_solve(prob)
+    assert np.abs(prob.core.res).sum() / prob.probsize.S < 1e-6
+    assert prob.stats.dyn_vio[-1].max < 1e-6 and prob.stats.newton_steps == 1
+
+
+def test_error_behaviour_emulated(emu_lib):
+    import algames_b200 as ab
+    model = ab.UnicycleGame(p=2)
+    con = ab.GameConstraintValues(ab.ProblemSize(10, model))
+    with pytest.raises(ValueError):                      # control_bound_constraint.jl:62-68
+        ab.add_control_bound(con, -np.ones(4), np.ones(4))
+    obj = ab.GameObjective([np.ones(4)] * 2, [np.ones(2)] * 2, [np.zeros(4)] * 2, [np.zeros(2)] * 2, 10, model)
+    with pytest.raises(ab.AlgamesError):
+        ab.GameBatch(model, 10, 0.1, obj, con, 0, lib_path=emu_lib)       # empty batch
+    with pytest.raises(ab.AlgamesError):
+        ab.GameBatch(model, 1, 0.1, obj, con, 1, lib_path=emu_lib)        # N < 2
+    gb = ab.GameBatch(model, 10, 0.1, obj, con, 1, lib_path=emu_lib)
+    with pytest.raises(ValueError):
+        gb.set_instance_params(x0=np.zeros((2, 8)))                       # ragged batch
+    gb.close()
+
+
+@pytest.mark.parametrize("f", ["solve_C.npz", "solve_E.npz"])
+def test_golden_emulated(emu_lib, f):
+    parity.check_golden(emu_lib, os.path.join(HERE, "golden", f))

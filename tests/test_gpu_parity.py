@@ -1,0 +1,143 @@
+"""GPU tier (-m gpu): the shipped libalgames_b200.so on a real B200, through the C ABI, against the NumPy oracle on the
+same seeded inputs, against the committed golden fixtures, and — at BASELINE sizes — through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = None      # default: the in-tree nvcc build
+FULL = {"B": 1024, "C": 512}
+if os.environ.get("AGB_GPU_TESTS_ON_EMULATOR"):      # developer aid: exercise this file's logic on the CPU emulator
+    LIB = os.path.join(HERE, "emu", "libagb_emu.so")
+    FULL = {"B": 136, "C": 133}
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+
+
+@pytest.mark.parametrize("name,N", [("A", None), ("A'", None), ("B", None), ("C", None), ("D", None), ("E", 30), ("B", 2), ("C", 3)])
+def test_per_function_parity(name, N):
+    parity.check_per_function(LIB, name, seed=2, N=N)
+
+
+@pytest.mark.parametrize("name", ["A", "A'", "B", "C"])
+def test_rollout(name):
+    parity.check_rollout(LIB, name)
+
+
+def test_solve_config_a():
+    out = parity.check_solve_vs_oracle(LIB, "A", B=1)
+    assert out["status"][0] == 0 and (out["stats"][0, 1:5] < 1e-3).all()
+
+
+def test_solve_config_a_prime():
+    parity.check_solve_vs_oracle(LIB, "A'", B=1)
+
+
+def test_solve_config_b_full_horizon():
+    parity.check_solve_vs_oracle(LIB, "B", B=8, which=[0, 5])
+
+
+def test_solve_config_c_short_horizon():
+    parity.check_solve_vs_oracle(LIB, "C", B=4, N=16, which=[1])
+
+
+def test_solve_config_d_short_horizon():
+    parity.check_solve_vs_oracle(LIB, "D", B=2, N=16, which=[0])
+
+
+def test_golden_fixtures():
+    files = sorted(f for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz"))
+    assert len(files) >= 5
+    for f in files:
+        parity.check_golden(LIB, os.path.join(HERE, "golden", f))
+
+
+@pytest.mark.parametrize("name", ["B", "C"])
+def test_full_size_properties(name):
+    """BASELINE sizes: record reproducibility, tolerances of converged instances, determinism, instance independence
+    (a sub-batch solved alone gives bit-identical results), and idempotence (a restart from the solution with the
+    returned multipliers takes no Newton step)."""
+    import algames_b200 as ab
+    B = FULL[name]
+    cfg, gb, Z0, L0, out = parity.solve_batch(LIB, name, B)
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    gb2, conv = parity.check_solution_properties(cfg, out, lambda: ab.GameBatch(model, N, dt, obj, con, B, lib_path=LIB))
+    assert conv.mean() > 0.9, conv.mean()
+    # determinism
+    out_b = gb.newton_solve(opts)
+    for k in ("Z", "L", "conlam", "conmu", "stats"):
+        assert np.array_equal(out[k], out_b[k]), k
+    # independence: instances 100..131 alone
+    sl = slice(100, 132)
+    gs = ab.GameBatch(model, N, dt, obj, con, 32, lib_path=LIB)
+    gs.set_instance_params(x0=x0[sl], xf=None if xf is None else xf[sl])
+    gs.set_initial(Z0[sl], L0[sl])
+    outs = gs.newton_solve(opts)
+    assert np.array_equal(outs["Z"], out["Z"][sl]) and np.array_equal(outs["L"], out["L"][sl])
+    # idempotence: restart at the solution, keep duals/penalties
+    # (newton_solve! always re-rolls the trajectory out with RK3 first, solver_methods.jl:17: exact for the double
+    # integrator up to round-off, an O(dt^3) perturbation for the unicycle — so only config B is a fixed point.)
+    o2 = ab.Options(**{**opts.to_dict(), "dual_reset": False})
+    out2 = gb2.newton_solve(o2)
+    if name == "B":
+        assert (out2["stats"][conv, 6] == 0).all()
+        assert np.abs(out2["Z"][conv] - out["Z"][conv]).max() < 1e-9
+    else:
+        assert out2["stats"][conv, 6].mean() < 0.5 * out["stats"][conv, 6].mean()
+    for g_ in (gb, gb2, gs):
+        g_.close()
+
+
+def test_mpc_shift_warm_start():
+    """init_traj! with shift=1 on device (primal_dual_traj.jl:34-41) vs the oracle's shift, then a warm-started re-solve."""
+    import algames_b200 as ab
+    import oracle.algames_oracle as O
+    cfg, gb, Z0, L0, out = parity.solve_batch(LIB, "D", 2, N=16)
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    rng = np.random.default_rng(7)
+    Zf = 1e-8 * rng.random(Z0.shape); Lf = 1e-8 * rng.random(L0.shape)
+    gb.shift_initial(1, Zf, Lf)
+    Z, L, _, _ = gb.get_state()
+    for b in range(2):
+        assert np.array_equal(Z[b, :-1], out["Z"][b, 1:]) and np.array_equal(Z[b, -1], Zf[b, -1])
+        assert np.array_equal(L[b, :, :-1], out["L"][b, :, 1:]) and np.array_equal(L[b, :, -1], Lf[b, :, -1])
+    x0n = out["Z"][:, 1, :model.n].copy()
+    gb.set_instance_params(x0=x0n)
+    out2 = gb.newton_solve(opts)
+    assert (out2["stats"][:, 6] <= out["stats"][:, 6]).all()      # warm start never needs more Newton steps here
+    assert np.isfinite(out2["Z"]).all()
+    gb.close()
+
+
+def test_numerical_failure_is_per_instance():
+    """A NaN initial state poisons only its own instance (status 2); the rest of the batch still converges."""
+    cfg = parity.small_config("B", 8)
+    import algames_b200 as ab
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    x0 = x0.copy(); x0[3, 0] = np.nan
+    gb = ab.GameBatch(model, N, dt, obj, con, 8, lib_path=LIB)
+    gb.set_instance_params(x0=x0)
+    gb.random_initial()
+    out = gb.newton_solve(opts)
+    assert out["status"][3] == 2 and (np.delete(out["status"], 3) == 0).all()
+    gb.close()
+
+
+def test_single_problem_api_matches_reference_tests():
+    """test/problem/solver_methods.jl:132-182 through the GameProblem / newton_solve surface."""
+    import algames_b200 as ab
+    model, N, dt, obj, con, opts, x0, _ = ab.workloads.config_a()
+    prob = ab.GameProblem(N, dt, x0[0], model, opts, obj, con, lib_path=LIB)
+    ab.newton_solve(prob)
+    assert np.abs(prob.core.res).sum() / prob.probsize.S < 1e-3
+    assert prob.stats.dyn_vio[-1].max < 1e-3 and prob.stats.sta_vio[-1].max < 1e-3
+    assert prob.stats.con_vio[-1].max < 1e-3 and prob.stats.opt_vio[-1].max < 1e-3
+    assert prob.status == "converged"
