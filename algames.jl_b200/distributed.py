@@ -62,3 +62,28 @@ def unpack_results(slab, N, n, m, p):
     B = a.shape[0]
     return {"Z": a[:, :zs].reshape(B, N, n + m), "L": a[:, zs:zs + ls].reshape(B, p, N - 1, n),
             "stats": a[:, zs + ls:zs + ls + 10], "status": a[:, -1].astype(np.int32)}
+
+
+def pack_host_results(out):
+    """Same slab as pack_results, built from the host arrays agb_newton_solve_batch returned."""
+    import torch
+    B = out["Z"].shape[0]
+    slab = np.concatenate([out["Z"].reshape(B, -1), out["L"].reshape(B, -1), out["stats"],
+                           out["status"].astype(np.float64)[:, None]], axis=1)
+    return torch.from_numpy(np.ascontiguousarray(slab))
+
+
+def solve_sharded(make_batch, x0, xf, Z0, L0, opts, rank, world, gather=True):
+    """Shard a batch contiguously across `world` ranks, solve the local shard, all-gather the results.
+    `make_batch(local_B)` returns a GameBatch on this rank's device."""
+    lo, hi = shard_bounds(x0.shape[0], world, rank)
+    gb = make_batch(hi - lo)
+    gb.set_instance_params(x0=x0[lo:hi], xf=None if xf is None else xf[lo:hi])
+    gb.set_initial(Z0[lo:hi], L0[lo:hi])
+    out = gb.newton_solve(opts)
+    slab = pack_host_results(out)
+    if gather and world > 1:
+        slab = all_gather_results(slab)
+    res = unpack_results(slab, gb.N, gb.n, gb.m, gb.p)
+    gb.close()
+    return res

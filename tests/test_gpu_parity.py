@@ -70,7 +70,9 @@ def test_full_size_properties(name):
     cfg, gb, Z0, L0, out = parity.solve_batch(LIB, name, B)
     model, N, dt, obj, con, opts, x0, xf = cfg
     gb2, conv = parity.check_solution_properties(cfg, out, lambda: ab.GameBatch(model, N, dt, obj, con, B, lib_path=LIB))
-    assert conv.mean() > 0.9, conv.mean()
+    # B: every instance converges; C (4 unicycles crossing at one point) leaves ~20% at outer_iter with tolerances unmet,
+    # in the oracle as well (test_nonconverged_instance_matches_oracle)
+    assert conv.mean() > (0.99 if name == "B" else 0.7), conv.mean()
     # determinism
     out_b = gb.newton_solve(opts)
     for k in ("Z", "L", "conlam", "conmu", "stats"):
