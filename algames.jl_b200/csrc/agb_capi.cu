@@ -5,203 +5,9 @@
 #include <string.h>
 #include <new>
 #include <string>
-#include "agb_solver.cuh"
+#include "agb_kernels.cuh"
 
 using namespace agb;
-
-// Kernel launch / dynamic shared memory go through two macros so that the test-only CTA emulator under tests/emu/
-// can compile this very file with g++ (AGB_EMULATE); the shipped library is always the nvcc build.
-#ifndef AGB_EMULATE
-#define AGB_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
-#define AGB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#endif
-
-// =============================================================================================================
-// Kernels
-// =============================================================================================================
-// newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
-template <int P>
-__global__ void __launch_bounds__(kThreads) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int batch) {
-  AGB_DYN_SMEM(sm);
-  Inst<P> I;
-  I.bind(dd, sm);
-  constexpr int n = Inst<P>::n;
-  const int K = I.K;
-  const double S = (double)(K * Inst<P>::b);
-  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
-    __syncthreads();
-    I.load_params(g, inst);
-    I.load_iterate(g.Z0, g.L0, inst);
-    I.load_duals(g, inst);
-    __syncthreads();
-    for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];     // x_1 ← x0 (primal_dual_traj.jl:42)
-    __syncthreads();
-    I.rollout();                                                                        // :17
-    if (o.dual_reset) I.reset_duals_penalties(o);                                       // :25
-    int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0;
-    double delta = 0.0;
-    Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int kout = 1; kout <= o.outer_iter; kout++) {                                  // :30
-      outer_done = kout;
-      int ls_count = 0;
-      for (int l = 1; l <= o.inner_iter; l++) {                                         // :38
-        const double l2 = (double)l * (double)l;
-        const double reg = o.reg_0 * (l2 * l2);                                         // :39
-        // ---- inner_iteration (:67-103)
-        rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                           // :73-75 (the reg terms vanish at Z)
-        n_eval++;
-        const double res_norm = rec.sum / S;                                            // :76
-        delta = 0.0;
-        if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
-        if (rec.opt < o.eps_opt) break;                                                 // :80-82
-        if (!I.kkt_solve(reg, reg)) failed = 1;                                         // :84-88
-        n_newton++;
-        double alpha; int j;
-        I.line_search(o, reg, res_norm, alpha, j, n_eval);                              // :91
-        ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;                                 // :92-93
-        delta = I.update_traj(alpha);                                                   // :94-95 (taken even when the search failed)
-        if (delta < o.delta_min) break;                                                 // :96-98
-        if (ls_count >= 1) break;                                                       // :43
-        if (!(delta == delta)) { failed = 1; break; }
-      }
-      if (failed) break;
-      if (kout == o.outer_iter || (rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt))
-        break;                                                                          // :49-55
-      I.dual_update(o);                                                                 // :57-58
-      I.penalty_update(o);                                                              // :61
-    }
-    rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                               // :63 final record
-    n_eval++;
-    const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
-    const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
-    I.store_iterate(g.Z, g.L, inst);
-    I.store_duals(g, inst);
-    if (I.tid == 0) {
-      double* st = g.stats + (size_t)inst * AGB_NSTATS;
-      st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;
-      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)outer_done; st[8] = (double)n_eval; st[9] = (double)failed;
-      g.status[inst] = conv ? AGB_CONVERGED : ((failed || !finite) ? AGB_NUMERICAL_FAILURE : AGB_NOT_CONVERGED);
-    }
-  }
-}
-
-// Per-function entry points on the resident batch (parity tests and stand-alone use of the exported reference API).
-template <int P>
-__global__ void __launch_bounds__(kThreads) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
-  AGB_DYN_SMEM(sm);
-  Inst<P> I;
-  I.bind(dd, sm);
-  constexpr int n = Inst<P>::n, m = Inst<P>::m, b = Inst<P>::b;
-  const int K = I.K, Sz = K * b, nrow = I.nrow;
-  const double S = (double)Sz;
-  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
-    __syncthreads();
-    I.load_params(g, inst);
-    I.load_iterate(g.Z, g.L, inst);
-    I.load_duals(g, inst);
-    __syncthreads();
-    for (int q = I.tid; q < n; q += kThreads) I.X[q] = g.x0[(size_t)inst * n + q];
-    __syncthreads();
-    double* D = g.D + (size_t)inst * Sz;
-    switch (a.op) {
-      case OP_ROLLOUT: {
-        I.rollout();
-        I.store_iterate(g.Z, g.L, inst);
-      } break;
-      case OP_RESIDUAL: {
-        Acc r;
-        double* out = a.out0 ? a.out0 + (size_t)inst * Sz : nullptr;
-        if (a.alpha == 0.0) {
-          r = I.template residual<false>(0.0, 0.0, 0.0, I.R);
-          if (out) for (int q = I.tid; q < Sz; q += kThreads) out[q] = I.R[q];
-        } else {
-          for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
-          __syncthreads();
-          r = I.template residual<true>(a.alpha, a.reg_x, a.reg_u, out);
-        }
-        if (a.out1 && I.tid == 0) {
-          double* nr = a.out1 + (size_t)inst * 5;
-          nr[0] = r.sum / S; nr[1] = r.dyn; nr[2] = r.con; nr[3] = r.sta; nr[4] = r.opt;
-        }
-      } break;
-      case OP_JAC_DENSE: {
-        // residual_jacobian! + regularize_residual_jacobian! written block by block in the reference's
-        // (vertical, horizontal) order (core/newton_core.jl:40-89); J_out must be zeroed by the caller.
-        I.template residual<false>(0.0, 0.0, 0.0, I.R);
-        __syncthreads();
-        double* J = a.out0 + (size_t)inst * Sz * Sz;
-        const int vdyn = P * K * (n + 2);
-        for (int item = I.tid; item < P * K; item += kThreads) {
-          const int s = item % K, i = item / K, k = s + 1;
-          const size_t vx = (size_t)(i * K + s) * (n + 2), vu = vx + n;
-          for (int r = 0; r < n; r++) {
-            double* row = J + (vx + r) * Sz;
-            for (int c = 0; c < n; c++) {
-              double v = (r == c) ? I.hd_entry(i, k, r, a.reg_x) : 0.0;
-              if (r < 2 * P && c < 2 * P) v += I.hpos_entry(i, k, r, c);
-              row[s * b + c] = v;                                               // (opt_i x_k, x_k)
-            }
-            row[s * b + n + m + i * n + r] = -1.0;                               // (opt_i x_k, λ_{i,k-1}) = −I
-            if (k < K) {
-              const int cr = r / P, ir = r % P;
-              for (int q = 0; q < 4; q++) row[k * b + n + m + i * n + q * P + ir] = I.Ael(k, ir, q, cr);   // A_kᵀ
-            }
-          }
-          for (int j = 0; j < 2; j++) {
-            double* row = J + (vu + j) * Sz;
-            row[s * b + n + i * 2 + j] = I.hu_entry(s, j * P + i, a.reg_u);       // (opt_i u_ik, u_ik)
-            for (int q = 0; q < 4; q++) row[s * b + n + m + i * n + q * P + i] = I.Bel(s, i, q, j);          // B_iᵀ
-          }
-        }
-        for (int item = I.tid; item < K * n; item += kThreads) {
-          const int r = item % n, s = item / n;
-          const int cr = r / P, ir = r % P;
-          double* row = J + (size_t)(vdyn + s * n + r) * Sz;
-          if (s > 0) for (int q = 0; q < 4; q++) row[(s - 1) * b + q * P + ir] = I.Ael(s, ir, cr, q);        // A_s
-          for (int j = 0; j < 2; j++) row[s * b + n + ir * 2 + j] = I.Bel(s, ir, cr, j);                    // B_i
-          row[s * b + r] = -1.0;                                                                            // −I
-        }
-      } break;
-      case OP_KKT_SOLVE: {
-        I.template residual<false>(0.0, 0.0, 0.0, I.R);
-        __syncthreads();
-        const bool ok = I.kkt_solve(a.reg_x, a.reg_u);
-        for (int q = I.tid; q < Sz; q += kThreads) D[q] = I.R[q];
-        if (a.iout && I.tid == 0) a.iout[inst] = ok ? 0 : 1;
-      } break;
-      case OP_LINE_SEARCH: {
-        for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
-        __syncthreads();
-        Acc r0 = I.template residual<true>(0.0, 0.0, 0.0, nullptr);
-        double alpha; int j, ne = 0;
-        const double reg = a.reg_x;
-        I.line_search(o, reg, r0.sum / S, alpha, j, ne);
-        if (I.tid == 0) { a.out0[inst] = alpha; a.iout[inst] = j; }
-      } break;
-      case OP_UPDATE: {
-        for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
-        __syncthreads();
-        const double delta = I.update_traj(a.in0[inst]);
-        __syncthreads();
-        I.store_iterate(g.Z, g.L, inst);
-        if (a.out0 && I.tid == 0) a.out0[inst] = delta;
-      } break;
-      case OP_DUAL_UPDATE: { I.dual_update(o); I.store_duals(g, inst); } break;
-      case OP_PENALTY_UPDATE: { I.penalty_update(o); I.store_duals(g, inst); } break;
-      case OP_RESET: { I.reset_duals_penalties(o); I.store_duals(g, inst); } break;
-      case OP_EVAL_CON: {
-        for (int q = I.tid; q < K * nrow; q += kThreads) a.out0[(size_t)inst * K * nrow + q] = I.con_value(q / nrow, q % nrow);
-      } break;
-      case OP_ACTIVE_SET: {
-        for (int q = I.tid; q < K * nrow; q += kThreads) {
-          const double c = I.con_value(q / nrow, q % nrow);
-          a.bout[(size_t)inst * K * nrow + q] = ((c >= -a.tol) || (I.CL[q] > 0.0)) ? 1 : 0;
-        }
-      } break;
-      default: break;
-    }
-  }
-}
 
 // internal stage-major layout → reference row ("vertical", mode 0) or column ("horizontal", mode 1) order
 __global__ void agb_export_kernel(const double* __restrict__ in, double* __restrict__ out, int batch, int P, int K, int mode) {
@@ -269,7 +75,7 @@ struct agb_handle {
   bool timed = false;
   // device buffers
   double *x0 = nullptr, *xf = nullptr, *Q = nullptr, *R = nullptr, *uf = nullptr;
-  double *Z0 = nullptr, *L0 = nullptr, *Z = nullptr, *L = nullptr, *conlam = nullptr, *conmu = nullptr, *D = nullptr, *stats = nullptr;
+  double *Z0 = nullptr, *L0 = nullptr, *Z = nullptr, *L = nullptr, *conlam = nullptr, *conmu = nullptr, *D = nullptr, *KUg = nullptr, *stats = nullptr;
   int* status = nullptr;
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
@@ -332,6 +138,12 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
   }
   for (int i = p; i <= AGB_MAX_P; i++) o->srow_off[i] = row;
   o->nrow_state = row;
+  o->has_pairs = o->has_cc; o->has_self = 0; o->has_sb = 0; o->has_cb = d->has_control_bound ? 1 : 0;
+  for (int i = 0; i < p; i++) if (d->has_state_bound[i]) o->has_sb = 1;
+  for (int i = 0; i < p; i++) {
+    for (int j = 0; j < p; j++) if (o->col_row[i][j] >= 0) o->has_pairs = 1;
+    if (o->n_walls[i] > 0 || o->n_circles[i] > 0) o->has_self = 1;
+  }
   for (int idx = 0; idx < AGB_MAX_M; idx++) { o->ub_row[idx] = -1; o->lb_row[idx] = -1; }
   if (d->has_control_bound) {
     for (int idx = 0; idx < m; idx++) {
@@ -347,15 +159,36 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
   int off = 0;
   auto take = [&](int cnt) { int r = off; off += (cnt + 1) & ~1; return r; };
   o->o_X = take(N * n); o->o_U = take(N * m); o->o_L = take(p * K * n); o->o_R = take(K * o->b);
-  o->o_KU = take(K * m * (n + 1));
-  o->o_AB = take(d->model == AGB_MODEL_DOUBLE_INTEGRATOR ? 0 : K * p * 24);
-  o->o_CL = take(K * o->nrow); o->o_CM = take(K * o->nrow); o->o_CW = take(K * o->nrow);
-  o->o_CC = take(o->has_cc ? N * o->npairs * 3 : 0);
-  o->o_P = take(2 * p * n * n); o->o_Sv = take(2 * p * n); o->o_Aug = take(m * W); o->o_Acl = take(n * (n + 1));
-  o->o_Hpos = take(p * 4 * p * p); o->o_Hd = take(p * n); o->o_par = take(2 * n + 2 * m); o->o_red = take(5 * (kThreads / 32));
+  o->o_KU = take(m * (n + 1));                 // gains of the current stage only; all stages live in Buffers::KUg
+  o->o_AB = take(d->model == AGB_MODEL_DOUBLE_INTEGRATOR ? 0 : K * p * 16);
+  o->o_CL = take(K * o->nrow); o->o_CM = take(K * o->nrow);
+  o->o_CW = take((o->has_sb || o->has_cb) ? K * o->nrow : 0);     // pair / wall / circle weights are folded into Hp / Hs
+  o->o_Hp = take(o->has_pairs ? N * o->npairs * 3 : 0); o->o_Hs = take(o->has_self ? N * p * 3 : 0);
+  o->o_P = take(p * n * n); o->o_Sv = take(p * n); o->o_Y = take(m * (n + 1)); o->o_Aug = take(m * W);
+  o->o_Base = take(p * n * (n + 1)); o->o_W = take(p * n * m); o->o_Ta = take(p * n);
+  {  // Gp / Gs live only inside one residual evaluation, Base / W / Ta only inside kkt_solve: alias them when they fit
+    const int need = (o->has_pairs ? N * o->npairs * 2 : 0) + (o->has_self ? N * p * 2 : 0);
+    const int have = off - o->o_Base;
+    if (need > have) take(need - have);
+    o->o_Gp = o->o_Base; o->o_Gs = o->o_Base + (o->has_pairs ? N * o->npairs * 2 : 0);
+  }
+  o->o_par = take(2 * n + 2 * m); o->o_red = take(5 * (kThreads / 32));
   o->smem_doubles = off;
   return AGB_OK;
 }
+
+namespace agb {
+cudaError_t set_attr(int p, int model, size_t smem) {
+  switch (p) { case 1: return set_attr_p1(model, smem); case 2: return set_attr_p2(model, smem);
+               case 3: return set_attr_p3(model, smem); default: return set_attr_p4(model, smem); }
+}
+void launch_solve(int p, const LaunchArgs& L) {
+  switch (p) { case 1: launch_solve_p1(L); break; case 2: launch_solve_p2(L); break; case 3: launch_solve_p3(L); break; default: launch_solve_p4(L); }
+}
+void launch_op(int p, const LaunchArgs& L) {
+  switch (p) { case 1: launch_op_p1(L); break; case 2: launch_op_p2(L); break; case 3: launch_op_p3(L); break; default: launch_op_p4(L); }
+}
+}  // namespace agb
 
 extern "C" {
 
@@ -381,20 +214,12 @@ int agb_sizes_of(const agb_problem_desc* d, agb_sizes* out) {
 
 const char* agb_last_error(const agb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
-static void* kernel_ptr(int p, bool solve) {
-  switch (p) {
-    case 1: return solve ? (void*)agb_newton_solve_kernel<1> : (void*)agb_op_kernel<1>;
-    case 2: return solve ? (void*)agb_newton_solve_kernel<2> : (void*)agb_op_kernel<2>;
-    case 3: return solve ? (void*)agb_newton_solve_kernel<3> : (void*)agb_op_kernel<3>;
-    default: return solve ? (void*)agb_newton_solve_kernel<4> : (void*)agb_op_kernel<4>;
-  }
-}
 
 void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->Z, h->L, h->conlam, h->conmu, h->D, h->stats, h->status, h->stage, h->stage2};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->Z, h->L, h->conlam, h->conmu, h->D, h->KUg, h->stats, h->status, h->stage, h->stage2};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -435,8 +260,7 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
     snprintf(buf, sizeof buf, "instance needs %zu B of shared memory per CTA, device allows %d B", h->smem_bytes, max_smem);
     g_create_err = buf; agb_destroy(h); return AGB_EUNSUPPORTED;
   }
-  CKC(cudaFuncSetAttribute(kernel_ptr(t.p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CKC(cudaFuncSetAttribute(kernel_ptr(t.p, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CKC(agb::set_attr(t.p, t.model, h->smem_bytes));
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
@@ -448,7 +272,7 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
   CK(alloc_d(h, &h->Z0, B * N * (n + m))); CK(alloc_d(h, &h->L0, B * p * K * n));
   CK(alloc_d(h, &h->Z, B * N * (n + m))); CK(alloc_d(h, &h->L, B * p * K * n));
   CK(alloc_d(h, &h->conlam, B * K * t.nrow)); CK(alloc_d(h, &h->conmu, B * K * t.nrow));
-  CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->stats, B * AGB_NSTATS));
+  CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 1))); CK(alloc_d(h, &h->stats, B * AGB_NSTATS));
   CKC(cudaMalloc((void**)&h->status, B * sizeof(int)));
   CKC(cudaMemsetAsync(h->status, 0, B * sizeof(int), h->stream));
   // descriptor defaults broadcast to every instance; μ starts at 1 (Altro ALConVal default)
@@ -483,7 +307,7 @@ int agb_get_sizes(const agb_handle* h, agb_sizes* out) {
 static Buffers buffers_of(agb_handle* h) {
   Buffers g;
   g.x0 = h->x0; g.xf = h->xf; g.Q = h->Q; g.R = h->R; g.uf = h->uf; g.Z0 = h->Z0; g.L0 = h->L0; g.Z = h->Z; g.L = h->L;
-  g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.stats = h->stats; g.status = h->status;
+  g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.KUg = h->KUg; g.stats = h->stats; g.status = h->status;
   return g;
 }
 
@@ -559,14 +383,10 @@ int agb_shift_initial(agb_handle* h, int s, const double* Zfresh, const double* 
 static int launch_op(agb_handle* h, const agb_options* o, const OpArgs& a) {
   agb_options od;
   if (o) od = *o; else agb_default_options(&od);
-  Buffers g = buffers_of(h);
-  const int grid = h->batch;
-  switch (h->hd.p) {
-    case 1: AGB_LAUNCH(agb_op_kernel<1>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
-    case 2: AGB_LAUNCH(agb_op_kernel<2>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
-    case 3: AGB_LAUNCH(agb_op_kernel<3>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
-    default: AGB_LAUNCH(agb_op_kernel<4>, grid, kThreads, h->smem_bytes, h->stream, h->dd, od, g, a, h->batch); break;
-  }
+  LaunchArgs L;
+  L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = h->stream; L.dd = h->dd; L.o = od;
+  L.g = buffers_of(h); L.a = a; L.batch = h->batch;
+  agb::launch_op(h->hd.p, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
   return AGB_OK;
@@ -695,14 +515,10 @@ int agb_active_set(agb_handle* h, double tol, unsigned char* active_out) {
 }
 
 static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
-  Buffers g = buffers_of(h);
-  const int grid = h->batch;
-  switch (h->hd.p) {
-    case 1: AGB_LAUNCH(agb_newton_solve_kernel<1>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
-    case 2: AGB_LAUNCH(agb_newton_solve_kernel<2>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
-    case 3: AGB_LAUNCH(agb_newton_solve_kernel<3>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
-    default: AGB_LAUNCH(agb_newton_solve_kernel<4>, grid, kThreads, h->smem_bytes, st, h->dd, *o, g, h->batch); break;
-  }
+  LaunchArgs L;
+  L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
+  L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch;
+  agb::launch_solve(h->hd.p, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
   return AGB_OK;

@@ -16,6 +16,7 @@ struct DevDesc {
   double dt, lf, lr;
   // objective (objective.jl:84-100)
   int has_cc, npairs;
+  int has_pairs, has_self, has_sb, has_cb;  // + any state bound; any control bound                  // any pair term (collision cost / avoidance); any wall / circle
   double cc_radius[AGB_MAX_P], cc_mu[AGB_MAX_P];
   // state-constraint rows of player i at one knot, canonical order:
   // [collision j!=i ascending | state bound max rows | min rows | walls | circles]
@@ -34,7 +35,7 @@ struct DevDesc {
   double u_max[AGB_MAX_M], u_min[AGB_MAX_M];
   int nrow_state, nrow_control, nrow;
   // shared-memory layout (offsets in doubles)
-  int o_X, o_U, o_L, o_R, o_KU, o_AB, o_CL, o_CM, o_CW, o_CC, o_P, o_Sv, o_Aug, o_Acl, o_Hpos, o_Hd, o_par, o_red;
+  int o_X, o_U, o_L, o_R, o_KU, o_AB, o_CL, o_CM, o_CW, o_Gp, o_Hp, o_Gs, o_Hs, o_P, o_Sv, o_Y, o_Aug, o_Base, o_W, o_Ta, o_par, o_red;
   int smem_doubles;
 };
 
@@ -52,6 +53,7 @@ struct Buffers {
   double* conlam;     // [B][K][nrow]
   double* conmu;
   double* D;          // [B][S] Newton step, internal stage-major layout
+  double* KUg;        // [B][K][m][n+1] feedback gains of the stage-wise factorisation (L2-resident scratch)
   double* stats;      // [B][AGB_NSTATS]
   int* status;        // [B]
 };

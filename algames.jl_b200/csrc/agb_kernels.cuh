@@ -1,0 +1,260 @@
+// agb_kernels.cuh — the two instance kernels (templated on player count and model) and their launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include "agb_solver.cuh"
+
+namespace agb {
+
+// Kernel launch / dynamic shared memory go through two macros so that the test-only CTA emulator under tests/emu/
+// can compile this very file with g++ (AGB_EMULATE); the shipped library is always the nvcc build.
+#ifndef AGB_EMULATE
+#define AGB_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+#define AGB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+// =============================================================================================================
+// Kernels
+// =============================================================================================================
+// newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
+template <int P, int MODEL>
+__global__ void __launch_bounds__(kThreads, (P <= 3 ? 4 : 1)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int batch) {
+  AGB_DYN_SMEM(sm);
+  Inst<P, MODEL> I;
+  I.bind(dd, sm);
+  constexpr int n = Inst<P, MODEL>::n;
+  const int K = I.K;
+  const double S = (double)(K * Inst<P, MODEL>::b);
+  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+    __syncthreads();
+    I.bind_instance(g, inst);
+    I.load_params(g, inst);
+    I.load_iterate(g.Z0, g.L0, inst);
+    I.load_duals(g, inst);
+    __syncthreads();
+    for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];     // x_1 ← x0 (primal_dual_traj.jl:42)
+    __syncthreads();
+    I.rollout();                                                                        // :17
+    if (o.dual_reset) I.reset_duals_penalties(o);                                       // :25
+    int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0;
+    double delta = 0.0;
+    Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int kout = 1; kout <= o.outer_iter; kout++) {                                  // :30
+      outer_done = kout;
+      int ls_count = 0;
+      for (int l = 1; l <= o.inner_iter; l++) {                                         // :38
+        const double l2 = (double)l * (double)l;
+        const double reg = o.reg_0 * (l2 * l2);                                         // :39
+        // ---- inner_iteration (:67-103)
+        rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                           // :73-75 (the reg terms vanish at Z)
+        n_eval++;
+        const double res_norm = rec.sum / S;                                            // :76
+        delta = 0.0;
+        if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
+        if (rec.opt < o.eps_opt) break;                                                 // :80-82
+        if (!I.kkt_solve(reg, reg)) failed = 1;                                         // :84-88
+        n_newton++;
+        double alpha; int j;
+        I.line_search(o, reg, res_norm, alpha, j, n_eval);                              // :91
+        ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;                                 // :92-93
+        delta = I.update_traj(alpha);                                                   // :94-95 (taken even when the search failed)
+        if (delta < o.delta_min) break;                                                 // :96-98
+        if (ls_count >= 1) break;                                                       // :43
+        if (!(delta == delta)) { failed = 1; break; }
+      }
+      if (failed) break;
+      if (kout == o.outer_iter || (rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt))
+        break;                                                                          // :49-55
+      I.dual_update(o);                                                                 // :57-58
+      I.penalty_update(o);                                                              // :61
+    }
+    rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                               // :63 final record
+    n_eval++;
+    const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
+    const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
+    I.store_iterate(g.Z, g.L, inst);
+    I.store_duals(g, inst);
+    if (I.tid == 0) {
+      double* st = g.stats + (size_t)inst * AGB_NSTATS;
+      st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;
+      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)outer_done; st[8] = (double)n_eval; st[9] = (double)failed;
+      g.status[inst] = conv ? AGB_CONVERGED : ((failed || !finite) ? AGB_NUMERICAL_FAILURE : AGB_NOT_CONVERGED);
+    }
+  }
+}
+
+// Per-function entry points on the resident batch (parity tests and stand-alone use of the exported reference API).
+template <int P, int MODEL>
+__global__ void __launch_bounds__(kThreads) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
+  AGB_DYN_SMEM(sm);
+  Inst<P, MODEL> I;
+  I.bind(dd, sm);
+  constexpr int n = Inst<P, MODEL>::n, m = Inst<P, MODEL>::m, b = Inst<P, MODEL>::b;
+  const int K = I.K, Sz = K * b, nrow = I.nrow;
+  const double S = (double)Sz;
+  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+    __syncthreads();
+    I.bind_instance(g, inst);
+    I.load_params(g, inst);
+    I.load_iterate(g.Z, g.L, inst);
+    I.load_duals(g, inst);
+    __syncthreads();
+    for (int q = I.tid; q < n; q += kThreads) I.X[q] = g.x0[(size_t)inst * n + q];
+    __syncthreads();
+    double* D = g.D + (size_t)inst * Sz;
+    switch (a.op) {
+      case OP_ROLLOUT: {
+        I.rollout();
+        I.store_iterate(g.Z, g.L, inst);
+      } break;
+      case OP_RESIDUAL: {
+        Acc r;
+        double* out = a.out0 ? a.out0 + (size_t)inst * Sz : nullptr;
+        if (a.alpha == 0.0) {
+          r = I.template residual<false>(0.0, 0.0, 0.0, I.R);
+          if (out) for (int q = I.tid; q < Sz; q += kThreads) out[q] = I.R[q];
+        } else {
+          for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
+          __syncthreads();
+          r = I.template residual<true>(a.alpha, a.reg_x, a.reg_u, out);
+        }
+        if (a.out1 && I.tid == 0) {
+          double* nr = a.out1 + (size_t)inst * 5;
+          nr[0] = r.sum / S; nr[1] = r.dyn; nr[2] = r.con; nr[3] = r.sta; nr[4] = r.opt;
+        }
+      } break;
+      case OP_JAC_DENSE: {
+        // residual_jacobian! + regularize_residual_jacobian! written block by block in the reference's
+        // (vertical, horizontal) order (core/newton_core.jl:40-89); J_out must be zeroed by the caller.
+        I.template residual<false>(0.0, 0.0, 0.0, I.R);
+        __syncthreads();
+        double* J = a.out0 + (size_t)inst * Sz * Sz;
+        const int vdyn = P * K * (n + 2);
+        for (int item = I.tid; item < P * K; item += kThreads) {
+          const int s = item % K, i = item / K, k = s + 1;
+          const size_t vx = (size_t)(i * K + s) * (n + 2), vu = vx + n;
+          for (int r = 0; r < n; r++) {
+            double* row = J + (vx + r) * Sz;
+            for (int c = 0; c < n; c++) {
+              row[s * b + c] = I.h_entry(i, k, r, c, a.reg_x);                                               // (opt_i x_k, x_k)
+            }
+            row[s * b + n + m + i * n + r] = -1.0;                               // (opt_i x_k, λ_{i,k-1}) = −I
+            if (k < K) {
+              const int cr = r / P, ir = r % P;
+              for (int q = 0; q < 4; q++) row[k * b + n + m + i * n + q * P + ir] = I.Ael(k, ir, q, cr);   // A_kᵀ
+            }
+          }
+          for (int j = 0; j < 2; j++) {
+            double* row = J + (vu + j) * Sz;
+            row[s * b + n + i * 2 + j] = I.hu_entry(s, j * P + i, a.reg_u);       // (opt_i u_ik, u_ik)
+            for (int q = 0; q < 4; q++) row[s * b + n + m + i * n + q * P + i] = I.Bel(s, i, q, j);          // B_iᵀ
+          }
+        }
+        for (int item = I.tid; item < K * n; item += kThreads) {
+          const int r = item % n, s = item / n;
+          const int cr = r / P, ir = r % P;
+          double* row = J + (size_t)(vdyn + s * n + r) * Sz;
+          if (s > 0) for (int q = 0; q < 4; q++) row[(s - 1) * b + q * P + ir] = I.Ael(s, ir, cr, q);        // A_s
+          for (int j = 0; j < 2; j++) row[s * b + n + ir * 2 + j] = I.Bel(s, ir, cr, j);                    // B_i
+          row[s * b + r] = -1.0;                                                                            // −I
+        }
+      } break;
+      case OP_KKT_SOLVE: {
+        I.template residual<false>(0.0, 0.0, 0.0, I.R);
+        __syncthreads();
+        const bool ok = I.kkt_solve(a.reg_x, a.reg_u);
+        for (int q = I.tid; q < Sz; q += kThreads) D[q] = I.R[q];
+        if (a.iout && I.tid == 0) a.iout[inst] = ok ? 0 : 1;
+      } break;
+      case OP_LINE_SEARCH: {
+        for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
+        __syncthreads();
+        Acc r0 = I.template residual<true>(0.0, 0.0, 0.0, nullptr);
+        double alpha; int j, ne = 0;
+        const double reg = a.reg_x;
+        I.line_search(o, reg, r0.sum / S, alpha, j, ne);
+        if (I.tid == 0) { a.out0[inst] = alpha; a.iout[inst] = j; }
+      } break;
+      case OP_UPDATE: {
+        for (int q = I.tid; q < Sz; q += kThreads) I.R[q] = D[q];
+        __syncthreads();
+        const double delta = I.update_traj(a.in0[inst]);
+        __syncthreads();
+        I.store_iterate(g.Z, g.L, inst);
+        if (a.out0 && I.tid == 0) a.out0[inst] = delta;
+      } break;
+      case OP_DUAL_UPDATE: { I.dual_update(o); I.store_duals(g, inst); } break;
+      case OP_PENALTY_UPDATE: { I.penalty_update(o); I.store_duals(g, inst); } break;
+      case OP_RESET: { I.reset_duals_penalties(o); I.store_duals(g, inst); } break;
+      case OP_EVAL_CON: {
+        for (int q = I.tid; q < K * nrow; q += kThreads) a.out0[(size_t)inst * K * nrow + q] = I.con_value(q / nrow, q % nrow);
+      } break;
+      case OP_ACTIVE_SET: {
+        for (int q = I.tid; q < K * nrow; q += kThreads) {
+          const double c = I.con_value(q / nrow, q % nrow);
+          a.bout[(size_t)inst * K * nrow + q] = ((c >= -a.tol) || (I.CL[q] > 0.0)) ? 1 : 0;
+        }
+      } break;
+      default: break;
+    }
+  }
+}
+
+
+// ---- launchers: one translation unit per player count (agb_kernels_p<P>.cu) instantiates these ---------------------
+struct LaunchArgs {
+  int model, grid;
+  size_t smem;
+  cudaStream_t stream;
+  const DevDesc* dd;
+  agb_options o;
+  Buffers g;
+  OpArgs a;
+  int batch;
+};
+
+template <int P, int MODEL> inline cudaError_t set_attr_pm(size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)agb_newton_solve_kernel<P, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)agb_op_kernel<P, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int P> inline cudaError_t set_attr_p(int model, size_t smem) {
+  switch (model) {
+    case AGB_MODEL_DOUBLE_INTEGRATOR: return set_attr_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR>(smem);
+    case AGB_MODEL_UNICYCLE: return set_attr_pm<P, AGB_MODEL_UNICYCLE>(smem);
+    default: return set_attr_pm<P, AGB_MODEL_BICYCLE>(smem);
+  }
+}
+template <int P, int MODEL> inline void launch_solve_pm(const LaunchArgs& L) {
+  auto kfn = agb_newton_solve_kernel<P, MODEL>;
+  AGB_LAUNCH(kfn, L.grid, kThreads, L.smem, L.stream, L.dd, L.o, L.g, L.batch);
+}
+template <int P, int MODEL> inline void launch_op_pm(const LaunchArgs& L) {
+  auto kfn = agb_op_kernel<P, MODEL>;
+  AGB_LAUNCH(kfn, L.grid, kThreads, L.smem, L.stream, L.dd, L.o, L.g, L.a, L.batch);
+}
+template <int P> inline void launch_solve_p(const LaunchArgs& L) {
+  switch (L.model) {
+    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_solve_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR>(L); break;
+    case AGB_MODEL_UNICYCLE: launch_solve_pm<P, AGB_MODEL_UNICYCLE>(L); break;
+    default: launch_solve_pm<P, AGB_MODEL_BICYCLE>(L); break;
+  }
+}
+template <int P> inline void launch_op_p(const LaunchArgs& L) {
+  switch (L.model) {
+    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_op_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR>(L); break;
+    case AGB_MODEL_UNICYCLE: launch_op_pm<P, AGB_MODEL_UNICYCLE>(L); break;
+    default: launch_op_pm<P, AGB_MODEL_BICYCLE>(L); break;
+  }
+}
+
+// defined in agb_kernels_p<P>.cu
+cudaError_t set_attr(int p, int model, size_t smem);
+void launch_solve(int p, const LaunchArgs& L);
+void launch_op(int p, const LaunchArgs& L);
+#define AGB_DECLARE_P(PP)                                   \
+  cudaError_t set_attr_p##PP(int model, size_t smem);      \
+  void launch_solve_p##PP(const LaunchArgs& L);            \
+  void launch_op_p##PP(const LaunchArgs& L);
+AGB_DECLARE_P(1) AGB_DECLARE_P(2) AGB_DECLARE_P(3) AGB_DECLARE_P(4)
+
+}  // namespace agb

@@ -1,0 +1,7 @@
+// agb_kernels_p1.cu — instantiates the instance kernels for 1 player(s) (one TU per player count: parallel builds).
+#include "agb_kernels.cuh"
+namespace agb {
+cudaError_t set_attr_p1(int model, size_t smem) { return set_attr_p<1>(model, smem); }
+void launch_solve_p1(const LaunchArgs& L) { launch_solve_p<1>(L); }
+void launch_op_p1(const LaunchArgs& L) { launch_op_p<1>(L); }
+}  // namespace agb

@@ -129,25 +129,71 @@ __device__ __forceinline__ void rk3_step(int model, double dt, double lf, double
 // ------------------------------------------------------------------------------------------------------------
 // Instance context: shared-memory views of one game instance
 // ------------------------------------------------------------------------------------------------------------
-template <int P>
+template <int P, int MODEL>
 struct Inst {
-  static constexpr int n = 4 * P, m = 2 * P, b = P * n + m + n, W = m + n + 1, KUS = m * (n + 1);
+  static constexpr int n = 4 * P, m = 2 * P, b = P * n + m + n, W = m + n + 1, KUS = m * (n + 1), n1 = n + 1;
   static constexpr int OX = 0, OU = P * n, OD = P * n + m;     // offsets inside one stage of R: [rx(p·n) | ru(m) | rd(n)]
+  static constexpr int NP = P * (P - 1);                       // ordered player pairs
+  // Structural non-zeros of the per-player RK2 Jacobians (bit q of the mask <-> At[q] / Bt[q], layouts below):
+  //   DoubleIntegrator  A = [I dt·I; 0 I], B = [dt²/2·I; dt·I]   (constants)
+  //   Unicycle          At rows x,y only;  B = [Bp (2x2); dt·I]
+  //   Bicycle           additionally ∂ψ⁺/∂v and the δ-column / ψ-row of B
+  static constexpr unsigned AT_NZ = MODEL == AGB_MODEL_DOUBLE_INTEGRATOR ? 0x09u : (MODEL == AGB_MODEL_UNICYCLE ? 0x0Fu : 0x4Fu);
+  static constexpr unsigned BT_NZ = MODEL == AGB_MODEL_DOUBLE_INTEGRATOR ? 0x99u : (MODEL == AGB_MODEL_UNICYCLE ? 0x9Fu : 0xDFu);
+  template <int CC> static __device__ __forceinline__ double at_dot(const double At[8], double x0, double x1, double x2, double x3) {
+    double v = 0.0;                                            // Σ_q At[q][CC]·x_q over structural non-zeros
+    if ((AT_NZ >> (0 + CC)) & 1u) v += At[0 + CC] * x0;
+    if ((AT_NZ >> (2 + CC)) & 1u) v += At[2 + CC] * x1;
+    if ((AT_NZ >> (4 + CC)) & 1u) v += At[4 + CC] * x2;
+    if ((AT_NZ >> (6 + CC)) & 1u) v += At[6 + CC] * x3;
+    return v;
+  }
+  template <int CC> static __device__ __forceinline__ double bt_dot(const double Bt[8], double x0, double x1, double x2, double x3) {
+    double v = 0.0;
+    if ((BT_NZ >> (0 + CC)) & 1u) v += Bt[0 + CC] * x0;
+    if ((BT_NZ >> (2 + CC)) & 1u) v += Bt[2 + CC] * x1;
+    if ((BT_NZ >> (4 + CC)) & 1u) v += Bt[4 + CC] * x2;
+    if ((BT_NZ >> (6 + CC)) & 1u) v += Bt[6 + CC] * x3;
+    return v;
+  }
+  static __device__ __forceinline__ double at_dot_sel(int cc, const double At[8], double x0, double x1, double x2, double x3) {
+    return cc == 0 ? at_dot<0>(At, x0, x1, x2, x3) : at_dot<1>(At, x0, x1, x2, x3);
+  }
+  static __device__ __forceinline__ double bt_dot_sel(int cc, const double Bt[8], double x0, double x1, double x2, double x3) {
+    return cc == 0 ? bt_dot<0>(Bt, x0, x1, x2, x3) : bt_dot<1>(Bt, x0, x1, x2, x3);
+  }
+  // row r of At / Bt times a 2-vector: At[r][0]·y0 + At[r][1]·y1
+  template <int RR> static __device__ __forceinline__ double at_row(const double At[8], double y0, double y1) {
+    double v = 0.0;
+    if ((AT_NZ >> (2 * RR)) & 1u) v += At[2 * RR] * y0;
+    if ((AT_NZ >> (2 * RR + 1)) & 1u) v += At[2 * RR + 1] * y1;
+    return v;
+  }
+  template <int RR> static __device__ __forceinline__ double bt_row(const double Bt[8], double y0, double y1) {
+    double v = 0.0;
+    if ((BT_NZ >> (2 * RR)) & 1u) v += Bt[2 * RR] * y0;
+    if ((BT_NZ >> (2 * RR + 1)) & 1u) v += Bt[2 * RR + 1] * y1;
+    return v;
+  }
 
   const DevDesc* __restrict__ d;
-  int N, K, nrow, model, npairs, has_cc;
+  int N, K, nrow, has_cc, has_pairs, has_self, has_sb, has_cb;
+  static constexpr int model = MODEL;
   double dt;
-  double *X, *U, *L, *R, *KU, *AB, *CL, *CM, *CW, *CC, *Pm, *Sv, *Aug, *Acl, *Hpos, *Hd, *xf, *Q, *Rw, *uf, *red;
+  double *X, *U, *L, *R, *KU, *AB, *CL, *CM, *CW, *Gp, *Hp, *Gs, *Hs, *Pm, *Sv, *Ym, *Aug, *Base, *Wm, *Ta, *xf, *Q, *Rw, *uf, *red;
+  double* KUg;            // this instance's slice of Buffers::KUg (global)
   int tid, lane, warp;
 
   __device__ void bind(const DevDesc* dd, double* sm) {
-    d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; model = dd->model; npairs = dd->npairs; has_cc = dd->has_cc; dt = dd->dt;
+    d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; has_cc = dd->has_cc; has_sb = dd->has_sb; has_cb = dd->has_cb;
+    has_pairs = dd->has_pairs; has_self = dd->has_self; dt = dd->dt;
     X = sm + dd->o_X; U = sm + dd->o_U; L = sm + dd->o_L; R = sm + dd->o_R; KU = sm + dd->o_KU; AB = sm + dd->o_AB;
-    CL = sm + dd->o_CL; CM = sm + dd->o_CM; CW = sm + dd->o_CW; CC = sm + dd->o_CC; Pm = sm + dd->o_P; Sv = sm + dd->o_Sv;
-    Aug = sm + dd->o_Aug; Acl = sm + dd->o_Acl; Hpos = sm + dd->o_Hpos; Hd = sm + dd->o_Hd;
-    xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
-    tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+    CL = sm + dd->o_CL; CM = sm + dd->o_CM; CW = sm + dd->o_CW; Gp = sm + dd->o_Gp; Hp = sm + dd->o_Hp; Gs = sm + dd->o_Gs;
+    Hs = sm + dd->o_Hs; Pm = sm + dd->o_P; Sv = sm + dd->o_Sv; Ym = sm + dd->o_Y; Aug = sm + dd->o_Aug; Base = sm + dd->o_Base;
+    Wm = sm + dd->o_W; Ta = sm + dd->o_Ta; xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
+    tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr;
   }
+  __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUS; }
 
   // ---- iterate accessors; TRIAL reads Z + alpha·Δ with Δ held in R (update_traj!, primal_dual_traj.jl:109-128)
   template <bool TRIAL> __device__ __forceinline__ double xg(int k, int a, double alpha) const {
@@ -166,30 +212,38 @@ struct Inst {
     return v;
   }
 
-  // [A|B] of stage s, player i at the last expansion point (DI: constant, never stored)
-  __device__ __forceinline__ void loadAB(int s, int i, double A[16], double B[8]) const {
-    if (model == AGB_MODEL_DOUBLE_INTEGRATOR) {
+  // Per-player discrete Jacobians of stage s at the last expansion point.  All in-scope models have dynamics that do
+  // not depend on position, so A_i = I + At with At non-zero only in columns 2,3: At[r*2 + (c-2)]; Bt[r*2 + j].
+  // DoubleIntegrator: constants, never stored.
+  __device__ __forceinline__ void loadAB(int s, int i, double At[8], double Bt[8]) const {
+    if constexpr (MODEL == AGB_MODEL_DOUBLE_INTEGRATOR) {
 #pragma unroll
-      for (int q = 0; q < 16; q++) A[q] = 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; q++) B[q] = 0.0;
-      A[0] = A[5] = A[10] = A[15] = 1.0; A[0 * 4 + 2] = dt; A[1 * 4 + 3] = dt;
-      B[0 * 2 + 0] = dt * (dt / 2); B[1 * 2 + 1] = dt * (dt / 2); B[2 * 2 + 0] = dt; B[3 * 2 + 1] = dt;
+      for (int q = 0; q < 8; q++) { At[q] = 0.0; Bt[q] = 0.0; }
+      At[0 * 2 + 0] = dt; At[1 * 2 + 1] = dt;
+      Bt[0 * 2 + 0] = dt * (dt / 2); Bt[1 * 2 + 1] = dt * (dt / 2); Bt[2 * 2 + 0] = dt; Bt[3 * 2 + 1] = dt;
     } else {
-      const double* src = AB + (s * P + i) * 24;
+      const double2* src = reinterpret_cast<const double2*>(AB + (s * P + i) * 16);
 #pragma unroll
-      for (int q = 0; q < 16; q++) A[q] = src[q];
+      for (int q = 0; q < 4; q++) { double2 v = src[q]; At[2 * q] = v.x; At[2 * q + 1] = v.y; }
 #pragma unroll
-      for (int q = 0; q < 8; q++) B[q] = src[16 + q];
+      for (int q = 0; q < 4; q++) { double2 v = src[4 + q]; Bt[2 * q] = v.x; Bt[2 * q + 1] = v.y; }
     }
   }
-  __device__ __forceinline__ double Ael(int s, int i, int r, int c) const {   // A_i[r][c] of stage s
-    if (model == AGB_MODEL_DOUBLE_INTEGRATOR) return (r == c) ? 1.0 : ((c == r + 2) ? dt : 0.0);
-    return AB[(s * P + i) * 24 + r * 4 + c];
+  __device__ __forceinline__ double Ael(int s, int i, int r, int c) const {   // A_i[r][c] of stage s (cold paths only)
+    double At[8], Bt[8]; loadAB(s, i, At, Bt);
+    double v = (r == c) ? 1.0 : 0.0;
+    if (c >= 2) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) if (q == r * 2 + (c - 2)) v += At[q];
+    }
+    return v;
   }
-  __device__ __forceinline__ double Bel(int s, int i, int r, int j) const {   // B_i[r][j] of stage s
-    if (model == AGB_MODEL_DOUBLE_INTEGRATOR) return (r == j) ? dt * (dt / 2) : ((r == j + 2) ? dt : 0.0);
-    return AB[(s * P + i) * 24 + 16 + r * 2 + j];
+  __device__ __forceinline__ double Bel(int s, int i, int r, int j) const {   // B_i[r][j] of stage s (cold paths only)
+    double At[8], Bt[8]; loadAB(s, i, At, Bt);
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) if (q == r * 2 + j) v = Bt[q];
+    return v;
   }
 
   __device__ __forceinline__ int pair_index(int i, int j) const { return i * (P - 1) + (j < i ? j : j - 1); }
@@ -205,11 +259,11 @@ struct Inst {
   // ---------------------------------------------------------------------------------------------------------
   // residual!  (problem/global_quantities.jl:9-65, constraints/constraint_derivatives.jl:39-74)
   // ---------------------------------------------------------------------------------------------------------
-  // pass 1: per (stage, player): RK2 step and its Jacobian blocks; dynamics rows.
-  template <bool TRIAL> __device__ void pass1(double alpha, double* Rout, Acc& acc) {
+  // pre-pass A, per (stage, player): RK2 step and its Jacobian blocks; dynamics rows.
+  template <bool TRIAL> __device__ void pass_dyn(double alpha, double* Rout, Acc& acc) {
     for (int item = tid; item < K * P; item += kThreads) {
       int s = item / P, i = item - s * P;
-      double st[4], u[2], xn[4], A[16], B[8];
+      double st[4], u[2], xn[4];
 #pragma unroll
       for (int c = 0; c < 4; c++) st[c] = xg<TRIAL>(s, c * P + i, alpha);
 #pragma unroll
@@ -217,12 +271,16 @@ struct Inst {
       if (model == AGB_MODEL_DOUBLE_INTEGRATOR) {
         rk2_only(model, dt, d->lf, d->lr, st, u, xn);
       } else {
+        double A[16], B[8];
         rk2_jac(model, dt, d->lf, d->lr, st, u, xn, A, B);
-        double* dst = AB + (s * P + i) * 24;
+        double* dst = AB + (s * P + i) * 16;
 #pragma unroll
-        for (int q = 0; q < 16; q++) dst[q] = A[q];
+        for (int r = 0; r < 4; r++) {
+          dst[r * 2 + 0] = A[r * 4 + 2] - (r == 2 ? 1.0 : 0.0);
+          dst[r * 2 + 1] = A[r * 4 + 3] - (r == 3 ? 1.0 : 0.0);
+        }
 #pragma unroll
-        for (int q = 0; q < 8; q++) dst[16 + q] = B[q];
+        for (int q = 0; q < 8; q++) dst[8 + q] = B[q];
       }
 #pragma unroll
       for (int c = 0; c < 4; c++) {
@@ -233,82 +291,105 @@ struct Inst {
     }
   }
 
+  // pre-pass B, per (knot k = 1..K, ordered pair (i,j)): collision cost (objective.jl:134-173) and collision-avoidance
+  // constraint of player i against j.  Gp = gradient contribution to rows (opt_i, pos_i) (rows (opt_i, pos_j) get −Gp);
+  // Hp = symmetric 2x2 block B with H[pos_i,pos_i] = H[pos_j,pos_j] = +B, H[pos_i,pos_j] = H[pos_j,pos_i] = −B.
+  template <bool TRIAL> __device__ void pass_pairs(double alpha, Acc& acc) {
+    if (!has_pairs) return;
+    constexpr int NPd = NP > 0 ? NP : 1, P1 = P > 1 ? P - 1 : 1;     // (single-player games have no pairs)
+    for (int item = tid; item < K * NP; item += kThreads) {
+      const int pr = item % NPd, k = item / NPd + 1, s = k - 1;
+      const int i = pr / P1, jj = pr - i * P1, j = jj < i ? jj : jj + 1;
+      const double dtx = (k < K) ? dt : 1.0;                   // terminal knot is not dt-scaled (objective test :52-64)
+      const double dx = xg<TRIAL>(k, i, alpha) - xg<TRIAL>(k, j, alpha);
+      const double dy = xg<TRIAL>(k, P + i, alpha) - xg<TRIAL>(k, P + j, alpha);
+      const double d2 = dx * dx + dy * dy;
+      double gx = 0.0, gy = 0.0, h00 = 0.0, h01 = 0.0, h11 = 0.0;
+      if (has_cc) {
+        const double dn = sqrt(d2);
+        const double rr = d->cc_radius[i], mu = d->cc_mu[i];
+        if (fmax(0.0, rr - dn) > 0.0) {
+          const double eps = 1e-10, eps_norm = eps * sqrt((double)n);
+          const double q = rr / (eps_norm + dn);
+          gx = -dtx * (mu * (q * (eps + dx) - dx));            // q[pxi] = −g
+          gy = -dtx * (mu * (q * (eps + dy) - dy));
+          if (!TRIAL) {
+            const double idn = 1.0 / dn, t = rr * idn, t3 = t * idn * idn;
+            h00 = dtx * mu * (1.0 - t + t3 * dx * dx);
+            h01 = dtx * mu * (t3 * dx * dy);
+            h11 = dtx * mu * (1.0 - t + t3 * dy * dy);
+          }
+        }
+      }
+      const int row = d->col_row[i][j];
+      if (row >= 0) {                                          // CollisionConstraint: c = r² − ‖xi−xj‖², ∇c[pos_i] = −2d
+        const double rad = d->col_radius[i][j];
+        const double cv = rad * rad - d2;
+        double w; const double g = al_row(s, row, cv, w);
+        gx -= 2.0 * dx * g; gy -= 2.0 * dy * g;
+        acc.sta = fmax(acc.sta, cv);
+        if (!TRIAL) { const double w4 = 4.0 * w; h00 += w4 * dx * dx; h01 += w4 * dx * dy; h11 += w4 * dy * dy; }
+      }
+      double* gp = Gp + (k * NP + pr) * 2; gp[0] = gx; gp[1] = gy;
+      if (!TRIAL) { double* hp = Hp + (k * NP + pr) * 3; hp[0] = h00; hp[1] = h01; hp[2] = h11; }
+    }
+  }
+
+  // pre-pass C, per (knot, player): walls and circles acting on the player's own position.
+  template <bool TRIAL> __device__ void pass_self(double alpha, Acc& acc) {
+    if (!has_self) return;
+    for (int item = tid; item < K * P; item += kThreads) {
+      const int i = item % P, k = item / P + 1, s = k - 1;
+      const double px = xg<TRIAL>(k, i, alpha), py = xg<TRIAL>(k, P + i, alpha);
+      double gx = 0.0, gy = 0.0, h00 = 0.0, h01 = 0.0, h11 = 0.0;
+      const int nw = d->n_walls[i];
+      for (int q = 0; q < nw; q++) {                           // WallConstraint (constraints/wall_constraint.jl:56-89)
+        const double* wl = d->walls[i][q];
+        const double x1 = wl[0], y1 = wl[1], x2 = wl[2], y2 = wl[3], xv = wl[4], yv = wl[5];
+        const bool left = (px - x1) * (x2 - x1) + (py - y1) * (y2 - y1) > 0.0;
+        const bool right = (px - x2) * (x1 - x2) + (py - y2) * (y1 - y2) > 0.0;
+        const double msk = (left && right) ? 1.0 : 0.0;
+        const double cv = ((px - x1) * xv + (py - y1) * yv) * msk;
+        double w; const double g = al_row(s, d->wall_row[i] + q, cv, w);
+        gx += msk * xv * g; gy += msk * yv * g;
+        acc.sta = fmax(acc.sta, cv);
+        const double wm = w * msk;
+        h00 += wm * xv * xv; h01 += wm * xv * yv; h11 += wm * yv * yv;
+      }
+      const int nc = d->n_circles[i];
+      for (int q = 0; q < nc; q++) {                           // CircleConstraint: c = r² − (x−xc)² − (y−yc)²
+        const double* cl = d->circles[i][q];
+        const double ex = px - cl[0], ey = py - cl[1];
+        const double cv = cl[2] * cl[2] - ex * ex - ey * ey;
+        double w; const double g = al_row(s, d->circle_row[i] + q, cv, w);
+        gx -= 2.0 * ex * g; gy -= 2.0 * ey * g;
+        acc.sta = fmax(acc.sta, cv);
+        const double w4 = 4.0 * w;
+        h00 += w4 * ex * ex; h01 += w4 * ex * ey; h11 += w4 * ey * ey;
+      }
+      double* gs = Gs + (k * P + i) * 2; gs[0] = gx; gs[1] = gy;
+      if (!TRIAL) { double* hs = Hs + (k * P + i) * 3; hs[0] = h00; hs[1] = h01; hs[2] = h11; }
+    }
+  }
+
   // one element of player i's stationarity row block w.r.t. x at knot k (1..K), joint comp a
   template <bool TRIAL> __device__ double xrow_elem(int i, int k, int a, double alpha, double reg_x, Acc& acc) {
     const int c = a / P, ia = a - c * P, s = k - 1;
-    const double dtx = (k < K) ? dt : 1.0;                      // terminal knot is not dt-scaled (objective test :52-64)
     const double xa = xg<TRIAL>(k, a, alpha);
     double v = 0.0;
-    if (ia == i) v = dtx * Q[a] * (xa - xf[a]);                 // LQR gradient (objective.jl:24-32)
+    if (ia == i) v = ((k < K) ? dt : 1.0) * Q[a] * (xa - xf[a]);      // LQR gradient (objective.jl:24-32)
     if (c < 2) {
-      for (int j = 0; j < P; j++) {
-        if (j == i) continue;
-        if (ia != i && ia != j) continue;
-        const double dx = xg<TRIAL>(k, i, alpha) - xg<TRIAL>(k, j, alpha);
-        const double dy = xg<TRIAL>(k, P + i, alpha) - xg<TRIAL>(k, P + j, alpha);
-        const double dc = (c == 0) ? dx : dy;
-        const double sgn = (ia == i) ? -1.0 : 1.0;
-        const bool owner = (ia == i) && (c == 0);
-        if (has_cc) {                                            // CollisionCost (objective.jl:134-173)
-          const double dn = sqrt(dx * dx + dy * dy);
-          const double rr = d->cc_radius[i], mu = d->cc_mu[i];
-          double b00 = 0.0, b01 = 0.0, b11 = 0.0;
-          if (fmax(0.0, rr - dn) > 0.0) {
-            const double eps = 1e-10, eps_norm = eps * sqrt((double)n);
-            const double g = mu * (rr * (eps + dc) / (eps_norm + dn) - dc);
-            v += sgn * g * dtx;
-            if (owner) {
-              const double dn3 = dn * dn * dn;
-              b00 = dtx * mu * (1.0 - rr / dn + rr * dx * dx / dn3);
-              b01 = dtx * mu * (rr * dx * dy / dn3);
-              b11 = dtx * mu * (1.0 - rr / dn + rr * dy * dy / dn3);
-            }
-          }
-          if (owner) {
-            double* cc = CC + (k * npairs + pair_index(i, j)) * 3;
-            cc[0] = b00; cc[1] = b01; cc[2] = b11;
-          }
-        }
-        const int row = d->col_row[i][j];
-        if (row >= 0) {                                          // CollisionConstraint: c = r² − ‖xi−xj‖²
-          const double rad = d->col_radius[i][j];
-          const double cv = rad * rad - (dx * dx + dy * dy);
-          double w; const double g = al_row(s, row, cv, w);
-          v += sgn * 2.0 * dc * g;
-          acc.sta = fmax(acc.sta, cv);
-          if (owner) CW[s * nrow + row] = w;
+      if (has_pairs) {
+        if (ia == i) {
+#pragma unroll
+          for (int jj = 0; jj < P - 1; jj++) v += Gp[(k * NP + i * (P - 1) + jj) * 2 + c];
+        } else {
+          v -= Gp[(k * NP + pair_index(i, ia)) * 2 + c];
         }
       }
-      if (ia == i) {
-        const double px = xg<TRIAL>(k, i, alpha), py = xg<TRIAL>(k, P + i, alpha);
-        const int nw = d->n_walls[i];
-        for (int q = 0; q < nw; q++) {                           // WallConstraint (constraints/wall_constraint.jl:56-89)
-          const double* wl = d->walls[i][q];
-          const double x1 = wl[0], y1 = wl[1], x2 = wl[2], y2 = wl[3], xv = wl[4], yv = wl[5];
-          const bool left = (px - x1) * (x2 - x1) + (py - y1) * (y2 - y1) > 0.0;
-          const bool right = (px - x2) * (x1 - x2) + (py - y2) * (y1 - y2) > 0.0;
-          const double msk = (left && right) ? 1.0 : 0.0;
-          const double cv = ((px - x1) * xv + (py - y1) * yv) * msk;
-          const int row = d->wall_row[i] + q;
-          double w; const double g = al_row(s, row, cv, w);
-          v += msk * ((c == 0) ? xv : yv) * g;
-          acc.sta = fmax(acc.sta, cv);
-          if (c == 0) CW[s * nrow + row] = w * msk;              // effective weight: the wall Jacobian carries the mask
-        }
-        const int nc = d->n_circles[i];
-        for (int q = 0; q < nc; q++) {                           // CircleConstraint: c = r² − (x−xc)² − (y−yc)²
-          const double* cl = d->circles[i][q];
-          const double ex = px - cl[0], ey = py - cl[1];
-          const double cv = cl[2] * cl[2] - ex * ex - ey * ey;
-          const int row = d->circle_row[i] + q;
-          double w; const double g = al_row(s, row, cv, w);
-          v += -2.0 * ((c == 0) ? ex : ey) * g;
-          acc.sta = fmax(acc.sta, cv);
-          if (c == 0) CW[s * nrow + row] = w;
-        }
-      }
+      if (has_self && ia == i) v += Gs[(k * P + i) * 2 + c];
     }
-    {                                                            // StateBoundConstraint (state_bound_constraint.jl:80-92)
+    if (has_sb) {                                                     // StateBoundConstraint (state_bound_constraint.jl:80-92)
       int row = d->sbmax_row[i][a];
       if (row >= 0) {
         const double cv = xa - d->x_max[i][a];
@@ -322,12 +403,16 @@ struct Inst {
         v -= g; acc.sta = fmax(acc.sta, cv); CW[s * nrow + row] = w;
       }
     }
-    if (k < K) {                                                 // + A_kᵀ λ_{i,k}   (global_quantities.jl:45-53)
-#pragma unroll
-      for (int q = 0; q < 4; q++) v += Ael(k, ia, q, c) * lg<TRIAL>(i, k, q * P + ia, alpha);
+    if (k < K) {                                                      // + A_kᵀ λ_{i,k}   (global_quantities.jl:45-53)
+      v += lg<TRIAL>(i, k, a, alpha);
+      if (c >= 2) {
+        double At[8], Bt[8]; loadAB(k, ia, At, Bt);
+        v += at_dot_sel(c - 2, At, lg<TRIAL>(i, k, ia, alpha), lg<TRIAL>(i, k, P + ia, alpha),
+                        lg<TRIAL>(i, k, 2 * P + ia, alpha), lg<TRIAL>(i, k, 3 * P + ia, alpha));
+      }
     }
-    v -= lg<TRIAL>(i, k - 1, a, alpha);                          // − λ_{i,k−1}
-    if (TRIAL) v += reg_x * (alpha * R[s * b + OD + a]);         // regularize_residual! (:67-86)
+    v -= lg<TRIAL>(i, k - 1, a, alpha);                               // − λ_{i,k−1}
+    if (TRIAL) v += reg_x * (alpha * R[s * b + OD + a]);              // regularize_residual! (:67-86)
     return v;
   }
 
@@ -336,19 +421,22 @@ struct Inst {
     const int idx = j * P + i;
     const double ua = ug<TRIAL>(s, idx, alpha);
     double v = dt * Rw[idx] * (ua - uf[idx]);
-#pragma unroll
-    for (int q = 0; q < 4; q++) v += Bel(s, i, q, j) * lg<TRIAL>(i, s, q * P + i, alpha);
-    int row = d->ub_row[idx];                                    // ControlBoundConstraint (control_bound_constraint.jl:94-106)
-    if (row >= 0) {
-      const double cv = ua - d->u_max[idx];
-      double w; const double g = al_row(s, row, cv, w);
-      v += g; acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
-    }
-    row = d->lb_row[idx];
-    if (row >= 0) {
-      const double cv = d->u_min[idx] - ua;
-      double w; const double g = al_row(s, row, cv, w);
-      v -= g; acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
+    double At[8], Bt[8]; loadAB(s, i, At, Bt);
+    v += bt_dot_sel(j, Bt, lg<TRIAL>(i, s, i, alpha), lg<TRIAL>(i, s, P + i, alpha), lg<TRIAL>(i, s, 2 * P + i, alpha),
+                    lg<TRIAL>(i, s, 3 * P + i, alpha));
+    if (has_cb) {                                                     // ControlBoundConstraint (control_bound_constraint.jl:94-106)
+      int row = d->ub_row[idx];
+      if (row >= 0) {
+        const double cv = ua - d->u_max[idx];
+        double w; const double g = al_row(s, row, cv, w);
+        v += g; acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
+      }
+      row = d->lb_row[idx];
+      if (row >= 0) {
+        const double cv = d->u_min[idx] - ua;
+        double w; const double g = al_row(s, row, cv, w);
+        v -= g; acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
+      }
     }
     if (TRIAL) v += reg_u * (alpha * R[s * b + OU + idx]);
     return v;
@@ -380,7 +468,9 @@ struct Inst {
   // NaN-safe maxima: fmax drops NaNs, so a non-finite residual is caught through `sum`.
   template <bool TRIAL> __device__ Acc residual(double alpha, double reg_x, double reg_u, double* Rout) {
     Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0};
-    pass1<TRIAL>(alpha, Rout, acc);
+    pass_dyn<TRIAL>(alpha, Rout, acc);
+    pass_pairs<TRIAL>(alpha, acc);
+    pass_self<TRIAL>(alpha, acc);
     __syncthreads();
     const int nx = P * K * n;
     for (int item = tid; item < nx; item += kThreads) {
@@ -403,79 +493,51 @@ struct Inst {
   }
 
   // ---------------------------------------------------------------------------------------------------------
-  // residual_jacobian! blocks (global_quantities.jl:109-193) at the last expansion point (uses CW, CC, AB, X)
+  // residual_jacobian! blocks (global_quantities.jl:109-193) at the last expansion point (uses Hp, Hs, CW, AB)
   // ---------------------------------------------------------------------------------------------------------
-  // H^x_{i,k}[a][b] on the position sub-block a,b < 2p (collision cost + Gauss-Newton terms of position constraints)
-  __device__ double hpos_entry(int i, int k, int a, int bq) const {
-    const int ca = a / P, ia = a - ca * P, cb = bq / P, ib = bq - cb * P, s = k - 1;
+  // H^x_{i,k}[a][bq] for position comps a = (ca,ia), bq = (cb,ib), ca,cb < 2
+  __device__ __forceinline__ double hpos_entry(int i, int k, int ca, int ia, int cb, int ib) const {
+    const int e = ca + cb;
     double v = 0.0;
-    for (int j = 0; j < P; j++) {
-      if (j == i) continue;
-      if ((ia != i && ia != j) || (ib != i && ib != j)) continue;
-      const double sg = (ia == ib) ? 1.0 : -1.0;
-      if (has_cc) v += sg * CC[(k * npairs + pair_index(i, j)) * 3 + ca + cb];
-      const int row = d->col_row[i][j];
-      if (row >= 0) {
-        const double w = CW[s * nrow + row];
-        if (w != 0.0) {
-          const double dx = X[k * n + i] - X[k * n + j], dy = X[k * n + P + i] - X[k * n + P + j];
-          v += sg * 4.0 * (ca ? dy : dx) * (cb ? dy : dx) * w;
+    if (ia == ib) {
+      if (ia == i) {
+        if (has_pairs) {
+#pragma unroll
+          for (int jj = 0; jj < P - 1; jj++) v += Hp[(k * NP + i * (P - 1) + jj) * 3 + e];
         }
+        if (has_self) v += Hs[(k * P + i) * 3 + e];
+      } else if (has_pairs) {
+        v = Hp[(k * NP + pair_index(i, ia)) * 3 + e];
       }
-    }
-    if (ia == i && ib == i) {
-      const int nw = d->n_walls[i];
-      for (int q = 0; q < nw; q++) {
-        const double* wl = d->walls[i][q];
-        v += CW[s * nrow + d->wall_row[i] + q] * (ca ? wl[5] : wl[4]) * (cb ? wl[5] : wl[4]);
-      }
-      const int nc = d->n_circles[i];
-      if (nc > 0) {
-        const double px = X[k * n + i], py = X[k * n + P + i];
-        for (int q = 0; q < nc; q++) {
-          const double* cl = d->circles[i][q];
-          const double ex = px - cl[0], ey = py - cl[1];
-          v += CW[s * nrow + d->circle_row[i] + q] * 4.0 * (ca ? ey : ex) * (cb ? ey : ex);
-        }
-      }
+    } else if (has_pairs) {
+      if (ia == i) v = -Hp[(k * NP + pair_index(i, ib)) * 3 + e];
+      else if (ib == i) v = -Hp[(k * NP + pair_index(i, ia)) * 3 + e];
     }
     return v;
   }
   // diagonal part of H^x_{i,k}: dt·Q_i + state-bound terms + reg.x
-  __device__ double hd_entry(int i, int k, int a, double reg_x) const {
+  __device__ __forceinline__ double hd_entry(int i, int k, int a, double reg_x) const {
     const int ia = a % P, s = k - 1;
     double v = reg_x;
     if (ia == i) v += ((k < K) ? dt : 1.0) * Q[a];
-    int row = d->sbmax_row[i][a]; if (row >= 0) v += CW[s * nrow + row];
-    row = d->sbmin_row[i][a];     if (row >= 0) v += CW[s * nrow + row];
+    if (has_sb) {
+      int row = d->sbmax_row[i][a]; if (row >= 0) v += CW[s * nrow + row];
+      row = d->sbmin_row[i][a];     if (row >= 0) v += CW[s * nrow + row];
+    }
+    return v;
+  }
+  __device__ __forceinline__ double h_entry(int i, int k, int a, int bq, double reg_x) const {
+    double v = (a == bq) ? hd_entry(i, k, a, reg_x) : 0.0;
+    if (a < 2 * P && bq < 2 * P) v += hpos_entry(i, k, a / P, a % P, bq / P, bq % P);
     return v;
   }
   // H^u diagonal of stage s, joint control comp idx: dt·R + control-bound terms + reg.u
-  __device__ double hu_entry(int s, int idx, double reg_u) const {
+  __device__ __forceinline__ double hu_entry(int s, int idx, double reg_u) const {
     double v = dt * Rw[idx] + reg_u;
-    int row = d->ub_row[idx]; if (row >= 0) v += CW[s * nrow + row];
-    row = d->lb_row[idx];     if (row >= 0) v += CW[s * nrow + row];
-    return v;
-  }
-
-  // assemble compact H^x_{·,k} into Hpos/Hd with the threads [t0, t0+nt) of the CTA
-  __device__ void assemble_H(int k, double reg_x, int t0, int nt) {
-    const int t = tid - t0;
-    if (t < 0 || t >= nt) return;
-    constexpr int q2 = 2 * P;
-    for (int item = t; item < P * q2 * q2; item += nt) {
-      int bq = item % q2, r = item / q2;
-      int a = r % q2, i = r / q2;
-      Hpos[item] = hpos_entry(i, k, a, bq);
+    if (has_cb) {
+      int row = d->ub_row[idx]; if (row >= 0) v += CW[s * nrow + row];
+      row = d->lb_row[idx];     if (row >= 0) v += CW[s * nrow + row];
     }
-    for (int item = t; item < P * n; item += nt) {
-      int a = item % n, i = item / n;
-      Hd[item] = hd_entry(i, k, a, reg_x);
-    }
-  }
-  __device__ __forceinline__ double Hc(int i, int a, int bq) const {
-    double v = (a == bq) ? Hd[i * n + a] : 0.0;
-    if (a < 2 * P && bq < 2 * P) v += Hpos[(i * 2 * P + a) * 2 * P + bq];
     return v;
   }
 
@@ -495,12 +557,13 @@ struct Inst {
 #pragma unroll
       for (int r = t + 1; r < m; r++) if (r == pr) { double tmp = a[r]; a[r] = a[t]; a[t] = tmp; }
       const double pv = __shfl_sync(AGB_FULL, a[t], t);
+      double f[m];
+#pragma unroll
+      for (int r = 0; r < m; r++) f[r] = (r != t) ? __shfl_sync(AGB_FULL, a[r], t) : 0.0;
       if (!(fabs(pv) > 0.0) || isinf(pv)) ok = false;
       const double at = a[t] * (1.0 / pv);
 #pragma unroll
-      for (int r = 0; r < m; r++) {
-        if (r != t) { const double f = __shfl_sync(AGB_FULL, a[r], t); a[r] = fma(-f, at, a[r]); }
-      }
+      for (int r = 0; r < m; r++) if (r != t) a[r] = fma(-f[r], at, a[r]);
       a[t] = at;
     }
     if (act) {
@@ -510,141 +573,251 @@ struct Inst {
     return ok;
   }
 
+  // Y_i = B_iᵀ P_i (+ affine column B_iᵀ s_i) for stage s, from the P rows of player i's own states
+  __device__ void compute_Y(int s) {
+    for (int item = tid; item < P * n1; item += kThreads) {
+      const int col = item % n1, i = item / n1;
+      double At[8], Bt[8]; loadAB(s, i, At, Bt);
+      double pv[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) pv[q] = (col < n) ? Pm[(i * n + q * P + i) * n + col] : Sv[i * n + q * P + i];
+      Ym[(0 * P + i) * n1 + col] = bt_dot<0>(Bt, pv[0], pv[1], pv[2], pv[3]);
+      Ym[(1 * P + i) * n1 + col] = bt_dot<1>(Bt, pv[0], pv[1], pv[2], pv[3]);
+    }
+  }
+
   // ---------------------------------------------------------------------------------------------------------
   // Δtraj = −(lu(jac) \ res)  (solver_methods.jl:87-88): R holds res on entry, Δ on exit (same stage-major slots:
   // rx(i,s) → Δλ_{i,s}, ru(s) → Δu_s, rd(s) → Δx_{s+1}).  Returns false on a singular / non-finite pivot.
+  //
+  // Per stage s (backward), with P_i, s_i of knot s+1 and Y = B_sᵀ P already in shared memory:
+  //   phase 1 (all warps)   Aug = [Hu + Y B | Y A | Y rd + Bᵀ s + ru];   t_i = P_i rd + s_i
+  //   phase 2 (warp 0)      Gauss-Jordan → K, κ                      ‖  (warps 1-3) everything of the P update that does
+  //                         not depend on K:  Base_i = H_{i,s} + Aᵀ P_i A,  base_i = r^x_{i,s} + Aᵀ t_i,  W_i = Aᵀ P_i B
+  //   phase 3 (all warps)   P_i ← Base_i − W_i K,  s_i ← base_i − W_i κ,  Y ← B_{s−1}ᵀ P_i
   // ---------------------------------------------------------------------------------------------------------
   __device__ bool kkt_solve(double reg_x, double reg_u) {
     int ok = 1;
-    double* Pc = Pm;                 // current P_i (knot s+1), [P][n][n]
-    double* Pn = Pm + P * n * n;     // next
-    double* sc = Sv;                 // [P][n]
-    double* sn = Sv + P * n;
     // terminal knot: P_i = H_{i,N}, s_i = r^x_{i,N}
-    assemble_H(K, reg_x, 0, kThreads);
-    __syncthreads();
     for (int item = tid; item < P * n * n; item += kThreads) {
       int bq = item % n, r = item / n;
       int a = r % n, i = r / n;
-      Pc[item] = Hc(i, a, bq);
+      Pm[item] = h_entry(i, K, a, bq, reg_x);
     }
     for (int item = tid; item < P * n; item += kThreads) {
       int a = item % n, i = item / n;
-      sc[item] = R[(K - 1) * b + OX + i * n + a];
+      Sv[item] = R[(K - 1) * b + OX + i * n + a];
     }
+    __syncthreads();
+    compute_Y(K - 1);
     __syncthreads();
     for (int s = K - 1; s >= 0; s--) {
       const double* Rs = R + s * b;
-      // ---- phase B: augmented system  [Hu + Y B | Y A | Y rd + Bᵀ s + ru],  Y_r = B_iᵀ P_i (row r = (j,i))
-      for (int item = tid; item < m * W; item += kThreads) {
-        const int col = item % W, r = item / W;
-        const int j = r / P, i = r - j * P;
-        const double* Pi = Pc + i * n * n;
-        double Bi[4];
+      // ---- phase 1
+      for (int item = tid; item < m * W + P * n; item += kThreads) {
+        if (item < m * W) {
+          const int col = item % W, r = item / W;
+          const double* yr = Ym + r * n1;
+          double v;
+          if (col < m) {
+            const int j2 = col / P, i2 = col - j2 * P;
+            double At[8], Bt[8]; loadAB(s, i2, At, Bt);
+            v = bt_dot_sel(j2, Bt, yr[i2], yr[P + i2], yr[2 * P + i2], yr[3 * P + i2]);
+            if (col == r) v += hu_entry(s, r, reg_u);
+          } else if (col < m + n) {
+            const int a2 = col - m, c2 = a2 / P, i2 = a2 - c2 * P;
+            v = yr[a2];
+            if (c2 >= 2) {
+              double At[8], Bt[8]; loadAB(s, i2, At, Bt);
+              v += at_dot_sel(c2 - 2, At, yr[i2], yr[P + i2], yr[2 * P + i2], yr[3 * P + i2]);
+            }
+          } else {
+            double v0 = yr[n] + Rs[OU + r], v1 = 0.0, v2 = 0.0, v3 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) Bi[q] = Bel(s, i, q, j);
-        double v;
-        if (col < m + n) {
-          int i2, c2; bool isB = col < m;
-          if (isB) { c2 = col / P; i2 = col - c2 * P; } else { int a2 = col - m; c2 = a2 / P; i2 = a2 - c2 * P; }
-          v = 0.0;
-#pragma unroll
-          for (int q = 0; q < 4; q++) {                 // Y[r][(q,i2)]
-            double y = 0.0;
-#pragma unroll
-            for (int q1 = 0; q1 < 4; q1++) y += Bi[q1] * Pi[(q1 * P + i) * n + q * P + i2];
-            v += y * (isB ? Bel(s, i2, q, c2) : Ael(s, i2, q, c2));
+            for (int a2 = 0; a2 < n; a2 += 4) {
+              v0 += yr[a2] * Rs[OD + a2]; v1 += yr[a2 + 1] * Rs[OD + a2 + 1];
+              v2 += yr[a2 + 2] * Rs[OD + a2 + 2]; v3 += yr[a2 + 3] * Rs[OD + a2 + 3];
+            }
+            v = (v0 + v1) + (v2 + v3);
           }
-          if (isB && col == r) v += hu_entry(s, r, reg_u);
-        } else {
-          v = Rs[OU + r];
+          Aug[r * W + col] = v;
+        } else if (s > 0) {                                  // t_i[a] = s_i[a] + Σ_c P_i[a][c] rd[c]
+          const int it = item - m * W;
+          const double* pr = Pm + it * n;
+          double v0 = Sv[it], v1 = 0.0, v2 = 0.0, v3 = 0.0;
 #pragma unroll
-          for (int q1 = 0; q1 < 4; q1++) {
-            const double* prow = Pi + (q1 * P + i) * n;
-            double y = sc[i * n + q1 * P + i];
-            for (int a2 = 0; a2 < n; a2++) y += prow[a2] * Rs[OD + a2];
-            v += Bi[q1] * y;
+          for (int a2 = 0; a2 < n; a2 += 4) {
+            v0 += pr[a2] * Rs[OD + a2]; v1 += pr[a2 + 1] * Rs[OD + a2 + 1];
+            v2 += pr[a2 + 2] * Rs[OD + a2 + 2]; v3 += pr[a2 + 3] * Rs[OD + a2 + 3];
           }
+          Ta[it] = (v0 + v1) + (v2 + v3);
         }
-        Aug[r * W + col] = v;
       }
       __syncthreads();
-      // ---- phase C: warp 0 solves for the gains; the other warps assemble H^x of knot s meanwhile
+      // ---- phase 2
       if (warp == 0) {
         if (!gj_warp(Aug)) ok = 0;
         if (lane >= m && lane < W) {
-          double* ku = KU + s * KUS;
+          double* kg = KUg + s * KUS;
 #pragma unroll
-          for (int r = 0; r < m; r++) ku[r * (n + 1) + (lane - m)] = Aug[r * W + lane];
+          for (int r = 0; r < m; r++) { const double v = Aug[r * W + lane]; KU[r * n1 + (lane - m)] = v; kg[r * n1 + (lane - m)] = v; }
         }
       } else if (s > 0) {
-        assemble_H(s, reg_x, 32, kThreads - 32);
+        constexpr int NB = P * P * n, NW = P * P * m, NA = P * P;
+        for (int item = tid - 32; item < NB + NW + NA; item += kThreads - 32) {
+          int kind, col, t;                                 // 0: Base column, 1: W column, 2: affine
+          if (item < NB) { kind = 0; col = item % n; t = item / n; }
+          else if (item < NB + NW) { kind = 1; col = (item - NB) % m; t = (item - NB) / m; }
+          else { kind = 2; col = n; t = item - NB - NW; }
+          const int i2 = t % P, i = t / P;                  // rows (·,i2) of player i's matrices
+          const double* Pi = Pm + i * n * n;
+          const double* p0 = Pi + (0 * P + i2) * n;
+          const double* p1 = Pi + (1 * P + i2) * n;
+          const double* p2 = Pi + (2 * P + i2) * n;
+          const double* p3 = Pi + (3 * P + i2) * n;
+          double T0, T1, T2, T3;
+          if (kind == 1) {                                  // T = (P_i B)[(q,i2)][col],  col = (j,i3)
+            const int j = col / P, i3 = col - j * P;
+            double At[8], Bt[8]; loadAB(s, i3, At, Bt);
+            T0 = bt_dot_sel(j, Bt, p0[i3], p0[P + i3], p0[2 * P + i3], p0[3 * P + i3]);
+            T1 = bt_dot_sel(j, Bt, p1[i3], p1[P + i3], p1[2 * P + i3], p1[3 * P + i3]);
+            T2 = bt_dot_sel(j, Bt, p2[i3], p2[P + i3], p2[2 * P + i3], p2[3 * P + i3]);
+            T3 = bt_dot_sel(j, Bt, p3[i3], p3[P + i3], p3[2 * P + i3], p3[3 * P + i3]);
+          } else if (kind == 0) {                           // T = (P_i A)[(q,i2)][col],  col = (c2,i3)
+            const int c2 = col / P, i3 = col - c2 * P;
+            T0 = p0[col]; T1 = p1[col]; T2 = p2[col]; T3 = p3[col];
+            if (c2 >= 2) {
+              double At[8], Bt[8]; loadAB(s, i3, At, Bt);
+              T0 += at_dot_sel(c2 - 2, At, p0[i3], p0[P + i3], p0[2 * P + i3], p0[3 * P + i3]);
+              T1 += at_dot_sel(c2 - 2, At, p1[i3], p1[P + i3], p1[2 * P + i3], p1[3 * P + i3]);
+              T2 += at_dot_sel(c2 - 2, At, p2[i3], p2[P + i3], p2[2 * P + i3], p2[3 * P + i3]);
+              T3 += at_dot_sel(c2 - 2, At, p3[i3], p3[P + i3], p3[2 * P + i3], p3[3 * P + i3]);
+            }
+          } else {                                          // T = t_i = P_i rd + s_i (phase 1)
+            T0 = Ta[i * n + i2]; T1 = Ta[i * n + P + i2]; T2 = Ta[i * n + 2 * P + i2]; T3 = Ta[i * n + 3 * P + i2];
+          }
+          // Aᵀ = I + Atᵀ: rows c = 2,3 pick up Σ_q At[q][c-2] T[q]
+          double At2[8], Bt2[8]; loadAB(s, i2, At2, Bt2);
+          const double o[4] = {T0, T1, T2 + at_dot<0>(At2, T0, T1, T2, T3), T3 + at_dot<1>(At2, T0, T1, T2, T3)};
+          if (kind == 1) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) Wm[(i * n + c * P + i2) * m + col] = o[c];
+          } else if (kind == 0) {
+            const int c2 = col / P, i3 = col - c2 * P;
+            double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;     // H^x_{i,s}[(c,i2)][col], c = 0..3
+            if (c2 < 2) {                                        // position block: ±Hp of one pair, or the own-block sum
+              if (i2 == i3) {
+                if (i2 == i) {
+                  if (has_pairs) {
+#pragma unroll
+                    for (int jj = 0; jj < P - 1; jj++) {
+                      const double* hp = Hp + (s * NP + i * (P - 1) + jj) * 3 + c2;
+                      h0 += hp[0]; h1 += hp[1];
+                    }
+                  }
+                  if (has_self) { const double* hs = Hs + (s * P + i) * 3 + c2; h0 += hs[0]; h1 += hs[1]; }
+                } else if (has_pairs) {
+                  const double* hp = Hp + (s * NP + pair_index(i, i2)) * 3 + c2;
+                  h0 = hp[0]; h1 = hp[1];
+                }
+              } else if (has_pairs && (i2 == i || i3 == i)) {
+                const double* hp = Hp + (s * NP + pair_index(i, i2 == i ? i3 : i2)) * 3 + c2;
+                h0 = -hp[0]; h1 = -hp[1];
+              }
+            }
+            if (i2 == i3) {
+              const double hd = hd_entry(i, s, col, reg_x);
+              if (c2 == 0) h0 += hd; else if (c2 == 1) h1 += hd; else if (c2 == 2) h2 = hd; else h3 = hd;
+            }
+            Base[(i * n + 0 * P + i2) * n1 + col] = o[0] + h0;
+            Base[(i * n + 1 * P + i2) * n1 + col] = o[1] + h1;
+            Base[(i * n + 2 * P + i2) * n1 + col] = o[2] + h2;
+            Base[(i * n + 3 * P + i2) * n1 + col] = o[3] + h3;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) Base[(i * n + c * P + i2) * n1 + n] = o[c] + R[(s - 1) * b + OX + i * n + c * P + i2];
+          }
+        }
       }
       __syncthreads();
       if (s == 0) break;
-      const double* ku = KU + s * KUS;
-      // ---- phase D: closed loop  Acl = A − B Ku,  ccl = rd − B ku   (n x (n+1))
-      for (int item = tid; item < n * (n + 1); item += kThreads) {
-        const int col = item % (n + 1), a = item / (n + 1);
-        const int c = a / P, i = a - c * P;
-        double v;
-        if (col < n) { const int c2 = col / P, i2 = col - c2 * P; v = (i2 == i) ? Ael(s, i, c, c2) : 0.0; }
-        else v = Rs[OD + a];
+      // ---- phase 3
+      {
+        const double* ku = KU;
+        for (int item = tid; item < P * P * n1; item += kThreads) {
+          const int col = item % n1, t = item / n1;
+          const int i2 = t % P, i = t / P;
+          double kc[m];
 #pragma unroll
-        for (int j = 0; j < 2; j++) v -= Bel(s, i, c, j) * ku[(j * P + i) * (n + 1) + col];
-        Acl[item] = v;
-      }
-      __syncthreads();
-      // ---- phase E: P_i ← H_{i,s} + Aᵀ P_i Acl,  s_i ← r^x_{i,s} + Aᵀ (P_i ccl + s_i)
-      for (int item = tid; item < P * P * (n + 1); item += kThreads) {
-        const int col = item % (n + 1), t = item / (n + 1);
-        const int i2 = t % P, i = t / P;
-        const double* Pi = Pc + i * n * n;
-        double T[4];
+          for (int r = 0; r < m; r++) kc[r] = ku[r * n1 + col];
+          double pn[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) T[q] = (col == n) ? sc[i * n + q * P + i2] : 0.0;
-        for (int a2 = 0; a2 < n; a2++) {
-          const double e = Acl[a2 * (n + 1) + col];
+          for (int c = 0; c < 4; c++) {
+            const int a = c * P + i2;
+            const double* w = Wm + (i * n + a) * m;
+            double v0 = Base[(i * n + a) * n1 + col], v1 = 0.0;
 #pragma unroll
-          for (int q = 0; q < 4; q++) T[q] += Pi[(q * P + i2) * n + a2] * e;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          double o = 0.0;
-#pragma unroll
-          for (int q = 0; q < 4; q++) o += Ael(s, i2, q, c) * T[q];
-          const int a = c * P + i2;
-          if (col < n) Pn[(i * n + a) * n + col] = o + Hc(i, a, col);
-          else sn[i * n + a] = o + R[(s - 1) * b + OX + i * n + a];
+            for (int r = 0; r < m; r += 2) { v0 -= w[r] * kc[r]; v1 -= w[r + 1] * kc[r + 1]; }
+            pn[c] = v0 + v1;
+            if (col < n) Pm[(i * n + a) * n + col] = pn[c]; else Sv[i * n + a] = pn[c];
+          }
+          if (i2 == i) {                                    // Y for the next stage (s-1)
+            double At[8], Bt[8]; loadAB(s - 1, i, At, Bt);
+            Ym[(0 * P + i) * n1 + col] = bt_dot<0>(Bt, pn[0], pn[1], pn[2], pn[3]);
+            Ym[(1 * P + i) * n1 + col] = bt_dot<1>(Bt, pn[0], pn[1], pn[2], pn[3]);
+          }
         }
       }
       __syncthreads();
-      { double* t = Pc; Pc = Pn; Pn = t; t = sc; sc = sn; sn = t; }
     }
-    // ---- forward sweep (warp 0): Δu_s = −Ku Δx_s − ku,  Δx_{s+1} = A Δx_s + B Δu_s + rd
+    // ---- forward sweep (warp 0): Δu_s = −Ku Δx_s − ku,  Δx_{s+1} = A Δx_s + B Δu_s + rd.  The gains come back from the
+    // L2-resident scratch two stages ahead of their use (register prefetch), staged through the one-stage smem buffer.
     if (warp == 0) {
+      constexpr int NQ = (KUS + 31) / 32;
+      double r0[NQ], r1[NQ];
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int idx = lane + 32 * q;
+        r0[q] = (idx < KUS) ? KUg[idx] : 0.0;
+        r1[q] = (idx < KUS && K > 1) ? KUg[KUS + idx] : 0.0;
+      }
       for (int s = 0; s < K; s++) {
-        const double* ku = KU + s * KUS;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const int idx = lane + 32 * q;
+          if (idx < KUS) KU[idx] = r0[q];
+          r0[q] = r1[q];
+          if (idx < KUS && s + 2 < K) r1[q] = KUg[(s + 2) * KUS + idx];
+        }
+        __syncwarp();
+        const double* ku = KU;
         double* Rs = R + s * b;
         const double* dxp = R + (s - 1) * b + OD;      // Δx_s (only read when s > 0)
-        double du = 0.0;
         if (lane < m) {
-          double acc = ku[lane * (n + 1) + n];
-          if (s > 0) for (int a = 0; a < n; a++) acc += ku[lane * (n + 1) + a] * dxp[a];
-          du = -acc;
-          Rs[OU + lane] = du;
+          double a0 = ku[lane * n1 + n], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          if (s > 0) {
+#pragma unroll
+            for (int a = 0; a < n; a += 4) {
+              a0 += ku[lane * n1 + a] * dxp[a]; a1 += ku[lane * n1 + a + 1] * dxp[a + 1];
+              a2 += ku[lane * n1 + a + 2] * dxp[a + 2]; a3 += ku[lane * n1 + a + 3] * dxp[a + 3];
+            }
+          }
+          Rs[OU + lane] = -((a0 + a1) + (a2 + a3));
         }
         __syncwarp();
         double v = 0.0;
         if (lane < n) {
           const int c = lane / P, i = lane - c * P;
+          double At[8], Bt[8]; loadAB(s, i, At, Bt);
           v = Rs[OD + lane];
-          if (s > 0) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) v += Ael(s, i, c, q) * dxp[q * P + i];
-          }
-#pragma unroll
-          for (int j = 0; j < 2; j++) v += Bel(s, i, c, j) * Rs[OU + j * P + i];
+          const double u0 = Rs[OU + i], u1 = Rs[OU + P + i];
+          double y0 = 0.0, y1 = 0.0;
+          if (s > 0) { v += dxp[lane]; y0 = dxp[2 * P + i]; y1 = dxp[3 * P + i]; }
+          if (c == 0) v += at_row<0>(At, y0, y1) + bt_row<0>(Bt, u0, u1);
+          else if (c == 1) v += at_row<1>(At, y0, y1) + bt_row<1>(Bt, u0, u1);
+          else if (c == 2) v += at_row<2>(At, y0, y1) + bt_row<2>(Bt, u0, u1);
+          else v += at_row<3>(At, y0, y1) + bt_row<3>(Bt, u0, u1);
         }
         __syncwarp();
         if (lane < n) Rs[OD + lane] = v;
@@ -656,10 +829,24 @@ struct Inst {
     for (int item = tid; item < P * K * n; item += kThreads) {
       const int a = item % n, t = item / n;
       const int s = t % K, i = t / K, k = s + 1;
+      const int c = a / P, ia = a - c * P;
       const double* dx = R + s * b + OD;
       double v = R[s * b + OX + i * n + a] + hd_entry(i, k, a, reg_x) * dx[a];
-      if (a < 2 * P) {
-        for (int bq = 0; bq < 2 * P; bq++) v += hpos_entry(i, k, a, bq) * dx[bq];
+      if (c < 2) {
+        if (ia == i) {
+          if (has_pairs) {
+#pragma unroll
+            for (int jj = 0; jj < P - 1; jj++) {
+              const int j = jj < i ? jj : jj + 1;
+              const double* hp = Hp + (k * NP + i * (P - 1) + jj) * 3;
+              v += hp[c] * (dx[i] - dx[j]) + hp[c + 1] * (dx[P + i] - dx[P + j]);
+            }
+          }
+          if (has_self) { const double* hs = Hs + (k * P + i) * 3; v += hs[c] * dx[i] + hs[c + 1] * dx[P + i]; }
+        } else if (has_pairs) {
+          const double* hp = Hp + (k * NP + pair_index(i, ia)) * 3;
+          v -= hp[c] * (dx[i] - dx[ia]) + hp[c + 1] * (dx[P + i] - dx[P + ia]);
+        }
       }
       R[s * b + OX + i * n + a] = v;
     }
@@ -670,9 +857,12 @@ struct Inst {
         double v = 0.0;
         if (lane < n) {
           const int c = lane / P, ia = lane - c * P;
-          v = R[s * b + OX + i * n + lane];
-#pragma unroll
-          for (int q = 0; q < 4; q++) v += Ael(s + 1, ia, q, c) * R[(s + 1) * b + OX + i * n + q * P + ia];
+          const double* ln = R + (s + 1) * b + OX + i * n;
+          v = R[s * b + OX + i * n + lane] + ln[lane];
+          if (c >= 2) {
+            double At[8], Bt[8]; loadAB(s + 1, ia, At, Bt);
+            v += at_dot_sel(c - 2, At, ln[ia], ln[P + ia], ln[2 * P + ia], ln[3 * P + ia]);
+          }
         }
         __syncwarp();
         if (lane < n) R[s * b + OX + i * n + lane] = v;

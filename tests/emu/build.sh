@@ -3,5 +3,14 @@
 set -e
 here="$(cd "$(dirname "$0")" && pwd)"
 root="$(cd "$here/../.." && pwd)"
-g++ -O2 -std=c++17 -fPIC -shared -DAGB_EMULATE -I "$here" -x c++ "$root/algames.jl_b200/csrc/agb_capi.cu" -x c++ "$here/emu.cpp" \
-    -o "$here/libagb_emu.so"
+src="$root/algames.jl_b200/csrc"
+mkdir -p "$here/obj"
+pids=""
+for f in agb_capi agb_kernels_p1 agb_kernels_p2 agb_kernels_p3 agb_kernels_p4; do
+  g++ -O2 -std=c++17 -fPIC -DAGB_EMULATE -I "$here" -x c++ -c "$src/$f.cu" -o "$here/obj/$f.o" &
+  pids="$pids $!"
+done
+g++ -O2 -std=c++17 -fPIC -DAGB_EMULATE -I "$here" -c "$here/emu.cpp" -o "$here/obj/emu.o" &
+pids="$pids $!"
+for p in $pids; do wait $p; done
+g++ -shared -o "$here/libagb_emu.so" "$here"/obj/*.o

@@ -26,6 +26,7 @@
 #define __align__(x)
 
 struct emu_dim3 { unsigned x, y, z; };
+struct alignas(16) double2 { double x, y; };
 extern emu_dim3 threadIdx, blockIdx, gridDim, blockDim;
 
 namespace emu {
@@ -77,7 +78,7 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 232448; return 0; }
-inline cudaError_t cudaFuncSetAttribute(void*, int, int) { return 0; }
+inline cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
