@@ -277,7 +277,7 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "agb_newton_solve_kernel<3>",
+                         "peak_source": peak_src, "kernel": "agb_newton_solve_kernel<3, DoubleIntegrator>",
                          "note": "achieved = algorithmic KKT-band bytes (%d B per Newton step, SURVEY 8d) x Newton steps per launch / launch time; "
                                  "the band is never materialised (structured on-chip factorisation), so real DRAM traffic is far lower" % bps},
             "clocks": clk.summary(),
