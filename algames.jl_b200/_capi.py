@@ -53,7 +53,8 @@ class Sizes(C.Structure):
 
 class DeviceView(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in
-                ("Z_dev", "L_dev", "conlam_dev", "conmu_dev", "stats_dev", "status_dev", "x0_dev", "Z0_dev", "L0_dev")]
+                ("Z_dev", "L_dev", "conlam_dev", "conmu_dev", "stats_dev", "status_dev", "x0_dev", "Z0_dev", "L0_dev",
+                 "results_dev")] + [("results_bytes", C.c_ulonglong)]
 
 
 # every symbol include/algames_b200.h declares: name -> (restype, argtypes)

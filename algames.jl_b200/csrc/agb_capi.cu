@@ -77,6 +77,7 @@ struct agb_handle {
   double *x0 = nullptr, *xf = nullptr, *Q = nullptr, *R = nullptr, *uf = nullptr;
   double *Z0 = nullptr, *L0 = nullptr, *Z = nullptr, *L = nullptr, *conlam = nullptr, *conmu = nullptr, *D = nullptr, *KUg = nullptr, *stats = nullptr;
   int* status = nullptr;
+  double* results = nullptr; size_t results_doubles = 0;   // owns Z, L, stats, status
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
   long long launches = 0;
@@ -219,7 +220,7 @@ void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->Z, h->L, h->conlam, h->conmu, h->D, h->KUg, h->stats, h->status, h->stage, h->stage2};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -270,11 +271,14 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
   CK(alloc_d(h, &h->x0, B * n)); CK(alloc_d(h, &h->xf, B * n)); CK(alloc_d(h, &h->Q, B * n));
   CK(alloc_d(h, &h->R, B * m)); CK(alloc_d(h, &h->uf, B * m));
   CK(alloc_d(h, &h->Z0, B * N * (n + m))); CK(alloc_d(h, &h->L0, B * p * K * n));
-  CK(alloc_d(h, &h->Z, B * N * (n + m))); CK(alloc_d(h, &h->L, B * p * K * n));
+  {  // results slab: [Z | L | stats | status] in one allocation (one collective gathers everything)
+    const size_t zs = B * N * (n + m), ls = B * p * K * n, ss = B * AGB_NSTATS, is = (B + 1) / 2;
+    h->results_doubles = zs + ls + ss + is;
+    CK(alloc_d(h, &h->results, h->results_doubles));
+    h->Z = h->results; h->L = h->Z + zs; h->stats = h->L + ls; h->status = (int*)(h->stats + ss);
+  }
   CK(alloc_d(h, &h->conlam, B * K * t.nrow)); CK(alloc_d(h, &h->conmu, B * K * t.nrow));
-  CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 1))); CK(alloc_d(h, &h->stats, B * AGB_NSTATS));
-  CKC(cudaMalloc((void**)&h->status, B * sizeof(int)));
-  CKC(cudaMemsetAsync(h->status, 0, B * sizeof(int), h->stream));
+  CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 1)));
   // descriptor defaults broadcast to every instance; μ starts at 1 (Altro ALConVal default)
   double tmp[2 * AGB_MAX_N + 2 * AGB_MAX_M];
   double* dtmp = nullptr;
@@ -552,6 +556,7 @@ int agb_get_device_view(agb_handle* h, agb_device_view* out) {
   if (!h || !out) return AGB_EINVAL;
   out->Z_dev = h->Z; out->L_dev = h->L; out->conlam_dev = h->conlam; out->conmu_dev = h->conmu; out->stats_dev = h->stats;
   out->status_dev = h->status; out->x0_dev = h->x0; out->Z0_dev = h->Z0; out->L0_dev = h->L0;
+  out->results_dev = h->results; out->results_bytes = (unsigned long long)h->results_doubles * sizeof(double);
   return AGB_OK;
 }
 

@@ -36,6 +36,31 @@ def result_views(batch):
     return out
 
 
+def results_slab(batch):
+    """Zero-copy FP64 view of the handle's whole result allocation [Z | L | stats | status(int32, padded)]."""
+    v = batch.device_view()
+    return device_tensor(v.results_dev, (v.results_bytes // 8,), "f8", batch.device)
+
+
+def all_gather_slabs(local_flat, out=None, group=None):
+    """The single collective of the path: every rank's result slab, rank-major, straight from the solver's buffers."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world * local_flat.numel(),), dtype=local_flat.dtype, device=local_flat.device)
+    dist.all_gather_into_tensor(out, local_flat, group=group)
+    return out
+
+
+def unpack_slab(flat, B, N, n, m, p):
+    """One rank's slab -> dict of numpy views."""
+    a = flat.cpu().numpy() if hasattr(flat, "cpu") else np.asarray(flat)
+    zs, ls, ss = B * N * (n + m), B * p * (N - 1) * n, B * 10
+    return {"Z": a[:zs].reshape(B, N, n + m), "L": a[zs:zs + ls].reshape(B, p, N - 1, n),
+            "stats": a[zs + ls:zs + ls + ss].reshape(B, 10), "status": a[zs + ls + ss:].view(np.int32)[:B]}
+
+
 def pack_results(views, out=None):
     """[B, zs+ls+10+1] FP64 slab (status widened to FP64) — one buffer, so one collective."""
     import torch

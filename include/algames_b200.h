@@ -191,6 +191,10 @@ typedef struct agb_device_view {
   double* x0_dev;     /* [B][n] */
   double* Z0_dev;     /* initial iterate [B][N][n+m] */
   double* L0_dev;
+  /* Z_dev, L_dev, stats_dev and status_dev are consecutive slices of ONE allocation, so a single collective on
+   * [results_dev, results_dev + results_bytes) moves every result of the batch (the path's only all-gather). */
+  void* results_dev;
+  unsigned long long results_bytes;
 } agb_device_view;
 int agb_get_device_view(agb_handle* h, agb_device_view* out);
 

@@ -143,3 +143,16 @@ def test_single_problem_api_matches_reference_tests():
     assert prob.stats.dyn_vio[-1].max < 1e-3 and prob.stats.sta_vio[-1].max < 1e-3
     assert prob.stats.con_vio[-1].max < 1e-3 and prob.stats.opt_vio[-1].max < 1e-3
     assert prob.status == "converged"
+
+
+def test_result_slab_view_matches_host_copy():
+    """agb_get_device_view: the single result allocation the all-gather ships equals what the host-buffer call returned."""
+    if os.environ.get("AGB_GPU_TESTS_ON_EMULATOR"):
+        pytest.skip("needs device pointers")
+    from algames_b200 import distributed as D
+    cfg, gb, Z0, L0, out = parity.solve_batch(LIB, "B", 16, N=12)
+    model, N = cfg[0], cfg[1]
+    got = D.unpack_slab(D.results_slab(gb), 16, N, model.n, model.m, model.p)
+    for k in ("Z", "L", "stats", "status"):
+        assert np.array_equal(got[k], out[k]), k
+    gb.close()
