@@ -5,7 +5,15 @@
 
 namespace agb {
 
-constexpr int kThreads = 128;      // one CTA (4 warps) owns one game instance
+// one CTA owns one game instance: 4 warps for up to 3 players, 8 warps for 4 players (whose 162 KB working set allows only
+// one CTA per SM, so the instance itself has to supply the parallelism)
+#ifdef __CUDACC__
+#define AGB_HD __host__ __device__
+#else
+#define AGB_HD
+#endif
+AGB_HD constexpr int threads_for(int p) { return p >= 4 ? 256 : 128; }
+constexpr int kMaxWarps = 8;
 constexpr int kMaxRows = 96;       // AL constraint rows per stage (state rows of knot k+1 + control rows of knot k)
 
 // Flattened, index-resolved form of agb_problem_desc, lives in device global memory (read through L1).

@@ -17,11 +17,11 @@ namespace agb {
 // =============================================================================================================
 // newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
 template <int P, int MODEL>
-__global__ void __launch_bounds__(kThreads, (P <= 3 ? 4 : 1)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int batch) {
+__global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL> I;
   I.bind(dd, sm);
-  constexpr int n = Inst<P, MODEL>::n;
+  constexpr int n = Inst<P, MODEL>::n, kThreads = threads_for(P);
   const int K = I.K;
   const double S = (double)(K * Inst<P, MODEL>::b);
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(kThreads, (P <= 3 ? 4 : 1)) agb_newton_solve_k
 
 // Per-function entry points on the resident batch (parity tests and stand-alone use of the exported reference API).
 template <int P, int MODEL>
-__global__ void __launch_bounds__(kThreads) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
+__global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL> I;
   I.bind(dd, sm);
-  constexpr int n = Inst<P, MODEL>::n, m = Inst<P, MODEL>::m, b = Inst<P, MODEL>::b;
+  constexpr int n = Inst<P, MODEL>::n, m = Inst<P, MODEL>::m, b = Inst<P, MODEL>::b, kThreads = threads_for(P);
   const int K = I.K, Sz = K * b, nrow = I.nrow;
   const double S = (double)Sz;
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
@@ -226,11 +226,11 @@ template <int P> inline cudaError_t set_attr_p(int model, size_t smem) {
 }
 template <int P, int MODEL> inline void launch_solve_pm(const LaunchArgs& L) {
   auto kfn = agb_newton_solve_kernel<P, MODEL>;
-  AGB_LAUNCH(kfn, L.grid, kThreads, L.smem, L.stream, L.dd, L.o, L.g, L.batch);
+  AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.batch);
 }
 template <int P, int MODEL> inline void launch_op_pm(const LaunchArgs& L) {
   auto kfn = agb_op_kernel<P, MODEL>;
-  AGB_LAUNCH(kfn, L.grid, kThreads, L.smem, L.stream, L.dd, L.o, L.g, L.a, L.batch);
+  AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.a, L.batch);
 }
 template <int P> inline void launch_solve_p(const LaunchArgs& L) {
   switch (L.model) {

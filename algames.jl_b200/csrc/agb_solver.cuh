@@ -1,6 +1,6 @@
 // agb_solver.cuh — device code of the batched ALGAMES Newton/KKT + augmented-Lagrangian solve (sm_100a, FP64).
 //
-// One CTA (kThreads = 128) owns one game instance; the whole iterate, the KKT right-hand side / Newton step, the
+// One CTA (128 threads; 256 for 4 players) owns one game instance; the whole iterate, the KKT right-hand side / Newton step, the
 // feedback gains of the stage-wise factorisation and the AL multipliers stay in shared memory for the entire
 // newton_solve! loop (reference: src/problem/solver_methods.jl:5-125).  The KKT system is never
 // formed: in time-major order it is block tridiagonal, and its block-LU with the pivot order
@@ -134,6 +134,7 @@ struct Inst {
   static constexpr int n = 4 * P, m = 2 * P, b = P * n + m + n, W = m + n + 1, KUS = m * (n + 1), n1 = n + 1;
   static constexpr int OX = 0, OU = P * n, OD = P * n + m;     // offsets inside one stage of R: [rx(p·n) | ru(m) | rd(n)]
   static constexpr int NP = P * (P - 1);                       // ordered player pairs
+  static constexpr int kThreads = threads_for(P);
   // Structural non-zeros of the per-player RK2 Jacobians (bit q of the mask <-> At[q] / Bt[q], layouts below):
   //   DoubleIntegrator  A = [I dt·I; 0 I], B = [dt²/2·I; dt·I]   (constants)
   //   Unicycle          At rows x,y only;  B = [Bp (2x2); dt·I]
@@ -663,12 +664,15 @@ struct Inst {
           for (int r = 0; r < m; r++) { const double v = Aug[r * W + lane]; KU[r * n1 + (lane - m)] = v; kg[r * n1 + (lane - m)] = v; }
         }
       } else if (s > 0) {
-        constexpr int NB = P * P * n, NW = P * P * m, NA = P * P;
-        for (int item = tid - 32; item < NB + NW + NA; item += kThreads - 32) {
+        // item order groups equal work per warp: Base columns that need the A product (velocity/heading columns),
+        // W columns, Base columns that are plain copies (position columns), affine column
+        constexpr int NH = P * P * 2 * P, NW = P * P * m, NC = P * P * 2 * P, NA = P * P;
+        for (int item = tid - 32; item < NH + NW + NC + NA; item += kThreads - 32) {
           int kind, col, t;                                 // 0: Base column, 1: W column, 2: affine
-          if (item < NB) { kind = 0; col = item % n; t = item / n; }
-          else if (item < NB + NW) { kind = 1; col = (item - NB) % m; t = (item - NB) / m; }
-          else { kind = 2; col = n; t = item - NB - NW; }
+          if (item < NH) { kind = 0; col = 2 * P + item % (2 * P); t = item / (2 * P); }
+          else if (item < NH + NW) { kind = 1; col = (item - NH) % m; t = (item - NH) / m; }
+          else if (item < NH + NW + NC) { kind = 0; col = (item - NH - NW) % (2 * P); t = (item - NH - NW) / (2 * P); }
+          else { kind = 2; col = n; t = item - NH - NW - NC; }
           const int i2 = t % P, i = t / P;                  // rows (·,i2) of player i's matrices
           const double* Pi = Pm + i * n * n;
           const double* p0 = Pi + (0 * P + i2) * n;
