@@ -38,59 +38,55 @@ def bytes_per_newton_step(p, n, m, N):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (restated reference algorithm) on host cores
+# CPU arm: the oracle's plain-C restatement of the reference algorithm (oracle/algames_oracle.c) on host cores
 # ---------------------------------------------------------------------------------------------------------------
-def _oracle_solve_one(args):
-    seed, idx = args
+def cpu_inputs(n_inst, seed=1234):
     import algames_b200 as ab
-    import oracle.algames_oracle as O
-    model, N, dt, obj, con, opts, x0, _ = workload(idx + 1, seed)
-    prob = ab.GameProblem(N, dt, x0[idx], model, opts, obj, con, lib_path="unused")
-    op = O.problem_from_spec(ab.spec_of(prob))
-    rng = np.random.default_rng(opts.seed + idx)
-    Z0 = opts.amplitude_init * rng.random((N, model.n + model.m))
-    L0 = opts.amplitude_init * rng.random((model.p, N - 1, model.n))
-    O.newton_solve(op, Z0=Z0, L0=L0)
-    return bool(op.converged), int(op.n_newton)
+    model, N, dt, obj, con, opts, x0, _ = workload(n_inst, seed)
+    p = model.p
+    J = ab.problem._joint
+    desc = ab.problem._make_desc(model, N, dt, obj, con)
+    tile = lambda v: np.tile(v, (n_inst, 1))
+    rng = np.random.default_rng(opts.seed)
+    Z0 = opts.amplitude_init * rng.random((n_inst, N, model.n + model.m))
+    L0 = opts.amplitude_init * rng.random((n_inst, p, N - 1, model.n))
+    return desc, opts.to_c(), (x0, tile(J(obj.xf, p, 4)), tile(J(obj.Q, p, 4)), tile(J(obj.R, p, 2)), tile(J(obj.uf, p, 2)), Z0, L0)
 
 
-def cpu_sample(n_inst, cores, seed=1234):
-    """Solve `n_inst` config-B instances with the NumPy oracle on `cores` processes; returns (converged/s, info)."""
-    jobs = [(seed, i) for i in range(n_inst)]
+def cpu_sample(n_inst, threads=0, seed=1234):
+    """Solve `n_inst` config-B instances with the C oracle on `threads` host threads (0 = all cores).
+    Returns (converged/s, seconds, converged, Newton steps, threads used)."""
+    from oracle import c_oracle
+    desc, oc, arrs = cpu_inputs(n_inst, seed)
     t0 = time.perf_counter()
-    if cores == 1:
-        res = [_oracle_solve_one(j) for j in jobs]
-    else:
-        import multiprocessing as mp
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_oracle_solve_one, jobs, chunksize=1)
+    out, used = c_oracle.newton_solve(desc, oc, *arrs, nthreads=threads)
     dt = time.perf_counter() - t0
-    conv = sum(r[0] for r in res)
-    return conv / dt, dt, conv, sum(r[1] for r in res)
+    conv = int((out["status"] == 0).sum())
+    return conv / dt, dt, conv, float(out["stats"][:, 6].sum()), used
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    cores = os.cpu_count() or 1
-    n_inst = max(cores, 8)
+    n_inst = args.batch                       # the same 1024-instance batch the GPU arm solves per step
     for _ in range(args.warmup):
-        cpu_sample(min(cores, n_inst), cores)
-    t_tot, conv_tot, newton_tot = 0.0, 0, 0
+        cpu_sample(n_inst)
+    t_tot, conv_tot, newton_tot, used = 0.0, 0, 0.0, 1
     for _ in range(args.steps):
-        _, dt, conv, nn = cpu_sample(n_inst, cores)
+        _, dt, conv, nn, used = cpu_sample(n_inst)
         t_tot += dt; conv_tot += conv; newton_tot += nn
     value = conv_tot / t_tot
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "B: 3-player DoubleIntegratorGame N=40 dt=0.1, collision cost + collision avoidance, jittered x0 (seed 1234)",
-                   "sample": f"{n_inst} instances per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {n_inst} config-B instances, NumPy oracle (restated Algames.jl newton_solve!), one process per core"},
+        "config": {"workload": "B: batch=%d x 3-player DoubleIntegratorGame N=40 dt=0.1, collision cost + collision avoidance, jittered x0 (seed 1234)" % n_inst,
+                   "options": "reference defaults"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
+                         "sample": f"{args.steps} steps x {n_inst} config-B instances; oracle/algames_oracle.c: C restatement of Algames.jl "
+                                   "newton_solve! (explicit KKT Jacobian + band LU with partial pivoting per Newton step), one pthread per core; "
+                                   "the Julia reference itself cannot run in this image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "newton_steps_per_s": newton_tot / t_tot,
     }
@@ -301,9 +297,10 @@ def run_gpu(args):
             "clocks": clk.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, dt_s, c, nn = cpu_sample(args.cpu_sample, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{args.cpu_sample} config-B instances, NumPy oracle (restated Algames.jl newton_solve!), {dt_s:.1f} s"}
+            v, dt_s, c, nn, used = cpu_sample(args.cpu_sample)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
+                                    "sample": f"{args.cpu_sample} config-B instances in {dt_s:.1f} s; oracle/algames_oracle.c (C restatement of "
+                                              "Algames.jl newton_solve!: explicit KKT Jacobian + band LU per Newton step), one pthread per core"}
         print(json.dumps(line), flush=True)
     gb.close()
     if world > 1:
@@ -318,7 +315,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="instances per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=6)
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="instances of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
