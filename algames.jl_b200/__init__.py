@@ -8,5 +8,6 @@ from .problem import *          # noqa: F401,F403
 from .problem import AlgamesError, init_traj
 from . import workloads
 from . import distributed
+from . import mpc
 
 __version__ = "0.1.0"

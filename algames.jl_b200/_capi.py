@@ -70,6 +70,7 @@ SYMBOLS = {
     "agb_set_initial": (C.c_int, [_H, _DP, _DP, _DP, _DP]),
     "agb_get_state": (C.c_int, [_H, _DP, _DP, _DP, _DP]),
     "agb_shift_initial": (C.c_int, [_H, C.c_int, _DP, _DP]),
+    "agb_mpc_advance": (C.c_int, [_H, C.c_int, _DP, _DP, _DP]),
     "agb_rollout": (C.c_int, [_H]),
     "agb_residual": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, _DP, _DP]),
     "agb_residual_jacobian_dense": (C.c_int, [_H, C.c_double, C.c_double, _DP]),

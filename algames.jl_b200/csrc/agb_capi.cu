@@ -54,6 +54,17 @@ __global__ void agb_shift_kernel(const double* __restrict__ Z, const double* __r
   }
 }
 
+// x0 <- x_{1+shift} of the resident solution (+ disturbance)
+__global__ void agb_advance_kernel(const double* __restrict__ Z, const double* __restrict__ dist, double* __restrict__ x0,
+                                   int batch, int P, int N, int shift) {
+  const int n = 4 * P, m = 2 * P;
+  const size_t total = (size_t)batch * n;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t inst = t / n; const int a = (int)(t % n);
+    x0[t] = Z[(inst * N + shift) * (n + m) + a] + (dist ? dist[t] : 0.0);
+  }
+}
+
 __global__ void agb_broadcast_kernel(double* dst, const double* src, int batch, int len) {
   const size_t total = (size_t)batch * len;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) dst[t] = src[t % len];
@@ -80,6 +91,7 @@ struct agb_handle {
   double* results = nullptr; size_t results_doubles = 0;   // owns Z, L, stats, status
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
+  double* stage3 = nullptr;                            // disturbance staging of agb_mpc_advance
   long long launches = 0;
   size_t smem_bytes = 0;
   std::string err;
@@ -220,7 +232,7 @@ void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -382,6 +394,21 @@ int agb_shift_initial(agb_handle* h, int s, const double* Zfresh, const double* 
   AGB_CUDA(h, cudaStreamSynchronize(h->stream));
   AGB_CUDA(h, cudaGetLastError());
   return AGB_OK;
+}
+
+int agb_mpc_advance(agb_handle* h, int s, const double* disturbance, const double* Zfresh, const double* Lfresh) {
+  if (!h || s < 1 || s >= h->hd.N) return fail(h, AGB_EINVAL, "shift must be in 1..N-1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, n = h->hd.n;
+  double* dd = nullptr;
+  if (disturbance) {
+    if (!h->stage3) AGB_CUDA(h, cudaMalloc((void**)&h->stage3, B * n * sizeof(double)));
+    dd = h->stage3;
+    AGB_TRY(h2d(h, dd, disturbance, B * n));
+  }
+  AGB_LAUNCH(agb_advance_kernel, grid_for(B * n), 256, 0, h->stream, h->Z, dd, h->x0, h->batch, h->hd.p, h->hd.N, s);
+  h->launches++;
+  return agb_shift_initial(h, s, Zfresh, Lfresh);
 }
 
 static int launch_op(agb_handle* h, const agb_options* o, const OpArgs& a) {

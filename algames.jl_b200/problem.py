@@ -393,6 +393,11 @@ class GameBatch:
         a = [self._arr(Zfresh, self._z()), self._arr(Lfresh, self._l())]
         self._ck(self.lib.agb_shift_initial(self.h, int(s), *[_capi.dptr(v) for v in a]))
 
+    def mpc_advance(self, s: int = 1, disturbance=None, Zfresh=None, Lfresh=None):
+        """x0 <- x_{1+s} of the resident solution (+ disturbance [B,n]) and init_traj! shift by s, all on device."""
+        a = [self._arr(disturbance, (self.batch, self.n)), self._arr(Zfresh, self._z()), self._arr(Lfresh, self._l())]
+        self._ck(self.lib.agb_mpc_advance(self.h, int(s), *[_capi.dptr(v) for v in a]))
+
     def get_state(self):
         Z, L = np.empty(self._z()), np.empty(self._l())
         cl, cm = np.empty(self._c()), np.empty(self._c())

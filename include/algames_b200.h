@@ -140,6 +140,10 @@ int agb_get_state(agb_handle* h, double* Z, double* L, double* conlam, double* c
  * solution is shifted by s knots; the tail is filled from Zfresh/Lfresh (same shapes
  * as Z0/L0; only the last s knots are read).  New x0 comes from agb_set_instance_params. */
 int agb_shift_initial(agb_handle* h, int s, const double* Zfresh, const double* Lfresh);
+/* One receding-horizon step, entirely on device: x0 <- x_{1+s} of the resident solution (+ disturbance [B][n], may be
+ * NULL), then agb_shift_initial(s, Zfresh, Lfresh).  Together with agb_newton_solve_async(dual_reset = 0) this is the MPC
+ * loop Options.shift / Options.dual_reset exist for (struct/options.jl:16-17, :114-115); no host round trip per step. */
+int agb_mpc_advance(agb_handle* h, int s, const double* disturbance, const double* Zfresh, const double* Lfresh);
 
 /* ---- per-function entry points (operate on the resident batch; parity tests) -------- */
 /* rollout!(RK3, model, traj)                                  solver_methods.jl:17     */

@@ -77,3 +77,16 @@ def test_error_behaviour_emulated(emu_lib):
 @pytest.mark.parametrize("f", ["solve_C.npz", "solve_E.npz"])
 def test_golden_emulated(emu_lib, f):
     parity.check_golden(emu_lib, os.path.join(HERE, "golden", f))
+
+
+def test_mpc_loop_emulated(emu_lib):
+    """Receding-horizon loop (config D shape, short horizon): closed-loop state follows x_2 of each solve, warm starts
+    keep duals, and every re-solve converges."""
+    import algames_b200 as ab
+    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_d(batch=2, N=10)
+    gb = ab.GameBatch(model, N, dt, obj, con, 2, lib_path=emu_lib)
+    stats, status, xs = ab.mpc.mpc_run(gb, opts, x0, 3, xf=xf, disturbance_std=1e-3, seed=3)
+    assert stats.shape == (3, 2, 10) and (status == 0).all()
+    assert np.isfinite(xs).all() and (xs[-1][:, 0] > xs[0][:, 0]).all()        # the cars move forward
+    assert (stats[1:, :, 6] <= stats[0, :, 6] + 2).all()                        # warm starts are not harder than the cold start
+    gb.close()

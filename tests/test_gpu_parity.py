@@ -156,3 +156,34 @@ def test_result_slab_view_matches_host_copy():
     for k in ("Z", "L", "stats", "status"):
         assert np.array_equal(got[k], out[k]), k
     gb.close()
+
+
+def test_mpc_receding_horizon_loop():
+    """BASELINE config D shape (3-player unicycle ramp merge, N=40, shift=1, dual_reset=false): 10 warm-started re-solves of
+    64 streams, on-device advance; every re-solve converges and the first re-solve matches the oracle run on the same
+    shifted iterate with the carried multipliers."""
+    import algames_b200 as ab
+    import oracle.algames_oracle as O
+    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_d(batch=64)
+    gb = ab.GameBatch(model, N, dt, obj, con, 64, lib_path=LIB)
+    stats, status, xs = ab.mpc.mpc_run(gb, opts, x0, 10, xf=xf, disturbance_std=1e-3, seed=3)
+    assert (status == 0).mean() > 0.95
+    assert (stats[1:, :, 6].mean() < stats[0, :, 6].mean())          # warm starts need fewer Newton steps on average
+    assert np.isfinite(xs).all() and (xs[-1][:, 0] > xs[0][:, 0] + 0.5).all()
+    gb.close()
+    # oracle cross-check of one warm-started re-solve (stream 0): same shifted iterate + carried duals/penalties
+    gb = ab.GameBatch(model, N, dt, obj, con, 1, lib_path=LIB)
+    gb.set_instance_params(x0=x0[:1], xf=xf[:1])
+    Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+    out1 = gb.newton_solve(opts)
+    gb.mpc_advance(1)
+    Zs, Ls, cl, cm = gb.get_state()
+    warm = ab.Options(**{**opts.to_dict(), "dual_reset": False, "shift": 1})
+    out2 = gb.newton_solve(warm)
+    op = parity.oracle_problem(model, N, dt, obj, con, warm, out1["Z"][0, 1, :model.n], xf[0])
+    O.unpack_multipliers(op, cl[0], cm[0])
+    O.newton_solve(op, Z0=Zs[0], L0=Ls[0])
+    Zo = np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1)
+    assert np.abs(out2["Z"][0] - Zo).max() < parity.TOL_SOLVE
+    assert int(out2["stats"][0, 6]) == op.n_newton
+    gb.close()
