@@ -82,6 +82,7 @@ SYMBOLS = {
     "agb_reset_duals_penalties": (C.c_int, [_H, C.POINTER(OptionsC)]),
     "agb_evaluate_constraints": (C.c_int, [_H, _DP]),
     "agb_active_set": (C.c_int, [_H, C.c_double, C.POINTER(C.c_ubyte)]),
+    "agb_debug_gain_solve": (C.c_int, [_H, _DP, _DP, _IP]),
     "agb_newton_solve_batch": (C.c_int, [_H, C.POINTER(OptionsC), _DP, _DP, _DP, _DP, _DP, _IP]),
     "agb_newton_solve_async": (C.c_int, [_H, C.POINTER(OptionsC), C.c_void_p]),
     "agb_get_device_view": (C.c_int, [_H, C.POINTER(DeviceView)]),

@@ -545,6 +545,20 @@ int agb_active_set(agb_handle* h, double tol, unsigned char* active_out) {
   return finish(h);
 }
 
+int agb_debug_gain_solve(agb_handle* h, const double* aug, double* aug_out, int* ok_out) {
+  if (!h || !aug || !aug_out) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, cnt = B * h->hd.m * (h->hd.m + h->hd.n + 1);
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, (2 * cnt + B) * sizeof(double)));
+  AGB_TRY(h2d(h, h->stage, aug, cnt));
+  OpArgs a = op_args(OP_GAIN_SOLVE);
+  a.in0 = h->stage; a.out0 = h->stage + cnt; a.iout = (int*)(h->stage + 2 * cnt);
+  AGB_TRY(launch_op(h, nullptr, a));
+  AGB_TRY(d2h(h, aug_out, h->stage + cnt, cnt));
+  if (ok_out) AGB_CUDA(h, cudaMemcpyAsync(ok_out, a.iout, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
 static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
   LaunchArgs L;
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;

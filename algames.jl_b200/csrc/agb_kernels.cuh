@@ -194,6 +194,16 @@ __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* _
           a.bout[(size_t)inst * K * nrow + q] = ((c >= -a.tol) || (I.CL[q] > 0.0)) ? 1 : 0;
         }
       } break;
+      case OP_GAIN_SOLVE: {
+        constexpr int W = Inst<P, MODEL>::W;
+        for (int q = I.tid; q < m * W; q += kThreads) I.Aug[q] = a.in0[(size_t)inst * m * W + q];
+        __syncthreads();
+        int ok = 1;
+        if (I.warp == 0) ok = I.gj_warp(I.Aug) ? 1 : 0;
+        __syncthreads();
+        for (int q = I.tid; q < m * W; q += kThreads) a.out0[(size_t)inst * m * W + q] = I.Aug[q];
+        if (I.tid == 0) a.iout[inst] = ok;
+      } break;
       default: break;
     }
   }

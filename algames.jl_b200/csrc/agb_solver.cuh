@@ -542,8 +542,59 @@ struct Inst {
     return v;
   }
 
-  // Gauss-Jordan with partial pivoting on the m x W augmented system, one column per lane (warp 0).
+  // 1/x to (almost) full double precision without the slow-path branches of a correctly rounded division:
+  // rcp.approx.ftz.f64 (≈ 20 bits) + two Newton steps.  x = 0 / inf / NaN propagate as inf / 0 / NaN like 1/x would.
+  static __device__ __forceinline__ double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+  }
+
+  // Gauss-Jordan on the m x W augmented gain system, one column per lane (warp 0).  Threshold pivoting like the
+  // reference's UMFPACK: the diagonal pivot is kept while |a_tt| >= 0.01·max_r |a_rt| (no row exchange, no index
+  // shuffles); only if some step violates the threshold is the system re-solved from shared memory with full partial
+  // pivoting.  Returns false on a zero / non-finite pivot.
   __device__ bool gj_warp(double* aug) {
+    double a[m];
+    const bool act = lane < W;
+#pragma unroll
+    for (int r = 0; r < m; r++) a[r] = act ? aug[r * W + lane] : 0.0;
+    bool weak = false;
+#pragma unroll
+    for (int t = 0; t < m; t++) {
+      if (lane == t) {
+        double cmax = 0.0;
+#pragma unroll
+        for (int r = t + 1; r < m; r++) cmax = fmax(cmax, fabs(a[r]));
+        if (!(fabs(a[t]) >= 0.01 * cmax) || !(fabs(a[t]) > 0.0) || isinf(a[t])) weak = true;
+      }
+      const double pv = __shfl_sync(AGB_FULL, a[t], t);
+      double f[m];
+#pragma unroll
+      for (int r = 0; r < m; r++) f[r] = (r != t) ? __shfl_sync(AGB_FULL, a[r], t) : 0.0;
+      const double at = a[t] * fast_rcp(pv);
+#pragma unroll
+      for (int r = 0; r < m; r++) if (r != t) a[r] = fma(-f[r], at, a[r]);
+      a[t] = at;
+    }
+    if (!__any_sync(AGB_FULL, weak)) {
+      if (act) {
+#pragma unroll
+        for (int r = 0; r < m; r++) aug[r * W + lane] = a[r];
+      }
+      return true;
+    }
+    return gj_warp_pivoted(aug);
+  }
+
+  // full partial pivoting (row exchanges), used when the threshold test above fails
+  __device__ bool gj_warp_pivoted(double* aug) {
     double a[m];
     const bool act = lane < W;
 #pragma unroll
@@ -775,57 +826,65 @@ struct Inst {
       __syncthreads();
     }
     // ---- forward sweep (warp 0): Δu_s = −Ku Δx_s − ku,  Δx_{s+1} = A Δx_s + B Δu_s + rd.  The gains come back from the
-    // L2-resident scratch two stages ahead of their use (register prefetch), staged through the one-stage smem buffer.
+    // L2-resident scratch through a 4-deep register ring (each load has three stage-times to land), staged through
+    // the one-stage smem buffer.
     if (warp == 0) {
-      constexpr int NQ = (KUS + 31) / 32;
-      double r0[NQ], r1[NQ];
+      constexpr int NQ = (KUS + 31) / 32, DEPTH = 4;
+      double ring[DEPTH][NQ];
       __syncwarp();
 #pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const int idx = lane + 32 * q;
-        r0[q] = (idx < KUS) ? KUg[idx] : 0.0;
-        r1[q] = (idx < KUS && K > 1) ? KUg[KUS + idx] : 0.0;
-      }
-      for (int s = 0; s < K; s++) {
+      for (int dd = 0; dd < DEPTH; dd++) {
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
           const int idx = lane + 32 * q;
-          if (idx < KUS) KU[idx] = r0[q];
-          r0[q] = r1[q];
-          if (idx < KUS && s + 2 < K) r1[q] = KUg[(s + 2) * KUS + idx];
+          ring[dd][q] = (idx < KUS && dd < K) ? KUg[dd * KUS + idx] : 0.0;
         }
-        __syncwarp();
-        const double* ku = KU;
-        double* Rs = R + s * b;
-        const double* dxp = R + (s - 1) * b + OD;      // Δx_s (only read when s > 0)
-        if (lane < m) {
-          double a0 = ku[lane * n1 + n], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-          if (s > 0) {
+      }
+      for (int s0 = 0; s0 < K; s0 += DEPTH) {
 #pragma unroll
-            for (int a = 0; a < n; a += 4) {
-              a0 += ku[lane * n1 + a] * dxp[a]; a1 += ku[lane * n1 + a + 1] * dxp[a + 1];
-              a2 += ku[lane * n1 + a + 2] * dxp[a + 2]; a3 += ku[lane * n1 + a + 3] * dxp[a + 3];
+        for (int dd = 0; dd < DEPTH; dd++) {
+          const int s = s0 + dd;
+          if (s < K) {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+              const int idx = lane + 32 * q;
+              if (idx < KUS) KU[idx] = ring[dd][q];
+              if (idx < KUS && s + DEPTH < K) ring[dd][q] = KUg[(s + DEPTH) * KUS + idx];
             }
+            __syncwarp();
+            const double* ku = KU;
+            double* Rs = R + s * b;
+            const double* dxp = R + (s - 1) * b + OD;      // Δx_s (only read when s > 0)
+            if (lane < m) {
+              double a0 = ku[lane * n1 + n], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+              if (s > 0) {
+#pragma unroll
+                for (int a = 0; a < n; a += 4) {
+                  a0 += ku[lane * n1 + a] * dxp[a]; a1 += ku[lane * n1 + a + 1] * dxp[a + 1];
+                  a2 += ku[lane * n1 + a + 2] * dxp[a + 2]; a3 += ku[lane * n1 + a + 3] * dxp[a + 3];
+                }
+              }
+              Rs[OU + lane] = -((a0 + a1) + (a2 + a3));
+            }
+            __syncwarp();
+            double v = 0.0;
+            if (lane < n) {
+              const int c = lane / P, i = lane - c * P;
+              double At[8], Bt[8]; loadAB(s, i, At, Bt);
+              v = Rs[OD + lane];
+              const double u0 = Rs[OU + i], u1 = Rs[OU + P + i];
+              double y0 = 0.0, y1 = 0.0;
+              if (s > 0) { v += dxp[lane]; y0 = dxp[2 * P + i]; y1 = dxp[3 * P + i]; }
+              if (c == 0) v += at_row<0>(At, y0, y1) + bt_row<0>(Bt, u0, u1);
+              else if (c == 1) v += at_row<1>(At, y0, y1) + bt_row<1>(Bt, u0, u1);
+              else if (c == 2) v += at_row<2>(At, y0, y1) + bt_row<2>(Bt, u0, u1);
+              else v += at_row<3>(At, y0, y1) + bt_row<3>(Bt, u0, u1);
+            }
+            __syncwarp();
+            if (lane < n) Rs[OD + lane] = v;
+            __syncwarp();
           }
-          Rs[OU + lane] = -((a0 + a1) + (a2 + a3));
         }
-        __syncwarp();
-        double v = 0.0;
-        if (lane < n) {
-          const int c = lane / P, i = lane - c * P;
-          double At[8], Bt[8]; loadAB(s, i, At, Bt);
-          v = Rs[OD + lane];
-          const double u0 = Rs[OU + i], u1 = Rs[OU + P + i];
-          double y0 = 0.0, y1 = 0.0;
-          if (s > 0) { v += dxp[lane]; y0 = dxp[2 * P + i]; y1 = dxp[3 * P + i]; }
-          if (c == 0) v += at_row<0>(At, y0, y1) + bt_row<0>(Bt, u0, u1);
-          else if (c == 1) v += at_row<1>(At, y0, y1) + bt_row<1>(Bt, u0, u1);
-          else if (c == 2) v += at_row<2>(At, y0, y1) + bt_row<2>(Bt, u0, u1);
-          else v += at_row<3>(At, y0, y1) + bt_row<3>(Bt, u0, u1);
-        }
-        __syncwarp();
-        if (lane < n) Rs[OD + lane] = v;
-        __syncwarp();
       }
     }
     __syncthreads();

@@ -459,6 +459,14 @@ class GameBatch:
         self._ck(self.lib.agb_active_set(self.h, float(tol), a.ctypes.data_as(C.POINTER(C.c_ubyte))))
         return a.astype(bool)
 
+    def debug_gain_solve(self, aug):
+        """agb_debug_gain_solve: the kernel's Gauss-Jordan on aug [B, m, m+n+1]; returns (reduced systems, ok flags)."""
+        aug = self._arr(aug, (self.batch, self.m, self.m + self.n + 1))
+        out = np.empty_like(aug)
+        ok = np.empty(self.batch, dtype=np.int32)
+        self._ck(self.lib.agb_debug_gain_solve(self.h, _capi.dptr(aug), _capi.dptr(out), _capi.iptr(ok)))
+        return out, ok.astype(bool)
+
     # ---- the hot path
     def newton_solve(self, opts: Options, want=("Z", "L", "conlam", "conmu", "stats", "status"), out=None):
         """agb_newton_solve_batch: solve every instance and copy the requested results to host arrays (`out` may hold

@@ -171,6 +171,11 @@ int agb_reset_duals_penalties(agb_handle* h, const agb_options* o);
 int agb_evaluate_constraints(agb_handle* h, double* c_out);
 int agb_active_set(agb_handle* h, double tol, unsigned char* active_out);
 
+/* Diagnostic: runs the kernel's m x (m+n+1) gain-system solver (threshold-pivoted Gauss-Jordan with partial-pivoting
+ * fallback) on caller-supplied systems aug [B][m][m+n+1]; the reduced systems come back in place of the
+ * input layout in aug_out, ok_out[B] = 0 when a pivot was zero / non-finite.  Unit-test hook for the pivoting logic. */
+int agb_debug_gain_solve(agb_handle* h, const double* aug, double* aug_out, int* ok_out);
+
 /* ---- the hot path: newton_solve!(prob) for every instance ---------------------------- */
 /* Host-buffer form.  All outputs may be NULL.  Z_out [B][N][n+m], L_out [B][p][N-1][n],
  * conlam_out/conmu_out [B][N-1][nrow], stats_out [B][AGB_NSTATS] =

@@ -65,6 +65,16 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src) {
   T r; memcpy(&r, &raw, sizeof(T));
   return r;
 }
+inline int __any_sync(unsigned, int pred) {
+  emu::State& s = emu::st();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s.slots[warp][lane] = pred ? 1ull : 0ull;
+  emu::yield(emu::WARP_BAR);
+  int any = 0;
+  for (int l = 0; l < 32; l++) any |= (int)s.slots[warp][l];
+  emu::yield(emu::WARP_BAR);
+  return any;
+}
 template <class T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return __shfl_sync(m, v, (int)((threadIdx.x & 31) ^ x)); }
 
 // ---- the slice of the CUDA runtime API agb_capi.cu uses, on host memory ---------------------------------------

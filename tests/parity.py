@@ -224,3 +224,33 @@ def check_golden(lib_path, path):
     assert np.array_equal(out["status"] == 0, g["converged"]), path
     assert np.array_equal(out["stats"][:, 6].astype(int), g["n_newton"]), path
     gb.close()
+
+
+def check_pivot_fallback(lib_path):
+    """The kernel's gain-system solver on systems [S | RHS]: diagonally dominant S (threshold test passes, no row
+    exchange), S with zero / tiny diagonal entries but well conditioned (must fall back to full partial pivoting),
+    and a singular S (must report failure)."""
+    for p in (2, 3, 4):
+        model = ab.DoubleIntegratorGame(p=p)
+        N = 4
+        obj = ab.GameObjective([np.ones(4)] * p, [np.ones(2)] * p, [np.zeros(4)] * p, [np.zeros(2)] * p, N, model)
+        con = ab.GameConstraintValues(ab.ProblemSize(N, model))
+        m, n = model.m, model.n
+        B = 6
+        rng = np.random.default_rng(p)
+        aug = rng.normal(size=(B, m, m + n + 1))
+        aug[0, :, :m] += 10 * np.eye(m)                       # dominant diagonal
+        aug[1, :, :m] += 10 * np.eye(m)
+        for b in (2, 3):                                      # zero diagonal, strong off-diagonal (a cyclic shift)
+            aug[b, :, :m] = 0.1 * rng.normal(size=(m, m)) + 5 * np.roll(np.eye(m), 1, axis=1)
+            aug[b, np.arange(m), np.arange(m)] = 0.0 if b == 2 else 1e-14
+        aug[4, :, :m] = np.diag(np.r_[1e-3, np.ones(m - 1)]) + 0.5 * np.roll(np.eye(m), 1, axis=0)   # weak leading pivot
+        aug[5, :, :m] = np.ones((m, m))                       # singular
+        gb = ab.GameBatch(model, N, 0.1, obj, con, B, lib_path=lib_path)
+        out, ok = gb.debug_gain_solve(aug)
+        gb.close()
+        for b in range(5):
+            ref = np.linalg.solve(aug[b, :, :m], aug[b, :, m:])
+            assert ok[b], (p, b)
+            assert np.abs(out[b, :, m:] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.linalg.cond(aug[b, :, :m]), (p, b)
+        assert not ok[5] or not np.isfinite(out[5]).all()

@@ -90,3 +90,7 @@ def test_mpc_loop_emulated(emu_lib):
     assert np.isfinite(xs).all() and (xs[-1][:, 0] > xs[0][:, 0]).all()        # the cars move forward
     assert (stats[1:, :, 6] <= stats[0, :, 6] + 2).all()                        # warm starts are not harder than the cold start
     gb.close()
+
+
+def test_gauss_jordan_pivot_fallback_emulated(emu_lib):
+    parity.check_pivot_fallback(emu_lib)

@@ -187,3 +187,7 @@ def test_mpc_receding_horizon_loop():
     assert np.abs(out2["Z"][0] - Zo).max() < parity.TOL_SOLVE
     assert int(out2["stats"][0, 6]) == op.n_newton
     gb.close()
+
+
+def test_gauss_jordan_pivot_fallback():
+    parity.check_pivot_fallback(LIB)
