@@ -47,6 +47,10 @@ class OptionsC(C.Structure):
     ]
 
 
+class IBROptionsC(C.Structure):
+    _fields_ = [("ibr_iter", C.c_int), ("ordering", C.c_int * MAX_P), ("delta_min", C.c_double)]
+
+
 class Sizes(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("n", "m", "p", "N", "S", "nrow", "nrow_state", "nrow_control")]
 
@@ -84,6 +88,9 @@ SYMBOLS = {
     "agb_active_set": (C.c_int, [_H, C.c_double, C.POINTER(C.c_ubyte)]),
     "agb_debug_gain_solve": (C.c_int, [_H, _DP, _DP, _IP]),
     "agb_newton_solve_batch": (C.c_int, [_H, C.POINTER(OptionsC), _DP, _DP, _DP, _DP, _DP, _IP]),
+    "agb_ibr_newton_solve_batch": (C.c_int, [_H, C.POINTER(OptionsC), C.POINTER(IBROptionsC), _DP, _DP, _DP, _DP, _DP, _IP]),
+    "agb_ibr_residual": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, _DP, _DP]),
+    "agb_ibr_kkt_solve": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, _DP]),
     "agb_newton_solve_async": (C.c_int, [_H, C.POINTER(OptionsC), C.c_void_p]),
     "agb_get_device_view": (C.c_int, [_H, C.POINTER(DeviceView)]),
     "agb_launch_count": (C.c_longlong, [_H]),

@@ -198,6 +198,9 @@ cudaError_t set_attr(int p, int model, size_t smem) {
 void launch_solve(int p, const LaunchArgs& L) {
   switch (p) { case 1: launch_solve_p1(L); break; case 2: launch_solve_p2(L); break; case 3: launch_solve_p3(L); break; default: launch_solve_p4(L); }
 }
+void launch_ibr(int p, const LaunchArgs& L) {
+  switch (p) { case 1: launch_ibr_p1(L); break; case 2: launch_ibr_p2(L); break; case 3: launch_ibr_p3(L); break; default: launch_ibr_p4(L); }
+}
 void launch_op(int p, const LaunchArgs& L) {
   switch (p) { case 1: launch_op_p1(L); break; case 2: launch_op_p2(L); break; case 3: launch_op_p3(L); break; default: launch_op_p4(L); }
 }
@@ -416,6 +419,7 @@ static int launch_op(agb_handle* h, const agb_options* o, const OpArgs& a) {
   if (o) od = *o; else agb_default_options(&od);
   LaunchArgs L;
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = h->stream; L.dd = h->dd; L.o = od;
+  memset(&L.io, 0, sizeof L.io);
   L.g = buffers_of(h); L.a = a; L.batch = h->batch;
   agb::launch_op(h->hd.p, L);
   h->launches++;
@@ -427,7 +431,7 @@ static int finish(agb_handle* h) {
   AGB_CUDA(h, cudaGetLastError());
   return AGB_OK;
 }
-static OpArgs op_args(int op) { OpArgs a; memset(&a, 0, sizeof a); a.op = op; return a; }
+static OpArgs op_args(int op) { OpArgs a; memset(&a, 0, sizeof a); a.op = op; a.player = -1; return a; }
 
 int agb_rollout(agb_handle* h) {
   if (!h) return AGB_EINVAL;
@@ -562,6 +566,7 @@ int agb_debug_gain_solve(agb_handle* h, const double* aug, double* aug_out, int*
 static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
   LaunchArgs L;
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
+  memset(&L.io, 0, sizeof L.io);
   L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch;
   agb::launch_solve(h->hd.p, L);
   h->launches++;
@@ -590,6 +595,57 @@ int agb_newton_solve_batch(agb_handle* h, const agb_options* o, double* Z_out, d
   AGB_TRY(d2h(h, conlam_out, h->conlam, B * cs)); AGB_TRY(d2h(h, conmu_out, h->conmu, B * cs));
   AGB_TRY(d2h(h, stats_out, h->stats, B * AGB_NSTATS));
   if (status_out) AGB_CUDA(h, cudaMemcpyAsync(status_out, h->status, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+int agb_ibr_newton_solve_batch(agb_handle* h, const agb_options* o, const agb_ibr_options* io, double* Z_out, double* L_out,
+                               double* conlam_out, double* conmu_out, double* stats_out, int* status_out) {
+  if (!h || !o || !io) return AGB_EINVAL;
+  if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1 || io->ibr_iter < 1)
+    return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter, ibr_iter must be >= 1");
+  unsigned seen = 0;
+  for (int i = 0; i < h->hd.p; i++) {
+    if (io->ordering[i] < 0 || io->ordering[i] >= h->hd.p || (seen >> io->ordering[i] & 1u)) return fail(h, AGB_EINVAL, "ordering must be a permutation of the players");
+    seen |= 1u << io->ordering[i];
+  }
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  LaunchArgs L;
+  L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = h->stream; L.dd = h->dd; L.o = *o; L.io = *io;
+  L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch;
+  AGB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  agb::launch_ibr(h->hd.p, L);
+  h->launches++;
+  AGB_CUDA(h, cudaGetLastError());
+  AGB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  const size_t B = h->batch, zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n, cs = (size_t)h->hd.K * h->hd.nrow;
+  AGB_TRY(d2h(h, Z_out, h->Z, B * zs)); AGB_TRY(d2h(h, L_out, h->L, B * ls));
+  AGB_TRY(d2h(h, conlam_out, h->conlam, B * cs)); AGB_TRY(d2h(h, conmu_out, h->conmu, B * cs));
+  AGB_TRY(d2h(h, stats_out, h->stats, B * AGB_NSTATS));
+  if (status_out) AGB_CUDA(h, cudaMemcpyAsync(status_out, h->status, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+int agb_ibr_residual(agb_handle* h, int player, double reg_x, double reg_u, double alpha, double* res_out, double* norms_out) {
+  if (!h || player < 0 || player >= h->hd.p) return fail(h, AGB_EINVAL, "bad player index");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, S = h->hd.S;
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, (B * S + B * 5) * sizeof(double)));
+  OpArgs a = op_args(OP_RESIDUAL);
+  a.player = player; a.reg_x = reg_x; a.reg_u = reg_u; a.alpha = alpha; a.out0 = h->stage; a.out1 = h->stage + B * S;
+  AGB_TRY(launch_op(h, nullptr, a));
+  if (res_out) AGB_TRY(export_to_host(h, h->stage, res_out, 0));
+  AGB_TRY(d2h(h, norms_out, h->stage + B * S, B * 5));
+  return finish(h);
+}
+
+int agb_ibr_kkt_solve(agb_handle* h, int player, double reg_x, double reg_u, double* dtraj_out) {
+  if (!h || player < 0 || player >= h->hd.p) return fail(h, AGB_EINVAL, "bad player index");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  OpArgs a = op_args(OP_KKT_SOLVE);
+  a.player = player; a.reg_x = reg_x; a.reg_u = reg_u;
+  AGB_TRY(launch_op(h, nullptr, a));
+  if (dtraj_out) AGB_TRY(export_to_host(h, h->D, dtraj_out, 1));
   return finish(h);
 }
 

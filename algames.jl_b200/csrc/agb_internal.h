@@ -80,6 +80,7 @@ struct OpArgs {
   int* iout;
   unsigned char* bout;
   const double* in0;     // e.g. per-instance alpha for OP_UPDATE
+  int player;            // iterative best response: player whose problem the op addresses, -1 = the full game
 };
 
 }  // namespace agb

@@ -82,6 +82,91 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
   }
 }
 
+// ibr_newton_solve!(prob; ibr_opts) for every instance (solver_methods.jl:133-224); one CTA per instance.
+template <int P, int MODEL>
+__global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_ibr_solve_kernel(const DevDesc* __restrict__ dd, agb_options o,
+                                                                                          agb_ibr_options io, Buffers g, int batch) {
+  AGB_DYN_SMEM(sm);
+  Inst<P, MODEL> I;
+  I.bind(dd, sm);
+  constexpr int n = Inst<P, MODEL>::n, kThreads = threads_for(P);
+  const int K = I.K;
+  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+    __syncthreads();
+    I.bind_instance(g, inst);
+    I.load_params(g, inst);
+    I.load_iterate(g.Z0, g.L0, inst);
+    I.load_duals(g, inst);
+    __syncthreads();
+    for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];
+    __syncthreads();
+    I.rollout();                                                                        // :145
+    int n_newton = 0, n_eval = 0, failed = 0, sweeps = 0;
+    unsigned change = (1u << P) - 1u;                                                   // Δ_change = trues(p) (:150)
+    double delta = 0.0, dmax = 0.0;                                                     // dmax = maximum(stats.Δ_traj)
+    for (int q = 0; q < io.ibr_iter && !failed; q++) {                                  // :151
+      sweeps = q + 1;
+      for (int id = 0; id < P && !failed; id++) {
+        const int i = io.ordering[id];
+        I.pl = i;
+        // ---- ibr_newton_solve!(prob, i) (:168-224)
+        if (o.dual_reset) {                                                             // :179-183
+          I.reset_duals_penalties(o);
+          for (int t = I.tid; t < P * K * n; t += kThreads) I.L[t] = 0.0;               // reset_duals!(pdtraj)
+          __syncthreads();
+        }
+        const double S = I.res_size();
+        delta = 0.0;
+        Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int kout = 1; kout <= o.outer_iter; kout++) {
+          int ls_count = 0;
+          for (int l = 1; l <= o.inner_iter; l++) {
+            const double l2 = (double)l * (double)l;
+            const double reg = o.reg_0 * (l2 * l2);
+            rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                       // ibr_inner_iteration (:226-265)
+            n_eval++;
+            const double res_norm = rec.sum / S;
+            delta = 0.0;
+            if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
+            if (rec.opt < o.eps_opt) break;
+            if (!I.kkt_solve(reg, reg)) failed = 1;
+            n_newton++;
+            double alpha; int j;
+            I.line_search(o, reg, res_norm, alpha, j, n_eval);
+            ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;
+            delta = I.update_traj(alpha);
+            dmax = fmax(dmax, delta);
+            if (delta < o.delta_min) break;
+            if (ls_count >= 1) break;
+            if (!(delta == delta)) { failed = 1; break; }
+          }
+          if (failed) break;
+          if (kout == o.outer_iter || (rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt))
+            break;
+          I.dual_update(o);
+          I.penalty_update(o);
+        }
+        if (!(io.delta_min > dmax)) change |= (1u << i); else change &= ~(1u << i);     // :156
+      }
+      if (change == 0u) break;                                                          // :163
+    }
+    I.pl = -1;
+    Acc rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                           // residual!(prob, prob.pdtraj) (:160)
+    n_eval++;
+    const double S = I.res_size();
+    const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
+    const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
+    I.store_iterate(g.Z, g.L, inst);
+    I.store_duals(g, inst);
+    if (I.tid == 0) {
+      double* st = g.stats + (size_t)inst * AGB_NSTATS;
+      st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;
+      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)sweeps; st[8] = (double)n_eval; st[9] = (double)failed;
+      g.status[inst] = conv ? AGB_CONVERGED : ((failed || !finite) ? AGB_NUMERICAL_FAILURE : AGB_NOT_CONVERGED);
+    }
+  }
+}
+
 // Per-function entry points on the resident batch (parity tests and stand-alone use of the exported reference API).
 template <int P, int MODEL>
 __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
@@ -90,7 +175,6 @@ __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* _
   I.bind(dd, sm);
   constexpr int n = Inst<P, MODEL>::n, m = Inst<P, MODEL>::m, b = Inst<P, MODEL>::b, kThreads = threads_for(P);
   const int K = I.K, Sz = K * b, nrow = I.nrow;
-  const double S = (double)Sz;
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
     __syncthreads();
     I.bind_instance(g, inst);
@@ -101,6 +185,8 @@ __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* _
     for (int q = I.tid; q < n; q += kThreads) I.X[q] = g.x0[(size_t)inst * n + q];
     __syncthreads();
     double* D = g.D + (size_t)inst * Sz;
+    I.pl = a.player;
+    const double S = I.res_size();
     switch (a.op) {
       case OP_ROLLOUT: {
         I.rollout();
@@ -217,6 +303,7 @@ struct LaunchArgs {
   cudaStream_t stream;
   const DevDesc* dd;
   agb_options o;
+  agb_ibr_options io;
   Buffers g;
   OpArgs a;
   int batch;
@@ -224,6 +311,8 @@ struct LaunchArgs {
 
 template <int P, int MODEL> inline cudaError_t set_attr_pm(size_t smem) {
   cudaError_t e = cudaFuncSetAttribute((const void*)agb_newton_solve_kernel<P, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((const void*)agb_ibr_solve_kernel<P, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute((const void*)agb_op_kernel<P, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
@@ -237,6 +326,17 @@ template <int P> inline cudaError_t set_attr_p(int model, size_t smem) {
 template <int P, int MODEL> inline void launch_solve_pm(const LaunchArgs& L) {
   auto kfn = agb_newton_solve_kernel<P, MODEL>;
   AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.batch);
+}
+template <int P, int MODEL> inline void launch_ibr_pm(const LaunchArgs& L) {
+  auto kfn = agb_ibr_solve_kernel<P, MODEL>;
+  AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.io, L.g, L.batch);
+}
+template <int P> inline void launch_ibr_p(const LaunchArgs& L) {
+  switch (L.model) {
+    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_ibr_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR>(L); break;
+    case AGB_MODEL_UNICYCLE: launch_ibr_pm<P, AGB_MODEL_UNICYCLE>(L); break;
+    default: launch_ibr_pm<P, AGB_MODEL_BICYCLE>(L); break;
+  }
 }
 template <int P, int MODEL> inline void launch_op_pm(const LaunchArgs& L) {
   auto kfn = agb_op_kernel<P, MODEL>;
@@ -261,10 +361,12 @@ template <int P> inline void launch_op_p(const LaunchArgs& L) {
 cudaError_t set_attr(int p, int model, size_t smem);
 void launch_solve(int p, const LaunchArgs& L);
 void launch_op(int p, const LaunchArgs& L);
+void launch_ibr(int p, const LaunchArgs& L);
 #define AGB_DECLARE_P(PP)                                   \
   cudaError_t set_attr_p##PP(int model, size_t smem);      \
   void launch_solve_p##PP(const LaunchArgs& L);            \
-  void launch_op_p##PP(const LaunchArgs& L);
+  void launch_op_p##PP(const LaunchArgs& L);              \
+  void launch_ibr_p##PP(const LaunchArgs& L);
 AGB_DECLARE_P(1) AGB_DECLARE_P(2) AGB_DECLARE_P(3) AGB_DECLARE_P(4)
 
 }  // namespace agb

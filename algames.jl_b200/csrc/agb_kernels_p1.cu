@@ -4,4 +4,5 @@ namespace agb {
 cudaError_t set_attr_p1(int model, size_t smem) { return set_attr_p<1>(model, smem); }
 void launch_solve_p1(const LaunchArgs& L) { launch_solve_p<1>(L); }
 void launch_op_p1(const LaunchArgs& L) { launch_op_p<1>(L); }
+void launch_ibr_p1(const LaunchArgs& L) { launch_ibr_p<1>(L); }
 }  // namespace agb

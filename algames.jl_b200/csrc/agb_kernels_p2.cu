@@ -4,4 +4,5 @@ namespace agb {
 cudaError_t set_attr_p2(int model, size_t smem) { return set_attr_p<2>(model, smem); }
 void launch_solve_p2(const LaunchArgs& L) { launch_solve_p<2>(L); }
 void launch_op_p2(const LaunchArgs& L) { launch_op_p<2>(L); }
+void launch_ibr_p2(const LaunchArgs& L) { launch_ibr_p<2>(L); }
 }  // namespace agb

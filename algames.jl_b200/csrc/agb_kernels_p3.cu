@@ -4,4 +4,5 @@ namespace agb {
 cudaError_t set_attr_p3(int model, size_t smem) { return set_attr_p<3>(model, smem); }
 void launch_solve_p3(const LaunchArgs& L) { launch_solve_p<3>(L); }
 void launch_op_p3(const LaunchArgs& L) { launch_op_p<3>(L); }
+void launch_ibr_p3(const LaunchArgs& L) { launch_ibr_p<3>(L); }
 }  // namespace agb

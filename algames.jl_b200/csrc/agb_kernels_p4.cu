@@ -4,4 +4,5 @@ namespace agb {
 cudaError_t set_attr_p4(int model, size_t smem) { return set_attr_p<4>(model, smem); }
 void launch_solve_p4(const LaunchArgs& L) { launch_solve_p<4>(L); }
 void launch_op_p4(const LaunchArgs& L) { launch_op_p<4>(L); }
+void launch_ibr_p4(const LaunchArgs& L) { launch_ibr_p<4>(L); }
 }  // namespace agb

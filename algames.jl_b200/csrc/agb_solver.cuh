@@ -183,6 +183,7 @@ struct Inst {
   double dt;
   double *X, *U, *L, *R, *KU, *AB, *CL, *CM, *CW, *Gp, *Hp, *Gs, *Hs, *Pm, *Sv, *Ym, *Aug, *Base, *Wm, *Ta, *xf, *Q, *Rw, *uf, *red;
   double* KUg;            // this instance's slice of Buffers::KUg (global)
+  int pl;                 // iterative best response: the player whose problem is being solved (-1: the full game)
   int tid, lane, warp;
 
   __device__ void bind(const DevDesc* dd, double* sm) {
@@ -192,7 +193,7 @@ struct Inst {
     CL = sm + dd->o_CL; CM = sm + dd->o_CM; CW = sm + dd->o_CW; Gp = sm + dd->o_Gp; Hp = sm + dd->o_Hp; Gs = sm + dd->o_Gs;
     Hs = sm + dd->o_Hs; Pm = sm + dd->o_P; Sv = sm + dd->o_Sv; Ym = sm + dd->o_Y; Aug = sm + dd->o_Aug; Base = sm + dd->o_Base;
     Wm = sm + dd->o_W; Ta = sm + dd->o_Ta; xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
-    tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr;
+    tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1;
   }
   __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUS; }
 
@@ -286,7 +287,8 @@ struct Inst {
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         double r = xn[c] - xg<TRIAL>(s + 1, c * P + i, alpha);      // local_quantities.jl:13
-        acc.sum += fabs(r); acc.dyn = fmax(acc.dyn, fabs(r));
+        acc.sum += fabs(r);
+        if (pl < 0 || i == pl) acc.dyn = fmax(acc.dyn, fabs(r));
         if (Rout) Rout[s * b + OD + c * P + i] = r;
       }
     }
@@ -328,7 +330,7 @@ struct Inst {
         const double cv = rad * rad - d2;
         double w; const double g = al_row(s, row, cv, w);
         gx -= 2.0 * dx * g; gy -= 2.0 * dy * g;
-        acc.sta = fmax(acc.sta, cv);
+        if (pl < 0 || i == pl) acc.sta = fmax(acc.sta, cv);
         if (!TRIAL) { const double w4 = 4.0 * w; h00 += w4 * dx * dx; h01 += w4 * dx * dy; h11 += w4 * dy * dy; }
       }
       double* gp = Gp + (k * NP + pr) * 2; gp[0] = gx; gp[1] = gy;
@@ -353,7 +355,7 @@ struct Inst {
         const double cv = ((px - x1) * xv + (py - y1) * yv) * msk;
         double w; const double g = al_row(s, d->wall_row[i] + q, cv, w);
         gx += msk * xv * g; gy += msk * yv * g;
-        acc.sta = fmax(acc.sta, cv);
+        if (pl < 0 || i == pl) acc.sta = fmax(acc.sta, cv);
         const double wm = w * msk;
         h00 += wm * xv * xv; h01 += wm * xv * yv; h11 += wm * yv * yv;
       }
@@ -364,7 +366,7 @@ struct Inst {
         const double cv = cl[2] * cl[2] - ex * ex - ey * ey;
         double w; const double g = al_row(s, d->circle_row[i] + q, cv, w);
         gx -= 2.0 * ex * g; gy -= 2.0 * ey * g;
-        acc.sta = fmax(acc.sta, cv);
+        if (pl < 0 || i == pl) acc.sta = fmax(acc.sta, cv);
         const double w4 = 4.0 * w;
         h00 += w4 * ex * ex; h01 += w4 * ex * ey; h11 += w4 * ey * ey;
       }
@@ -430,13 +432,13 @@ struct Inst {
       if (row >= 0) {
         const double cv = ua - d->u_max[idx];
         double w; const double g = al_row(s, row, cv, w);
-        v += g; acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
+        v += g; if (pl < 0) acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
       }
       row = d->lb_row[idx];
       if (row >= 0) {
         const double cv = d->u_min[idx] - ua;
         double w; const double g = al_row(s, row, cv, w);
-        v -= g; acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
+        v -= g; if (pl < 0) acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
       }
     }
     if (TRIAL) v += reg_u * (alpha * R[s * b + OU + idx]);
@@ -464,6 +466,9 @@ struct Inst {
     return t;
   }
 
+  // rows of the system being solved: the full game, or player pl's best-response problem (newton_core.jl:205-245)
+  __device__ __forceinline__ double res_size() const { return pl < 0 ? (double)(K * b) : (double)(K * (2 * n + 2)); }
+
   // Full residual evaluation.  !TRIAL: at Z, rows stored to Rout (= R).  TRIAL: at Z + alpha·Δ (Δ in R) with the proximal
   // terms of regularize_residual!; rows go to Rout if non-null (may be global memory), norms are always returned.
   // NaN-safe maxima: fmax drops NaNs, so a non-finite residual is caught through `sum`.
@@ -477,6 +482,7 @@ struct Inst {
     for (int item = tid; item < nx; item += kThreads) {
       int a = item % n, t = item / n;
       int s = t % K, i = t / K;
+      if (pl >= 0 && i != pl) { if (Rout) Rout[s * b + OX + i * n + a] = 0.0; continue; }    // IBR: rows of player pl only
       double v = xrow_elem<TRIAL>(i, s + 1, a, alpha, reg_x, acc);
       acc.sum += fabs(v); acc.opt = fmax(acc.opt, fabs(v));
       if (Rout) Rout[s * b + OX + i * n + a] = v;
@@ -485,9 +491,18 @@ struct Inst {
     for (int item = tid; item < nu; item += kThreads) {
       int idx = item % m, s = item / m;
       int j = idx / P, i = idx - j * P;
+      if (pl >= 0 && i != pl) { if (Rout) Rout[s * b + OU + idx] = 0.0; continue; }
       double v = urow_elem<TRIAL>(i, s, j, alpha, reg_u, acc);
       acc.sum += fabs(v); acc.opt = fmax(acc.opt, fabs(v));
       if (Rout) Rout[s * b + OU + idx] = v;
+    }
+    if (pl >= 0 && has_cb && !TRIAL) {
+      // control_violation(game_con, pdtraj, i) (violations.jl:69-82) indexes the stacked bound rows with pu[i]: rows
+      // pu[i] of the control-bound conval, whatever bound they belong to — restated as is
+      for (int item = tid; item < K * 2; item += kThreads) {
+        const int j = item & 1, s = item >> 1, local = j * P + pl;
+        if (local < d->nrow_control) acc.con = fmax(acc.con, con_value(s, d->nrow_state + local));
+      }
     }
     Acc t = block_reduce(acc);
     return t;
@@ -639,6 +654,138 @@ struct Inst {
   }
 
   // ---------------------------------------------------------------------------------------------------------
+  // Iterative best response (solver_methods.jl:226-265, global_quantities.jl:288-365): Newton step of player pl's own
+  // optimal-control problem, Δtraj[horiz_mask] = −(lu(jac[verti_mask, horiz_mask]) \ res[verti_mask]).  Unknowns x,
+  // u_pl, λ_pl; the other players' controls and multipliers do not move.  Same stage-wise factorisation as kkt_solve
+  // with one value matrix P (n x n) and a 2 x 2 gain system per stage; R holds the masked residual on entry (rows of
+  // the other players zero) and the step on exit.
+  // ---------------------------------------------------------------------------------------------------------
+  __device__ bool kkt_solve_ibr(double reg_x, double reg_u) {
+    const int i = pl;
+    int ok = 1;
+    for (int item = tid; item < m * n1; item += kThreads) KU[item] = 0.0;       // gain rows of the other players stay zero
+    for (int item = tid; item < n * n; item += kThreads) Pm[item] = h_entry(i, K, item / n, item % n, reg_x);
+    for (int a = tid; a < n; a += kThreads) Sv[a] = R[(K - 1) * b + OX + i * n + a];
+    __syncthreads();
+    for (int col = tid; col < n1; col += kThreads) {
+      double At[8], Bt[8]; loadAB(K - 1, i, At, Bt);
+      double pv[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) pv[q] = (col < n) ? Pm[(q * P + i) * n + col] : Sv[q * P + i];
+      Ym[col] = bt_dot<0>(Bt, pv[0], pv[1], pv[2], pv[3]);
+      Ym[n1 + col] = bt_dot<1>(Bt, pv[0], pv[1], pv[2], pv[3]);
+    }
+    __syncthreads();
+    for (int s = K - 1; s >= 0; s--) {
+      const double* Rs = R + s * b;
+      constexpr int NK = n1, NB = P * n, NW = P * 2, NA = P;
+      // ---- phase A: gains (one column per thread, 2 x 2 solve with partial pivoting) and the K-independent parts
+      for (int item = tid; item < NK + NB + NW + NA; item += kThreads) {
+        if (item < NK) {
+          const int col = item;
+          double At[8], Bt[8]; loadAB(s, i, At, Bt);
+          const double* y0 = Ym; const double* y1 = Ym + n1;
+          double s00 = bt_dot<0>(Bt, y0[i], y0[P + i], y0[2 * P + i], y0[3 * P + i]) + hu_entry(s, i, reg_u);
+          double s01 = bt_dot<1>(Bt, y0[i], y0[P + i], y0[2 * P + i], y0[3 * P + i]);
+          double s10 = bt_dot<0>(Bt, y1[i], y1[P + i], y1[2 * P + i], y1[3 * P + i]);
+          double s11 = bt_dot<1>(Bt, y1[i], y1[P + i], y1[2 * P + i], y1[3 * P + i]) + hu_entry(s, P + i, reg_u);
+          double r0, r1;
+          if (col < n) {
+            const int c2 = col / P, i2 = col - c2 * P;
+            r0 = y0[col]; r1 = y1[col];
+            if (c2 >= 2) {
+              double At2[8], Bt2[8]; loadAB(s, i2, At2, Bt2);
+              r0 += at_dot_sel(c2 - 2, At2, y0[i2], y0[P + i2], y0[2 * P + i2], y0[3 * P + i2]);
+              r1 += at_dot_sel(c2 - 2, At2, y1[i2], y1[P + i2], y1[2 * P + i2], y1[3 * P + i2]);
+            }
+          } else {
+            r0 = y0[n] + Rs[OU + i]; r1 = y1[n] + Rs[OU + P + i];
+            for (int a2 = 0; a2 < n; a2++) { r0 += y0[a2] * Rs[OD + a2]; r1 += y1[a2] * Rs[OD + a2]; }
+          }
+          if (fabs(s10) > fabs(s00)) { double t = s00; s00 = s10; s10 = t; t = s01; s01 = s11; s11 = t; t = r0; r0 = r1; r1 = t; }
+          if (!(fabs(s00) > 0.0) || isinf(s00)) ok = 0;
+          const double f = s10 / s00, d11 = s11 - f * s01;
+          if (!(fabs(d11) > 0.0) || isinf(d11)) ok = 0;
+          const double k1 = (r1 - f * r0) / d11, k0 = (r0 - s01 * k1) / s00;
+          KU[i * n1 + col] = k0; KU[(P + i) * n1 + col] = k1;
+        } else if (s > 0) {
+          const int it = item - NK;
+          int kind, col, i2;                               // 0: Base column, 1: W column, 2: affine
+          if (it < NB) { kind = 0; col = it % n; i2 = it / n; }
+          else if (it < NB + NW) { kind = 1; col = (it - NB) & 1; i2 = (it - NB) >> 1; }
+          else { kind = 2; col = n; i2 = it - NB - NW; }
+          const double* p0 = Pm + (0 * P + i2) * n;
+          const double* p1 = Pm + (1 * P + i2) * n;
+          const double* p2 = Pm + (2 * P + i2) * n;
+          const double* p3 = Pm + (3 * P + i2) * n;
+          double T0, T1, T2, T3;
+          if (kind == 1) {                                  // (P B_pl)[(q,i2)][j]
+            double At[8], Bt[8]; loadAB(s, i, At, Bt);
+            T0 = bt_dot_sel(col, Bt, p0[i], p0[P + i], p0[2 * P + i], p0[3 * P + i]);
+            T1 = bt_dot_sel(col, Bt, p1[i], p1[P + i], p1[2 * P + i], p1[3 * P + i]);
+            T2 = bt_dot_sel(col, Bt, p2[i], p2[P + i], p2[2 * P + i], p2[3 * P + i]);
+            T3 = bt_dot_sel(col, Bt, p3[i], p3[P + i], p3[2 * P + i], p3[3 * P + i]);
+          } else if (kind == 0) {                           // (P A)[(q,i2)][col]
+            const int c2 = col / P, i3 = col - c2 * P;
+            T0 = p0[col]; T1 = p1[col]; T2 = p2[col]; T3 = p3[col];
+            if (c2 >= 2) {
+              double At[8], Bt[8]; loadAB(s, i3, At, Bt);
+              T0 += at_dot_sel(c2 - 2, At, p0[i3], p0[P + i3], p0[2 * P + i3], p0[3 * P + i3]);
+              T1 += at_dot_sel(c2 - 2, At, p1[i3], p1[P + i3], p1[2 * P + i3], p1[3 * P + i3]);
+              T2 += at_dot_sel(c2 - 2, At, p2[i3], p2[P + i3], p2[2 * P + i3], p2[3 * P + i3]);
+              T3 += at_dot_sel(c2 - 2, At, p3[i3], p3[P + i3], p3[2 * P + i3], p3[3 * P + i3]);
+            }
+          } else {                                          // P rd + s
+            T0 = Sv[i2]; T1 = Sv[P + i2]; T2 = Sv[2 * P + i2]; T3 = Sv[3 * P + i2];
+            for (int a2 = 0; a2 < n; a2++) {
+              const double e = Rs[OD + a2];
+              T0 += p0[a2] * e; T1 += p1[a2] * e; T2 += p2[a2] * e; T3 += p3[a2] * e;
+            }
+          }
+          double At2[8], Bt2[8]; loadAB(s, i2, At2, Bt2);
+          const double o[4] = {T0, T1, T2 + at_dot<0>(At2, T0, T1, T2, T3), T3 + at_dot<1>(At2, T0, T1, T2, T3)};
+          if (kind == 1) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) Wm[(c * P + i2) * 2 + col] = o[c];
+          } else if (kind == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) Base[(c * P + i2) * n1 + col] = o[c] + h_entry(i, s, c * P + i2, col, reg_x);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) Base[(c * P + i2) * n1 + n] = o[c] + R[(s - 1) * b + OX + i * n + c * P + i2];
+          }
+        }
+      }
+      __syncthreads();
+      for (int item = tid; item < m * n1; item += kThreads) KUg[s * KUS + item] = KU[item];
+      if (s == 0) break;
+      // ---- phase B: P ← Base − W K,  s ← base − W κ,  Y ← B_{s−1}ᵀ P
+      for (int item = tid; item < P * n1; item += kThreads) {
+        const int col = item % n1, i2 = item / n1;
+        const double k0 = KU[i * n1 + col], k1 = KU[(P + i) * n1 + col];
+        double pn[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int a = c * P + i2;
+          pn[c] = Base[a * n1 + col] - Wm[a * 2] * k0 - Wm[a * 2 + 1] * k1;
+        }
+        if (i2 == i) {
+          double At[8], Bt[8]; loadAB(s - 1, i, At, Bt);
+          Ym[col] = bt_dot<0>(Bt, pn[0], pn[1], pn[2], pn[3]);
+          Ym[n1 + col] = bt_dot<1>(Bt, pn[0], pn[1], pn[2], pn[3]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) { const int a = c * P + i2; if (col < n) Pm[a * n + col] = pn[c]; else Sv[a] = pn[c]; }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    ok = __syncthreads_and(ok);
+    forward_and_costate(reg_x);
+    return ok != 0;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------
   // Δtraj = −(lu(jac) \ res)  (solver_methods.jl:87-88): R holds res on entry, Δ on exit (same stage-major slots:
   // rx(i,s) → Δλ_{i,s}, ru(s) → Δu_s, rd(s) → Δx_{s+1}).  Returns false on a singular / non-finite pivot.
   //
@@ -649,6 +796,7 @@ struct Inst {
   //   phase 3 (all warps)   P_i ← Base_i − W_i K,  s_i ← base_i − W_i κ,  Y ← B_{s−1}ᵀ P_i
   // ---------------------------------------------------------------------------------------------------------
   __device__ bool kkt_solve(double reg_x, double reg_u) {
+    if (pl >= 0) return kkt_solve_ibr(reg_x, reg_u);
     int ok = 1;
     // terminal knot: P_i = H_{i,N}, s_i = r^x_{i,N}
     for (int item = tid; item < P * n * n; item += kThreads) {
@@ -825,6 +973,13 @@ struct Inst {
       }
       __syncthreads();
     }
+    ok = __syncthreads_and(ok);
+    forward_and_costate(reg_x);
+    return ok != 0;
+  }
+
+  // forward sweep + costate recursion shared by the game and the best-response factorisations
+  __device__ void forward_and_costate(double reg_x) {
     // ---- forward sweep (warp 0): Δu_s = −Ku Δx_s − ku,  Δx_{s+1} = A Δx_s + B Δu_s + rd.  The gains come back from the
     // L2-resident scratch through a 4-deep register ring (each load has three stage-times to land), staged through
     // the one-stage smem buffer.
@@ -893,6 +1048,7 @@ struct Inst {
       const int a = item % n, t = item / n;
       const int s = t % K, i = t / K, k = s + 1;
       const int c = a / P, ia = a - c * P;
+      if (pl >= 0 && i != pl) { R[s * b + OX + i * n + a] = 0.0; continue; }       // IBR: Δλ_j = 0 for j != pl
       const double* dx = R + s * b + OD;
       double v = R[s * b + OX + i * n + a] + hd_entry(i, k, a, reg_x) * dx[a];
       if (c < 2) {
@@ -914,7 +1070,7 @@ struct Inst {
       R[s * b + OX + i * n + a] = v;
     }
     __syncthreads();
-    if (warp < P) {
+    if (warp < P && (pl < 0 || warp == pl)) {
       const int i = warp;
       for (int s = K - 2; s >= 0; s--) {
         double v = 0.0;
@@ -933,13 +1089,12 @@ struct Inst {
       }
     }
     __syncthreads();
-    ok = __syncthreads_and(ok);
-    return ok != 0;
   }
+
 
   // line_search (solver_methods.jl:105-125): returns alpha, j through references; n_eval counts residual evaluations
   __device__ void line_search(const agb_options& o, double reg, double res_norm, double& alpha, int& j, int& n_eval) {
-    const double S = (double)(K * b);
+    const double S = res_size();
     const double rr = o.regularize ? reg : 0.0;
     alpha = 1.0; j = 1;
     while (j < o.ls_iter) {

@@ -24,7 +24,7 @@ __all__ = [
     "add_collision_cost", "GameConstraintValues", "add_collision_avoidance", "add_control_bound", "add_state_bound",
     "add_circle_constraint", "add_wall_constraint", "Wall", "GameProblem", "GameBatch", "newton_solve",
     "residual", "residual_jacobian", "kkt_solve", "line_search", "update_traj", "rollout", "dual_update",
-    "penalty_update", "reset", "evaluate", "active_set", "Statistics", "spec_of",
+    "penalty_update", "reset", "evaluate", "active_set", "Statistics", "spec_of", "IBROptions", "ibr_newton_solve",
 ]
 
 
@@ -129,6 +129,24 @@ class Options:
     def to_dict(self) -> dict:
         return {f.name: (list(getattr(self, f.name)) if f.name == "alphax_dual" else getattr(self, f.name))
                 for f in fields(self)}
+
+
+@dataclass
+class IBROptions:
+    """struct/options.jl:123-136.  `ordering` lists players 0-based (the reference's default is 1:100)."""
+    ibr_iter: int = 100
+    ordering: Optional[List[int]] = None
+    delta_min: float = 1e-9
+
+    def to_c(self, p: int) -> _capi.IBROptionsC:
+        o = _capi.IBROptionsC()
+        o.ibr_iter, o.delta_min = int(self.ibr_iter), float(self.delta_min)
+        order = list(range(p)) if self.ordering is None else list(self.ordering)[:p]
+        if sorted(order) != list(range(p)):
+            raise ValueError("ordering must be a permutation of the players")
+        for i in range(_capi.MAX_P):
+            o.ordering[i] = order[i] if i < p else 0
+        return o
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -490,6 +508,26 @@ class GameBatch:
             _capi.dptr(out.get("conmu")), _capi.dptr(out.get("stats")), _capi.iptr(out.get("status"))))
         return out
 
+    def ibr_newton_solve(self, opts: Options, ibr_opts: Optional[IBROptions] = None):
+        """agb_ibr_newton_solve_batch: ibr_newton_solve!(prob; ibr_opts) for every instance (solver_methods.jl:133-166)."""
+        out = {"Z": np.empty(self._z()), "L": np.empty(self._l()), "conlam": np.empty(self._c()), "conmu": np.empty(self._c()),
+               "stats": np.empty((self.batch, _capi.NSTATS)), "status": np.empty(self.batch, dtype=np.int32)}
+        oc, ic = opts.to_c(), (ibr_opts or IBROptions()).to_c(self.p)
+        self._ck(self.lib.agb_ibr_newton_solve_batch(
+            self.h, C.byref(oc), C.byref(ic), _capi.dptr(out["Z"]), _capi.dptr(out["L"]), _capi.dptr(out["conlam"]),
+            _capi.dptr(out["conmu"]), _capi.dptr(out["stats"]), _capi.iptr(out["status"])))
+        return out
+
+    def ibr_residual(self, player: int, reg_x=0.0, reg_u=0.0, alpha=0.0):
+        res, norms = np.empty((self.batch, self.S)), np.empty((self.batch, 5))
+        self._ck(self.lib.agb_ibr_residual(self.h, int(player), reg_x, reg_u, alpha, _capi.dptr(res), _capi.dptr(norms)))
+        return res, norms
+
+    def ibr_kkt_solve(self, player: int, reg_x=0.0, reg_u=0.0):
+        d = np.empty((self.batch, self.S))
+        self._ck(self.lib.agb_ibr_kkt_solve(self.h, int(player), reg_x, reg_u, _capi.dptr(d)))
+        return d
+
     def newton_solve_async(self, opts: Options, stream: int = 0):
         oc = opts.to_c()
         self._ck(self.lib.agb_newton_solve_async(self.h, C.byref(oc), C.c_void_p(stream)))
@@ -638,6 +676,43 @@ def newton_solve(probs, init: bool = True):
         batch.set_initial(Z0, L0, np.stack([q.conlam for q in plist]) if have_duals else None,
                           np.stack([q.conmu for q in plist]) if have_duals else None)
         out = batch.newton_solve(p0.opts)
+        res, _ = batch.residual()
+        for b, q in enumerate(plist):
+            q.pdtraj.X[:], q.pdtraj.U[:], q.pdtraj.du[:] = out["Z"][b, :, :ps.n], out["Z"][b, :, ps.n:], out["L"][b]
+            q.conlam, q.conmu = out["conlam"][b], out["conmu"][b]
+            q.stats = Statistics(); q.stats.record(out["stats"][b])
+            q.status = _capi.STATUS_NAMES[int(out["status"][b])]
+            q.core.res[:] = res[b]
+    finally:
+        if B > 1:
+            batch.close()
+    return None
+
+
+def ibr_newton_solve(probs, ibr_opts: Optional[IBROptions] = None, init: bool = True):
+    """ibr_newton_solve!(prob; ibr_opts) for one GameProblem or a list sharing one schema (solver_methods.jl:133-166)."""
+    single = isinstance(probs, GameProblem)
+    plist = [probs] if single else list(probs)
+    if not plist:
+        return None
+    p0 = plist[0]
+    for q in plist[1:]:
+        if not _same_schema(p0, q):
+            raise ValueError("all problems of a batch must share model, sizes and constraint schema")
+    B, ps = len(plist), p0.probsize
+    batch = p0.batch() if B == 1 else GameBatch(p0.model, p0.N, p0.dt, p0.game_obj, p0.game_con, B, p0._device, p0._lib_path)
+    try:
+        if init:
+            for q in plist:
+                init_traj(q)
+        obj = [q.game_obj for q in plist]
+        batch.set_instance_params(
+            x0=np.stack([q.x0 for q in plist]),
+            xf=np.stack([_joint(o.xf, ps.p, 4) for o in obj]), Q=np.stack([_joint(o.Q, ps.p, 4) for o in obj]),
+            R=np.stack([_joint(o.R, ps.p, 2) for o in obj]), uf=np.stack([_joint(o.uf, ps.p, 2) for o in obj]))
+        batch.set_initial(np.stack([np.concatenate([q.pdtraj.X, q.pdtraj.U], axis=1) for q in plist]),
+                          np.stack([q.pdtraj.du for q in plist]))
+        out = batch.ibr_newton_solve(p0.opts, ibr_opts)
         res, _ = batch.residual()
         for b, q in enumerate(plist):
             q.pdtraj.X[:], q.pdtraj.U[:], q.pdtraj.du[:] = out["Z"][b, :, :ps.n], out["Z"][b, :, ps.n:], out["L"][b]

@@ -109,6 +109,13 @@ typedef struct agb_options {
   int dual_reset;               /* :115 */
 } agb_options;
 
+/* IBROptions (src/struct/options.jl:123-136); players in `ordering` are 0-based here. */
+typedef struct agb_ibr_options {
+  int ibr_iter;                 /* :126 (default 100) */
+  int ordering[AGB_MAX_P];      /* :129 (default 0,1,2,…) */
+  double delta_min;             /* :132 (default 1e-9) */
+} agb_ibr_options;
+
 typedef struct agb_handle agb_handle;
 
 /* Fills *o with the reference defaults (options.jl). */
@@ -184,6 +191,22 @@ int agb_debug_gain_solve(agb_handle* h, const double* aug, double* aug_out, int*
 int agb_newton_solve_batch(agb_handle* h, const agb_options* o,
                            double* Z_out, double* L_out, double* conlam_out, double* conmu_out,
                            double* stats_out, int* status_out);
+
+/* ---- iterative best response (the reference's second solver, solver_methods.jl:133-289) --------------------------- */
+/* ibr_newton_solve!(prob; ibr_opts) for every instance: sweeps over the players in `ordering`, each player solving its own
+ * augmented-Lagrangian optimal-control problem with the others' strategies fixed (ibr_newton_solve!(prob, i), :168-224).
+ * Outputs as agb_newton_solve_batch; stats = full-game record at the returned iterate, Newton steps and residual
+ * evaluations summed over all best responses, stats[7] = IBR sweeps executed; status is taken on that full-game record. */
+int agb_ibr_newton_solve_batch(agb_handle* h, const agb_options* o, const agb_ibr_options* io,
+                               double* Z_out, double* L_out, double* conlam_out, double* conmu_out,
+                               double* stats_out, int* status_out);
+/* ibr_residual! + regularize_ibr_residual! of player `player` (0-based) at (Z + alpha·Δ): the rows of the other players
+ * are returned as zero (the reference masks them out, newton_core.jl:205-245); norms_out [B][5] = masked ‖res‖₁ / mask
+ * length and the player-i violations of record!(…, i) (statistics.jl:59-72). */
+int agb_ibr_residual(agb_handle* h, int player, double reg_x, double reg_u, double alpha,
+                     double* res_out, double* norms_out);
+/* Δtraj[horiz_mask] = −(lu(jac[verti_mask, horiz_mask]) \ res[verti_mask]), zeros elsewhere (solver_methods.jl:248-250). */
+int agb_ibr_kkt_solve(agb_handle* h, int player, double reg_x, double reg_u, double* dtraj_out);
 
 /* Device-resident form: enqueue the solve on `stream` (a cudaStream_t, 0 = legacy default)
  * with no host copies and no synchronisation; results stay in the handle's device buffers. */

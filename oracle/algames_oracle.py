@@ -1169,3 +1169,254 @@ def unpack_multipliers(prob: GameProblem, lam, mu):
         for cv in gc.control_conval:
             P = cv.con.length()
             cv.lam[k - 1] = lam[k - 1, o:o + P]; cv.mu[k - 1] = mu[k - 1, o:o + P]; o += P
+
+
+# --------------------------------------------------------------------------------------
+# Iterative best response (src/problem/solver_methods.jl:133-289, global_quantities.jl:199-365,
+# core/newton_core.jl:205-294, struct/violations.jl:28-37,69-82,116-134,170-183)
+# Players are 1-based here, like the reference.
+# --------------------------------------------------------------------------------------
+def vertical_mask(core: NewtonCore, i: int, splitted_state: bool = False):
+    """newton_core.jl:205-245: rows of player i's best-response problem: opt_i x, opt_i u_i, dyn."""
+    ps = core.ps
+    pi = np.asarray(ps.pz[i - 1]) if splitted_state else np.arange(ps.n)
+    msk = []
+    for k in range(2, ps.N + 1):
+        msk.extend(core.vert[("opt", i, "x", k)][pi])
+    for k in range(1, ps.N):
+        msk.extend(core.vert[("opt", i, "u", k)])
+    for k in range(1, ps.N):
+        msk.extend(core.vert[("dyn", k)][pi])
+    return np.array(msk)
+
+
+def horizontal_mask(core: NewtonCore, i: int, splitted_state: bool = False):
+    """newton_core.jl:248-294: columns x, u_i, λ_i."""
+    ps = core.ps
+    pi = np.asarray(ps.pz[i - 1]) if splitted_state else np.arange(ps.n)
+    msk = []
+    for k in range(2, ps.N + 1):
+        msk.extend(core.horiz[("x", k)][pi])
+    for k in range(1, ps.N):
+        msk.extend(core.horiz[("u", i, k)])
+    for k in range(1, ps.N):
+        msk.extend(core.horiz[("λ", i, k)][pi])
+    return np.array(msk)
+
+
+def ibr_residual(prob: GameProblem, pd: PrimalDualTraj, i: int):
+    """global_quantities.jl:204-256: cost and dynamics-penalty terms of player i only; constraint terms of every
+    player (harmless: the caller masks the rows); dynamics rows."""
+    ps, core, model, obj = prob.probsize, prob.core, prob.model, prob.game_obj
+    N, pu = ps.N, ps.pu
+    res = core.res
+    res[:] = 0.0
+    for k in range(1, N + 1):
+        q, r = obj.gradient(i - 1, k, pd.X[k - 1], pd.U[k - 1], pd.dt)
+        if k >= 2:
+            res[core.vert[("opt", i, "x", k)]] += q
+        if k <= N - 1:
+            res[core.vert[("opt", i, "u", k)]] += r[pu[i - 1]]
+    for k in range(1, N):
+        A, B = rk2_jacobian(model, pd.X[k - 1], pd.U[k - 1], pd.dt)
+        lam = pd.du[i - 1, k - 1]
+        if k >= 2:
+            res[core.vert[("opt", i, "x", k)]] += A.T @ lam
+        res[core.vert[("opt", i, "u", k)]] += B[:, pu[i - 1]].T @ lam
+        res[core.vert[("opt", i, "x", k + 1)]] += -lam
+    _constraint_residual(prob, pd)
+    for k in range(1, N):
+        res[core.vert[("dyn", k)]] += dynamics_residual(model, pd, k)
+    return res
+
+
+def regularize_ibr_residual(prob, pd, pd_ref, i):
+    """global_quantities.jl:258-276."""
+    ps, core, reg = prob.probsize, prob.core, prob.opts.reg
+    for k in range(1, ps.N):
+        core.res[core.vert[("opt", i, "x", k + 1)]] += reg.x * (pd.X[k] - pd_ref.X[k])
+        core.res[core.vert[("opt", i, "u", k)]] += reg.u * (pd.U[k - 1] - pd_ref.U[k - 1])[ps.pu[i - 1]]
+
+
+def ibr_residual_jacobian(prob: GameProblem, pd: PrimalDualTraj, i: int, regularize=True):
+    """global_quantities.jl:288-365 (dense S×S; only player i's cost/dynamics blocks, every player's constraint blocks)."""
+    ps, core, model, obj, gc = prob.probsize, prob.core, prob.model, prob.game_obj, prob.game_con
+    N, n, pu, S = ps.N, ps.n, ps.pu, ps.S
+    J = np.zeros((S, S))
+    V, H = core.vert, core.horiz
+
+    def add(vkey, hkey, M):
+        J[np.ix_(V[vkey], H[hkey])] += M
+
+    for k in range(1, N + 1):
+        Qh, Rh = obj.hessian(i - 1, k, pd.X[k - 1], pd.U[k - 1], pd.dt)
+        if k >= 2:
+            add(("opt", i, "x", k), ("x", k), Qh)
+        if k <= N - 1:
+            add(("opt", i, "u", k), ("u", i, k), Rh[np.ix_(pu[i - 1], pu[i - 1])])
+    _expand_convals(prob, pd)
+    for pl in range(1, ps.p + 1):
+        for cv in gc.state_conval[pl - 1]:
+            for j, k in enumerate(cv.inds):
+                if 2 <= k <= N:
+                    add(("opt", pl, "x", k), ("x", k), cv.hess[j])
+    for cv in gc.control_conval:
+        for j, k in enumerate(cv.inds):
+            for pl in range(1, ps.p + 1):
+                add(("opt", pl, "u", k), ("u", pl, k), cv.hess[j][np.ix_(pu[pl - 1], pu[pl - 1])])
+    for k in range(1, N):
+        A, B = rk2_jacobian(model, pd.X[k - 1], pd.U[k - 1], pd.dt)
+        if k >= 2:
+            add(("dyn", k), ("x", k), A)
+        add(("dyn", k), ("u", i, k), B[:, pu[i - 1]])
+        add(("dyn", k), ("x", k + 1), -np.eye(n))
+        if k >= 2:
+            add(("opt", i, "x", k), ("λ", i, k), A.T)
+        add(("opt", i, "u", k), ("λ", i, k), B[:, pu[i - 1]].T)
+        add(("opt", i, "x", k + 1), ("λ", i, k), -np.eye(n))
+    if regularize:
+        reg = prob.opts.reg
+        for k in range(1, N):
+            add(("opt", i, "x", k + 1), ("x", k + 1), reg.x * np.eye(n))
+            add(("opt", i, "u", k), ("u", i, k), reg.u * np.eye(ps.mi[i - 1]))
+    core.jac = J
+    return J
+
+
+def record_ibr(prob, pd, delta, k_out, i):
+    """statistics.jl:59-72: player-i violations (violations.jl:28-37, 69-82, 116-134, 170-183).
+    res is the full-game residual norm (logging only)."""
+    ps, core = prob.probsize, prob.core
+    residual(prob, pd)
+    res_full = float(np.abs(core.res).sum() / ps.S)
+    pz, pui = np.asarray(ps.pz[i - 1]), np.asarray(ps.pu[i - 1])
+    dyn = max(np.max(np.abs(dynamics_residual(prob.model, pd, k)[pz])) for k in range(1, prob.N))
+    con = np.zeros(prob.N - 1)
+    for cv in prob.game_con.control_conval:
+        cv.evaluate(pd.X, pd.U)
+        # the reference indexes the stacked [u-u_max; u_min-u] rows with pu[i]; with all bounds finite those are the
+        # upper-bound rows of player i (violations.jl:69-82)
+        cmax = np.array([max(0.0, float(np.max(v[pui]))) for v in cv.vals])
+        idx = np.array(cv.inds) - 1
+        con[idx] = np.maximum(con[idx], cmax)
+    sta = np.zeros(prob.N)
+    for cv in prob.game_con.state_conval[i - 1]:
+        cv.evaluate(pd.X, pd.U)
+        cv.max_violation()
+        idx = np.array(cv.inds) - 1
+        sta[idx] = np.maximum(sta[idx], cv.c_max)
+    opt = 0.0
+    for k in range(1, ps.N + 1):
+        if k >= 2:
+            opt = max(opt, float(np.max(np.abs(core.res[core.vert[("opt", i, "x", k)]]))))
+        if k <= ps.N - 1:
+            opt = max(opt, float(np.max(np.abs(core.res[core.vert[("opt", i, "u", k)]]))))
+    rec = Record(outer=k_out, res=res_full, dyn=float(dyn), con=float(con.max()) if len(con) else 0.0,
+                 sta=float(sta.max()), opt=opt, delta=delta)
+    prob.stats.append(rec)
+    return rec
+
+
+def ibr_line_search(prob, res_norm, i):
+    """solver_methods.jl:267-289."""
+    opts, core = prob.opts, prob.core
+    vm = vertical_mask(core, i)
+    j, alpha = 1, 1.0
+    while j < opts.ls_iter:
+        update_traj(prob.pdtraj_trial, prob.pdtraj, alpha, prob.dpdtraj)
+        ibr_residual(prob, prob.pdtraj_trial, i)
+        if opts.regularize:
+            regularize_ibr_residual(prob, prob.pdtraj_trial, prob.pdtraj, i)
+        if np.abs(core.res[vm]).sum() / len(vm) <= (1.0 - alpha * opts.beta) * res_norm:
+            break
+        alpha *= opts.alpha_decrease
+        j += 1
+    return alpha, j
+
+
+def ibr_inner_iteration(prob, LS_count, delta, k, l, i):
+    """solver_methods.jl:226-265."""
+    core, opts = prob.core, prob.opts
+    vm, hm = vertical_mask(core, i), horizontal_mask(core, i)
+    ibr_residual(prob, prob.pdtraj, i)
+    masked = core.res.copy()
+    rec = record_ibr(prob, prob.pdtraj, delta, k, i)          # (re-runs the full residual!, like the reference's record!)
+    core.res[:] = masked
+    # NB the reference's optimality_violation(core, i) is taken on core.res as left by residual_norm → residual!, whose
+    # player-i rows equal the ibr_residual! ones; record_ibr above already used the full residual for them.
+    res_norm = np.abs(core.res[vm]).sum() / len(vm)
+    delta = 0.0
+    if rec.opt < opts.eps_opt:
+        return LS_count, "break", delta
+    J = ibr_residual_jacobian(prob, prob.pdtraj, i, regularize=True)
+    dtraj = np.zeros(prob.probsize.S)
+    dtraj[hm] = -np.linalg.solve(J[np.ix_(vm, hm)], core.res[vm])
+    prob.last_dtraj = dtraj
+    prob.n_newton += 1
+    set_traj(core, prob.dpdtraj, dtraj)
+    alpha, j = ibr_line_search(prob, res_norm, i)
+    LS_count = LS_count + 1 if j == opts.ls_iter else 0
+    update_traj(prob.pdtraj, prob.pdtraj, alpha, prob.dpdtraj)
+    delta = delta_step(prob.dpdtraj, alpha)
+    if delta < opts.delta_min:
+        return LS_count, "break", delta
+    return LS_count, "continue", delta
+
+
+def ibr_newton_solve_player(prob: GameProblem, i: int):
+    """solver_methods.jl:168-224: best response of player i (1-based)."""
+    opts, gc = prob.opts, prob.game_con
+    if opts.dual_reset:
+        gc.reset()
+        prob.pdtraj.du[:] = 0.0                               # reset_duals!(pdtraj) (primal_dual_traj.jl:149-158)
+        prob.pdtraj_trial.du[:] = 0.0
+    delta, out = 0.0, 0
+    for k in range(1, opts.outer_iter + 1):
+        out = k
+        LS_count = 0
+        for l in range(1, opts.inner_iter + 1):
+            opts.reg.set(opts.reg_0 * l ** 4)
+            LS_count, flow, delta = ibr_inner_iteration(prob, LS_count, delta, k, l, i)
+            if LS_count >= 1 or flow == "break":
+                break
+        last = prob.stats[-1]
+        if k == opts.outer_iter or (last.dyn < opts.eps_dyn and last.con < opts.eps_con and
+                                    last.sta < opts.eps_sta and last.opt < opts.eps_opt):
+            break
+        gc.evaluate(prob.pdtraj.X, prob.pdtraj.U)
+        gc.dual_update()
+        gc.penalty_update()
+    record_ibr(prob, prob.pdtraj, delta, out, i)
+    return prob
+
+
+def ibr_newton_solve(prob: GameProblem, Z0=None, L0=None, ibr_iter=100, ordering=None, delta_min=1e-9, rng=None):
+    """solver_methods.jl:133-166.  Z0/L0 as in newton_solve."""
+    opts, ps = prob.opts, prob.probsize
+    ordering = list(ordering) if ordering is not None else list(range(1, ps.p + 1))
+    prob.stats = []
+    prob.n_newton = 0
+    rng = rng or np.random.default_rng(opts.seed)
+    if Z0 is not None:
+        prob.pdtraj.X[:] = np.asarray(Z0)[:, : ps.n]
+        prob.pdtraj.U[:] = np.asarray(Z0)[:, ps.n:]
+        prob.pdtraj.du[:] = np.asarray(L0)
+        prob.pdtraj.X[0] = prob.x0
+    else:
+        init_traj(prob.pdtraj, prob.x0, lambda k: rng.random(k), opts.amplitude_init, opts.shift)
+    prob.pdtraj_trial = prob.pdtraj.copy()
+    prob.dpdtraj.X[:] = 0; prob.dpdtraj.U[:] = 0; prob.dpdtraj.du[:] = 0
+    rollout_rk3(prob.model, prob.pdtraj)
+    change = [True] * ps.p
+    prob.ibr_sweeps = 0
+    for q in range(ibr_iter):
+        prob.ibr_sweeps = q + 1
+        for idx in range(ps.p):
+            i = ordering[idx]
+            ibr_newton_solve_player(prob, i)
+            # maximum over the WHOLE recorded history (stats is never reset inside the loop, :156)
+            change[i - 1] = not (delta_min > max(r.delta for r in prob.stats))
+        residual(prob, prob.pdtraj)
+        if all(not c for c in change):
+            break
+    return prob

@@ -254,3 +254,69 @@ def check_pivot_fallback(lib_path):
             assert ok[b], (p, b)
             assert np.abs(out[b, :, m:] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.linalg.cond(aug[b, :, :m]), (p, b)
         assert not ok[5] or not np.isfinite(out[5]).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Iterative best response
+# ---------------------------------------------------------------------------------------------------------------
+def check_ibr_per_function(lib_path, name, seed=4, reg=1e-3, N=None):
+    """ibr_residual! (+ proximal term) and the masked Newton step of every player on a random iterate."""
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, 1, N)
+    rng = np.random.default_rng(seed)
+    gb = ab.GameBatch(model, N, dt, obj, con, 1, lib_path=lib_path)
+    gb.set_instance_params(x0=x0[:1], xf=None if xf is None else xf[:1])
+    op = oracle_problem(model, N, dt, obj, con, opts, x0[0], None if xf is None else xf[0])
+    Z, L, lam, mu = random_state(op, x0[0], rng)
+    has_con = lam.size > 0
+    gb.set_initial(Z[None], L[None], lam[None] if has_con else None, mu[None] if has_con else None)
+    op.opts.reg.set(reg)
+    for i in range(1, model.p + 1):
+        vm, hm = O.vertical_mask(op.core, i), O.horizontal_mask(op.core, i)
+        res, norms = gb.ibr_residual(i - 1)
+        ores = O.ibr_residual(op, op.pdtraj, i).copy()
+        masked = np.zeros_like(ores); masked[vm] = ores[vm]
+        assert np.abs(res[0] - masked).max() <= TOL_FUNC * np.abs(masked).max()
+        stats0 = list(op.stats)
+        rec = O.record_ibr(op, op.pdtraj, 0.0, 1, i)
+        op.stats = stats0
+        assert np.allclose(norms[0], [np.abs(ores[vm]).sum() / len(vm), rec.dyn, rec.con, rec.sta, rec.opt], rtol=1e-12, atol=1e-12)
+        d = gb.ibr_kkt_solve(i - 1, reg, reg)[0]
+        O.ibr_residual(op, op.pdtraj, i)
+        J = O.ibr_residual_jacobian(op, op.pdtraj, i)
+        ref = np.zeros(op.probsize.S)
+        ref[hm] = -np.linalg.solve(J[np.ix_(vm, hm)], ores[vm])
+        assert np.abs(d - ref).max() <= 1e-9 * np.abs(ref).max(), (i, np.abs(d - ref).max() / np.abs(ref).max())
+        # trial residual with the proximal term
+        rt, _ = gb.ibr_residual(i - 1, reg, reg, 0.5)
+        O.set_traj(op.core, op.dpdtraj, d)
+        op.pdtraj_trial = op.pdtraj.copy()
+        O.update_traj(op.pdtraj_trial, op.pdtraj, 0.5, op.dpdtraj)
+        O.ibr_residual(op, op.pdtraj_trial, i)
+        O.regularize_ibr_residual(op, op.pdtraj_trial, op.pdtraj, i)
+        mt = np.zeros_like(ores); mt[vm] = op.core.res[vm]
+        assert np.abs(rt[0] - mt).max() <= TOL_FUNC * np.abs(mt).max()
+    gb.close()
+
+
+def check_ibr_solve(lib_path, name, B=1, N=None, ibr_iter=3, opts_override=None):
+    """ibr_newton_solve! on the same initial iterate: trajectories, Newton counts, final full-game record."""
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, B, N)
+    if x0.shape[0] < B:
+        x0 = np.tile(x0[:1], (B, 1))
+    for k, v in (opts_override or {}).items():
+        setattr(opts, k, v)
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path)
+    gb.set_instance_params(x0=x0, xf=xf)
+    Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+    out = gb.ibr_newton_solve(opts, ab.IBROptions(ibr_iter=ibr_iter))
+    for b in range(B):
+        op = oracle_problem(model, N, dt, obj, con, opts, x0[b], None if xf is None else xf[b])
+        O.ibr_newton_solve(op, Z0=Z0[b], L0=L0[b], ibr_iter=ibr_iter)
+        Zo = np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1)
+        assert np.abs(out["Z"][b] - Zo).max() < TOL_SOLVE
+        assert np.abs(out["L"][b] - op.pdtraj.du).max() < TOL_SOLVE * max(1.0, np.abs(op.pdtraj.du).max())
+        assert int(out["stats"][b, 6]) == op.n_newton and int(out["stats"][b, 7]) == op.ibr_sweeps
+        O.residual(op, op.pdtraj)
+        assert abs(out["stats"][b, 0] - np.abs(op.core.res).sum() / op.probsize.S) < TOL_SOLVE
+    gb.close()
+    return out

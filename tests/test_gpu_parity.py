@@ -191,3 +191,31 @@ def test_mpc_receding_horizon_loop():
 
 def test_gauss_jordan_pivot_fallback():
     parity.check_pivot_fallback(LIB)
+
+
+# ---- iterative best response (solver_methods.jl:133-289) --------------------------------------------------------------
+@pytest.mark.parametrize("name,N", [("A", None), ("A'", None), ("B", None), ("C", 20), ("D", 20)])
+def test_ibr_per_function_parity(name, N):
+    parity.check_ibr_per_function(LIB, name, N=N)
+
+
+def test_ibr_solve_vs_oracle():
+    parity.check_ibr_solve(LIB, "B", B=2, N=20, ibr_iter=3)
+    parity.check_ibr_solve(LIB, "A", B=1, ibr_iter=2)
+
+
+def test_ibr_reference_scenarios():
+    """test/problem/solver_methods.jl:187-315 through GameProblem / ibr_newton_solve."""
+    import algames_b200 as ab
+    N, dt = 20, 0.1
+    for mdl, p, outer, inner, ibr_iter, tol in [(ab.DoubleIntegratorGame, 1, 1, 1, 1, 1e-6), (ab.UnicycleGame, 1, 7, 20, 1, 1e-6),
+                                                 (ab.DoubleIntegratorGame, 2, 1, 1, 100, 5e-2), (ab.UnicycleGame, 2, 7, 20, 100, 5e-2)]:
+        model = mdl(p=p)
+        x0 = {1: [1.0, 1.0, 0.0, 0.9], 2: [1.0, 2.0, 1.0, 2.0, 0, 0, 0.9, 0.9]}[p]
+        obj = ab.GameObjective([np.ones(4)] * p, [0.5 * np.ones(2)] * p, [np.zeros(4)] * p, [-np.ones(2)] * p, N, model)
+        con = ab.GameConstraintValues(ab.ProblemSize(N, model))
+        opts = ab.Options(outer_iter=outer, inner_iter=inner, ls_iter=25, reg_0=1e-7, eps_dyn=1e-10, eps_opt=1e-10)
+        prob = ab.GameProblem(N, dt, x0, model, opts, obj, con, lib_path=LIB)
+        ab.ibr_newton_solve(prob, ab.IBROptions(ibr_iter=ibr_iter))
+        assert np.abs(prob.core.res).sum() / prob.probsize.S < tol
+        assert prob.stats.dyn_vio[-1].max < 1e-6

@@ -427,3 +427,57 @@ def test_dense_jacobian_matches_finite_difference_of_residual_for_lq_game():
         v = v0.copy(); v[c] += 1e-6
         O.set_traj(prob.core, d, v)
         assert np.allclose((O.residual(prob, d) - r0) / 1e-6, J[:, c], atol=1e-6)
+
+
+# ---------------------------------------------------------------- iterative best response
+def test_player_masks():
+    # test/core/newton_core.jl:118-160
+    N, p = 6, 5
+    mdl = O.UnicycleGame(p=p)
+    ps = O.ProblemSize(N, mdl)
+    core = O.NewtonCore(ps)
+    n, ni, mi = ps.n, 4, 2
+    for fn in (O.vertical_mask, O.horizontal_mask):
+        split = []
+        for i in range(1, p + 1):
+            assert len(fn(core, i)) == (N - 1) * (2 * n + mi)
+            ms = fn(core, i, splitted_state=True)
+            assert len(ms) == (N - 1) * (2 * ni + mi)
+            split.append(set(ms.tolist()))
+        assert not set.intersection(*split)
+
+
+@pytest.mark.parametrize("model,p,outer,inner,tol", [
+    ("double_integrator", 1, 1, 1, 1e-6),      # test/problem/solver_methods.jl:187-218
+    ("unicycle", 1, 7, 20, 1e-6),              # :220-250
+    ("double_integrator", 2, 1, 1, 5e-2),      # :252-282
+    ("unicycle", 2, 7, 20, 5e-2),              # :284-314
+])
+def test_ibr_solver(model, p, outer, inner, tol):
+    prob = _solver_case(model, p, False, outer, inner)
+    if p == 1:
+        rng = np.random.default_rng(100)
+        O.init_traj(prob.pdtraj, prob.x0, lambda k: rng.random(k), prob.opts.amplitude_init)
+        prob.pdtraj_trial = prob.pdtraj.copy()
+        O.rollout_rk3(prob.model, prob.pdtraj)
+        prob.stats, prob.n_newton = [], 0
+        O.ibr_newton_solve_player(prob, 1)
+        O.residual(prob, prob.pdtraj)
+    else:
+        O.ibr_newton_solve(prob)
+    assert np.abs(prob.core.res).sum() / prob.probsize.S < tol
+    assert O.dynamics_violation(prob, prob.pdtraj) < 1e-6
+
+
+def test_ibr_masked_system_is_the_single_player_problem():
+    # the masked Jacobian of player i is exactly the KKT Jacobian of the 1-player problem obtained by freezing the others
+    prob = _solver_case("unicycle", 2, True, 7, 20)
+    rng = np.random.default_rng(3)
+    pd = prob.pdtraj
+    pd.X[:] = rng.normal(size=pd.X.shape); pd.U[:] = rng.normal(size=pd.U.shape); pd.du[:] = rng.normal(size=pd.du.shape)
+    prob.opts.reg.set(1e-3)
+    Jf = O.residual_jacobian(prob, pd)
+    for i in (1, 2):
+        vm, hm = O.vertical_mask(prob.core, i), O.horizontal_mask(prob.core, i)
+        Ji = O.ibr_residual_jacobian(prob, pd, i)
+        assert np.array_equal(Ji[np.ix_(vm, hm)], Jf[np.ix_(vm, hm)])
