@@ -91,6 +91,7 @@ SYMBOLS = {
     "agb_ibr_newton_solve_batch": (C.c_int, [_H, C.POINTER(OptionsC), C.POINTER(IBROptionsC), _DP, _DP, _DP, _DP, _DP, _IP]),
     "agb_ibr_residual": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, _DP, _DP]),
     "agb_ibr_kkt_solve": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, _DP]),
+    "agb_solve_from_host": (C.c_int, [_H, C.POINTER(OptionsC), _DP, _DP, _DP, _DP, _DP, _DP, _DP, _DP, _IP]),
     "agb_newton_solve_async": (C.c_int, [_H, C.POINTER(OptionsC), C.c_void_p]),
     "agb_get_device_view": (C.c_int, [_H, C.POINTER(DeviceView)]),
     "agb_launch_count": (C.c_longlong, [_H]),

@@ -82,6 +82,7 @@ struct agb_handle {
   DevDesc hd;
   DevDesc* dd = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t chunk_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // agb_solve_from_host pipeline
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // device buffers
@@ -239,6 +240,7 @@ void agb_destroy(agb_handle* h) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (cudaStream_t cs : h->chunk_stream) if (cs) cudaStreamDestroy(cs);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -567,7 +569,7 @@ static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
   LaunchArgs L;
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
   memset(&L.io, 0, sizeof L.io);
-  L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch;
+  L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch; L.inst0 = 0;
   agb::launch_solve(h->hd.p, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
@@ -647,6 +649,42 @@ int agb_ibr_kkt_solve(agb_handle* h, int player, double reg_x, double reg_u, dou
   AGB_TRY(launch_op(h, nullptr, a));
   if (dtraj_out) AGB_TRY(export_to_host(h, h->D, dtraj_out, 1));
   return finish(h);
+}
+
+int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, const double* Z0, const double* L0,
+                        double* Z_out, double* L_out, double* conlam_out, double* conmu_out, double* stats_out, int* status_out) {
+  if (!h || !o || !x0 || !Z0 || !L0) return AGB_EINVAL;
+  if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1) return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter must be >= 1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int B = h->batch, n = h->hd.n;
+  const size_t zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n, cs = (size_t)h->hd.K * h->hd.nrow;
+  const int chunks = B >= 512 ? 4 : 1;                     // each chunk: H2D -> solve -> D2H on its own stream
+  for (int c = 0; c < chunks; c++) {
+    if (!h->chunk_stream[c]) AGB_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
+    cudaStream_t st = h->chunk_stream[c];
+    const int lo = (int)((long long)B * c / chunks), hi = (int)((long long)B * (c + 1) / chunks), cnt = hi - lo;
+    if (cnt <= 0) continue;
+    AGB_CUDA(h, cudaMemcpyAsync(h->x0 + (size_t)lo * n, x0 + (size_t)lo * n, (size_t)cnt * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    AGB_CUDA(h, cudaMemcpyAsync(h->Z0 + lo * zs, Z0 + lo * zs, cnt * zs * sizeof(double), cudaMemcpyHostToDevice, st));
+    AGB_CUDA(h, cudaMemcpyAsync(h->L0 + lo * ls, L0 + lo * ls, cnt * ls * sizeof(double), cudaMemcpyHostToDevice, st));
+    LaunchArgs L;
+    L.model = h->hd.model; L.grid = cnt; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
+    memset(&L.io, 0, sizeof L.io); memset(&L.a, 0, sizeof L.a);
+    L.g = buffers_of(h); L.batch = hi; L.inst0 = lo;
+    agb::launch_solve(h->hd.p, L);
+    h->launches++;
+    AGB_CUDA(h, cudaGetLastError());
+    if (Z_out) AGB_CUDA(h, cudaMemcpyAsync(Z_out + lo * zs, h->Z + lo * zs, cnt * zs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (L_out) AGB_CUDA(h, cudaMemcpyAsync(L_out + lo * ls, h->L + lo * ls, cnt * ls * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (conlam_out && cs) AGB_CUDA(h, cudaMemcpyAsync(conlam_out + lo * cs, h->conlam + lo * cs, cnt * cs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (conmu_out && cs) AGB_CUDA(h, cudaMemcpyAsync(conmu_out + lo * cs, h->conmu + lo * cs, cnt * cs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (stats_out) AGB_CUDA(h, cudaMemcpyAsync(stats_out + (size_t)lo * AGB_NSTATS, h->stats + (size_t)lo * AGB_NSTATS, (size_t)cnt * AGB_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status_out) AGB_CUDA(h, cudaMemcpyAsync(status_out + lo, h->status + lo, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  for (int c = 0; c < chunks; c++) if (h->chunk_stream[c]) AGB_CUDA(h, cudaStreamSynchronize(h->chunk_stream[c]));
+  AGB_CUDA(h, cudaGetLastError());
+  return AGB_OK;
 }
 
 int agb_get_device_view(agb_handle* h, agb_device_view* out) {

@@ -17,14 +17,14 @@ namespace agb {
 // =============================================================================================================
 // newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
 template <int P, int MODEL>
-__global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int batch) {
+__global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL> I;
   I.bind(dd, sm);
   constexpr int n = Inst<P, MODEL>::n, kThreads = threads_for(P);
   const int K = I.K;
   const double S = (double)(K * Inst<P, MODEL>::b);
-  for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+  for (int inst = inst0 + blockIdx.x; inst < batch; inst += gridDim.x) {   // instances [inst0, batch)
     __syncthreads();
     I.bind_instance(g, inst);
     I.load_params(g, inst);
@@ -307,6 +307,7 @@ struct LaunchArgs {
   Buffers g;
   OpArgs a;
   int batch;
+  int inst0;             // first instance of the launch (newton_solve only; chunked host pipeline)
 };
 
 template <int P, int MODEL> inline cudaError_t set_attr_pm(size_t smem) {
@@ -325,7 +326,7 @@ template <int P> inline cudaError_t set_attr_p(int model, size_t smem) {
 }
 template <int P, int MODEL> inline void launch_solve_pm(const LaunchArgs& L) {
   auto kfn = agb_newton_solve_kernel<P, MODEL>;
-  AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.batch);
+  AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.inst0, L.batch);
 }
 template <int P, int MODEL> inline void launch_ibr_pm(const LaunchArgs& L) {
   auto kfn = agb_ibr_solve_kernel<P, MODEL>;

@@ -528,6 +528,18 @@ class GameBatch:
         self._ck(self.lib.agb_ibr_kkt_solve(self.h, int(player), reg_x, reg_u, _capi.dptr(d)))
         return d
 
+    def solve_from_host(self, opts: Options, x0, Z0, L0, out=None):
+        """agb_solve_from_host: one call from host buffers to host results, copies pipelined with the solve in chunks."""
+        x0, Z0, L0 = self._arr(x0, (self.batch, self.n)), self._arr(Z0, self._z()), self._arr(L0, self._l())
+        if out is None:
+            out = {"Z": np.empty(self._z()), "L": np.empty(self._l()), "conlam": np.empty(self._c()), "conmu": np.empty(self._c()),
+                   "stats": np.empty((self.batch, _capi.NSTATS)), "status": np.empty(self.batch, dtype=np.int32)}
+        oc = opts.to_c()
+        self._ck(self.lib.agb_solve_from_host(
+            self.h, C.byref(oc), _capi.dptr(x0), _capi.dptr(Z0), _capi.dptr(L0), _capi.dptr(out.get("Z")), _capi.dptr(out.get("L")),
+            _capi.dptr(out.get("conlam")), _capi.dptr(out.get("conmu")), _capi.dptr(out.get("stats")), _capi.iptr(out.get("status"))))
+        return out
+
     def newton_solve_async(self, opts: Options, stream: int = 0):
         oc = opts.to_c()
         self._ck(self.lib.agb_newton_solve_async(self.h, C.byref(oc), C.c_void_p(stream)))

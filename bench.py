@@ -250,9 +250,8 @@ def run_gpu(args):
         h_out["conlam"], h_out["conmu"] = pinned((B, N - 1, nrow)).numpy(), pinned((B, N - 1, nrow)).numpy()
 
     def e2e_step():
-        gb.set_instance_params(x0=h_x0.numpy())
-        gb.set_initial(h_Z0.numpy(), h_L0.numpy())
-        gb.newton_solve(opts, out=h_out)
+        # one public API call: pinned host inputs -> solve -> pinned host results (chunked copy/solve pipeline inside)
+        gb.solve_from_host(opts, h_x0.numpy(), h_Z0.numpy(), h_L0.numpy(), out=h_out)
         return int((h_out["status"] == 0).sum())
 
     for _ in range(2):

@@ -208,6 +208,15 @@ int agb_ibr_residual(agb_handle* h, int player, double reg_x, double reg_u, doub
 /* Δtraj[horiz_mask] = −(lu(jac[verti_mask, horiz_mask]) \ res[verti_mask]), zeros elsewhere (solver_methods.jl:248-250). */
 int agb_ibr_kkt_solve(agb_handle* h, int player, double reg_x, double reg_u, double* dtraj_out);
 
+/* One-shot host form: x0 [B][n] and the initial iterate Z0 / L0 (as agb_set_initial) go in, results come out, with the
+ * batch cut into chunks whose host->device copy, solve and device->host copy are pipelined on separate streams (pass
+ * page-locked buffers for the copies to overlap).  Equivalent to agb_set_instance_params(x0) + agb_set_initial(Z0, L0) +
+ * agb_newton_solve_batch, except that the per-function "resident iterate" is the result, and o->dual_reset should be 1
+ * (the multipliers start from the handle's resident values otherwise).  Outputs may be NULL. */
+int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, const double* Z0, const double* L0,
+                        double* Z_out, double* L_out, double* conlam_out, double* conmu_out,
+                        double* stats_out, int* status_out);
+
 /* Device-resident form: enqueue the solve on `stream` (a cudaStream_t, 0 = legacy default)
  * with no host copies and no synchronisation; results stay in the handle's device buffers. */
 int agb_newton_solve_async(agb_handle* h, const agb_options* o, void* stream);

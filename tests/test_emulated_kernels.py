@@ -122,3 +122,17 @@ def test_ibr_reference_scenarios_emulated(emu_lib):
         ab.ibr_newton_solve(prob, ab.IBROptions(ibr_iter=ibr_iter))
         assert np.abs(prob.core.res).sum() / prob.probsize.S < tol
         assert prob.stats.dyn_vio[-1].max < 1e-6
+
+
+def test_solve_from_host_matches_staged_calls_emulated(emu_lib):
+    """agb_solve_from_host (chunked pipeline) == set_instance_params + set_initial + newton_solve_batch, bit for bit."""
+    import algames_b200 as ab
+    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=5, N=8)
+    gb = ab.GameBatch(model, N, dt, obj, con, 5, lib_path=emu_lib)
+    gb.set_instance_params(x0=x0)
+    Z0, L0 = gb.random_initial()
+    ref = gb.newton_solve(opts)
+    got = gb.solve_from_host(opts, x0, Z0, L0)
+    for k in ("Z", "L", "conlam", "conmu", "stats", "status"):
+        assert np.array_equal(ref[k], got[k]), k
+    gb.close()

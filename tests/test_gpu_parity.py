@@ -219,3 +219,18 @@ def test_ibr_reference_scenarios():
         ab.ibr_newton_solve(prob, ab.IBROptions(ibr_iter=ibr_iter))
         assert np.abs(prob.core.res).sum() / prob.probsize.S < tol
         assert prob.stats.dyn_vio[-1].max < 1e-6
+
+
+def test_solve_from_host_matches_staged_calls():
+    """agb_solve_from_host (4-chunk copy/solve pipeline at B >= 512) == the staged calls, bit for bit."""
+    import algames_b200 as ab
+    for B in (7, 600):
+        model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=B, N=16)
+        gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=LIB)
+        gb.set_instance_params(x0=x0)
+        Z0, L0 = gb.random_initial()
+        ref = gb.newton_solve(opts)
+        got = gb.solve_from_host(opts, x0, Z0, L0)
+        for k in ("Z", "L", "conlam", "conmu", "stats", "status"):
+            assert np.array_equal(ref[k], got[k]), (B, k)
+        gb.close()
