@@ -14,7 +14,6 @@ namespace agb {
 #endif
 AGB_HD constexpr int threads_for(int p) { return p >= 4 ? 256 : 128; }
 constexpr int kMaxWarps = 8;
-constexpr int kMaxRows = 96;       // AL constraint rows per stage (state rows of knot k+1 + control rows of knot k)
 
 // Flattened, index-resolved form of agb_problem_desc, lives in device global memory (read through L1).
 // Index conventions follow the reference's component-major joint layout (src/dynamics/unicycle.jl:18-20):

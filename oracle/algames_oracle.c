@@ -30,7 +30,7 @@
 #include <unistd.h>
 #include "../include/algames_b200.h"
 
-#define MAXROW 160
+#define MAXROW 256   /* >= p(p-1) + p(2n + walls + circles) + 2m at the ABI maxima (220) */
 
 typedef struct {
   const agb_problem_desc* d;
@@ -39,12 +39,10 @@ typedef struct {
   double dt;
   const double *xf, *Q, *R, *uf;            /* joint, this instance */
   /* row schema */
-  int col_row[AGB_MAX_P][AGB_MAX_P], sbmax_row[AGB_MAX_P][AGB_MAX_N], sbmin_row[AGB_MAX_P][AGB_MAX_N];
-  int wall_row[AGB_MAX_P], circle_row[AGB_MAX_P], ub_row[AGB_MAX_M], lb_row[AGB_MAX_M], nrow_state;
+  int nrow_state;
   int row_owner[MAXROW];
   /* state */
   double *X, *U, *L, *Xt, *Ut, *Lt, *dX, *dU, *dL, *lam, *mu, *res, *band, *rhs;
-  double reg;
   int n_newton, n_eval;
 } Work;
 
