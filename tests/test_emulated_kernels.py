@@ -136,3 +136,48 @@ def test_solve_from_host_matches_staged_calls_emulated(emu_lib):
     for k in ("Z", "L", "conlam", "conmu", "stats", "status"):
         assert np.array_equal(ref[k], got[k]), k
     gb.close()
+
+
+@pytest.mark.parametrize("model_name,p,N", [("double_integrator", 1, 2), ("unicycle", 1, 3), ("bicycle", 4, 5), ("unicycle", 2, 2)])
+def test_edge_shapes_emulated(emu_lib, model_name, p, N):
+    """Smallest horizons (N = 2: one stage, no backward recursion), single player, and a 4-player bicycle game carrying every
+    constraint type: full solve vs oracle."""
+    import algames_b200 as ab
+    import oracle.algames_oracle as O
+    model = {"double_integrator": ab.DoubleIntegratorGame, "unicycle": ab.UnicycleGame, "bicycle": ab.BicycleGame}[model_name](p=p)
+    rng = np.random.default_rng(p * 10 + N)
+    obj = ab.GameObjective([1 + rng.random(4) for _ in range(p)], [0.1 + rng.random(2) for _ in range(p)],
+                           [rng.normal(size=4) for _ in range(p)], [0.1 * rng.normal(size=2) for _ in range(p)], N, model)
+    con = ab.GameConstraintValues(ab.ProblemSize(N, model))
+    if p > 1:
+        ab.add_collision_cost(obj, 0.5 * np.ones(p), 2.0 * np.ones(p))
+        ab.add_collision_avoidance(con, 0.05)
+    if model_name == "bicycle":
+        ab.add_control_bound(con, np.r_[2 * np.ones(p), 0.5 * np.ones(p)], np.r_[-2 * np.ones(p), -np.inf * np.ones(p)])
+        ab.add_state_bound(con, 1, 5 * np.ones(model.n), np.r_[-5 * np.ones(model.n - 2), -np.inf, -np.inf])
+        ab.add_wall_constraint(con, [ab.Wall([0.0, -0.4], [1.0, -0.4], [0.0, -1.0])], 2)
+        ab.add_circle_constraint(con, [1.0], [1.0], [0.2])
+    x0 = rng.normal(size=model.n)
+    opts = ab.Options()
+    gb = ab.GameBatch(model, N, 0.1, obj, con, 1, lib_path=emu_lib)
+    gb.set_instance_params(x0=x0[None])
+    Z0, L0 = gb.random_initial()
+    out = gb.newton_solve(opts)
+    prob = ab.GameProblem(N, 0.1, x0, model, opts, obj, con, lib_path=emu_lib)
+    op = O.problem_from_spec(ab.spec_of(prob))
+    O.newton_solve(op, Z0=Z0[0], L0=L0[0])
+    Zo = np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1)
+    assert np.abs(out["Z"][0] - Zo).max() < parity.TOL_SOLVE
+    assert int(out["stats"][0, 6]) == op.n_newton and (out["status"][0] == 0) == op.converged
+    gb.close()
+
+
+def test_working_set_too_large_is_rejected_emulated(emu_lib):
+    import algames_b200 as ab
+    model = ab.UnicycleGame(p=4)
+    N = 120
+    obj = ab.GameObjective([np.ones(4)] * 4, [np.ones(2)] * 4, [np.zeros(4)] * 4, [np.zeros(2)] * 4, N, model)
+    con = ab.GameConstraintValues(ab.ProblemSize(N, model))
+    ab.add_collision_avoidance(con, 0.1)
+    with pytest.raises(ab.AlgamesError, match="shared memory"):
+        ab.GameBatch(model, N, 0.1, obj, con, 1, lib_path=emu_lib)
