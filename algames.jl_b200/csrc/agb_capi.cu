@@ -186,7 +186,7 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     if (need > have) take(need - have);
     o->o_Gp = o->o_Base; o->o_Gs = o->o_Base + (o->has_pairs ? N * o->npairs * 2 : 0);
   }
-  o->o_par = take(2 * n + 2 * m); o->o_red = take(5 * kMaxWarps);
+  o->o_par = take(2 * n + 2 * m); o->o_red = take(6 * kMaxWarps);
   o->smem_doubles = off;
   return AGB_OK;
 }

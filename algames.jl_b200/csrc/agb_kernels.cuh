@@ -36,8 +36,10 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
     I.rollout();                                                                        // :17
     if (o.dual_reset) I.reset_duals_penalties(o);                                       // :25
     int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0;
+    bool kept = false;               // R's successor (rows at the accepted trial point = the current iterate) is in Rtrial
+    Acc kept_rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double delta = 0.0;
-    Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0};
+    Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int kout = 1; kout <= o.outer_iter; kout++) {                                  // :30
       outer_done = kout;
       int ls_count = 0;
@@ -45,8 +47,8 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
         const double l2 = (double)l * (double)l;
         const double reg = o.reg_0 * (l2 * l2);                                         // :39
         // ---- inner_iteration (:67-103)
-        rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                           // :73-75 (the reg terms vanish at Z)
-        n_eval++;
+        if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; }             // accepted trial point: already evaluated
+        else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }        // :73-75 (the reg terms vanish at Z)
         const double res_norm = rec.sum / S;                                            // :76
         delta = 0.0;
         if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
         if (!I.kkt_solve(reg, reg)) failed = 1;                                         // :84-88
         n_newton++;
         double alpha; int j;
-        I.line_search(o, reg, res_norm, alpha, j, n_eval);                              // :91
+        kept = I.line_search(o, reg, res_norm, alpha, j, n_eval, &kept_rec);            // :91
         ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;                                 // :92-93
         delta = I.update_traj(alpha);                                                   // :94-95 (taken even when the search failed)
         if (delta < o.delta_min) break;                                                 // :96-98
@@ -66,9 +68,10 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
         break;                                                                          // :49-55
       I.dual_update(o);                                                                 // :57-58
       I.penalty_update(o);                                                              // :61
+      kept = false;                                                                     // multipliers changed
     }
-    rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                               // :63 final record
-    n_eval++;
+    if (kept) { I.load_kept_residual(); rec = kept_rec; }                               // :63 final record
+    else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }
     const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
     const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
     I.store_iterate(g.Z, g.L, inst);
@@ -117,14 +120,15 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_ibr_solv
         }
         const double S = I.res_size();
         delta = 0.0;
-        Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0};
+        bool kept = false;
+        Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, kept_rec = rec;
         for (int kout = 1; kout <= o.outer_iter; kout++) {
           int ls_count = 0;
           for (int l = 1; l <= o.inner_iter; l++) {
             const double l2 = (double)l * (double)l;
             const double reg = o.reg_0 * (l2 * l2);
-            rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);                       // ibr_inner_iteration (:226-265)
-            n_eval++;
+            if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; }
+            else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }    // ibr_inner_iteration (:226-265)
             const double res_norm = rec.sum / S;
             delta = 0.0;
             if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_ibr_solv
             if (!I.kkt_solve(reg, reg)) failed = 1;
             n_newton++;
             double alpha; int j;
-            I.line_search(o, reg, res_norm, alpha, j, n_eval);
+            kept = I.line_search(o, reg, res_norm, alpha, j, n_eval, &kept_rec);
             ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;
             delta = I.update_traj(alpha);
             dmax = fmax(dmax, delta);
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_ibr_solv
             break;
           I.dual_update(o);
           I.penalty_update(o);
+          kept = false;
         }
         if (!(io.delta_min > dmax)) change |= (1u << i); else change &= ~(1u << i);     // :156
       }

@@ -17,6 +17,7 @@ namespace agb {
 
 struct Acc {            // norms of one residual evaluation (statistics.jl:44-57, violations.jl:18-168)
   double sum, opt, dyn, con, sta;
+  double psum;          // Σ|row| without the proximal terms (trial evaluations that are kept, see Inst::residual)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -183,6 +184,8 @@ struct Inst {
   double dt;
   double *X, *U, *L, *R, *KU, *AB, *CL, *CM, *CW, *Gp, *Hp, *Gs, *Hs, *Pm, *Sv, *Ym, *Aug, *Base, *Wm, *Ta, *xf, *Q, *Rw, *uf, *red;
   double* KUg;            // this instance's slice of Buffers::KUg (global)
+  double* Rtrial;         // global scratch [S]: un-regularised residual rows of the last trial point (reused if accepted)
+  bool keep;              // trial evaluation also produces what the next inner iteration needs (rows, Hessian blocks)
   int pl;                 // iterative best response: the player whose problem is being solved (-1: the full game)
   int tid, lane, warp;
 
@@ -193,24 +196,24 @@ struct Inst {
     CL = sm + dd->o_CL; CM = sm + dd->o_CM; CW = sm + dd->o_CW; Gp = sm + dd->o_Gp; Hp = sm + dd->o_Hp; Gs = sm + dd->o_Gs;
     Hs = sm + dd->o_Hs; Pm = sm + dd->o_P; Sv = sm + dd->o_Sv; Ym = sm + dd->o_Y; Aug = sm + dd->o_Aug; Base = sm + dd->o_Base;
     Wm = sm + dd->o_W; Ta = sm + dd->o_Ta; xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
-    tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1;
+    tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
   }
-  __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUS; }
+  __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUS; Rtrial = g.D + (size_t)inst * K * b; }
 
   // ---- iterate accessors; TRIAL reads Z + alpha·Δ with Δ held in R (update_traj!, primal_dual_traj.jl:109-128)
   template <bool TRIAL> __device__ __forceinline__ double xg(int k, int a, double alpha) const {
     double v = X[k * n + a];
-    if (TRIAL) { if (k > 0) v += alpha * R[(k - 1) * b + OD + a]; }
+    if (TRIAL) { if (k > 0) v = fma(alpha, R[(k - 1) * b + OD + a], v); }     // same expression as update_traj
     return v;
   }
   template <bool TRIAL> __device__ __forceinline__ double ug(int s, int idx, double alpha) const {
     double v = U[s * m + idx];
-    if (TRIAL) v += alpha * R[s * b + OU + idx];
+    if (TRIAL) v = fma(alpha, R[s * b + OU + idx], v);
     return v;
   }
   template <bool TRIAL> __device__ __forceinline__ double lg(int i, int s, int a, double alpha) const {
     double v = L[(i * K + s) * n + a];
-    if (TRIAL) v += alpha * R[s * b + OX + i * n + a];
+    if (TRIAL) v = fma(alpha, R[s * b + OX + i * n + a], v);
     return v;
   }
 
@@ -316,7 +319,7 @@ struct Inst {
           const double q = rr / (eps_norm + dn);
           gx = -dtx * (mu * (q * (eps + dx) - dx));            // q[pxi] = −g
           gy = -dtx * (mu * (q * (eps + dy) - dy));
-          if (!TRIAL) {
+          if (!TRIAL || keep) {
             const double idn = 1.0 / dn, t = rr * idn, t3 = t * idn * idn;
             h00 = dtx * mu * (1.0 - t + t3 * dx * dx);
             h01 = dtx * mu * (t3 * dx * dy);
@@ -331,10 +334,10 @@ struct Inst {
         double w; const double g = al_row(s, row, cv, w);
         gx -= 2.0 * dx * g; gy -= 2.0 * dy * g;
         if (pl < 0 || i == pl) acc.sta = fmax(acc.sta, cv);
-        if (!TRIAL) { const double w4 = 4.0 * w; h00 += w4 * dx * dx; h01 += w4 * dx * dy; h11 += w4 * dy * dy; }
+        if (!TRIAL || keep) { const double w4 = 4.0 * w; h00 += w4 * dx * dx; h01 += w4 * dx * dy; h11 += w4 * dy * dy; }
       }
       double* gp = Gp + (k * NP + pr) * 2; gp[0] = gx; gp[1] = gy;
-      if (!TRIAL) { double* hp = Hp + (k * NP + pr) * 3; hp[0] = h00; hp[1] = h01; hp[2] = h11; }
+      if (!TRIAL || keep) { double* hp = Hp + (k * NP + pr) * 3; hp[0] = h00; hp[1] = h01; hp[2] = h11; }
     }
   }
 
@@ -371,12 +374,12 @@ struct Inst {
         h00 += w4 * ex * ex; h01 += w4 * ex * ey; h11 += w4 * ey * ey;
       }
       double* gs = Gs + (k * P + i) * 2; gs[0] = gx; gs[1] = gy;
-      if (!TRIAL) { double* hs = Hs + (k * P + i) * 3; hs[0] = h00; hs[1] = h01; hs[2] = h11; }
+      if (!TRIAL || keep) { double* hs = Hs + (k * P + i) * 3; hs[0] = h00; hs[1] = h01; hs[2] = h11; }
     }
   }
 
   // one element of player i's stationarity row block w.r.t. x at knot k (1..K), joint comp a
-  template <bool TRIAL> __device__ double xrow_elem(int i, int k, int a, double alpha, double reg_x, Acc& acc) {
+  template <bool TRIAL> __device__ double xrow_elem(int i, int k, int a, double alpha, double reg_x, Acc& acc, double& plain) {
     const int c = a / P, ia = a - c * P, s = k - 1;
     const double xa = xg<TRIAL>(k, a, alpha);
     double v = 0.0;
@@ -415,12 +418,13 @@ struct Inst {
       }
     }
     v -= lg<TRIAL>(i, k - 1, a, alpha);                               // − λ_{i,k−1}
+    plain = v;
     if (TRIAL) v += reg_x * (alpha * R[s * b + OD + a]);              // regularize_residual! (:67-86)
     return v;
   }
 
   // one element of player i's stationarity row block w.r.t. u_{i,s}: own control comp j
-  template <bool TRIAL> __device__ double urow_elem(int i, int s, int j, double alpha, double reg_u, Acc& acc) {
+  template <bool TRIAL> __device__ double urow_elem(int i, int s, int j, double alpha, double reg_u, Acc& acc, double& plain) {
     const int idx = j * P + i;
     const double ua = ug<TRIAL>(s, idx, alpha);
     double v = dt * Rw[idx] * (ua - uf[idx]);
@@ -441,6 +445,7 @@ struct Inst {
         v -= g; if (pl < 0) acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
       }
     }
+    plain = v;
     if (TRIAL) v += reg_u * (alpha * R[s * b + OU + idx]);
     return v;
   }
@@ -449,19 +454,20 @@ struct Inst {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       a.sum += __shfl_xor_sync(AGB_FULL, a.sum, o);
+      a.psum += __shfl_xor_sync(AGB_FULL, a.psum, o);
       a.opt = fmax(a.opt, __shfl_xor_sync(AGB_FULL, a.opt, o));
       a.dyn = fmax(a.dyn, __shfl_xor_sync(AGB_FULL, a.dyn, o));
       a.con = fmax(a.con, __shfl_xor_sync(AGB_FULL, a.con, o));
       a.sta = fmax(a.sta, __shfl_xor_sync(AGB_FULL, a.sta, o));
     }
     __syncthreads();            // red[] may still be read from the previous reduction
-    if (lane == 0) { double* r = red + warp * 5; r[0] = a.sum; r[1] = a.opt; r[2] = a.dyn; r[3] = a.con; r[4] = a.sta; }
+    if (lane == 0) { double* r = red + warp * 6; r[0] = a.sum; r[1] = a.opt; r[2] = a.dyn; r[3] = a.con; r[4] = a.sta; r[5] = a.psum; }
     __syncthreads();
-    Acc t = {0.0, 0.0, 0.0, 0.0, 0.0};
+    Acc t = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int w = 0; w < kThreads / 32; w++) {
-      const double* r = red + w * 5;
-      t.sum += r[0]; t.opt = fmax(t.opt, r[1]); t.dyn = fmax(t.dyn, r[2]); t.con = fmax(t.con, r[3]); t.sta = fmax(t.sta, r[4]);
+      const double* r = red + w * 6;
+      t.sum += r[0]; t.opt = fmax(t.opt, r[1]); t.dyn = fmax(t.dyn, r[2]); t.con = fmax(t.con, r[3]); t.sta = fmax(t.sta, r[4]); t.psum += r[5];
     }
     return t;
   }
@@ -472,9 +478,13 @@ struct Inst {
   // Full residual evaluation.  !TRIAL: at Z, rows stored to Rout (= R).  TRIAL: at Z + alpha·Δ (Δ in R) with the proximal
   // terms of regularize_residual!; rows go to Rout if non-null (may be global memory), norms are always returned.
   // NaN-safe maxima: fmax drops NaNs, so a non-finite residual is caught through `sum`.
-  template <bool TRIAL> __device__ Acc residual(double alpha, double reg_x, double reg_u, double* Rout) {
-    Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0};
+  // With `plain` (trial evaluations of the line search): Rout receives the UN-regularised rows and *plain their norms, so
+  // that an accepted trial point needs no re-evaluation at the next inner iteration.
+  template <bool TRIAL> __device__ Acc residual(double alpha, double reg_x, double reg_u, double* Rout, Acc* plain = nullptr) {
+    Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    keep = TRIAL && plain != nullptr;
     pass_dyn<TRIAL>(alpha, Rout, acc);
+    acc.psum = acc.sum;               // dynamics rows carry no proximal term
     pass_pairs<TRIAL>(alpha, acc);
     pass_self<TRIAL>(alpha, acc);
     __syncthreads();
@@ -483,8 +493,12 @@ struct Inst {
       int a = item % n, t = item / n;
       int s = t % K, i = t / K;
       if (pl >= 0 && i != pl) { if (Rout) Rout[s * b + OX + i * n + a] = 0.0; continue; }    // IBR: rows of player pl only
-      double v = xrow_elem<TRIAL>(i, s + 1, a, alpha, reg_x, acc);
-      acc.sum += fabs(v); acc.opt = fmax(acc.opt, fabs(v));
+      double pv;
+      double v = xrow_elem<TRIAL>(i, s + 1, a, alpha, reg_x, acc, pv);
+      acc.sum += fabs(v);
+      acc.psum += fabs(pv);
+      if (keep) v = pv;
+      acc.opt = fmax(acc.opt, fabs(v));
       if (Rout) Rout[s * b + OX + i * n + a] = v;
     }
     const int nu = K * m;
@@ -492,8 +506,12 @@ struct Inst {
       int idx = item % m, s = item / m;
       int j = idx / P, i = idx - j * P;
       if (pl >= 0 && i != pl) { if (Rout) Rout[s * b + OU + idx] = 0.0; continue; }
-      double v = urow_elem<TRIAL>(i, s, j, alpha, reg_u, acc);
-      acc.sum += fabs(v); acc.opt = fmax(acc.opt, fabs(v));
+      double pv;
+      double v = urow_elem<TRIAL>(i, s, j, alpha, reg_u, acc, pv);
+      acc.sum += fabs(v);
+      acc.psum += fabs(pv);
+      if (keep) v = pv;
+      acc.opt = fmax(acc.opt, fabs(v));
       if (Rout) Rout[s * b + OU + idx] = v;
     }
     if (pl >= 0 && has_cb && !TRIAL) {
@@ -505,6 +523,8 @@ struct Inst {
       }
     }
     Acc t = block_reduce(acc);
+    if (plain) { *plain = t; plain->sum = t.psum; }
+    keep = false;
     return t;
   }
 
@@ -1092,19 +1112,33 @@ struct Inst {
   }
 
 
-  // line_search (solver_methods.jl:105-125): returns alpha, j through references; n_eval counts residual evaluations
-  __device__ void line_search(const agb_options& o, double reg, double res_norm, double& alpha, int& j, int& n_eval) {
+  // line_search (solver_methods.jl:105-125): returns alpha, j through references; n_eval counts residual evaluations.
+  // With `accepted_rec` every trial also leaves its un-regularised rows in Rtrial (global) and, on acceptance, its norms
+  // in *accepted_rec: the accepted point IS the next iterate, so the next inner iteration can skip its residual!.
+  __device__ bool line_search(const agb_options& o, double reg, double res_norm, double& alpha, int& j, int& n_eval,
+                              Acc* accepted_rec = nullptr) {
     const double S = res_size();
     const double rr = o.regularize ? reg : 0.0;
     alpha = 1.0; j = 1;
     while (j < o.ls_iter) {
-      Acc t = residual<true>(alpha, rr, rr, nullptr);
+      Acc plain;
+      Acc t = accepted_rec ? residual<true>(alpha, rr, rr, Rtrial, &plain) : residual<true>(alpha, rr, rr, nullptr);
       n_eval++;
       const double trial = t.sum / S;
-      if (trial <= (1.0 - alpha * o.beta) * res_norm) break;
+      if (trial <= (1.0 - alpha * o.beta) * res_norm) {
+        if (accepted_rec) *accepted_rec = plain;
+        return true;
+      }
       alpha *= o.alpha_decrease;
       j++;
     }
+    return false;
+  }
+
+  // R <- rows kept by the accepted trial evaluation
+  __device__ void load_kept_residual() {
+    for (int q = tid; q < K * b; q += kThreads) R[q] = Rtrial[q];
+    __syncthreads();
   }
 
   // update_traj!(pdtraj, pdtraj, α, Δpdtraj) + Δ_step (primal_dual_traj.jl:109-147)
@@ -1113,11 +1147,11 @@ struct Inst {
     for (int item = tid; item < K * b; item += kThreads) {
       const int q = item % b, s = item / b;
       const double dv = R[item];
-      if (q < OU) { const int i = q / n, a = q - i * n; L[(i * K + s) * n + a] += alpha * dv; }
-      else if (q < OD) { U[s * m + (q - OU)] += alpha * dv; loc += fabs(dv); }
-      else { X[(s + 1) * n + (q - OD)] += alpha * dv; loc += fabs(dv); }
+      if (q < OU) { const int i = q / n, a = q - i * n; double* t = &L[(i * K + s) * n + a]; *t = fma(alpha, dv, *t); }
+      else if (q < OD) { double* t = &U[s * m + (q - OU)]; *t = fma(alpha, dv, *t); loc += fabs(dv); }
+      else { double* t = &X[(s + 1) * n + (q - OD)]; *t = fma(alpha, dv, *t); loc += fabs(dv); }
     }
-    Acc a = {loc, 0.0, 0.0, 0.0, 0.0};
+    Acc a = {loc, 0.0, 0.0, 0.0, 0.0, 0.0};
     a = block_reduce(a);
     return a.sum * alpha / (double)(K * (n + m));
   }
