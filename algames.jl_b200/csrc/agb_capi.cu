@@ -186,6 +186,8 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     if (need > have) take(need - have);
     o->o_Gp = o->o_Base; o->o_Gs = o->o_Base + (o->has_pairs ? N * o->npairs * 2 : 0);
   }
+  // the forward sweep lays a 4-stage ring of padded gain blocks (Inst::KUSP = m*(n+2)) over [o_P, end of Ta)
+  if (off - o->o_P < 4 * m * (n + 2)) take(4 * m * (n + 2) - (off - o->o_P));
   o->o_par = take(2 * n + 2 * m); o->o_red = take(6 * kMaxWarps);
   o->smem_doubles = off;
   return AGB_OK;
@@ -295,7 +297,7 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
     h->Z = h->results; h->L = h->Z + zs; h->stats = h->L + ls; h->status = (int*)(h->stats + ss);
   }
   CK(alloc_d(h, &h->conlam, B * K * t.nrow)); CK(alloc_d(h, &h->conmu, B * K * t.nrow));
-  CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 1)));
+  CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 2)));       // rows padded to n+2 (Inst::n1p)
   // descriptor defaults broadcast to every instance; μ starts at 1 (Altro ALConVal default)
   double tmp[2 * AGB_MAX_N + 2 * AGB_MAX_M];
   double* dtmp = nullptr;

@@ -60,7 +60,7 @@ struct Buffers {
   double* conlam;     // [B][K][nrow]
   double* conmu;
   double* D;          // [B][S] Newton step, internal stage-major layout
-  double* KUg;        // [B][K][m][n+1] feedback gains of the stage-wise factorisation (L2-resident scratch)
+  double* KUg;        // [B][K][m][n+2] (rows padded to even length) feedback gains of the stage-wise factorisation (L2-resident scratch)
   double* stats;      // [B][AGB_NSTATS]
   int* status;        // [B]
 };

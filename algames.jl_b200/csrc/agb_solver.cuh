@@ -15,6 +15,31 @@ namespace agb {
 
 #define AGB_FULL 0xffffffffu
 
+// 16-byte asynchronous global → shared copies (the emulator build copies synchronously)
+#ifndef AGB_EMULATE
+typedef unsigned SmemAddr;                                   // 32-bit shared-window address
+__device__ __forceinline__ SmemAddr smem_addr(double* p) { return (SmemAddr)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ SmemAddr smem_off(SmemAddr a, int doubles) { return a + 8u * (unsigned)doubles; }
+__device__ __forceinline__ void cp_async16(SmemAddr dst, const double* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+#else
+typedef double* SmemAddr;
+inline SmemAddr smem_addr(double* p) { return p; }
+inline SmemAddr smem_off(SmemAddr a, int doubles) { return a + doubles; }
+inline void cp_async16(SmemAddr dst, const double* gmem_src) { dst[0] = gmem_src[0]; dst[1] = gmem_src[1]; }
+#endif
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef AGB_EMULATE
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int NPENDING> __device__ __forceinline__ void cp_async_wait() {
+#ifndef AGB_EMULATE
+  asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory");
+#endif
+}
+
 struct Acc {            // norms of one residual evaluation (statistics.jl:44-57, violations.jl:18-168)
   double sum, opt, dyn, con, sta;
   double psum;          // Σ|row| without the proximal terms (trial evaluations that are kept, see Inst::residual)
@@ -133,6 +158,8 @@ __device__ __forceinline__ void rk3_step(int model, double dt, double lf, double
 template <int P, int MODEL>
 struct Inst {
   static constexpr int n = 4 * P, m = 2 * P, b = P * n + m + n, W = m + n + 1, KUS = m * (n + 1), n1 = n + 1;
+  // rows of the gain scratch in global memory are padded to an even length (16-byte row alignment for 128-bit loads)
+  static constexpr int n1p = n + 2, KUSP = m * n1p;
   static constexpr int OX = 0, OU = P * n, OD = P * n + m;     // offsets inside one stage of R: [rx(p·n) | ru(m) | rd(n)]
   static constexpr int NP = P * (P - 1);                       // ordered player pairs
   static constexpr int kThreads = threads_for(P);
@@ -198,7 +225,7 @@ struct Inst {
     Wm = sm + dd->o_W; Ta = sm + dd->o_Ta; xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
   }
-  __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUS; Rtrial = g.D + (size_t)inst * K * b; }
+  __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUSP; Rtrial = g.D + (size_t)inst * K * b; }
 
   // ---- iterate accessors; TRIAL reads Z + alpha·Δ with Δ held in R (update_traj!, primal_dual_traj.jl:109-128)
   template <bool TRIAL> __device__ __forceinline__ double xg(int k, int a, double alpha) const {
@@ -600,25 +627,23 @@ struct Inst {
     const bool act = lane < W;
 #pragma unroll
     for (int r = 0; r < m; r++) a[r] = act ? aug[r * W + lane] : 0.0;
-    bool weak = false;
+    bool weak = false;                                   // warp-uniform: evaluated on the broadcast pivot column
 #pragma unroll
     for (int t = 0; t < m; t++) {
-      if (lane == t) {
-        double cmax = 0.0;
-#pragma unroll
-        for (int r = t + 1; r < m; r++) cmax = fmax(cmax, fabs(a[r]));
-        if (!(fabs(a[t]) >= 0.01 * cmax) || !(fabs(a[t]) > 0.0) || isinf(a[t])) weak = true;
-      }
       const double pv = __shfl_sync(AGB_FULL, a[t], t);
       double f[m];
 #pragma unroll
       for (int r = 0; r < m; r++) f[r] = (r != t) ? __shfl_sync(AGB_FULL, a[r], t) : 0.0;
+      const double apv = fabs(pv), tpv = 100.0 * apv;
+      if (!(apv > 0.0 && apv <= 1.7976931348623157e308)) weak = true;
+#pragma unroll
+      for (int r = t + 1; r < m; r++) if (!(tpv >= fabs(f[r]))) weak = true;
       const double at = a[t] * fast_rcp(pv);
 #pragma unroll
       for (int r = 0; r < m; r++) if (r != t) a[r] = fma(-f[r], at, a[r]);
       a[t] = at;
     }
-    if (!__any_sync(AGB_FULL, weak)) {
+    if (!weak) {
       if (act) {
 #pragma unroll
         for (int r = 0; r < m; r++) aug[r * W + lane] = a[r];
@@ -777,7 +802,7 @@ struct Inst {
         }
       }
       __syncthreads();
-      for (int item = tid; item < m * n1; item += kThreads) KUg[s * KUS + item] = KU[item];
+      for (int item = tid; item < m * n1; item += kThreads) KUg[s * KUSP + (item / n1) * n1p + item % n1] = KU[item];
       if (s == 0) break;
       // ---- phase B: P ← Base − W K,  s ← base − W κ,  Y ← B_{s−1}ᵀ P
       for (int item = tid; item < P * n1; item += kThreads) {
@@ -833,54 +858,48 @@ struct Inst {
     __syncthreads();
     for (int s = K - 1; s >= 0; s--) {
       const double* Rs = R + s * b;
-      // ---- phase 1
-      for (int item = tid; item < m * W + P * n; item += kThreads) {
-        if (item < m * W) {
-          const int col = item % W, r = item / W;
+      // ---- phase 1: Aug = [Hu + Y B | Y A | Y rd + (Bᵀ s) + ru], items grouped by kind so that warps stay convergent
+      for (int item = tid; item < m * W; item += kThreads) {
+        double v;
+        int r, col;
+        if (item < m * m) {                                  // S block
+          r = item / m; col = item - r * m;
           const double* yr = Ym + r * n1;
-          double v;
-          if (col < m) {
-            const int j2 = col / P, i2 = col - j2 * P;
+          const int j2 = col / P, i2 = col - j2 * P;
+          double At[8], Bt[8]; loadAB(s, i2, At, Bt);
+          v = bt_dot_sel(j2, Bt, yr[i2], yr[P + i2], yr[2 * P + i2], yr[3 * P + i2]);
+          if (col == r) v += hu_entry(s, r, reg_u);
+        } else if (item < m * m + m * n) {                   // Y A block
+          const int it = item - m * m;
+          r = it / n; const int a2 = it - r * n; col = m + a2;
+          const double* yr = Ym + r * n1;
+          const int c2 = a2 / P, i2 = a2 - c2 * P;
+          v = yr[a2];
+          if (c2 >= 2) {
             double At[8], Bt[8]; loadAB(s, i2, At, Bt);
-            v = bt_dot_sel(j2, Bt, yr[i2], yr[P + i2], yr[2 * P + i2], yr[3 * P + i2]);
-            if (col == r) v += hu_entry(s, r, reg_u);
-          } else if (col < m + n) {
-            const int a2 = col - m, c2 = a2 / P, i2 = a2 - c2 * P;
-            v = yr[a2];
-            if (c2 >= 2) {
-              double At[8], Bt[8]; loadAB(s, i2, At, Bt);
-              v += at_dot_sel(c2 - 2, At, yr[i2], yr[P + i2], yr[2 * P + i2], yr[3 * P + i2]);
-            }
-          } else {
-            double v0 = yr[n] + Rs[OU + r], v1 = 0.0, v2 = 0.0, v3 = 0.0;
-#pragma unroll
-            for (int a2 = 0; a2 < n; a2 += 4) {
-              v0 += yr[a2] * Rs[OD + a2]; v1 += yr[a2 + 1] * Rs[OD + a2 + 1];
-              v2 += yr[a2 + 2] * Rs[OD + a2 + 2]; v3 += yr[a2 + 3] * Rs[OD + a2 + 3];
-            }
-            v = (v0 + v1) + (v2 + v3);
+            v += at_dot_sel(c2 - 2, At, yr[i2], yr[P + i2], yr[2 * P + i2], yr[3 * P + i2]);
           }
-          Aug[r * W + col] = v;
-        } else if (s > 0) {                                  // t_i[a] = s_i[a] + Σ_c P_i[a][c] rd[c]
-          const int it = item - m * W;
-          const double* pr = Pm + it * n;
-          double v0 = Sv[it], v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        } else {                                             // affine column
+          r = item - m * m - m * n; col = m + n;
+          const double* yr = Ym + r * n1;
+          double v0 = yr[n] + Rs[OU + r], v1 = 0.0, v2 = 0.0, v3 = 0.0;
 #pragma unroll
           for (int a2 = 0; a2 < n; a2 += 4) {
-            v0 += pr[a2] * Rs[OD + a2]; v1 += pr[a2 + 1] * Rs[OD + a2 + 1];
-            v2 += pr[a2 + 2] * Rs[OD + a2 + 2]; v3 += pr[a2 + 3] * Rs[OD + a2 + 3];
+            v0 += yr[a2] * Rs[OD + a2]; v1 += yr[a2 + 1] * Rs[OD + a2 + 1];
+            v2 += yr[a2 + 2] * Rs[OD + a2 + 2]; v3 += yr[a2 + 3] * Rs[OD + a2 + 3];
           }
-          Ta[it] = (v0 + v1) + (v2 + v3);
+          v = (v0 + v1) + (v2 + v3);
         }
+        Aug[r * W + col] = v;
       }
       __syncthreads();
       // ---- phase 2
       if (warp == 0) {
         if (!gj_warp(Aug)) ok = 0;
         if (lane >= m && lane < W) {
-          double* kg = KUg + s * KUS;
+          double* kg = KUg + s * KUSP;
 #pragma unroll
-          for (int r = 0; r < m; r++) { const double v = Aug[r * W + lane]; KU[r * n1 + (lane - m)] = v; kg[r * n1 + (lane - m)] = v; }
+          for (int r = 0; r < m; r++) { const double v = Aug[r * W + lane]; KU[r * n1 + (lane - m)] = v; kg[r * n1p + (lane - m)] = v; }
         }
       } else if (s > 0) {
         // item order groups equal work per warp: Base columns that need the A product (velocity/heading columns),
@@ -916,8 +935,18 @@ struct Inst {
               T2 += at_dot_sel(c2 - 2, At, p2[i3], p2[P + i3], p2[2 * P + i3], p2[3 * P + i3]);
               T3 += at_dot_sel(c2 - 2, At, p3[i3], p3[P + i3], p3[2 * P + i3], p3[3 * P + i3]);
             }
-          } else {                                          // T = t_i = P_i rd + s_i (phase 1)
-            T0 = Ta[i * n + i2]; T1 = Ta[i * n + P + i2]; T2 = Ta[i * n + 2 * P + i2]; T3 = Ta[i * n + 3 * P + i2];
+          } else {                                          // T = t_i = P_i rd + s_i, rows (·,i2)
+            const double* sv = Sv + i * n;
+            const double* rd = Rs + OD;
+            T0 = sv[i2]; T1 = sv[P + i2]; T2 = sv[2 * P + i2]; T3 = sv[3 * P + i2];
+            double U0 = 0.0, U1 = 0.0, U2 = 0.0, U3 = 0.0;
+#pragma unroll
+            for (int a2 = 0; a2 < n; a2 += 2) {
+              const double e0 = rd[a2], e1 = rd[a2 + 1];
+              T0 += p0[a2] * e0; T1 += p1[a2] * e0; T2 += p2[a2] * e0; T3 += p3[a2] * e0;
+              U0 += p0[a2 + 1] * e1; U1 += p1[a2 + 1] * e1; U2 += p2[a2 + 1] * e1; U3 += p3[a2 + 1] * e1;
+            }
+            T0 += U0; T1 += U1; T2 += U2; T3 += U3;
           }
           // Aᵀ = I + Atᵀ: rows c = 2,3 pick up Σ_q At[q][c-2] T[q]
           double At2[8], Bt2[8]; loadAB(s, i2, At2, Bt2);
@@ -998,114 +1027,148 @@ struct Inst {
     return ok != 0;
   }
 
+  // g_{i,k}[a] = r^x_{i,k}[a] + (H_{i,k} Δx_k)[a], k = s+1 (the opt-x row of player i without its multiplier terms)
+  __device__ __forceinline__ double costate_g(int i, int s, int a, double reg_x) const {
+    const int k = s + 1, c = a / P, ia = a - c * P;
+    const double* dx = R + s * b + OD;
+    double v = R[s * b + OX + i * n + a] + hd_entry(i, k, a, reg_x) * dx[a];
+    if (c < 2) {
+      if (ia == i) {
+        if (has_pairs) {
+#pragma unroll
+          for (int jj = 0; jj < P - 1; jj++) {
+            const int j = jj < i ? jj : jj + 1;
+            const double* hp = Hp + (k * NP + i * (P - 1) + jj) * 3;
+            v += hp[c] * (dx[i] - dx[j]) + hp[c + 1] * (dx[P + i] - dx[P + j]);
+          }
+        }
+        if (has_self) { const double* hs = Hs + (k * P + i) * 3; v += hs[c] * dx[i] + hs[c + 1] * dx[P + i]; }
+      } else if (has_pairs) {
+        const double* hp = Hp + (k * NP + pair_index(i, ia)) * 3;
+        v -= hp[c] * (dx[i] - dx[ia]) + hp[c + 1] * (dx[P + i] - dx[P + ia]);
+      }
+    }
+    return v;
+  }
+
   // forward sweep + costate recursion shared by the game and the best-response factorisations
   __device__ void forward_and_costate(double reg_x) {
-    // ---- forward sweep (warp 0): Δu_s = −Ku Δx_s − ku,  Δx_{s+1} = A Δx_s + B Δu_s + rd.  The gains come back from the
-    // L2-resident scratch through a 4-deep register ring (each load has three stage-times to land), staged through
-    // the one-stage smem buffer.
+    // ---- forward sweep (warp 0): Δu_s = −Ku Δx_s − ku,  Δx_{s+1} = A Δx_s + B Δu_s + rd.  Δx_s lives in registers (lane a
+    // owns component a and recomputes its player's two controls), so the only dependent chain per stage is
+    // shuffle-broadcast → dot product → A/B update.  The gains come back from the L2-resident scratch with cp.async into
+    // a 4-stage shared-memory ring laid over the factorisation's scratch (P, s, Y, Aug, Base …: free at this point).
     if (warp == 0) {
-      constexpr int NQ = (KUS + 31) / 32, DEPTH = 4;
-      double ring[DEPTH][NQ];
+      constexpr int DEPTH = 4, NV = KUSP / 2;             // 16-byte vectors per stage
+      constexpr int NI = (NV + 31) / 32;
+      double* const ring = Pm;
+      const SmemAddr ring_s = smem_off(smem_addr(ring), 2 * lane);
+      const double* gsrc = KUg + 2 * lane;                // next stage to fetch
+      int s_fetch = 0;
       __syncwarp();
 #pragma unroll
-      for (int dd = 0; dd < DEPTH; dd++) {
+      for (int dd = 0; dd < DEPTH - 1; dd++) {
+        if (s_fetch < K) {
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-          const int idx = lane + 32 * q;
-          ring[dd][q] = (idx < KUS && dd < K) ? KUg[dd * KUS + idx] : 0.0;
+          for (int q = 0; q < NI; q++)
+            if (lane + 32 * q < NV) cp_async16(smem_off(ring_s, dd * KUSP + 64 * q), gsrc + 64 * q);
         }
+        cp_async_commit();
+        gsrc += KUSP; s_fetch++;
       }
+      const bool act = lane < n;
+      const int c = act ? lane / P : 0, i = act ? lane - c * P : 0;
+      double at0 = 0.0, at1 = 0.0, bt0 = 0.0, bt1 = 0.0;   // row c of [At | Bt] of player i (constant for the double integrator)
+      if constexpr (MODEL == AGB_MODEL_DOUBLE_INTEGRATOR) {
+        double At[8], Bt[8]; loadAB(0, i, At, Bt);
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (q == c) { at0 = At[2 * q]; at1 = At[2 * q + 1]; bt0 = Bt[2 * q]; bt1 = Bt[2 * q + 1]; }
+      }
+      const double* krow0 = ring + i * n1p;               // gain rows of player i's two controls inside a ring slot
+      const double* krow1 = ring + (P + i) * n1p;
+      double* rdp = R + OD + (act ? lane : 0);            // rd_s[lane] / Δx_{s+1}[lane]
+      double* up = R + OU + (c == 0 ? i : P + i);         // Δu slot written by the lanes of component rows 0 and 1
+      const double2* dxp = reinterpret_cast<const double2*>(R + OD) ;   // Δx_s = row s-1 (unused at s = 0)
+      const double* abp = AB + i * 16;
       for (int s0 = 0; s0 < K; s0 += DEPTH) {
 #pragma unroll
         for (int dd = 0; dd < DEPTH; dd++) {
           const int s = s0 + dd;
           if (s < K) {
+            cp_async_wait<DEPTH - 2>();                   // this lane's pieces of stage s have landed …
+            __syncwarp();                                 // … everyone's have, Δx_s is visible, and slot (dd+3)%4 is free
+            if (s_fetch < K) {
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-              const int idx = lane + 32 * q;
-              if (idx < KUS) KU[idx] = ring[dd][q];
-              if (idx < KUS && s + DEPTH < K) ring[dd][q] = KUg[(s + DEPTH) * KUS + idx];
+              for (int q = 0; q < NI; q++)
+                if (lane + 32 * q < NV) cp_async16(smem_off(ring_s, ((dd + DEPTH - 1) % DEPTH) * KUSP + 64 * q), gsrc + 64 * q);
             }
-            __syncwarp();
-            const double* ku = KU;
-            double* Rs = R + s * b;
-            const double* dxp = R + (s - 1) * b + OD;      // Δx_s (only read when s > 0)
-            if (lane < m) {
-              double a0 = ku[lane * n1 + n], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-              if (s > 0) {
+            cp_async_commit();
+            gsrc += KUSP; s_fetch++;
+            const double2* k0 = reinterpret_cast<const double2*>(krow0 + dd * KUSP);
+            const double2* k1 = reinterpret_cast<const double2*>(krow1 + dd * KUSP);
+            if constexpr (MODEL != AGB_MODEL_DOUBLE_INTEGRATOR) {
+              const double2* ab = reinterpret_cast<const double2*>(abp);
+              const double2 ar = ab[c], br = ab[4 + c];
+              at0 = ar.x; at1 = ar.y; bt0 = br.x; bt1 = br.y;
+              abp += P * 16;
+            }
+            const double rd = *rdp;
+            const double2 kap0 = k0[n / 2], kap1 = k1[n / 2];
+            double a0 = kap0.x, a1 = 0.0, b0 = kap1.x, b1 = 0.0, dxl = 0.0, y0 = 0.0, y1 = 0.0;
+            if (s > 0) {
+              const double2* dx = dxp - b / 2;            // row s-1
+              dxl = rdp[-b];
+              y0 = (R + OD + 2 * P + i)[(s - 1) * b]; y1 = (R + OD + 3 * P + i)[(s - 1) * b];
 #pragma unroll
-                for (int a = 0; a < n; a += 4) {
-                  a0 += ku[lane * n1 + a] * dxp[a]; a1 += ku[lane * n1 + a + 1] * dxp[a + 1];
-                  a2 += ku[lane * n1 + a + 2] * dxp[a + 2]; a3 += ku[lane * n1 + a + 3] * dxp[a + 3];
-                }
+              for (int a = 0; a < n / 2; a += 2) {
+                const double2 x0 = dx[a], x1 = dx[a + 1], p0 = k0[a], p1 = k0[a + 1], q0 = k1[a], q1 = k1[a + 1];
+                a0 += p0.x * x0.x; a1 += p0.y * x0.y; a0 += p1.x * x1.x; a1 += p1.y * x1.y;
+                b0 += q0.x * x0.x; b1 += q0.y * x0.y; b0 += q1.x * x1.x; b1 += q1.y * x1.y;
               }
-              Rs[OU + lane] = -((a0 + a1) + (a2 + a3));
             }
-            __syncwarp();
-            double v = 0.0;
-            if (lane < n) {
-              const int c = lane / P, i = lane - c * P;
-              double At[8], Bt[8]; loadAB(s, i, At, Bt);
-              v = Rs[OD + lane];
-              const double u0 = Rs[OU + i], u1 = Rs[OU + P + i];
-              double y0 = 0.0, y1 = 0.0;
-              if (s > 0) { v += dxp[lane]; y0 = dxp[2 * P + i]; y1 = dxp[3 * P + i]; }
-              if (c == 0) v += at_row<0>(At, y0, y1) + bt_row<0>(Bt, u0, u1);
-              else if (c == 1) v += at_row<1>(At, y0, y1) + bt_row<1>(Bt, u0, u1);
-              else if (c == 2) v += at_row<2>(At, y0, y1) + bt_row<2>(Bt, u0, u1);
-              else v += at_row<3>(At, y0, y1) + bt_row<3>(Bt, u0, u1);
+            const double u0 = -(a0 + a1), u1 = -(b0 + b1);
+            const double v = (rd + dxl) + ((at0 * y0 + at1 * y1) + (bt0 * u0 + bt1 * u1));
+            if (act) {
+              *rdp = v;
+              if (c < 2) *up = (c == 0) ? u0 : u1;
             }
-            __syncwarp();
-            if (lane < n) Rs[OD + lane] = v;
-            __syncwarp();
+            rdp += b; up += b; dxp += b / 2;
           }
         }
       }
+      cp_async_wait<0>();
     }
     __syncthreads();
-    // ---- costate: g_{i,k} = H_{i,k} Δx_k + r^x_{i,k} (parallel), then Δλ_{i,k−1} = g_{i,k} + A_kᵀ Δλ_{i,k} (per-player warp)
+    // ---- costate: Δλ_{i,k−1} = g_{i,k} + A_kᵀ Δλ_{i,k} with g_{i,k} = H_{i,k} Δx_k + r^x_{i,k} (exactly the opt-x rows).
+    // One warp per player, Δλ in registers (lane a owns component a); g of the next step is evaluated ahead of the
+    // dependent shuffle → Aᵀ chain.
     for (int item = tid; item < P * K * n; item += kThreads) {
       const int a = item % n, t = item / n;
-      const int s = t % K, i = t / K, k = s + 1;
-      const int c = a / P, ia = a - c * P;
-      if (pl >= 0 && i != pl) { R[s * b + OX + i * n + a] = 0.0; continue; }       // IBR: Δλ_j = 0 for j != pl
-      const double* dx = R + s * b + OD;
-      double v = R[s * b + OX + i * n + a] + hd_entry(i, k, a, reg_x) * dx[a];
-      if (c < 2) {
-        if (ia == i) {
-          if (has_pairs) {
-#pragma unroll
-            for (int jj = 0; jj < P - 1; jj++) {
-              const int j = jj < i ? jj : jj + 1;
-              const double* hp = Hp + (k * NP + i * (P - 1) + jj) * 3;
-              v += hp[c] * (dx[i] - dx[j]) + hp[c + 1] * (dx[P + i] - dx[P + j]);
-            }
-          }
-          if (has_self) { const double* hs = Hs + (k * P + i) * 3; v += hs[c] * dx[i] + hs[c + 1] * dx[P + i]; }
-        } else if (has_pairs) {
-          const double* hp = Hp + (k * NP + pair_index(i, ia)) * 3;
-          v -= hp[c] * (dx[i] - dx[ia]) + hp[c + 1] * (dx[P + i] - dx[P + ia]);
-        }
-      }
-      R[s * b + OX + i * n + a] = v;
+      const int s = t % K, i = t / K;
+      R[s * b + OX + i * n + a] = (pl >= 0 && i != pl) ? 0.0 : costate_g(i, s, a, reg_x);       // IBR: Δλ_j = 0 for j != pl
     }
     __syncthreads();
     if (warp < P && (pl < 0 || warp == pl)) {
       const int i = warp;
-      for (int s = K - 2; s >= 0; s--) {
-        double v = 0.0;
-        if (lane < n) {
-          const int c = lane / P, ia = lane - c * P;
-          const double* ln = R + (s + 1) * b + OX + i * n;
-          v = R[s * b + OX + i * n + lane] + ln[lane];
+      const bool act = lane < n;
+      const int a = act ? lane : 0, c = a / P, ia = a - c * P;
+      const double* gi = R + OX + i * n + a;
+      double ln = 0.0;
+      double g = gi[(K - 1) * b];
+      for (int s = K - 1; s >= 0; s--) {
+        const double gn = (s > 0) ? gi[(s - 1) * b] : 0.0;
+        double v = g;
+        if (s < K - 1) {
+          const double l0 = __shfl_sync(AGB_FULL, ln, ia), l1 = __shfl_sync(AGB_FULL, ln, P + ia);
+          const double l2 = __shfl_sync(AGB_FULL, ln, 2 * P + ia), l3 = __shfl_sync(AGB_FULL, ln, 3 * P + ia);
+          v += ln;
           if (c >= 2) {
             double At[8], Bt[8]; loadAB(s + 1, ia, At, Bt);
-            v += at_dot_sel(c - 2, At, ln[ia], ln[P + ia], ln[2 * P + ia], ln[3 * P + ia]);
+            v += at_dot_sel(c - 2, At, l0, l1, l2, l3);
           }
         }
-        __syncwarp();
-        if (lane < n) R[s * b + OX + i * n + lane] = v;
-        __syncwarp();
+        if (act) R[s * b + OX + i * n + lane] = v;
+        ln = v;
+        g = gn;
       }
     }
     __syncthreads();
