@@ -173,13 +173,13 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
   int off = 0;
   auto take = [&](int cnt) { int r = off; off += (cnt + 1) & ~1; return r; };
   o->o_X = take(N * n); o->o_U = take(N * m); o->o_L = take(p * K * n); o->o_R = take(K * o->b);
-  o->o_KU = take(m * (n + 1));                 // gains of the current stage only; all stages live in Buffers::KUg
   o->o_AB = take(d->model == AGB_MODEL_DOUBLE_INTEGRATOR ? 0 : K * p * 16);
   o->o_CL = take(K * o->nrow); o->o_CM = take(K * o->nrow);
   o->o_CW = take((o->has_sb || o->has_cb) ? K * o->nrow : 0);     // pair / wall / circle weights are folded into Hp / Hs
   o->o_Hp = take(o->has_pairs ? N * o->npairs * 3 : 0); o->o_Hs = take(o->has_self ? N * p * 3 : 0);
   o->o_P = take(p * n * n); o->o_Sv = take(p * n); o->o_Y = take(m * (n + 1)); o->o_Aug = take(m * W);
-  o->o_Base = take(p * n * (n + 1)); o->o_W = take(p * n * m); o->o_Ta = take(p * n);
+  o->o_KU = o->o_Aug;                          // one-stage gain buffer of the best-response factorisation (Aug is unused there)
+  o->o_Base = take(p * n * (n + 1)); o->o_W = take(p * n * m); o->o_Ta = take(2 * p * (4 * p * p + n));   // Hm: double-buffered per-stage H^x blocks (Inst::HmS per player)
   {  // Gp / Gs live only inside one residual evaluation, Base / W / Ta only inside kkt_solve: alias them when they fit
     const int need = (o->has_pairs ? N * o->npairs * 2 : 0) + (o->has_self ? N * p * 2 : 0);
     const int have = off - o->o_Base;

@@ -160,6 +160,9 @@ struct Inst {
   static constexpr int n = 4 * P, m = 2 * P, b = P * n + m + n, W = m + n + 1, KUS = m * (n + 1), n1 = n + 1;
   // rows of the gain scratch in global memory are padded to an even length (16-byte row alignment for 128-bit loads)
   static constexpr int n1p = n + 2, KUSP = m * n1p;
+  // per-stage H^x_{i,s} in compact form: dense 2P x 2P position block + diagonal, per player (kkt_solve phases 2/3)
+  static constexpr int HmS = 4 * P * P + n;
+  static constexpr int HB = 32 + ((P * n + 31) / 32) * 32;      // first thread of the H builders (after GJ warp + row threads)
   static constexpr int OX = 0, OU = P * n, OD = P * n + m;     // offsets inside one stage of R: [rx(p·n) | ru(m) | rd(n)]
   static constexpr int NP = P * (P - 1);                       // ordered player pairs
   static constexpr int kThreads = threads_for(P);
@@ -209,7 +212,7 @@ struct Inst {
   int N, K, nrow, has_cc, has_pairs, has_self, has_sb, has_cb;
   static constexpr int model = MODEL;
   double dt;
-  double *X, *U, *L, *R, *KU, *AB, *CL, *CM, *CW, *Gp, *Hp, *Gs, *Hs, *Pm, *Sv, *Ym, *Aug, *Base, *Wm, *Ta, *xf, *Q, *Rw, *uf, *red;
+  double *X, *U, *L, *R, *KU, *AB, *CL, *CM, *CW, *Gp, *Hp, *Gs, *Hs, *Pm, *Sv, *Ym, *Aug, *Base, *Wm, *Hm, *xf, *Q, *Rw, *uf, *red;
   double* KUg;            // this instance's slice of Buffers::KUg (global)
   double* Rtrial;         // global scratch [S]: un-regularised residual rows of the last trial point (reused if accepted)
   bool keep;              // trial evaluation also produces what the next inner iteration needs (rows, Hessian blocks)
@@ -222,7 +225,7 @@ struct Inst {
     X = sm + dd->o_X; U = sm + dd->o_U; L = sm + dd->o_L; R = sm + dd->o_R; KU = sm + dd->o_KU; AB = sm + dd->o_AB;
     CL = sm + dd->o_CL; CM = sm + dd->o_CM; CW = sm + dd->o_CW; Gp = sm + dd->o_Gp; Hp = sm + dd->o_Hp; Gs = sm + dd->o_Gs;
     Hs = sm + dd->o_Hs; Pm = sm + dd->o_P; Sv = sm + dd->o_Sv; Ym = sm + dd->o_Y; Aug = sm + dd->o_Aug; Base = sm + dd->o_Base;
-    Wm = sm + dd->o_W; Ta = sm + dd->o_Ta; xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
+    Wm = sm + dd->o_W; Hm = sm + dd->o_Ta; xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
   }
   __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUSP; Rtrial = g.D + (size_t)inst * K * b; }
@@ -830,6 +833,35 @@ struct Inst {
     return ok != 0;
   }
 
+  // H^x_{i,s} of every player in compact dense form (position block [2P][2P], then the diagonal), one thread per
+  // 2x2 position block (i; i2, ib); laid out one stage ahead of its use by spare warps of the factorisation
+  __device__ void build_hm(double* hmb, int s, double reg_x, int t0, int stride) {
+    for (int blk = t0; blk >= 0 && blk < P * P * P; blk += stride) {
+      const int i = blk / (P * P), rem = blk - i * P * P, i2 = rem / P, ib = rem - i2 * P;
+      double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+      if (i2 == ib) {
+        if (i2 == i) {
+          if (has_pairs) {
+#pragma unroll
+            for (int jj = 0; jj < P - 1; jj++) { const double* hp = Hp + (s * NP + i * (P - 1) + jj) * 3; h0 += hp[0]; h1 += hp[1]; h2 += hp[2]; }
+          }
+          if (has_self) { const double* hs = Hs + (s * P + i) * 3; h0 += hs[0]; h1 += hs[1]; h2 += hs[2]; }
+        } else if (has_pairs) {
+          const double* hp = Hp + (s * NP + pair_index(i, i2)) * 3; h0 = hp[0]; h1 = hp[1]; h2 = hp[2];
+        }
+      } else if (has_pairs && (i2 == i || ib == i)) {
+        const double* hp = Hp + (s * NP + pair_index(i, i2 == i ? ib : i2)) * 3; h0 = -hp[0]; h1 = -hp[1]; h2 = -hp[2];
+      }
+      double* hm = hmb + i * HmS;
+      hm[i2 * (2 * P) + ib] = h0; hm[i2 * (2 * P) + P + ib] = h1;
+      hm[(P + i2) * (2 * P) + ib] = h1; hm[(P + i2) * (2 * P) + P + ib] = h2;
+      if (i2 == ib) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) hm[4 * P * P + c * P + i2] = hd_entry(i, s, c * P + i2, reg_x);
+      }
+    }
+  }
+
   // ---------------------------------------------------------------------------------------------------------
   // Δtraj = −(lu(jac) \ res)  (solver_methods.jl:87-88): R holds res on entry, Δ on exit (same stage-major slots:
   // rx(i,s) → Δλ_{i,s}, ru(s) → Δu_s, rd(s) → Δx_{s+1}).  Returns false on a singular / non-finite pivot.
@@ -853,6 +885,7 @@ struct Inst {
       int a = item % n, i = item / n;
       Sv[item] = R[(K - 1) * b + OX + i * n + a];
     }
+    if (K - 1 > 0) build_hm(Hm + ((K - 1) & 1) * P * HmS, K - 1, reg_x, tid, kThreads);
     __syncthreads();
     compute_Y(K - 1);
     __syncthreads();
@@ -899,109 +932,82 @@ struct Inst {
         if (lane >= m && lane < W) {
           double* kg = KUg + s * KUSP;
 #pragma unroll
-          for (int r = 0; r < m; r++) { const double v = Aug[r * W + lane]; KU[r * n1 + (lane - m)] = v; kg[r * n1p + (lane - m)] = v; }
+          for (int r = 0; r < m; r++) kg[r * n1p + (lane - m)] = Aug[r * W + lane];      // K, κ stay in Aug for phase 3
         }
       } else if (s > 0) {
-        // item order groups equal work per warp: Base columns that need the A product (velocity/heading columns),
-        // W columns, Base columns that are plain copies (position columns), affine column
-        constexpr int NH = P * P * 2 * P, NW = P * P * m, NC = P * P * 2 * P, NA = P * P;
-        for (int item = tid - 32; item < NH + NW + NC + NA; item += kThreads - 32) {
-          int kind, col, t;                                 // 0: Base column, 1: W column, 2: affine
-          if (item < NH) { kind = 0; col = 2 * P + item % (2 * P); t = item / (2 * P); }
-          else if (item < NH + NW) { kind = 1; col = (item - NH) % m; t = (item - NH) / m; }
-          else if (item < NH + NW + NC) { kind = 0; col = (item - NH - NW) % (2 * P); t = (item - NH - NW) / (2 * P); }
-          else { kind = 2; col = n; t = item - NH - NW - NC; }
-          const int i2 = t % P, i = t / P;                  // rows (·,i2) of player i's matrices
+        // one thread per row a = (c,i2) of player i's Base_i = H_{i,s} + Aᵀ P_i A, W_i = Aᵀ P_i B and base_i:
+        // X = (Aᵀ P_i)[a,:] is a combination of at most four rows of P_i held in registers; A and B are block diagonal
+        // per player, so the columns of player i3 need only X[(·,i3)], with the models' zero structure compiled out
+        for (int row = tid - 32; row < P * n; row += kThreads - 32) {
+          const int i = row / n, a = row - i * n, c = a / P, i2 = a - c * P;
           const double* Pi = Pm + i * n * n;
-          const double* p0 = Pi + (0 * P + i2) * n;
-          const double* p1 = Pi + (1 * P + i2) * n;
-          const double* p2 = Pi + (2 * P + i2) * n;
-          const double* p3 = Pi + (3 * P + i2) * n;
-          double T0, T1, T2, T3;
-          if (kind == 1) {                                  // T = (P_i B)[(q,i2)][col],  col = (j,i3)
-            const int j = col / P, i3 = col - j * P;
-            double At[8], Bt[8]; loadAB(s, i3, At, Bt);
-            T0 = bt_dot_sel(j, Bt, p0[i3], p0[P + i3], p0[2 * P + i3], p0[3 * P + i3]);
-            T1 = bt_dot_sel(j, Bt, p1[i3], p1[P + i3], p1[2 * P + i3], p1[3 * P + i3]);
-            T2 = bt_dot_sel(j, Bt, p2[i3], p2[P + i3], p2[2 * P + i3], p2[3 * P + i3]);
-            T3 = bt_dot_sel(j, Bt, p3[i3], p3[P + i3], p3[2 * P + i3], p3[3 * P + i3]);
-          } else if (kind == 0) {                           // T = (P_i A)[(q,i2)][col],  col = (c2,i3)
-            const int c2 = col / P, i3 = col - c2 * P;
-            T0 = p0[col]; T1 = p1[col]; T2 = p2[col]; T3 = p3[col];
-            if (c2 >= 2) {
-              double At[8], Bt[8]; loadAB(s, i3, At, Bt);
-              T0 += at_dot_sel(c2 - 2, At, p0[i3], p0[P + i3], p0[2 * P + i3], p0[3 * P + i3]);
-              T1 += at_dot_sel(c2 - 2, At, p1[i3], p1[P + i3], p1[2 * P + i3], p1[3 * P + i3]);
-              T2 += at_dot_sel(c2 - 2, At, p2[i3], p2[P + i3], p2[2 * P + i3], p2[3 * P + i3]);
-              T3 += at_dot_sel(c2 - 2, At, p3[i3], p3[P + i3], p3[2 * P + i3], p3[3 * P + i3]);
-            }
-          } else {                                          // T = t_i = P_i rd + s_i, rows (·,i2)
-            const double* sv = Sv + i * n;
-            const double* rd = Rs + OD;
-            T0 = sv[i2]; T1 = sv[P + i2]; T2 = sv[2 * P + i2]; T3 = sv[3 * P + i2];
-            double U0 = 0.0, U1 = 0.0, U2 = 0.0, U3 = 0.0;
+          const double* sv = Sv + i * n;
+          double X[n];
+          {
+            const double2* pr = reinterpret_cast<const double2*>(Pi + a * n);
 #pragma unroll
-            for (int a2 = 0; a2 < n; a2 += 2) {
-              const double e0 = rd[a2], e1 = rd[a2 + 1];
-              T0 += p0[a2] * e0; T1 += p1[a2] * e0; T2 += p2[a2] * e0; T3 += p3[a2] * e0;
-              U0 += p0[a2 + 1] * e1; U1 += p1[a2 + 1] * e1; U2 += p2[a2 + 1] * e1; U3 += p3[a2 + 1] * e1;
-            }
-            T0 += U0; T1 += U1; T2 += U2; T3 += U3;
+            for (int q = 0; q < n / 2; q++) { const double2 v = pr[q]; X[2 * q] = v.x; X[2 * q + 1] = v.y; }
           }
-          // Aᵀ = I + Atᵀ: rows c = 2,3 pick up Σ_q At[q][c-2] T[q]
-          double At2[8], Bt2[8]; loadAB(s, i2, At2, Bt2);
-          const double o[4] = {T0, T1, T2 + at_dot<0>(At2, T0, T1, T2, T3), T3 + at_dot<1>(At2, T0, T1, T2, T3)};
-          if (kind == 1) {
+          double xs = sv[a];
+          if (c >= 2) {
+            if constexpr (MODEL == AGB_MODEL_DOUBLE_INTEGRATOR) {            // Aᵀ[(c,i2)][(c-2,i2)] = dt
+              const double2* pq = reinterpret_cast<const double2*>(Pi + ((c - 2) * P + i2) * n);
 #pragma unroll
-            for (int c = 0; c < 4; c++) Wm[(i * n + c * P + i2) * m + col] = o[c];
-          } else if (kind == 0) {
-            const int c2 = col / P, i3 = col - c2 * P;
-            double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;     // H^x_{i,s}[(c,i2)][col], c = 0..3
-            if (c2 < 2) {                                        // position block: ±Hp of one pair, or the own-block sum
-              if (i2 == i3) {
-                if (i2 == i) {
-                  if (has_pairs) {
+              for (int q = 0; q < n / 2; q++) { const double2 v = pq[q]; X[2 * q] = fma(dt, v.x, X[2 * q]); X[2 * q + 1] = fma(dt, v.y, X[2 * q + 1]); }
+              xs = fma(dt, sv[(c - 2) * P + i2], xs);
+            } else {
+              double At2[8], Bt2[8]; loadAB(s, i2, At2, Bt2);
 #pragma unroll
-                    for (int jj = 0; jj < P - 1; jj++) {
-                      const double* hp = Hp + (s * NP + i * (P - 1) + jj) * 3 + c2;
-                      h0 += hp[0]; h1 += hp[1];
-                    }
-                  }
-                  if (has_self) { const double* hs = Hs + (s * P + i) * 3 + c2; h0 += hs[0]; h1 += hs[1]; }
-                } else if (has_pairs) {
-                  const double* hp = Hp + (s * NP + pair_index(i, i2)) * 3 + c2;
-                  h0 = hp[0]; h1 = hp[1];
+              for (int q = 0; q < 4; q++) {
+                if (((AT_NZ >> (2 * q)) & 3u) != 0u) {                       // row q of Ã has a structural non-zero
+                  const double cf = (c == 2) ? At2[2 * q] : At2[2 * q + 1];
+                  const double2* pq = reinterpret_cast<const double2*>(Pi + (q * P + i2) * n);
+#pragma unroll
+                  for (int q2 = 0; q2 < n / 2; q2++) { const double2 v = pq[q2]; X[2 * q2] = fma(cf, v.x, X[2 * q2]); X[2 * q2 + 1] = fma(cf, v.y, X[2 * q2 + 1]); }
+                  xs = fma(cf, sv[q * P + i2], xs);
                 }
-              } else if (has_pairs && (i2 == i || i3 == i)) {
-                const double* hp = Hp + (s * NP + pair_index(i, i2 == i ? i3 : i2)) * 3 + c2;
-                h0 = -hp[0]; h1 = -hp[1];
               }
             }
-            if (i2 == i3) {
-              const double hd = hd_entry(i, s, col, reg_x);
-              if (c2 == 0) h0 += hd; else if (c2 == 1) h1 += hd; else if (c2 == 2) h2 = hd; else h3 = hd;
-            }
-            Base[(i * n + 0 * P + i2) * n1 + col] = o[0] + h0;
-            Base[(i * n + 1 * P + i2) * n1 + col] = o[1] + h1;
-            Base[(i * n + 2 * P + i2) * n1 + col] = o[2] + h2;
-            Base[(i * n + 3 * P + i2) * n1 + col] = o[3] + h3;
-          } else {
+          }
+          double* brow = Base + (i * n + a) * n1;
+          double* wrow = Wm + (i * n + a) * m;
+          {                                                                  // affine: r^x_{i,s}[a] + (Aᵀ(P_i rd + s_i))[a]
+            const double2* rd2 = reinterpret_cast<const double2*>(Rs + OD);
+            double v0 = xs + R[(s - 1) * b + OX + i * n + a], v1 = 0.0;
 #pragma unroll
-            for (int c = 0; c < 4; c++) Base[(i * n + c * P + i2) * n1 + n] = o[c] + R[(s - 1) * b + OX + i * n + c * P + i2];
+            for (int q = 0; q < n / 2; q++) { const double2 e = rd2[q]; v0 = fma(X[2 * q], e.x, v0); v1 = fma(X[2 * q + 1], e.y, v1); }
+            brow[n] = v0 + v1;
+          }
+          const double* hm = Hm + (s & 1) * P * HmS + i * HmS;            // H^x_{i,s}, laid out during the previous stage
+          const double hd = hm[4 * P * P + a];
+          const double* hrow = hm + (c < 2 ? a : 0) * (2 * P);
+#pragma unroll
+          for (int i3 = 0; i3 < P; i3++) {
+            double At3[8], Bt3[8]; loadAB(s, i3, At3, Bt3);
+            const double x0 = X[i3], x1 = X[P + i3], x2 = X[2 * P + i3], x3 = X[3 * P + i3];
+            double o0 = x0, o1 = x1;
+            double o2 = x2 + at_dot<0>(At3, x0, x1, x2, x3), o3 = x3 + at_dot<1>(At3, x0, x1, x2, x3);
+            if (c < 2) { o0 += hrow[i3]; o1 += hrow[P + i3]; }
+            if (i3 == i2) { if (c == 0) o0 += hd; else if (c == 1) o1 += hd; else if (c == 2) o2 += hd; else o3 += hd; }
+            brow[i3] = o0; brow[P + i3] = o1; brow[2 * P + i3] = o2; brow[3 * P + i3] = o3;
+            wrow[i3] = bt_dot<0>(Bt3, x0, x1, x2, x3);
+            wrow[P + i3] = bt_dot<1>(Bt3, x0, x1, x2, x3);
           }
         }
+        // the remaining warps lay out H^x_{i,s-1} for the next stage
+        if (s - 1 > 0) build_hm(Hm + ((s - 1) & 1) * P * HmS, s - 1, reg_x, tid - HB, kThreads - HB);
       }
       __syncthreads();
       if (s == 0) break;
       // ---- phase 3
       {
-        const double* ku = KU;
+        const double* ku = Aug + m;                         // K | κ: columns m.. of the reduced system
         for (int item = tid; item < P * P * n1; item += kThreads) {
           const int col = item % n1, t = item / n1;
           const int i2 = t % P, i = t / P;
           double kc[m];
 #pragma unroll
-          for (int r = 0; r < m; r++) kc[r] = ku[r * n1 + col];
+          for (int r = 0; r < m; r++) kc[r] = ku[r * W + col];
           double pn[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
