@@ -520,8 +520,8 @@ struct Inst {
     __syncthreads();
     const int nx = P * K * n;
     for (int item = tid; item < nx; item += kThreads) {
-      int a = item % n, t = item / n;
-      int s = t % K, i = t / K;
+      const int s = item / (P * n), rem = item - s * (P * n);                // stage-major: compile-time divisors only
+      const int i = rem / n, a = rem - i * n;
       if (pl >= 0 && i != pl) { if (Rout) Rout[s * b + OX + i * n + a] = 0.0; continue; }    // IBR: rows of player pl only
       double pv;
       double v = xrow_elem<TRIAL>(i, s + 1, a, alpha, reg_x, acc, pv);
@@ -633,10 +633,18 @@ struct Inst {
     bool weak = false;                                   // warp-uniform: evaluated on the broadcast pivot column
 #pragma unroll
     for (int t = 0; t < m; t++) {
-      const double pv = __shfl_sync(AGB_FULL, a[t], t);
+      // pivot column t → every lane, through shared memory (Ym is free between phases 1 and 3; one slot per step)
+      double2* piv = reinterpret_cast<double2*>(Ym + t * m);
+      if (lane == t) {
+#pragma unroll
+        for (int r = 0; r < m; r += 2) piv[r / 2] = make_double2(a[r], a[r + 1]);
+      }
+      __syncwarp();
       double f[m];
 #pragma unroll
-      for (int r = 0; r < m; r++) f[r] = (r != t) ? __shfl_sync(AGB_FULL, a[r], t) : 0.0;
+      for (int r = 0; r < m; r += 2) { const double2 v = piv[r / 2]; f[r] = v.x; f[r + 1] = v.y; }
+      const double pv = f[t];
+      f[t] = 0.0;
       const double apv = fabs(pv), tpv = 100.0 * apv;
       if (!(apv > 0.0 && apv <= 1.7976931348623157e308)) weak = true;
 #pragma unroll
@@ -1148,9 +1156,9 @@ struct Inst {
     // One warp per player, Δλ in registers (lane a owns component a); g of the next step is evaluated ahead of the
     // dependent shuffle → Aᵀ chain.
     for (int item = tid; item < P * K * n; item += kThreads) {
-      const int a = item % n, t = item / n;
-      const int s = t % K, i = t / K;
-      R[s * b + OX + i * n + a] = (pl >= 0 && i != pl) ? 0.0 : costate_g(i, s, a, reg_x);       // IBR: Δλ_j = 0 for j != pl
+      const int s = item / (P * n), rem = item - s * (P * n);
+      const int i = rem / n, a = rem - i * n;
+      R[s * b + OX + rem] = (pl >= 0 && i != pl) ? 0.0 : costate_g(i, s, a, reg_x);             // IBR: Δλ_j = 0 for j != pl
     }
     __syncthreads();
     if (warp < P && (pl < 0 || warp == pl)) {

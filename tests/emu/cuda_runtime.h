@@ -27,6 +27,7 @@
 
 struct emu_dim3 { unsigned x, y, z; };
 struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 extern emu_dim3 threadIdx, blockIdx, gridDim, blockDim;
 
 namespace emu {
