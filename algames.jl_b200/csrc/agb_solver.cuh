@@ -40,6 +40,18 @@ template <int NPENDING> __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
+// Handle of one array inside the CTA's dynamic shared memory: a 32-bit offset (in doubles) from the window base, so that
+// the compiler addresses it as [offset + constant] instead of carrying 64-bit generic pointers through the kernel.
+#ifndef AGB_EMULATE
+__device__ __forceinline__ double* smem_base() { extern __shared__ __align__(16) double agb_smem_[]; return agb_smem_; }
+#else
+inline double* smem_base() { return emu::st().smem; }
+#endif
+struct SP {
+  int off;
+  __device__ __forceinline__ operator double*() const { return smem_base() + off; }
+};
+
 struct Acc {            // norms of one residual evaluation (statistics.jl:44-57, violations.jl:18-168)
   double sum, opt, dyn, con, sta;
   double psum;          // Σ|row| without the proximal terms (trial evaluations that are kept, see Inst::residual)
@@ -212,7 +224,7 @@ struct Inst {
   int N, K, nrow, has_cc, has_pairs, has_self, has_sb, has_cb;
   static constexpr int model = MODEL;
   double dt;
-  double *X, *U, *L, *R, *KU, *AB, *CL, *CM, *CW, *Gp, *Hp, *Gs, *Hs, *Pm, *Sv, *Ym, *Aug, *Base, *Wm, *Hm, *xf, *Q, *Rw, *uf, *red;
+  SP X, U, L, R, KU, AB, CL, CM, CW, Gp, Hp, Gs, Hs, Pm, Sv, Ym, Aug, Base, Wm, Hm, xf, Q, Rw, uf, red;
   double* KUg;            // this instance's slice of Buffers::KUg (global)
   double* Rtrial;         // global scratch [S]: un-regularised residual rows of the last trial point (reused if accepted)
   bool keep;              // trial evaluation also produces what the next inner iteration needs (rows, Hessian blocks)
@@ -222,10 +234,11 @@ struct Inst {
   __device__ void bind(const DevDesc* dd, double* sm) {
     d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; has_cc = dd->has_cc; has_sb = dd->has_sb; has_cb = dd->has_cb;
     has_pairs = dd->has_pairs; has_self = dd->has_self; dt = dd->dt;
-    X = sm + dd->o_X; U = sm + dd->o_U; L = sm + dd->o_L; R = sm + dd->o_R; KU = sm + dd->o_KU; AB = sm + dd->o_AB;
-    CL = sm + dd->o_CL; CM = sm + dd->o_CM; CW = sm + dd->o_CW; Gp = sm + dd->o_Gp; Hp = sm + dd->o_Hp; Gs = sm + dd->o_Gs;
-    Hs = sm + dd->o_Hs; Pm = sm + dd->o_P; Sv = sm + dd->o_Sv; Ym = sm + dd->o_Y; Aug = sm + dd->o_Aug; Base = sm + dd->o_Base;
-    Wm = sm + dd->o_W; Hm = sm + dd->o_Ta; xf = sm + dd->o_par; Q = xf + n; Rw = Q + n; uf = Rw + m; red = sm + dd->o_red;
+    (void)sm;
+    X.off = dd->o_X; U.off = dd->o_U; L.off = dd->o_L; R.off = dd->o_R; KU.off = dd->o_KU; AB.off = dd->o_AB;
+    CL.off = dd->o_CL; CM.off = dd->o_CM; CW.off = dd->o_CW; Gp.off = dd->o_Gp; Hp.off = dd->o_Hp; Gs.off = dd->o_Gs;
+    Hs.off = dd->o_Hs; Pm.off = dd->o_P; Sv.off = dd->o_Sv; Ym.off = dd->o_Y; Aug.off = dd->o_Aug; Base.off = dd->o_Base;
+    Wm.off = dd->o_W; Hm.off = dd->o_Ta; xf.off = dd->o_par; Q.off = xf.off + n; Rw.off = Q.off + n; uf.off = Rw.off + m; red.off = dd->o_red;
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
   }
   __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUSP; Rtrial = g.D + (size_t)inst * K * b; }
