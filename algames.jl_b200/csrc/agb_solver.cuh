@@ -1009,11 +1009,11 @@ struct Inst {
             double o0 = x0, o1 = x1;
             double o2 = x2 + at_dot<0>(At3, x0, x1, x2, x3), o3 = x3 + at_dot<1>(At3, x0, x1, x2, x3);
             if (c < 2) { o0 += hrow[i3]; o1 += hrow[P + i3]; }
-            if (i3 == i2) { if (c == 0) o0 += hd; else if (c == 1) o1 += hd; else if (c == 2) o2 += hd; else o3 += hd; }
             brow[i3] = o0; brow[P + i3] = o1; brow[2 * P + i3] = o2; brow[3 * P + i3] = o3;
             wrow[i3] = bt_dot<0>(Bt3, x0, x1, x2, x3);
             wrow[P + i3] = bt_dot<1>(Bt3, x0, x1, x2, x3);
           }
+          brow[a] += hd;                                                     // diagonal of H^x_{i,s} (same thread wrote brow[a])
         }
         // the remaining warps lay out H^x_{i,s-1} for the next stage
         if (s - 1 > 0) build_hm(Hm + ((s - 1) & 1) * P * HmS, s - 1, reg_x, tid - HB, kThreads - HB);
@@ -1227,7 +1227,16 @@ struct Inst {
 
   // R <- rows kept by the accepted trial evaluation
   __device__ void load_kept_residual() {
-    for (int q = tid; q < K * b; q += kThreads) R[q] = Rtrial[q];
+    // K·b is even and both arrays are 16-byte aligned: 128-bit copies, four loads in flight per thread (L2 latency)
+    const double2* src = reinterpret_cast<const double2*>(Rtrial);
+    double2* dst = reinterpret_cast<double2*>((double*)R);
+    const int nv = (K * b) >> 1;
+    int q = tid;
+    for (; q + 3 * kThreads < nv; q += 4 * kThreads) {
+      const double2 v0 = src[q], v1 = src[q + kThreads], v2 = src[q + 2 * kThreads], v3 = src[q + 3 * kThreads];
+      dst[q] = v0; dst[q + kThreads] = v1; dst[q + 2 * kThreads] = v2; dst[q + 3 * kThreads] = v3;
+    }
+    for (; q < nv; q += kThreads) dst[q] = src[q];
     __syncthreads();
   }
 
@@ -1334,13 +1343,16 @@ struct Inst {
     for (int a = tid; a < m; a += kThreads) { Rw[a] = g.R[(size_t)inst * m + a]; uf[a] = g.uf[(size_t)inst * m + a]; }
   }
   __device__ void load_iterate(const double* Zg, const double* Lg, int inst) {
-    const double* z = Zg + (size_t)inst * N * (n + m);
+    const double* __restrict__ z = Zg + (size_t)inst * N * (n + m);
+#pragma unroll 4
     for (int item = tid; item < N * (n + m); item += kThreads) {
       const int q = item % (n + m), k = item / (n + m);
-      if (q < n) X[k * n + q] = z[item]; else U[k * m + (q - n)] = z[item];
+      const double v = __ldg(z + item);
+      if (q < n) X[k * n + q] = v; else U[k * m + (q - n)] = v;
     }
-    const double* l = Lg + (size_t)inst * P * K * n;
-    for (int item = tid; item < P * K * n; item += kThreads) L[item] = l[item];
+    const double* __restrict__ l = Lg + (size_t)inst * P * K * n;
+#pragma unroll 4
+    for (int item = tid; item < P * K * n; item += kThreads) L[item] = __ldg(l + item);
   }
   __device__ void store_iterate(double* Zg, double* Lg, int inst) const {
     double* z = Zg + (size_t)inst * N * (n + m);

@@ -51,6 +51,7 @@ void launch(int grid, int block, size_t smem_bytes, const std::function<void()>&
 #define AGB_LAUNCH(kern, grid, block, smem, stream, ...) \
   emu::launch((int)(grid), (int)(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
 
+template <class T> inline T __ldg(const T* p) { return *p; }
 inline void __syncthreads() { emu::st().f[emu::st().cur].pred = 1; emu::yield(emu::BLOCK_BAR); }
 inline int __syncthreads_and(int p) { emu::st().f[emu::st().cur].pred = p ? 1 : 0; emu::yield(emu::BLOCK_BAR); return emu::st().and_result; }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield(emu::WARP_BAR); }
