@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS = 4, 16, 8, 8, 8, 10
+MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST = 4, 16, 8, 8, 8, 10, 8
 MODEL_IDS = {"double_integrator": 0, "unicycle": 1, "bicycle": 2}
 STATUS_NAMES = {0: "converged", 1: "not_converged", 2: "numerical_failure"}
 
@@ -94,6 +94,8 @@ SYMBOLS = {
     "agb_solve_from_host": (C.c_int, [_H, C.POINTER(OptionsC), _DP, _DP, _DP, _DP, _DP, _DP, _DP, _DP, _IP]),
     "agb_newton_solve_async": (C.c_int, [_H, C.POINTER(OptionsC), C.c_void_p]),
     "agb_get_device_view": (C.c_int, [_H, C.POINTER(DeviceView)]),
+    "agb_set_history": (C.c_int, [_H, C.c_int]),
+    "agb_get_history": (C.c_int, [_H, _DP, _IP]),
     "agb_launch_count": (C.c_longlong, [_H]),
     "agb_last_solve_ms": (C.c_float, [_H]),
 }

@@ -89,6 +89,7 @@ struct agb_handle {
   double *x0 = nullptr, *xf = nullptr, *Q = nullptr, *R = nullptr, *uf = nullptr;
   double *Z0 = nullptr, *L0 = nullptr, *Z = nullptr, *L = nullptr, *conlam = nullptr, *conmu = nullptr, *D = nullptr, *KUg = nullptr, *stats = nullptr;
   int* status = nullptr;
+  double* hist = nullptr; int* hist_count = nullptr; int hist_max = 0;   // agb_set_history
   double* results = nullptr; size_t results_doubles = 0;   // owns Z, L, stats, status
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
@@ -238,7 +239,7 @@ void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -331,6 +332,7 @@ static Buffers buffers_of(agb_handle* h) {
   Buffers g;
   g.x0 = h->x0; g.xf = h->xf; g.Q = h->Q; g.R = h->R; g.uf = h->uf; g.Z0 = h->Z0; g.L0 = h->L0; g.Z = h->Z; g.L = h->L;
   g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.KUg = h->KUg; g.stats = h->stats; g.status = h->status;
+  g.hist = h->hist; g.hist_count = h->hist_count; g.hist_max = h->hist_max;
   return g;
 }
 
@@ -694,6 +696,35 @@ int agb_get_device_view(agb_handle* h, agb_device_view* out) {
   out->Z_dev = h->Z; out->L_dev = h->L; out->conlam_dev = h->conlam; out->conmu_dev = h->conmu; out->stats_dev = h->stats;
   out->status_dev = h->status; out->x0_dev = h->x0; out->Z0_dev = h->Z0; out->L0_dev = h->L0;
   out->results_dev = h->results; out->results_bytes = (unsigned long long)h->results_doubles * sizeof(double);
+  return AGB_OK;
+}
+
+int agb_set_history(agb_handle* h, int max_records) {
+  if (!h || max_records < 0) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->hist) { cudaFree(h->hist); h->hist = nullptr; }
+  if (h->hist_count) { cudaFree(h->hist_count); h->hist_count = nullptr; }
+  h->hist_max = 0;
+  if (max_records == 0) return AGB_OK;
+  const size_t B = h->batch;
+  AGB_CUDA(h, cudaMalloc((void**)&h->hist, B * max_records * AGB_NHIST * sizeof(double)));
+  AGB_CUDA(h, cudaMalloc((void**)&h->hist_count, B * sizeof(int)));
+  AGB_CUDA(h, cudaMemsetAsync(h->hist, 0, B * max_records * AGB_NHIST * sizeof(double), h->stream));
+  AGB_CUDA(h, cudaMemsetAsync(h->hist_count, 0, B * sizeof(int), h->stream));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->hist_max = max_records;
+  return AGB_OK;
+}
+
+int agb_get_history(agb_handle* h, double* hist_out, int* count_out) {
+  if (!h || !hist_out || !count_out) return AGB_EINVAL;
+  if (!h->hist) return fail(h, AGB_EINVAL, "agb_get_history: no history (call agb_set_history first)");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch;
+  AGB_CUDA(h, cudaMemcpyAsync(hist_out, h->hist, B * h->hist_max * AGB_NHIST * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  AGB_CUDA(h, cudaMemcpyAsync(count_out, h->hist_count, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
   return AGB_OK;
 }
 

@@ -63,6 +63,9 @@ struct Buffers {
   double* KUg;        // [B][K][m][n+2] (rows padded to even length) feedback gains of the stage-wise factorisation (L2-resident scratch)
   double* stats;      // [B][AGB_NSTATS]
   int* status;        // [B]
+  double* hist;       // [B][hist_max][AGB_NHIST] record!(stats, …) log, or nullptr
+  int* hist_count;    // [B]
+  int hist_max;
 };
 
 enum Op {

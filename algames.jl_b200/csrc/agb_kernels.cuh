@@ -35,7 +35,18 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
     __syncthreads();
     I.rollout();                                                                        // :17
     if (o.dual_reset) I.reset_duals_penalties(o);                                       // :25
-    int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0;
+    int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0, n_rec = 0;
+    // record!(stats, …) (statistics.jl:44-57): optional per-instance log of every record of the solve
+    auto log_record = [&](const Acc& r, double dlt, int kk, int ll) {
+      if (g.hist != nullptr && I.tid == 0) {
+        if (n_rec < g.hist_max) {
+          double* hrec = g.hist + ((size_t)inst * g.hist_max + n_rec) * AGB_NHIST;
+          hrec[0] = (double)kk; hrec[1] = r.sum / S; hrec[2] = r.dyn; hrec[3] = r.con; hrec[4] = r.sta; hrec[5] = r.opt;
+          hrec[6] = dlt; hrec[7] = (double)ll;
+        }
+      }
+      n_rec++;
+    };
     bool kept = false;               // R's successor (rows at the accepted trial point = the current iterate) is in Rtrial
     Acc kept_rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double delta = 0.0;
@@ -50,6 +61,7 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
         if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; }             // accepted trial point: already evaluated
         else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }        // :73-75 (the reg terms vanish at Z)
         const double res_norm = rec.sum / S;                                            // :76
+        log_record(rec, delta, kout, l);                                                // :75
         delta = 0.0;
         if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
         if (rec.opt < o.eps_opt) break;                                                 // :80-82
@@ -72,6 +84,8 @@ __global__ void __launch_bounds__(threads_for(P), (P <= 3 ? 4 : 1)) agb_newton_s
     }
     if (kept) { I.load_kept_residual(); rec = kept_rec; }                               // :63 final record
     else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }
+    log_record(rec, delta, outer_done, 0);                                              // :63
+    if (g.hist != nullptr && I.tid == 0) g.hist_count[inst] = n_rec;
     const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
     const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
     I.store_iterate(g.Z, g.L, inst);

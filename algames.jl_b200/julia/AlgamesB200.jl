@@ -156,11 +156,16 @@ function newton_solve!(probs::AbstractVector{<:GameProblem}; device::Integer=0)
         check(ccall((:agb_set_initial, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
             h[], Z0, L0, C_NULL, C_NULL), h[])
         Z = similar(Z0); L = similar(L0); stats = Array{Float64}(undef, NSTATS, B); status = Vector{Cint}(undef, B)
+        # one log entry per record!(stats, …) of the reference loop (statistics.jl:44-57)
+        maxrec = opts.outer_iter * opts.inner_iter + 1
+        check(ccall((:agb_set_history, LIB), Cint, (Ptr{Cvoid}, Cint), h[], maxrec), h[])
+        hist = Array{Float64}(undef, 8, maxrec, B); nrec = Vector{Cint}(undef, B)
         o = Ref(AgbOptions(opts))
-        GC.@preserve Z L stats status begin
+        GC.@preserve Z L stats status hist nrec begin
             check(ccall((:agb_newton_solve_batch, LIB), Cint,
                 (Ptr{Cvoid}, Ref{AgbOptions}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
                 h[], o, Z, L, C_NULL, C_NULL, stats, status), h[])
+            check(ccall((:agb_get_history, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cint}), h[], hist, nrec), h[])
         end
         for (b, q) in enumerate(probs)
             for k in 1:N
@@ -169,7 +174,15 @@ function newton_solve!(probs::AbstractVector{<:GameProblem}; device::Integer=0)
             end
             for i in 1:p, k in 1:N-1; q.pdtraj.du[i][k] = SVector{n}(L[:, k, i, b]); end
             residual!(q)                                   # prob.core.res, as the reference leaves it
-            record!(q.stats, q, q.model, q.game_con, q.pdtraj, 0.0, stats[6, b], Int(stats[8, b]))
+            reset!(q.stats)                                # the device log replays every record! of the solve
+            for r in 1:min(nrec[b], maxrec)
+                k, res, dyn, con, sta, opt, Δ = hist[1:7, r, b]
+                dv = DynamicsViolation(N); dv.max = dyn        # violations.jl:11-16 (per-knot vectors stay zero)
+                cv = ControlViolation(N); cv.max = con
+                sv = StateViolation(N); sv.max = sta
+                ov = OptimalityViolation(N); ov.max = opt
+                record!(q.stats, 0.0, res, Δ, dv, cv, sv, ov, Int(k))      # statistics.jl:30-42
+            end
         end
         return status
     finally

@@ -508,6 +508,18 @@ class GameBatch:
             _capi.dptr(out.get("conmu")), _capi.dptr(out.get("stats")), _capi.iptr(out.get("status"))))
         return out
 
+    def set_history(self, max_records: int):
+        """agb_set_history: keep every record!(stats, …) of later newton_solve calls (statistics.jl:44-57); 0 switches it off."""
+        self._ck(self.lib.agb_set_history(self.h, int(max_records)))
+        self._hist_max = int(max_records)
+
+    def get_history(self):
+        """agb_get_history → (hist [B, max_records, 8], count [B]); columns: outer k, res, dyn, con, sta, opt, Δ_traj, inner l."""
+        hist = np.empty((self.batch, self._hist_max, _capi.NHIST))
+        count = np.empty(self.batch, dtype=np.int32)
+        self._ck(self.lib.agb_get_history(self.h, _capi.dptr(hist), _capi.iptr(count)))
+        return hist, count
+
     def ibr_newton_solve(self, opts: Options, ibr_opts: Optional[IBROptions] = None):
         """agb_ibr_newton_solve_batch: ibr_newton_solve!(prob; ibr_opts) for every instance (solver_methods.jl:133-166)."""
         out = {"Z": np.empty(self._z()), "L": np.empty(self._l()), "conlam": np.empty(self._c()), "conmu": np.empty(self._c()),
@@ -565,7 +577,9 @@ class Violation:
 
 
 class Statistics:
-    """Final-record subset of struct/statistics.jl:5-57 (the device keeps the last record only)."""
+    """struct/statistics.jl:5-57: one entry per record!(stats, …) of the solve (newton_solve fills the whole history from
+    the device log; the best-response solver reports its final record only).  `t_elap` is not kept: instances of a batch
+    share one kernel launch, its duration is GameBatch.last_solve_ms()."""
 
     def __init__(self):
         self.iter = 0
@@ -578,6 +592,15 @@ class Statistics:
         self.opt_vio: List[Violation] = []
         self.newton_steps = 0
         self.residual_evals = 0
+
+    def record_history(self, hist):
+        """hist [count, 8] rows of agb_get_history."""
+        for h in hist:
+            self.iter += 1
+            self.outer_iter.append(int(h[0])); self.res.append(float(h[1]))
+            self.dyn_vio.append(Violation(float(h[2]))); self.con_vio.append(Violation(float(h[3])))
+            self.sta_vio.append(Violation(float(h[4]))); self.opt_vio.append(Violation(float(h[5])))
+            self.delta.append(float(h[6]))
 
     def record(self, st):
         self.iter += 1
@@ -687,12 +710,16 @@ def newton_solve(probs, init: bool = True):
         have_duals = all(q.conlam is not None for q in plist)
         batch.set_initial(Z0, L0, np.stack([q.conlam for q in plist]) if have_duals else None,
                           np.stack([q.conmu for q in plist]) if have_duals else None)
+        max_rec = p0.opts.outer_iter * p0.opts.inner_iter + 1          # every record!(stats, …) the loop can make
+        batch.set_history(max_rec)
         out = batch.newton_solve(p0.opts)
+        hist, count = batch.get_history()
         res, _ = batch.residual()
         for b, q in enumerate(plist):
             q.pdtraj.X[:], q.pdtraj.U[:], q.pdtraj.du[:] = out["Z"][b, :, :ps.n], out["Z"][b, :, ps.n:], out["L"][b]
             q.conlam, q.conmu = out["conlam"][b], out["conmu"][b]
-            q.stats = Statistics(); q.stats.record(out["stats"][b])
+            q.stats = Statistics(); q.stats.record_history(hist[b, :min(int(count[b]), max_rec)])
+            q.stats.newton_steps, q.stats.residual_evals = int(out["stats"][b, 6]), int(out["stats"][b, 8])
             q.status = _capi.STATUS_NAMES[int(out["status"][b])]
             q.core.res[:] = res[b]
     finally:

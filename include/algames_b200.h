@@ -239,6 +239,17 @@ typedef struct agb_device_view {
 } agb_device_view;
 int agb_get_device_view(agb_handle* h, agb_device_view* out);
 
+/* Full convergence history of newton_solve!: one record per record!(stats, …) call of the reference
+ * (src/struct/statistics.jl:44-57, called from inner_iteration src/problem/solver_methods.jl:75 and once more at :63).
+ * agb_set_history(h, max_records) makes every later agb_newton_solve_batch / agb_solve_from_host keep up to max_records
+ * records per instance on the device (0 switches the log off and frees it); agb_get_history copies them out:
+ * hist_out [B][max_records][AGB_NHIST] = {outer iteration k, res = ‖res‖₁/S, dyn_vio.max, con_vio.max, sta_vio.max,
+ * opt_vio.max, Δ_traj, inner iteration l (0 for the final record)}, count_out [B] = records the solve produced
+ * (may exceed max_records: later records were dropped).  The iterative-best-response solver keeps no history. */
+#define AGB_NHIST 8
+int agb_set_history(agb_handle* h, int max_records);
+int agb_get_history(agb_handle* h, double* hist_out, int* count_out);
+
 /* Number of kernels this library has launched on the handle since creation. */
 long long agb_launch_count(const agb_handle* h);
 /* Device time of the last agb_newton_solve_* kernel (CUDA events on its own stream), ms;

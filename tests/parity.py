@@ -167,7 +167,9 @@ def solve_batch(lib_path, name, B, N=None, opts_override=None):
     gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path)
     gb.set_instance_params(x0=x0, xf=xf)
     Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+    gb.set_history(opts.outer_iter * opts.inner_iter + 1)
     out = gb.newton_solve(opts)
+    out["hist"], out["hist_count"] = gb.get_history()
     return (model, N, dt, obj, con, opts, x0, xf), gb, Z0, L0, out
 
 
@@ -184,6 +186,13 @@ def check_solve_vs_oracle(lib_path, name, B=2, N=None, which=None):
         assert np.abs(out["L"][b] - op.pdtraj.du).max() < TOL_SOLVE * max(1.0, np.abs(op.pdtraj.du).max())
         assert np.allclose(st[:5], [last.res, last.dyn, last.con, last.sta, last.opt], atol=TOL_SOLVE)
         assert (out["status"][b] == 0) == op.converged
+        # the whole Statistics history (statistics.jl:44-57): one record per inner iteration + the final one
+        cnt = int(out["hist_count"][b])
+        assert cnt == len(op.stats)
+        ho = np.array([[r.outer, r.res, r.dyn, r.con, r.sta, r.opt, r.delta] for r in op.stats])
+        hd = out["hist"][b, :cnt, :7]
+        assert np.array_equal(hd[:, 0], ho[:, 0])
+        assert np.allclose(hd[:, 1:], ho[:, 1:], rtol=1e-6, atol=TOL_SOLVE), np.abs(hd[:, 1:] - ho[:, 1:]).max(axis=0)
         lam_o, mu_o = O.pack_multipliers(op)
         if lam_o.size:
             assert np.allclose(out["conlam"][b], lam_o, atol=TOL_SOLVE * max(1.0, np.abs(lam_o).max()))

@@ -57,6 +57,25 @@ def test_unconstrained_lq_game_one_newton_step_emulated(emu_lib):
     assert prob.stats.dyn_vio[-1].max < 1e-6 and prob.stats.newton_steps == 1
 
 
+def test_statistics_history_single_problem_emulated(emu_lib):
+    # prob.stats keeps one entry per record!(stats, …) like the reference's Statistics (struct/statistics.jl:44-57)
+    import algames_b200 as ab
+    import oracle.algames_oracle as O
+    model, N, dt, obj, con, opts, x0, _ = ab.workloads.config_a()
+    prob = ab.GameProblem(N, dt, x0[0], model, opts, obj, con, lib_path=emu_lib)
+    ab.init_traj(prob)
+    Z0 = np.concatenate([prob.pdtraj.X, prob.pdtraj.U], axis=1).copy(); L0 = prob.pdtraj.du.copy()
+    ab.newton_solve(prob, init=False)
+    op = O.newton_solve(O.problem_from_spec(ab.spec_of(prob)), Z0=Z0, L0=L0)
+    st = prob.stats
+    assert st.iter == len(op.stats) == len(st.res) == len(st.opt_vio) and st.iter > opts.outer_iter
+    assert st.outer_iter == [r.outer for r in op.stats]
+    assert np.allclose(st.res, [r.res for r in op.stats], rtol=1e-6, atol=1e-9)
+    assert np.allclose([v.max for v in st.dyn_vio], [r.dyn for r in op.stats], rtol=1e-6, atol=1e-9)
+    assert np.allclose(st.delta, [r.delta for r in op.stats], rtol=1e-6, atol=1e-9)
+    assert st.sta_vio[-1].max < 1e-3 and st.con_vio[-1].max < 1e-3          # test/problem/solver_methods.jl:178-182
+
+
 def test_error_behaviour_emulated(emu_lib):
     import algames_b200 as ab
     model = ab.UnicycleGame(p=2)
