@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <cstdlib>
 #include <string>
 #include "agb_kernels.cuh"
 
@@ -90,6 +91,7 @@ struct agb_handle {
   double *Z0 = nullptr, *L0 = nullptr, *Z = nullptr, *L = nullptr, *conlam = nullptr, *conmu = nullptr, *D = nullptr, *KUg = nullptr, *stats = nullptr;
   int* status = nullptr;
   double* hist = nullptr; int* hist_count = nullptr; int hist_max = 0;   // agb_set_history
+  double* Hpg = nullptr; int hpg_stride = 0;                              // big layout: pair / self Hessian blocks
   double* results = nullptr; size_t results_doubles = 0;   // owns Z, L, stats, status
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
@@ -169,44 +171,55 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
   }
   o->nrow = row;
   o->nrow_control = row - o->nrow_state;
-  // shared-memory layout
+  // shared-memory layout: small (everything resident) or big (L, CL, CM, Hp, Hs in global memory, agb_internal.h)
   const int N = o->N, K = o->K, W = m + n + 1;
-  int off = 0;
-  auto take = [&](int cnt) { int r = off; off += (cnt + 1) & ~1; return r; };
-  o->o_X = take(N * n); o->o_U = take(N * m); o->o_L = take(p * K * n); o->o_R = take(K * o->b);
-  o->o_AB = take(d->model == AGB_MODEL_DOUBLE_INTEGRATOR ? 0 : K * p * 16);
-  o->o_CL = take(K * o->nrow); o->o_CM = take(K * o->nrow);
-  o->o_CW = take((o->has_sb || o->has_cb) ? K * o->nrow : 0);     // pair / wall / circle weights are folded into Hp / Hs
-  o->o_Hp = take(o->has_pairs ? N * o->npairs * 3 : 0); o->o_Hs = take(o->has_self ? N * p * 3 : 0);
-  o->o_P = take(p * n * n); o->o_Sv = take(p * n); o->o_Y = take(m * (n + 1)); o->o_Aug = take(m * W);
-  o->o_KU = o->o_Aug;                          // one-stage gain buffer of the best-response factorisation (Aug is unused there)
-  o->o_Base = take(p * n * (n + 1)); o->o_W = take(p * n * m); o->o_Ta = take(2 * p * (4 * p * p + n));   // Hm: double-buffered per-stage H^x blocks (Inst::HmS per player)
-  {  // Gp / Gs live only inside one residual evaluation, Base / W / Ta only inside kkt_solve: alias them when they fit
-    const int need = (o->has_pairs ? N * o->npairs * 2 : 0) + (o->has_self ? N * p * 2 : 0);
-    const int have = off - o->o_Base;
-    if (need > have) take(need - have);
-    o->o_Gp = o->o_Base; o->o_Gs = o->o_Base + (o->has_pairs ? N * o->npairs * 2 : 0);
-  }
-  // the forward sweep lays a 4-stage ring of padded gain blocks (Inst::KUSP = m*(n+2)) over [o_P, end of Ta)
-  if (off - o->o_P < 4 * m * (n + 2)) take(4 * m * (n + 2) - (off - o->o_P));
-  o->o_par = take(2 * n + 2 * m); o->o_red = take(6 * kMaxWarps);
-  o->smem_doubles = off;
+  auto layout = [&](bool big) {
+    int off = 0;
+    auto take = [&](int cnt) { int r = off; off += (cnt + 1) & ~1; return r; };
+    o->o_X = take(N * n); o->o_U = take(N * m); o->o_L = take(big ? 0 : p * K * n); o->o_R = take(K * o->b);
+    o->o_AB = take(d->model == AGB_MODEL_DOUBLE_INTEGRATOR ? 0 : K * p * 16);
+    o->o_CL = take(big ? 0 : K * o->nrow); o->o_CM = take(big ? 0 : K * o->nrow);
+    o->o_CW = take((o->has_sb || o->has_cb) ? K * o->nrow : 0);     // pair / wall / circle weights are folded into Hp / Hs
+    o->o_Hp = take((o->has_pairs && !big) ? N * o->npairs * 3 : 0); o->o_Hs = take((o->has_self && !big) ? N * p * 3 : 0);
+    o->o_P = take(p * n * n); o->o_Sv = take(p * n); o->o_Y = take(m * (n + 1)); o->o_Aug = take(m * W);
+    o->o_KU = o->o_Aug;                          // one-stage gain buffer of the best-response factorisation (Aug is unused there)
+    o->o_Base = take(p * n * (n + 1)); o->o_W = take(p * n * m); o->o_Ta = take(2 * p * (4 * p * p + n));   // Hm: double-buffered per-stage H^x blocks (Inst::HmS per player)
+    {  // Gp / Gs live only inside one residual evaluation, Base / W / Hm only inside kkt_solve: alias them when they fit
+      const int need = (o->has_pairs ? N * o->npairs * 2 : 0) + (o->has_self ? N * p * 2 : 0);
+      const int have = off - o->o_Base;
+      if (need > have) take(need - have);
+      o->o_Gp = o->o_Base; o->o_Gs = o->o_Base + (o->has_pairs ? N * o->npairs * 2 : 0);
+    }
+    // the forward sweep lays a 4-stage ring of padded gain blocks (Inst::KUSP = m*(n+2)) over [o_P, end of Hm)
+    if (off - o->o_P < 4 * m * (n + 2)) take(4 * m * (n + 2) - (off - o->o_P));
+    o->o_par = take(2 * n + 2 * m); o->o_red = take(6 * kMaxWarps);
+    o->smem_doubles = off;
+    o->big = big ? 1 : 0;
+  };
+  layout(false);
+  // one CTA per SM (more than half of the 228 KB minus the per-CTA reserve) → big layout; 4-player kernels exist only in it
+  const size_t two_per_sm = (228u * 1024u - 2u * 1024u) / 2u;
+  const char* force = getenv("AGB_FORCE_BIG_LAYOUT");         // test hook: exercise the big layout on small 3-player instances
+  if (p >= 4 || (p == 3 && ((size_t)o->smem_doubles * sizeof(double) > two_per_sm || (force && force[0] == '1')))) layout(true);
   return AGB_OK;
 }
 
 namespace agb {
-cudaError_t set_attr(int p, int model, size_t smem) {
+cudaError_t set_attr(int p, int big, int model, size_t smem) {
   switch (p) { case 1: return set_attr_p1(model, smem); case 2: return set_attr_p2(model, smem);
-               case 3: return set_attr_p3(model, smem); default: return set_attr_p4(model, smem); }
+               case 3: return big ? set_attr_p3b(model, smem) : set_attr_p3(model, smem); default: return set_attr_p4(model, smem); }
 }
-void launch_solve(int p, const LaunchArgs& L) {
-  switch (p) { case 1: launch_solve_p1(L); break; case 2: launch_solve_p2(L); break; case 3: launch_solve_p3(L); break; default: launch_solve_p4(L); }
+void launch_solve(int p, int big, const LaunchArgs& L) {
+  switch (p) { case 1: launch_solve_p1(L); break; case 2: launch_solve_p2(L); break;
+               case 3: if (big) launch_solve_p3b(L); else launch_solve_p3(L); break; default: launch_solve_p4(L); }
 }
-void launch_ibr(int p, const LaunchArgs& L) {
-  switch (p) { case 1: launch_ibr_p1(L); break; case 2: launch_ibr_p2(L); break; case 3: launch_ibr_p3(L); break; default: launch_ibr_p4(L); }
+void launch_ibr(int p, int big, const LaunchArgs& L) {
+  switch (p) { case 1: launch_ibr_p1(L); break; case 2: launch_ibr_p2(L); break;
+               case 3: if (big) launch_ibr_p3b(L); else launch_ibr_p3(L); break; default: launch_ibr_p4(L); }
 }
-void launch_op(int p, const LaunchArgs& L) {
-  switch (p) { case 1: launch_op_p1(L); break; case 2: launch_op_p2(L); break; case 3: launch_op_p3(L); break; default: launch_op_p4(L); }
+void launch_op(int p, int big, const LaunchArgs& L) {
+  switch (p) { case 1: launch_op_p1(L); break; case 2: launch_op_p2(L); break;
+               case 3: if (big) launch_op_p3b(L); else launch_op_p3(L); break; default: launch_op_p4(L); }
 }
 }  // namespace agb
 
@@ -239,7 +252,7 @@ void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count, h->Hpg};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -281,7 +294,7 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
     snprintf(buf, sizeof buf, "instance needs %zu B of shared memory per CTA, device allows %d B", h->smem_bytes, max_smem);
     g_create_err = buf; agb_destroy(h); return AGB_EUNSUPPORTED;
   }
-  CKC(agb::set_attr(t.p, t.model, h->smem_bytes));
+  CKC(agb::set_attr(t.p, t.big, t.model, h->smem_bytes));
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
@@ -299,6 +312,7 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
   }
   CK(alloc_d(h, &h->conlam, B * K * t.nrow)); CK(alloc_d(h, &h->conmu, B * K * t.nrow));
   CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 2)));       // rows padded to n+2 (Inst::n1p)
+  if (t.big) { h->hpg_stride = N * t.npairs * 3 + N * p * 3; CK(alloc_d(h, &h->Hpg, B * (size_t)h->hpg_stride)); }
   // descriptor defaults broadcast to every instance; μ starts at 1 (Altro ALConVal default)
   double tmp[2 * AGB_MAX_N + 2 * AGB_MAX_M];
   double* dtmp = nullptr;
@@ -333,6 +347,7 @@ static Buffers buffers_of(agb_handle* h) {
   g.x0 = h->x0; g.xf = h->xf; g.Q = h->Q; g.R = h->R; g.uf = h->uf; g.Z0 = h->Z0; g.L0 = h->L0; g.Z = h->Z; g.L = h->L;
   g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.KUg = h->KUg; g.stats = h->stats; g.status = h->status;
   g.hist = h->hist; g.hist_count = h->hist_count; g.hist_max = h->hist_max;
+  g.Hpg = h->Hpg; g.hpg_stride = h->hpg_stride;
   return g;
 }
 
@@ -427,7 +442,7 @@ static int launch_op(agb_handle* h, const agb_options* o, const OpArgs& a) {
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = h->stream; L.dd = h->dd; L.o = od;
   memset(&L.io, 0, sizeof L.io);
   L.g = buffers_of(h); L.a = a; L.batch = h->batch;
-  agb::launch_op(h->hd.p, L);
+  agb::launch_op(h->hd.p, h->hd.big, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
   return AGB_OK;
@@ -574,7 +589,7 @@ static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
   memset(&L.io, 0, sizeof L.io);
   L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch; L.inst0 = 0;
-  agb::launch_solve(h->hd.p, L);
+  agb::launch_solve(h->hd.p, h->hd.big, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
   return AGB_OK;
@@ -619,7 +634,7 @@ int agb_ibr_newton_solve_batch(agb_handle* h, const agb_options* o, const agb_ib
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = h->stream; L.dd = h->dd; L.o = *o; L.io = *io;
   L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch;
   AGB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  agb::launch_ibr(h->hd.p, L);
+  agb::launch_ibr(h->hd.p, h->hd.big, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
   AGB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -676,7 +691,7 @@ int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, c
     L.model = h->hd.model; L.grid = cnt; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
     memset(&L.io, 0, sizeof L.io); memset(&L.a, 0, sizeof L.a);
     L.g = buffers_of(h); L.batch = hi; L.inst0 = lo;
-    agb::launch_solve(h->hd.p, L);
+    agb::launch_solve(h->hd.p, h->hd.big, L);
     h->launches++;
     AGB_CUDA(h, cudaGetLastError());
     if (Z_out) AGB_CUDA(h, cudaMemcpyAsync(Z_out + lo * zs, h->Z + lo * zs, cnt * zs * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -5,14 +5,15 @@
 
 namespace agb {
 
-// one CTA owns one game instance: 4 warps for up to 3 players, 8 warps for 4 players (whose 162 KB working set allows only
-// one CTA per SM, so the instance itself has to supply the parallelism)
+// one CTA of 4 warps owns one game instance.  Instances whose working set would leave a single CTA per SM (4 players; long
+// horizons with many constraint rows) use the "big" layout: duals, AL multipliers/penalties and the pair/self Hessian
+// blocks live in L2-resident global memory instead of shared memory, so that two CTAs fit per SM.
 #ifdef __CUDACC__
 #define AGB_HD __host__ __device__
 #else
 #define AGB_HD
 #endif
-AGB_HD constexpr int threads_for(int p) { return p >= 4 ? 256 : 128; }
+AGB_HD constexpr int threads_for(int) { return 128; }
 constexpr int kMaxWarps = 8;
 
 // Flattened, index-resolved form of agb_problem_desc, lives in device global memory (read through L1).
@@ -44,6 +45,7 @@ struct DevDesc {
   // shared-memory layout (offsets in doubles)
   int o_X, o_U, o_L, o_R, o_KU, o_AB, o_CL, o_CM, o_CW, o_Gp, o_Hp, o_Gs, o_Hs, o_P, o_Sv, o_Y, o_Aug, o_Base, o_W, o_Ta, o_par, o_red;
   int smem_doubles;
+  int big;                                 // 1: L, CL, CM, Hp, Hs in global memory (kernels instantiated with BIG = true)
 };
 
 // Per-batch device buffers (all FP64 unless noted); layouts as in include/algames_b200.h.
@@ -66,6 +68,8 @@ struct Buffers {
   double* hist;       // [B][hist_max][AGB_NHIST] record!(stats, …) log, or nullptr
   int* hist_count;    // [B]
   int hist_max;
+  double* Hpg;        // big layout only: [B][N·p(p-1)·3 + N·p·3] pair / self Hessian blocks
+  int hpg_stride;
 };
 
 enum Op {

@@ -51,6 +51,13 @@ struct SP {
   int off;
   __device__ __forceinline__ operator double*() const { return smem_base() + off; }
 };
+// Same interface for an array that lives in global memory (the "big" instance layout, agb_internal.h).
+struct GPh {
+  double* p;
+  __device__ __forceinline__ operator double*() const { return p; }
+};
+template <bool BIG> struct SpillSel { typedef SP type; };
+template <> struct SpillSel<true> { typedef GPh type; };
 
 struct Acc {            // norms of one residual evaluation (statistics.jl:44-57, violations.jl:18-168)
   double sum, opt, dyn, con, sta;
@@ -167,7 +174,7 @@ __device__ __forceinline__ void rk3_step(int model, double dt, double lf, double
 // ------------------------------------------------------------------------------------------------------------
 // Instance context: shared-memory views of one game instance
 // ------------------------------------------------------------------------------------------------------------
-template <int P, int MODEL>
+template <int P, int MODEL, bool BIG = false>
 struct Inst {
   static constexpr int n = 4 * P, m = 2 * P, b = P * n + m + n, W = m + n + 1, KUS = m * (n + 1), n1 = n + 1;
   // rows of the gain scratch in global memory are padded to an even length (16-byte row alignment for 128-bit loads)
@@ -224,7 +231,8 @@ struct Inst {
   int N, K, nrow, has_cc, has_pairs, has_self, has_sb, has_cb;
   static constexpr int model = MODEL;
   double dt;
-  SP X, U, L, R, KU, AB, CL, CM, CW, Gp, Hp, Gs, Hs, Pm, Sv, Ym, Aug, Base, Wm, Hm, xf, Q, Rw, uf, red;
+  SP X, U, R, KU, AB, CW, Gp, Gs, Pm, Sv, Ym, Aug, Base, Wm, Hm, xf, Q, Rw, uf, red;
+  typename SpillSel<BIG>::type L, CL, CM, Hp, Hs;      // shared memory, or global memory in the big layout
   double* KUg;            // this instance's slice of Buffers::KUg (global)
   double* Rtrial;         // global scratch [S]: un-regularised residual rows of the last trial point (reused if accepted)
   bool keep;              // trial evaluation also produces what the next inner iteration needs (rows, Hessian blocks)
@@ -235,13 +243,22 @@ struct Inst {
     d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; has_cc = dd->has_cc; has_sb = dd->has_sb; has_cb = dd->has_cb;
     has_pairs = dd->has_pairs; has_self = dd->has_self; dt = dd->dt;
     (void)sm;
-    X.off = dd->o_X; U.off = dd->o_U; L.off = dd->o_L; R.off = dd->o_R; KU.off = dd->o_KU; AB.off = dd->o_AB;
-    CL.off = dd->o_CL; CM.off = dd->o_CM; CW.off = dd->o_CW; Gp.off = dd->o_Gp; Hp.off = dd->o_Hp; Gs.off = dd->o_Gs;
-    Hs.off = dd->o_Hs; Pm.off = dd->o_P; Sv.off = dd->o_Sv; Ym.off = dd->o_Y; Aug.off = dd->o_Aug; Base.off = dd->o_Base;
+    X.off = dd->o_X; U.off = dd->o_U; R.off = dd->o_R; KU.off = dd->o_KU; AB.off = dd->o_AB;
+    CW.off = dd->o_CW; Gp.off = dd->o_Gp; Gs.off = dd->o_Gs;
+    if constexpr (!BIG) { L.off = dd->o_L; CL.off = dd->o_CL; CM.off = dd->o_CM; Hp.off = dd->o_Hp; Hs.off = dd->o_Hs; }
+    else { L.p = nullptr; CL.p = nullptr; CM.p = nullptr; Hp.p = nullptr; Hs.p = nullptr; }
+    Pm.off = dd->o_P; Sv.off = dd->o_Sv; Ym.off = dd->o_Y; Aug.off = dd->o_Aug; Base.off = dd->o_Base;
     Wm.off = dd->o_W; Hm.off = dd->o_Ta; xf.off = dd->o_par; Q.off = xf.off + n; Rw.off = Q.off + n; uf.off = Rw.off + m; red.off = dd->o_red;
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
   }
-  __device__ void bind_instance(const Buffers& g, int inst) { KUg = g.KUg + (size_t)inst * K * KUSP; Rtrial = g.D + (size_t)inst * K * b; }
+  __device__ void bind_instance(const Buffers& g, int inst) {
+    KUg = g.KUg + (size_t)inst * K * KUSP; Rtrial = g.D + (size_t)inst * K * b;
+    if constexpr (BIG) {      // the result / multiplier buffers have exactly the shared-memory layouts: work in place
+      L.p = g.L + (size_t)inst * P * K * n;
+      CL.p = g.conlam + (size_t)inst * K * nrow; CM.p = g.conmu + (size_t)inst * K * nrow;
+      Hp.p = g.Hpg + (size_t)inst * g.hpg_stride; Hs.p = Hp.p + N * NP * 3;
+    }
+  }
 
   // ---- iterate accessors; TRIAL reads Z + alpha·Δ with Δ held in R (update_traj!, primal_dual_traj.jl:109-128)
   template <bool TRIAL> __device__ __forceinline__ double xg(int k, int a, double alpha) const {

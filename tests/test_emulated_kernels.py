@@ -76,6 +76,20 @@ def test_statistics_history_single_problem_emulated(emu_lib):
     assert st.sta_vio[-1].max < 1e-3 and st.con_vio[-1].max < 1e-3          # test/problem/solver_methods.jl:178-182
 
 
+# ---- big layout (duals, AL multipliers and pair/self Hessian blocks in global memory; agb_internal.h): 4-player games always
+# use it (config C above); the test hook forces it on small 3-player instances
+@pytest.mark.parametrize("name,N", [("A'", None), ("B", 12), ("E", 12)])
+def test_big_layout_per_function_parity_emulated(emu_lib, monkeypatch, name, N):
+    monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", "1")
+    parity.check_per_function(emu_lib, name, seed=2, N=N)
+
+
+def test_big_layout_solve_emulated(emu_lib, monkeypatch):
+    monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", "1")
+    parity.check_solve_vs_oracle(emu_lib, "B", B=2, N=12)
+    parity.check_ibr_solve(emu_lib, "B", B=1, N=8, ibr_iter=1)
+
+
 def test_error_behaviour_emulated(emu_lib):
     import algames_b200 as ab
     model = ab.UnicycleGame(p=2)
@@ -194,7 +208,7 @@ def test_edge_shapes_emulated(emu_lib, model_name, p, N):
 def test_working_set_too_large_is_rejected_emulated(emu_lib):
     import algames_b200 as ab
     model = ab.UnicycleGame(p=4)
-    N = 120
+    N = 200          # (N = 120 fits since the big layout keeps duals and multipliers in global memory)
     obj = ab.GameObjective([np.ones(4)] * 4, [np.ones(2)] * 4, [np.zeros(4)] * 4, [np.zeros(2)] * 4, N, model)
     con = ab.GameConstraintValues(ab.ProblemSize(N, model))
     ab.add_collision_avoidance(con, 0.1)
