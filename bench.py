@@ -279,13 +279,14 @@ def run_gpu(args):
         bps = bytes_per_newton_step(p, n, m, N)
         newton_per_launch = newton / world
         achieved = bps * newton_per_launch / (kernel_ms / 1e3) / 1e9       # the solve kernel's own launch duration
-        traffic = None
+        traffic, ncu = None, {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                ncu = json.load(open(tpath))
+                traffic = ncu.get("dram_bytes_per_launch")
             except Exception:
-                traffic = None
+                traffic, ncu = None, {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -300,6 +301,9 @@ def run_gpu(args):
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "agb_newton_solve_kernel<3, DoubleIntegrator>",
+                         "true_limiter": {"kind": "per-warp issue latency (FP64, short dependent chains)",
+                                          "fp64_pipe_busy_pct": ncu.get("fp64_pipe_busy_pct"), "issue_active_pct": ncu.get("issue_active_pct"),
+                                          "source": "ncu --set full capture committed under profiles/"},
                          "note": "achieved = algorithmic KKT-band bytes (%d B per Newton step, SURVEY 8d) x Newton steps per launch / launch time; "
                                  "the band is never materialised (structured on-chip factorisation), so real DRAM traffic is far lower" % bps},
             "clocks": clk.summary(),

@@ -10,10 +10,10 @@ import parity
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = None      # default: the in-tree nvcc build
-FULL = {"B": 1024, "C": 512}
+FULL = {"B": 1024, "C": 512, "E": 512}
 if os.environ.get("AGB_GPU_TESTS_ON_EMULATOR"):      # developer aid: exercise this file's logic on the CPU emulator
     LIB = os.path.join(HERE, "emu", "libagb_emu.so")
-    FULL = {"B": 136, "C": 133}
+    FULL = {"B": 136, "C": 133, "E": 133}
 
 
 @pytest.fixture(scope="session", autouse=True)
@@ -75,7 +75,7 @@ def test_golden_fixtures():
         parity.check_golden(LIB, os.path.join(HERE, "golden", f))
 
 
-@pytest.mark.parametrize("name", ["B", "C"])
+@pytest.mark.parametrize("name", ["B", "C", "E"])
 def test_full_size_properties(name):
     """BASELINE sizes: record reproducibility, tolerances of converged instances, determinism, instance independence
     (a sub-batch solved alone gives bit-identical results), and idempotence (a restart from the solution with the
@@ -87,7 +87,7 @@ def test_full_size_properties(name):
     gb2, conv = parity.check_solution_properties(cfg, out, lambda: ab.GameBatch(model, N, dt, obj, con, B, lib_path=LIB))
     # B: every instance converges; C (4 unicycles crossing at one point) leaves ~20% at outer_iter with tolerances unmet,
     # in the oracle as well (test_nonconverged_instance_matches_oracle)
-    assert conv.mean() > (0.99 if name == "B" else 0.7), conv.mean()
+    assert conv.mean() > {"B": 0.99, "C": 0.7, "E": 0.6}[name], conv.mean()     # E: 71 % in the oracle too (dense highway starts)
     # determinism
     out_b = gb.newton_solve(opts)
     for k in ("Z", "L", "conlam", "conmu", "stats"):
