@@ -150,6 +150,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     # weak-scaling control: every rank solves the same 1024-instance set, so per-GPU work is identical by construction
