@@ -1155,12 +1155,12 @@ struct Inst {
               at0 = ar.x; at1 = ar.y; bt0 = br.x; bt1 = br.y;
               abp += P * 16;
             }
-            const double rd = *rdp;
+            const double rd = act ? *rdp : 0.0;           // (idle lanes must not touch row s: lane 0 rewrites it below)
             const double2 kap0 = k0[n / 2], kap1 = k1[n / 2];
             double a0 = kap0.x, a1 = 0.0, b0 = kap1.x, b1 = 0.0, dxl = 0.0, y0 = 0.0, y1 = 0.0;
             if (s > 0) {
               const double2* dx = dxp - b / 2;            // row s-1
-              dxl = rdp[-b];
+              dxl = act ? rdp[-b] : 0.0;
               y0 = (R + OD + 2 * P + i)[(s - 1) * b]; y1 = (R + OD + 3 * P + i)[(s - 1) * b];
 #pragma unroll
               for (int a = 0; a < n / 2; a += 2) {
@@ -1197,9 +1197,9 @@ struct Inst {
       const int a = act ? lane : 0, c = a / P, ia = a - c * P;
       const double* gi = R + OX + i * n + a;
       double ln = 0.0;
-      double g = gi[(K - 1) * b];
+      double g = act ? gi[(K - 1) * b] : 0.0;
       for (int s = K - 1; s >= 0; s--) {
-        const double gn = (s > 0) ? gi[(s - 1) * b] : 0.0;
+        const double gn = (act && s > 0) ? gi[(s - 1) * b] : 0.0;     // (idle lanes must not read rows lane 0 rewrites)
         double v = g;
         if (s < K - 1) {
           const double l0 = __shfl_sync(AGB_FULL, ln, ia), l1 = __shfl_sync(AGB_FULL, ln, P + ia);
