@@ -128,7 +128,7 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
   o->has_cc = d->has_collision_cost ? 1 : 0;
   o->npairs = p * (p - 1);
   for (int i = 0; i < p; i++) { o->cc_radius[i] = d->cc_radius[i]; o->cc_mu[i] = d->cc_mu[i]; }
-  int row = 0;
+  int row = 0, ncw = 0;
   for (int i = 0; i < AGB_MAX_P; i++) {
     for (int j = 0; j < AGB_MAX_P; j++) o->col_row[i][j] = -1;
     for (int a = 0; a < AGB_MAX_N; a++) { o->sbmax_row[i][a] = -1; o->sbmin_row[i][a] = -1; }
@@ -138,12 +138,15 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     for (int j = 0; j < p; j++) {
       if (j != i && d->col_radius[i][j] > 0) { o->col_radius[i][j] = d->col_radius[i][j]; o->col_row[i][j] = row++; }
     }
+    o->sb_shift[i] = row - ncw;                 // this player's state-bound rows (if any) start here
     if (d->has_state_bound[i]) {
       for (int a = 0; a < n; a++) {
         if (!(d->x_max[i][a] >= d->x_min[i][a])) { *why = "Upper bounds must be greater than or equal to lower bounds"; return AGB_EINVAL; }
       }
+      const int row0 = row;
       for (int a = 0; a < n; a++) if (isfinite(d->x_max[i][a])) { o->x_max[i][a] = d->x_max[i][a]; o->sbmax_row[i][a] = row++; }
       for (int a = 0; a < n; a++) if (isfinite(d->x_min[i][a])) { o->x_min[i][a] = d->x_min[i][a]; o->sbmin_row[i][a] = row++; }
+      ncw += row - row0;
     }
     if (d->n_walls[i] < 0 || d->n_walls[i] > AGB_MAX_WALLS || d->n_circles[i] < 0 || d->n_circles[i] > AGB_MAX_CIRCLES) {
       *why = "too many walls / circles"; return AGB_EINVAL;
@@ -162,6 +165,7 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     if (o->n_walls[i] > 0 || o->n_circles[i] > 0) o->has_self = 1;
   }
   for (int idx = 0; idx < AGB_MAX_M; idx++) { o->ub_row[idx] = -1; o->lb_row[idx] = -1; }
+  o->cb_shift = row - ncw;
   if (d->has_control_bound) {
     for (int idx = 0; idx < m; idx++) {
       if (!(d->u_max[idx] >= d->u_min[idx])) { *why = "Upper bounds must be greater than or equal to lower bounds"; return AGB_EINVAL; }
@@ -171,6 +175,8 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
   }
   o->nrow = row;
   o->nrow_control = row - o->nrow_state;
+  ncw += o->nrow_control;
+  o->ncw = ncw;
   // shared-memory layout: small (everything resident) or big (L, CL, CM, Hp, Hs in global memory, agb_internal.h)
   const int N = o->N, K = o->K, W = m + n + 1;
   auto layout = [&](bool big) {
@@ -179,7 +185,7 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     o->o_X = take(N * n); o->o_U = take(N * m); o->o_L = take(big ? 0 : p * K * n); o->o_R = take(K * o->b);
     o->o_AB = take(d->model == AGB_MODEL_DOUBLE_INTEGRATOR ? 0 : K * p * 16);
     o->o_CL = take(big ? 0 : K * o->nrow); o->o_CM = take(big ? 0 : K * o->nrow);
-    o->o_CW = take((o->has_sb || o->has_cb) ? K * o->nrow : 0);     // pair / wall / circle weights are folded into Hp / Hs
+    o->o_CW = take((o->has_sb || o->has_cb) ? K * o->ncw : 0);     // pair / wall / circle weights are folded into Hp / Hs
     o->o_Hp = take((o->has_pairs && !big) ? N * o->npairs * 3 : 0); o->o_Hs = take((o->has_self && !big) ? N * p * 3 : 0);
     o->o_P = take(p * n * n); o->o_Sv = take(p * n); o->o_Y = take(m * (n + 1)); o->o_Aug = take(m * W);
     o->o_KU = o->o_Aug;                          // one-stage gain buffer of the best-response factorisation (Aug is unused there)
@@ -197,29 +203,37 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     o->big = big ? 1 : 0;
   };
   layout(false);
-  // one CTA per SM (more than half of the 228 KB minus the per-CTA reserve) → big layout; 4-player kernels exist only in it
-  const size_t two_per_sm = (228u * 1024u - 2u * 1024u) / 2u;
-  const char* force = getenv("AGB_FORCE_BIG_LAYOUT");         // test hook: exercise the big layout on small 3-player instances
-  if (p >= 4 || (p == 3 && ((size_t)o->smem_doubles * sizeof(double) > two_per_sm || (force && force[0] == '1')))) layout(true);
+  // layout choice (DevDesc::big: 0 small / 1 big storage, 2 CTAs per SM / 2 big storage, 4 CTAs per SM):
+  //   small if it gives 4 CTAs per SM; else big storage with 4 CTAs/SM if that fits (mid-size 3-player games);
+  //   else big storage with 2 CTAs/SM and up to 255 registers.  4-player kernels exist only as layout 1.
+  const size_t four_per_sm = (228u * 1024u - 4u * 1024u) / 4u;
+  const char* force = getenv("AGB_FORCE_BIG_LAYOUT");         // test hook: "1" / "2" force that layout on 3-player instances
+  const size_t small_bytes = (size_t)o->smem_doubles * sizeof(double);
+  if (p >= 4) { layout(true); o->big = 1; }
+  else if (p == 3 && force && (force[0] == '1' || force[0] == '2')) { layout(true); o->big = force[0] - '0'; }
+  else if (p == 3 && small_bytes > four_per_sm) {
+    layout(true);
+    o->big = ((size_t)o->smem_doubles * sizeof(double) <= four_per_sm) ? 2 : 1;
+  }
   return AGB_OK;
 }
 
 namespace agb {
 cudaError_t set_attr(int p, int big, int model, size_t smem) {
   switch (p) { case 1: return set_attr_p1(model, smem); case 2: return set_attr_p2(model, smem);
-               case 3: return big ? set_attr_p3b(model, smem) : set_attr_p3(model, smem); default: return set_attr_p4(model, smem); }
+               case 3: return big == 1 ? set_attr_p3b(model, smem) : (big == 2 ? set_attr_p3m(model, smem) : set_attr_p3(model, smem)); default: return set_attr_p4(model, smem); }
 }
 void launch_solve(int p, int big, const LaunchArgs& L) {
   switch (p) { case 1: launch_solve_p1(L); break; case 2: launch_solve_p2(L); break;
-               case 3: if (big) launch_solve_p3b(L); else launch_solve_p3(L); break; default: launch_solve_p4(L); }
+               case 3: if (big == 1) launch_solve_p3b(L); else if (big == 2) launch_solve_p3m(L); else launch_solve_p3(L); break; default: launch_solve_p4(L); }
 }
 void launch_ibr(int p, int big, const LaunchArgs& L) {
   switch (p) { case 1: launch_ibr_p1(L); break; case 2: launch_ibr_p2(L); break;
-               case 3: if (big) launch_ibr_p3b(L); else launch_ibr_p3(L); break; default: launch_ibr_p4(L); }
+               case 3: if (big == 1) launch_ibr_p3b(L); else if (big == 2) launch_ibr_p3m(L); else launch_ibr_p3(L); break; default: launch_ibr_p4(L); }
 }
 void launch_op(int p, int big, const LaunchArgs& L) {
   switch (p) { case 1: launch_op_p1(L); break; case 2: launch_op_p2(L); break;
-               case 3: if (big) launch_op_p3b(L); else launch_op_p3(L); break; default: launch_op_p4(L); }
+               case 3: if (big == 1) launch_op_p3b(L); else if (big == 2) launch_op_p3m(L); else launch_op_p3(L); break; default: launch_op_p4(L); }
 }
 }  // namespace agb
 

@@ -42,10 +42,13 @@ struct DevDesc {
   int ub_row[AGB_MAX_M], lb_row[AGB_MAX_M];   // row inside the stage row block, -1 = none
   double u_max[AGB_MAX_M], u_min[AGB_MAX_M];
   int nrow_state, nrow_control, nrow;
+  // CW (active weights) is kept for bound rows only: compact index = row - sb_shift[i] (state bounds of player i) or
+  // row - cb_shift (control bounds); ncw compact rows per stage
+  int sb_shift[AGB_MAX_P], cb_shift, ncw;
   // shared-memory layout (offsets in doubles)
   int o_X, o_U, o_L, o_R, o_KU, o_AB, o_CL, o_CM, o_CW, o_Gp, o_Hp, o_Gs, o_Hs, o_P, o_Sv, o_Y, o_Aug, o_Base, o_W, o_Ta, o_par, o_red;
   int smem_doubles;
-  int big;                                 // 1: L, CL, CM, Hp, Hs in global memory (kernels instantiated with BIG = true)
+  int big;                                 // layout: 0 small; 1, 2: L, CL, CM, Hp, Hs in global memory (2 resp. 4 CTAs per SM)
 };
 
 // Per-batch device buffers (all FP64 unless noted); layouts as in include/algames_b200.h.

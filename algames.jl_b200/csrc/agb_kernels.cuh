@@ -16,14 +16,14 @@ namespace agb {
 // Kernels
 // =============================================================================================================
 // newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
-template <int P, int MODEL, bool BIG>
-__global__ void __launch_bounds__(threads_for(P), (BIG ? 2 : 4)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch) {
+template <int P, int MODEL, int LAY>
+__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : 4)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch) {
   AGB_DYN_SMEM(sm);
-  Inst<P, MODEL, BIG> I;
+  Inst<P, MODEL, (LAY != 0)> I;
   I.bind(dd, sm);
-  constexpr int n = Inst<P, MODEL, BIG>::n, kThreads = threads_for(P);
+  constexpr int n = Inst<P, MODEL, (LAY != 0)>::n, kThreads = threads_for(P);
   const int K = I.K;
-  const double S = (double)(K * Inst<P, MODEL, BIG>::b);
+  const double S = (double)(K * Inst<P, MODEL, (LAY != 0)>::b);
   for (int inst = inst0 + blockIdx.x; inst < batch; inst += gridDim.x) {   // instances [inst0, batch)
     __syncthreads();
     I.bind_instance(g, inst);
@@ -100,13 +100,13 @@ __global__ void __launch_bounds__(threads_for(P), (BIG ? 2 : 4)) agb_newton_solv
 }
 
 // ibr_newton_solve!(prob; ibr_opts) for every instance (solver_methods.jl:133-224); one CTA per instance.
-template <int P, int MODEL, bool BIG>
-__global__ void __launch_bounds__(threads_for(P), (BIG ? 2 : 4)) agb_ibr_solve_kernel(const DevDesc* __restrict__ dd, agb_options o,
+template <int P, int MODEL, int LAY>
+__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : 4)) agb_ibr_solve_kernel(const DevDesc* __restrict__ dd, agb_options o,
                                                                                           agb_ibr_options io, Buffers g, int batch) {
   AGB_DYN_SMEM(sm);
-  Inst<P, MODEL, BIG> I;
+  Inst<P, MODEL, (LAY != 0)> I;
   I.bind(dd, sm);
-  constexpr int n = Inst<P, MODEL, BIG>::n, kThreads = threads_for(P);
+  constexpr int n = Inst<P, MODEL, (LAY != 0)>::n, kThreads = threads_for(P);
   const int K = I.K;
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
     __syncthreads();
@@ -187,12 +187,12 @@ __global__ void __launch_bounds__(threads_for(P), (BIG ? 2 : 4)) agb_ibr_solve_k
 }
 
 // Per-function entry points on the resident batch (parity tests and stand-alone use of the exported reference API).
-template <int P, int MODEL, bool BIG>
+template <int P, int MODEL, int LAY>
 __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
   AGB_DYN_SMEM(sm);
-  Inst<P, MODEL, BIG> I;
+  Inst<P, MODEL, (LAY != 0)> I;
   I.bind(dd, sm);
-  constexpr int n = Inst<P, MODEL, BIG>::n, m = Inst<P, MODEL, BIG>::m, b = Inst<P, MODEL, BIG>::b, kThreads = threads_for(P);
+  constexpr int n = Inst<P, MODEL, (LAY != 0)>::n, m = Inst<P, MODEL, (LAY != 0)>::m, b = Inst<P, MODEL, (LAY != 0)>::b, kThreads = threads_for(P);
   const int K = I.K, Sz = K * b, nrow = I.nrow;
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
     __syncthreads();
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* _
         }
       } break;
       case OP_GAIN_SOLVE: {
-        constexpr int W = Inst<P, MODEL, BIG>::W;
+        constexpr int W = Inst<P, MODEL, (LAY != 0)>::W;
         for (int q = I.tid; q < m * W; q += kThreads) I.Aug[q] = a.in0[(size_t)inst * m * W + q];
         __syncthreads();
         int ok = 1;
@@ -329,55 +329,56 @@ struct LaunchArgs {
   int inst0;             // first instance of the launch (newton_solve only; chunked host pipeline)
 };
 
-template <int P, int MODEL, bool BIG> inline cudaError_t set_attr_pm(size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)agb_newton_solve_kernel<P, MODEL, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int P, int MODEL, int LAY> inline cudaError_t set_attr_pm(size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)agb_newton_solve_kernel<P, MODEL, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute((const void*)agb_ibr_solve_kernel<P, MODEL, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute((const void*)agb_ibr_solve_kernel<P, MODEL, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)agb_op_kernel<P, MODEL, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute((const void*)agb_op_kernel<P, MODEL, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <int P, bool BIG> inline cudaError_t set_attr_p(int model, size_t smem) {
+template <int P, int LAY> inline cudaError_t set_attr_p(int model, size_t smem) {
   switch (model) {
-    case AGB_MODEL_DOUBLE_INTEGRATOR: return set_attr_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, BIG>(smem);
-    case AGB_MODEL_UNICYCLE: return set_attr_pm<P, AGB_MODEL_UNICYCLE, BIG>(smem);
-    default: return set_attr_pm<P, AGB_MODEL_BICYCLE, BIG>(smem);
+    case AGB_MODEL_DOUBLE_INTEGRATOR: return set_attr_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, LAY>(smem);
+    case AGB_MODEL_UNICYCLE: return set_attr_pm<P, AGB_MODEL_UNICYCLE, LAY>(smem);
+    default: return set_attr_pm<P, AGB_MODEL_BICYCLE, LAY>(smem);
   }
 }
-template <int P, int MODEL, bool BIG> inline void launch_solve_pm(const LaunchArgs& L) {
-  auto kfn = agb_newton_solve_kernel<P, MODEL, BIG>;
+template <int P, int MODEL, int LAY> inline void launch_solve_pm(const LaunchArgs& L) {
+  auto kfn = agb_newton_solve_kernel<P, MODEL, LAY>;
   AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.inst0, L.batch);
 }
-template <int P, int MODEL, bool BIG> inline void launch_ibr_pm(const LaunchArgs& L) {
-  auto kfn = agb_ibr_solve_kernel<P, MODEL, BIG>;
+template <int P, int MODEL, int LAY> inline void launch_ibr_pm(const LaunchArgs& L) {
+  auto kfn = agb_ibr_solve_kernel<P, MODEL, LAY>;
   AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.io, L.g, L.batch);
 }
-template <int P, bool BIG> inline void launch_ibr_p(const LaunchArgs& L) {
+template <int P, int LAY> inline void launch_ibr_p(const LaunchArgs& L) {
   switch (L.model) {
-    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_ibr_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, BIG>(L); break;
-    case AGB_MODEL_UNICYCLE: launch_ibr_pm<P, AGB_MODEL_UNICYCLE, BIG>(L); break;
-    default: launch_ibr_pm<P, AGB_MODEL_BICYCLE, BIG>(L); break;
+    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_ibr_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, LAY>(L); break;
+    case AGB_MODEL_UNICYCLE: launch_ibr_pm<P, AGB_MODEL_UNICYCLE, LAY>(L); break;
+    default: launch_ibr_pm<P, AGB_MODEL_BICYCLE, LAY>(L); break;
   }
 }
-template <int P, int MODEL, bool BIG> inline void launch_op_pm(const LaunchArgs& L) {
-  auto kfn = agb_op_kernel<P, MODEL, BIG>;
+template <int P, int MODEL, int LAY> inline void launch_op_pm(const LaunchArgs& L) {
+  auto kfn = agb_op_kernel<P, MODEL, LAY>;
   AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.a, L.batch);
 }
-template <int P, bool BIG> inline void launch_solve_p(const LaunchArgs& L) {
+template <int P, int LAY> inline void launch_solve_p(const LaunchArgs& L) {
   switch (L.model) {
-    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_solve_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, BIG>(L); break;
-    case AGB_MODEL_UNICYCLE: launch_solve_pm<P, AGB_MODEL_UNICYCLE, BIG>(L); break;
-    default: launch_solve_pm<P, AGB_MODEL_BICYCLE, BIG>(L); break;
+    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_solve_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, LAY>(L); break;
+    case AGB_MODEL_UNICYCLE: launch_solve_pm<P, AGB_MODEL_UNICYCLE, LAY>(L); break;
+    default: launch_solve_pm<P, AGB_MODEL_BICYCLE, LAY>(L); break;
   }
 }
-template <int P, bool BIG> inline void launch_op_p(const LaunchArgs& L) {
+template <int P, int LAY> inline void launch_op_p(const LaunchArgs& L) {
   switch (L.model) {
-    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_op_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, BIG>(L); break;
-    case AGB_MODEL_UNICYCLE: launch_op_pm<P, AGB_MODEL_UNICYCLE, BIG>(L); break;
-    default: launch_op_pm<P, AGB_MODEL_BICYCLE, BIG>(L); break;
+    case AGB_MODEL_DOUBLE_INTEGRATOR: launch_op_pm<P, AGB_MODEL_DOUBLE_INTEGRATOR, LAY>(L); break;
+    case AGB_MODEL_UNICYCLE: launch_op_pm<P, AGB_MODEL_UNICYCLE, LAY>(L); break;
+    default: launch_op_pm<P, AGB_MODEL_BICYCLE, LAY>(L); break;
   }
 }
 
-// defined in agb_kernels_p<P>.cu (small layout: P = 1..3) and agb_kernels_p3b.cu / agb_kernels_p4.cu (big layout: P = 3, 4)
+// layouts (DevDesc::big): 0 = small, 4 CTAs/SM (agb_kernels_p1..p3.cu); 1 = big storage, 2 CTAs/SM, up to 255 registers
+// (agb_kernels_p3b.cu, agb_kernels_p4.cu); 2 = big storage, 4 CTAs/SM, 128 registers (agb_kernels_p3m.cu: mid-size 3-player games)
 cudaError_t set_attr(int p, int big, int model, size_t smem);
 void launch_solve(int p, int big, const LaunchArgs& L);
 void launch_op(int p, int big, const LaunchArgs& L);
@@ -387,6 +388,6 @@ void launch_ibr(int p, int big, const LaunchArgs& L);
   void launch_solve_p##PP(const LaunchArgs& L);            \
   void launch_op_p##PP(const LaunchArgs& L);              \
   void launch_ibr_p##PP(const LaunchArgs& L);
-AGB_DECLARE_P(1) AGB_DECLARE_P(2) AGB_DECLARE_P(3) AGB_DECLARE_P(3b) AGB_DECLARE_P(4)
+AGB_DECLARE_P(1) AGB_DECLARE_P(2) AGB_DECLARE_P(3) AGB_DECLARE_P(3b) AGB_DECLARE_P(3m) AGB_DECLARE_P(4)
 
 }  // namespace agb

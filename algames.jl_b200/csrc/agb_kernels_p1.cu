@@ -1,8 +1,8 @@
-// agb_kernels_p1.cu — instantiates the instance kernels for 1 player(s), small layout (one TU each: parallel builds).
+// agb_kernels_p1.cu — instantiates the instance kernels for 1 player(s), layout 0 (see agb_kernels.cuh; one TU each: parallel builds).
 #include "agb_kernels.cuh"
 namespace agb {
-cudaError_t set_attr_p1(int model, size_t smem) { return set_attr_p<1, false>(model, smem); }
-void launch_solve_p1(const LaunchArgs& L) { launch_solve_p<1, false>(L); }
-void launch_op_p1(const LaunchArgs& L) { launch_op_p<1, false>(L); }
-void launch_ibr_p1(const LaunchArgs& L) { launch_ibr_p<1, false>(L); }
+cudaError_t set_attr_p1(int model, size_t smem) { return set_attr_p<1, 0>(model, smem); }
+void launch_solve_p1(const LaunchArgs& L) { launch_solve_p<1, 0>(L); }
+void launch_op_p1(const LaunchArgs& L) { launch_op_p<1, 0>(L); }
+void launch_ibr_p1(const LaunchArgs& L) { launch_ibr_p<1, 0>(L); }
 }  // namespace agb

@@ -1,0 +1,8 @@
+// agb_kernels_p3m.cu — instantiates the instance kernels for 3 player(s), layout 2 (see agb_kernels.cuh; one TU each: parallel builds).
+#include "agb_kernels.cuh"
+namespace agb {
+cudaError_t set_attr_p3m(int model, size_t smem) { return set_attr_p<3, 2>(model, smem); }
+void launch_solve_p3m(const LaunchArgs& L) { launch_solve_p<3, 2>(L); }
+void launch_op_p3m(const LaunchArgs& L) { launch_op_p<3, 2>(L); }
+void launch_ibr_p3m(const LaunchArgs& L) { launch_ibr_p<3, 2>(L); }
+}  // namespace agb

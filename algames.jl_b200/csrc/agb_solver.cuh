@@ -228,7 +228,7 @@ struct Inst {
   }
 
   const DevDesc* __restrict__ d;
-  int N, K, nrow, has_cc, has_pairs, has_self, has_sb, has_cb;
+  int N, K, nrow, ncw, has_cc, has_pairs, has_self, has_sb, has_cb;
   static constexpr int model = MODEL;
   double dt;
   SP X, U, R, KU, AB, CW, Gp, Gs, Pm, Sv, Ym, Aug, Base, Wm, Hm, xf, Q, Rw, uf, red;
@@ -240,7 +240,7 @@ struct Inst {
   int tid, lane, warp;
 
   __device__ void bind(const DevDesc* dd, double* sm) {
-    d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; has_cc = dd->has_cc; has_sb = dd->has_sb; has_cb = dd->has_cb;
+    d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; ncw = dd->ncw; has_cc = dd->has_cc; has_sb = dd->has_sb; has_cb = dd->has_cb;
     has_pairs = dd->has_pairs; has_self = dd->has_self; dt = dd->dt;
     (void)sm;
     X.off = dd->o_X; U.off = dd->o_U; R.off = dd->o_R; KU.off = dd->o_KU; AB.off = dd->o_AB;
@@ -460,13 +460,13 @@ struct Inst {
       if (row >= 0) {
         const double cv = xa - d->x_max[i][a];
         double w; const double g = al_row(s, row, cv, w);
-        v += g; acc.sta = fmax(acc.sta, cv); CW[s * nrow + row] = w;
+        v += g; acc.sta = fmax(acc.sta, cv); CW[s * ncw + row - d->sb_shift[i]] = w;
       }
       row = d->sbmin_row[i][a];
       if (row >= 0) {
         const double cv = d->x_min[i][a] - xa;
         double w; const double g = al_row(s, row, cv, w);
-        v -= g; acc.sta = fmax(acc.sta, cv); CW[s * nrow + row] = w;
+        v -= g; acc.sta = fmax(acc.sta, cv); CW[s * ncw + row - d->sb_shift[i]] = w;
       }
     }
     if (k < K) {                                                      // + A_kᵀ λ_{i,k}   (global_quantities.jl:45-53)
@@ -496,13 +496,13 @@ struct Inst {
       if (row >= 0) {
         const double cv = ua - d->u_max[idx];
         double w; const double g = al_row(s, row, cv, w);
-        v += g; if (pl < 0) acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
+        v += g; if (pl < 0) acc.con = fmax(acc.con, cv); CW[s * ncw + row - d->cb_shift] = w;
       }
       row = d->lb_row[idx];
       if (row >= 0) {
         const double cv = d->u_min[idx] - ua;
         double w; const double g = al_row(s, row, cv, w);
-        v -= g; if (pl < 0) acc.con = fmax(acc.con, cv); CW[s * nrow + row] = w;
+        v -= g; if (pl < 0) acc.con = fmax(acc.con, cv); CW[s * ncw + row - d->cb_shift] = w;
       }
     }
     plain = v;
@@ -617,8 +617,8 @@ struct Inst {
     double v = reg_x;
     if (ia == i) v += ((k < K) ? dt : 1.0) * Q[a];
     if (has_sb) {
-      int row = d->sbmax_row[i][a]; if (row >= 0) v += CW[s * nrow + row];
-      row = d->sbmin_row[i][a];     if (row >= 0) v += CW[s * nrow + row];
+      int row = d->sbmax_row[i][a]; if (row >= 0) v += CW[s * ncw + row - d->sb_shift[i]];
+      row = d->sbmin_row[i][a];     if (row >= 0) v += CW[s * ncw + row - d->sb_shift[i]];
     }
     return v;
   }
@@ -631,8 +631,8 @@ struct Inst {
   __device__ __forceinline__ double hu_entry(int s, int idx, double reg_u) const {
     double v = dt * Rw[idx] + reg_u;
     if (has_cb) {
-      int row = d->ub_row[idx]; if (row >= 0) v += CW[s * nrow + row];
-      row = d->lb_row[idx];     if (row >= 0) v += CW[s * nrow + row];
+      int row = d->ub_row[idx]; if (row >= 0) v += CW[s * ncw + row - d->cb_shift];
+      row = d->lb_row[idx];     if (row >= 0) v += CW[s * ncw + row - d->cb_shift];
     }
     return v;
   }

@@ -27,16 +27,19 @@ def test_per_function_parity(name, N):
     parity.check_per_function(LIB, name, seed=2, N=N)
 
 
-@pytest.mark.parametrize("name,N", [("A'", None), ("B", None), ("D", None), ("E", None)])
-def test_big_layout_per_function_parity(monkeypatch, name, N):
+@pytest.mark.parametrize("lay", ["1", "2"])
+@pytest.mark.parametrize("name,N", [("A'", None), ("B", None), ("D", None), ("E", 30)])
+def test_big_layout_per_function_parity(monkeypatch, name, N, lay):
     """3-player instances in the big layout (duals / multipliers / pair blocks in global memory): E at its full N = 60 uses it
-    by itself, the hook forces it on the others; config C (4 players) always runs in it."""
-    monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", "1")
+    by itself (test_full_size_properties), the hook forces layout 1 (2 CTAs/SM) or 2 (4 CTAs/SM, what mid-size games such as
+    config D get) on the others; config C (4 players) always runs in layout 1."""
+    monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", lay)
     parity.check_per_function(LIB, name, seed=3, N=N)
 
 
-def test_big_layout_solves(monkeypatch):
-    monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", "1")
+@pytest.mark.parametrize("lay", ["1", "2"])
+def test_big_layout_solves(monkeypatch, lay):
+    monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", lay)
     parity.check_solve_vs_oracle(LIB, "B", B=2)
     parity.check_solve_vs_oracle(LIB, "D", B=1, N=12)
     parity.check_ibr_solve(LIB, "B", B=1, N=10, ibr_iter=2)
