@@ -190,11 +190,11 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     o->o_P = take(p * n * n); o->o_Sv = take(p * n); o->o_Y = take(m * (n + 1)); o->o_Aug = take(m * W);
     o->o_KU = o->o_Aug;                          // one-stage gain buffer of the best-response factorisation (Aug is unused there)
     o->o_Base = take(p * n * (n + 1)); o->o_W = take(p * n * m); o->o_Ta = take(2 * p * (4 * p * p + n));   // Hm: double-buffered per-stage H^x blocks (Inst::HmS per player)
-    {  // Gp / Gs live only inside one residual evaluation, Base / W / Hm only inside kkt_solve: alias them when they fit
+    {  // Gp / Gs live only inside one residual evaluation, the factorisation scratch (P … Hm) only inside kkt_solve: alias them
       const int need = (o->has_pairs ? N * o->npairs * 2 : 0) + (o->has_self ? N * p * 2 : 0);
-      const int have = off - o->o_Base;
+      const int have = off - o->o_P;
       if (need > have) take(need - have);
-      o->o_Gp = o->o_Base; o->o_Gs = o->o_Base + (o->has_pairs ? N * o->npairs * 2 : 0);
+      o->o_Gp = o->o_P; o->o_Gs = o->o_P + (o->has_pairs ? N * o->npairs * 2 : 0);
     }
     // the forward sweep lays a 4-stage ring of padded gain blocks (Inst::KUSP = m*(n+2)) over [o_P, end of Hm)
     if (off - o->o_P < 4 * m * (n + 2)) take(4 * m * (n + 2) - (off - o->o_P));
@@ -203,17 +203,18 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     o->big = big ? 1 : 0;
   };
   layout(false);
-  // layout choice (DevDesc::big: 0 small / 1 big storage, 2 CTAs per SM / 2 big storage, 4 CTAs per SM):
-  //   small if it gives 4 CTAs per SM; else big storage with 4 CTAs/SM if that fits (mid-size 3-player games);
-  //   else big storage with 2 CTAs/SM and up to 255 registers.  4-player kernels exist only as layout 1.
+  // layout choice (DevDesc::big: 0 small / big storage with 1: 2, 2: 4, 3: 3 CTAs per SM):
+  //   small if it gives 4 CTAs per SM; else big storage with as many CTAs per SM as its footprint allows (4 at 128
+  //   registers, 3 at 168, 2 at 255).  4-player kernels exist only as layout 1.
   const size_t four_per_sm = (228u * 1024u - 4u * 1024u) / 4u;
-  const char* force = getenv("AGB_FORCE_BIG_LAYOUT");         // test hook: "1" / "2" force that layout on 3-player instances
+  const char* force = getenv("AGB_FORCE_BIG_LAYOUT");         // test hook: "1" / "2" / "3" force that layout on 3-player instances
   const size_t small_bytes = (size_t)o->smem_doubles * sizeof(double);
   if (p >= 4) { layout(true); o->big = 1; }
-  else if (p == 3 && force && (force[0] == '1' || force[0] == '2')) { layout(true); o->big = force[0] - '0'; }
+  else if (p == 3 && force && force[0] >= '1' && force[0] <= '3') { layout(true); o->big = force[0] - '0'; }
   else if (p == 3 && small_bytes > four_per_sm) {
     layout(true);
-    o->big = ((size_t)o->smem_doubles * sizeof(double) <= four_per_sm) ? 2 : 1;
+    const size_t big_bytes = (size_t)o->smem_doubles * sizeof(double), three_per_sm = (228u * 1024u - 3u * 1024u) / 3u;
+    o->big = big_bytes <= four_per_sm ? 2 : (big_bytes <= three_per_sm ? 3 : 1);
   }
   return AGB_OK;
 }
@@ -221,19 +222,19 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
 namespace agb {
 cudaError_t set_attr(int p, int big, int model, size_t smem) {
   switch (p) { case 1: return set_attr_p1(model, smem); case 2: return set_attr_p2(model, smem);
-               case 3: return big == 1 ? set_attr_p3b(model, smem) : (big == 2 ? set_attr_p3m(model, smem) : set_attr_p3(model, smem)); default: return set_attr_p4(model, smem); }
+               case 3: return big == 1 ? set_attr_p3b(model, smem) : (big == 2 ? set_attr_p3m(model, smem) : (big == 3 ? set_attr_p3t(model, smem) : set_attr_p3(model, smem))); default: return set_attr_p4(model, smem); }
 }
 void launch_solve(int p, int big, const LaunchArgs& L) {
   switch (p) { case 1: launch_solve_p1(L); break; case 2: launch_solve_p2(L); break;
-               case 3: if (big == 1) launch_solve_p3b(L); else if (big == 2) launch_solve_p3m(L); else launch_solve_p3(L); break; default: launch_solve_p4(L); }
+               case 3: if (big == 1) launch_solve_p3b(L); else if (big == 2) launch_solve_p3m(L); else if (big == 3) launch_solve_p3t(L); else launch_solve_p3(L); break; default: launch_solve_p4(L); }
 }
 void launch_ibr(int p, int big, const LaunchArgs& L) {
   switch (p) { case 1: launch_ibr_p1(L); break; case 2: launch_ibr_p2(L); break;
-               case 3: if (big == 1) launch_ibr_p3b(L); else if (big == 2) launch_ibr_p3m(L); else launch_ibr_p3(L); break; default: launch_ibr_p4(L); }
+               case 3: if (big == 1) launch_ibr_p3b(L); else if (big == 2) launch_ibr_p3m(L); else if (big == 3) launch_ibr_p3t(L); else launch_ibr_p3(L); break; default: launch_ibr_p4(L); }
 }
 void launch_op(int p, int big, const LaunchArgs& L) {
   switch (p) { case 1: launch_op_p1(L); break; case 2: launch_op_p2(L); break;
-               case 3: if (big == 1) launch_op_p3b(L); else if (big == 2) launch_op_p3m(L); else launch_op_p3(L); break; default: launch_op_p4(L); }
+               case 3: if (big == 1) launch_op_p3b(L); else if (big == 2) launch_op_p3m(L); else if (big == 3) launch_op_p3t(L); else launch_op_p3(L); break; default: launch_op_p4(L); }
 }
 }  // namespace agb
 

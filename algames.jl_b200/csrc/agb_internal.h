@@ -48,7 +48,7 @@ struct DevDesc {
   // shared-memory layout (offsets in doubles)
   int o_X, o_U, o_L, o_R, o_KU, o_AB, o_CL, o_CM, o_CW, o_Gp, o_Hp, o_Gs, o_Hs, o_P, o_Sv, o_Y, o_Aug, o_Base, o_W, o_Ta, o_par, o_red;
   int smem_doubles;
-  int big;                                 // layout: 0 small; 1, 2: L, CL, CM, Hp, Hs in global memory (2 resp. 4 CTAs per SM)
+  int big;                                 // layout: 0 small; 1, 2, 3: L, CL, CM, Hp, Hs in global memory (2, 4, 3 CTAs per SM)
 };
 
 // Per-batch device buffers (all FP64 unless noted); layouts as in include/algames_b200.h.

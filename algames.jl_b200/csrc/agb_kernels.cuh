@@ -17,7 +17,7 @@ namespace agb {
 // =============================================================================================================
 // newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
 template <int P, int MODEL, int LAY>
-__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : 4)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch) {
+__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 : 4))) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;
   I.bind(dd, sm);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : 4)) agb_newton
 
 // ibr_newton_solve!(prob; ibr_opts) for every instance (solver_methods.jl:133-224); one CTA per instance.
 template <int P, int MODEL, int LAY>
-__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : 4)) agb_ibr_solve_kernel(const DevDesc* __restrict__ dd, agb_options o,
+__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 : 4))) agb_ibr_solve_kernel(const DevDesc* __restrict__ dd, agb_options o,
                                                                                           agb_ibr_options io, Buffers g, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;
@@ -378,7 +378,7 @@ template <int P, int LAY> inline void launch_op_p(const LaunchArgs& L) {
 }
 
 // layouts (DevDesc::big): 0 = small, 4 CTAs/SM (agb_kernels_p1..p3.cu); 1 = big storage, 2 CTAs/SM, up to 255 registers
-// (agb_kernels_p3b.cu, agb_kernels_p4.cu); 2 = big storage, 4 CTAs/SM, 128 registers (agb_kernels_p3m.cu: mid-size 3-player games)
+// (agb_kernels_p3b.cu, agb_kernels_p4.cu); 2 / 3 = big storage, 4 CTAs/SM at 128 registers / 3 CTAs/SM at 168 (agb_kernels_p3m.cu, agb_kernels_p3t.cu: mid-size 3-player games)
 cudaError_t set_attr(int p, int big, int model, size_t smem);
 void launch_solve(int p, int big, const LaunchArgs& L);
 void launch_op(int p, int big, const LaunchArgs& L);
@@ -388,6 +388,6 @@ void launch_ibr(int p, int big, const LaunchArgs& L);
   void launch_solve_p##PP(const LaunchArgs& L);            \
   void launch_op_p##PP(const LaunchArgs& L);              \
   void launch_ibr_p##PP(const LaunchArgs& L);
-AGB_DECLARE_P(1) AGB_DECLARE_P(2) AGB_DECLARE_P(3) AGB_DECLARE_P(3b) AGB_DECLARE_P(3m) AGB_DECLARE_P(4)
+AGB_DECLARE_P(1) AGB_DECLARE_P(2) AGB_DECLARE_P(3) AGB_DECLARE_P(3b) AGB_DECLARE_P(3m) AGB_DECLARE_P(3t) AGB_DECLARE_P(4)
 
 }  // namespace agb

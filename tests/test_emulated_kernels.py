@@ -78,14 +78,14 @@ def test_statistics_history_single_problem_emulated(emu_lib):
 
 # ---- big layout (duals, AL multipliers and pair/self Hessian blocks in global memory; agb_internal.h): 4-player games always
 # use it (config C above); the test hook forces it on small 3-player instances
-@pytest.mark.parametrize("lay", ["1", "2"])
+@pytest.mark.parametrize("lay", ["1", "2", "3"])
 @pytest.mark.parametrize("name,N", [("A'", None), ("B", 12), ("E", 12)])
 def test_big_layout_per_function_parity_emulated(emu_lib, monkeypatch, name, N, lay):
     monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", lay)
     parity.check_per_function(emu_lib, name, seed=2, N=N)
 
 
-@pytest.mark.parametrize("lay", ["1", "2"])
+@pytest.mark.parametrize("lay", ["1", "2", "3"])
 def test_big_layout_solve_emulated(emu_lib, monkeypatch, lay):
     monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", lay)
     parity.check_solve_vs_oracle(emu_lib, "B", B=2, N=12)

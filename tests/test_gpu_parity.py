@@ -27,7 +27,7 @@ def test_per_function_parity(name, N):
     parity.check_per_function(LIB, name, seed=2, N=N)
 
 
-@pytest.mark.parametrize("lay", ["1", "2"])
+@pytest.mark.parametrize("lay", ["1", "2", "3"])
 @pytest.mark.parametrize("name,N", [("A'", None), ("B", None), ("D", None), ("E", 30)])
 def test_big_layout_per_function_parity(monkeypatch, name, N, lay):
     """3-player instances in the big layout (duals / multipliers / pair blocks in global memory): E at its full N = 60 uses it
@@ -37,7 +37,7 @@ def test_big_layout_per_function_parity(monkeypatch, name, N, lay):
     parity.check_per_function(LIB, name, seed=3, N=N)
 
 
-@pytest.mark.parametrize("lay", ["1", "2"])
+@pytest.mark.parametrize("lay", ["1", "2", "3"])
 def test_big_layout_solves(monkeypatch, lay):
     monkeypatch.setenv("AGB_FORCE_BIG_LAYOUT", lay)
     parity.check_solve_vs_oracle(LIB, "B", B=2)
