@@ -439,12 +439,14 @@ struct Inst {
   }
 
   // one element of player i's stationarity row block w.r.t. x at knot k (1..K), joint comp a
-  template <bool TRIAL> __device__ double xrow_elem(int i, int k, int a, double alpha, double reg_x, Acc& acc, double& plain) {
+  // HALF: 0 = the caller guarantees a position component (c < 2), 1 = a velocity / heading component (c >= 2), -1 = unknown
+  template <bool TRIAL, int HALF = -1> __device__ double xrow_elem(int i, int k, int a, double alpha, double reg_x, Acc& acc, double& plain) {
     const int c = a / P, ia = a - c * P, s = k - 1;
+    const bool is_pos = HALF < 0 ? (c < 2) : (HALF == 0);
     const double xa = xg<TRIAL>(k, a, alpha);
     double v = 0.0;
     if (ia == i) v = ((k < K) ? dt : 1.0) * Q[a] * (xa - xf[a]);      // LQR gradient (objective.jl:24-32)
-    if (c < 2) {
+    if (is_pos) {
       if (has_pairs) {
         if (ia == i) {
 #pragma unroll
@@ -471,7 +473,7 @@ struct Inst {
     }
     if (k < K) {                                                      // + A_kᵀ λ_{i,k}   (global_quantities.jl:45-53)
       v += lg<TRIAL>(i, k, a, alpha);
-      if (c >= 2) {
+      if (!is_pos) {
         double At[8], Bt[8]; loadAB(k, ia, At, Bt);
         v += at_dot_sel(c - 2, At, lg<TRIAL>(i, k, ia, alpha), lg<TRIAL>(i, k, P + ia, alpha),
                         lg<TRIAL>(i, k, 2 * P + ia, alpha), lg<TRIAL>(i, k, 3 * P + ia, alpha));
@@ -548,18 +550,23 @@ struct Inst {
     pass_pairs<TRIAL>(alpha, acc);
     pass_self<TRIAL>(alpha, acc);
     __syncthreads();
-    const int nx = P * K * n;
-    for (int item = tid; item < nx; item += kThreads) {
-      const int s = item / (P * n), rem = item - s * (P * n);                // stage-major: compile-time divisors only
-      const int i = rem / n, a = rem - i * n;
-      if (pl >= 0 && i != pl) { if (Rout) Rout[s * b + OX + i * n + a] = 0.0; continue; }    // IBR: rows of player pl only
-      double pv;
-      double v = xrow_elem<TRIAL>(i, s + 1, a, alpha, reg_x, acc, pv);
-      acc.sum += fabs(v);
-      acc.psum += fabs(pv);
-      if (keep) v = pv;
-      acc.opt = fmax(acc.opt, fabs(v));
-      if (Rout) Rout[s * b + OX + i * n + a] = v;
+    // x rows in two passes — position components (pair / wall / circle terms), then velocity / heading components (Aᵀλ
+    // terms) — so that the lanes of a warp follow one path; stage-major item order, compile-time divisors only
+    const int nxh = P * K * 2 * P;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      for (int item = tid; item < nxh; item += kThreads) {
+        const int s = item / (P * 2 * P), rem = item - s * (P * 2 * P);
+        const int i = rem / (2 * P), a = half * 2 * P + (rem - i * (2 * P));
+        if (pl >= 0 && i != pl) { if (Rout) Rout[s * b + OX + i * n + a] = 0.0; continue; }    // IBR: rows of player pl only
+        double pv;
+        double v = half == 0 ? xrow_elem<TRIAL, 0>(i, s + 1, a, alpha, reg_x, acc, pv) : xrow_elem<TRIAL, 1>(i, s + 1, a, alpha, reg_x, acc, pv);
+        acc.sum += fabs(v);
+        acc.psum += fabs(pv);
+        if (keep) v = pv;
+        acc.opt = fmax(acc.opt, fabs(v));
+        if (Rout) Rout[s * b + OX + i * n + a] = v;
+      }
     }
     const int nu = K * m;
     for (int item = tid; item < nu; item += kThreads) {
@@ -1072,11 +1079,12 @@ struct Inst {
   }
 
   // g_{i,k}[a] = r^x_{i,k}[a] + (H_{i,k} Δx_k)[a], k = s+1 (the opt-x row of player i without its multiplier terms)
-  __device__ __forceinline__ double costate_g(int i, int s, int a, double reg_x) const {
+  template <int HALF = -1> __device__ __forceinline__ double costate_g(int i, int s, int a, double reg_x) const {
     const int k = s + 1, c = a / P, ia = a - c * P;
+    const bool is_pos = HALF < 0 ? (c < 2) : (HALF == 0);
     const double* dx = R + s * b + OD;
     double v = R[s * b + OX + i * n + a] + hd_entry(i, k, a, reg_x) * dx[a];
-    if (c < 2) {
+    if (is_pos) {
       if (ia == i) {
         if (has_pairs) {
 #pragma unroll
@@ -1185,10 +1193,15 @@ struct Inst {
     // ---- costate: Δλ_{i,k−1} = g_{i,k} + A_kᵀ Δλ_{i,k} with g_{i,k} = H_{i,k} Δx_k + r^x_{i,k} (exactly the opt-x rows).
     // One warp per player, Δλ in registers (lane a owns component a); g of the next step is evaluated ahead of the
     // dependent shuffle → Aᵀ chain.
-    for (int item = tid; item < P * K * n; item += kThreads) {
-      const int s = item / (P * n), rem = item - s * (P * n);
-      const int i = rem / n, a = rem - i * n;
-      R[s * b + OX + rem] = (pl >= 0 && i != pl) ? 0.0 : costate_g(i, s, a, reg_x);             // IBR: Δλ_j = 0 for j != pl
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {                  // position components first, then velocity / heading: convergent warps
+      for (int item = tid; item < P * K * 2 * P; item += kThreads) {
+        const int s = item / (P * 2 * P), rem = item - s * (P * 2 * P);
+        const int i = rem / (2 * P), a = half * 2 * P + (rem - i * (2 * P));
+        double v = 0.0;                                     // IBR: Δλ_j = 0 for j != pl
+        if (pl < 0 || i == pl) v = half == 0 ? costate_g<0>(i, s, a, reg_x) : costate_g<1>(i, s, a, reg_x);
+        R[s * b + OX + i * n + a] = v;
+      }
     }
     __syncthreads();
     if (warp < P && (pl < 0 || warp == pl)) {
