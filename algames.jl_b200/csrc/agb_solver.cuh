@@ -1057,10 +1057,10 @@ struct Inst {
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const int a = c * P + i2;
-            const double* w = Wm + (i * n + a) * m;
+            const double2* w = reinterpret_cast<const double2*>(Wm + (i * n + a) * m);      // rows of W are 16-byte aligned (m even)
             double v0 = Base[(i * n + a) * n1 + col], v1 = 0.0;
 #pragma unroll
-            for (int r = 0; r < m; r += 2) { v0 -= w[r] * kc[r]; v1 -= w[r + 1] * kc[r + 1]; }
+            for (int r = 0; r < m; r += 2) { const double2 wv = w[r / 2]; v0 -= wv.x * kc[r]; v1 -= wv.y * kc[r + 1]; }
             pn[c] = v0 + v1;
             if (col < n) Pm[(i * n + a) * n + col] = pn[c]; else Sv[i * n + a] = pn[c];
           }
