@@ -1273,12 +1273,35 @@ struct Inst {
   // update_traj!(pdtraj, pdtraj, α, Δpdtraj) + Δ_step (primal_dual_traj.jl:109-147)
   __device__ double update_traj(double alpha) {
     double loc = 0.0;
-    for (int item = tid; item < K * b; item += kThreads) {
-      const int q = item % b, s = item / b;
-      const double dv = R[item];
-      if (q < OU) { const int i = q / n, a = q - i * n; double* t = &L[(i * K + s) * n + a]; *t = fma(alpha, dv, *t); }
-      else if (q < OD) { double* t = &U[s * m + (q - OU)]; *t = fma(alpha, dv, *t); loc += fabs(dv); }
-      else { double* t = &X[(s + 1) * n + (q - OD)]; *t = fma(alpha, dv, *t); loc += fabs(dv); }
+    // duals: Λ_{i,s} += α·Δλ_{i,s} (stage-major items; four independent read-modify-writes in flight — Λ may live in L2)
+    {
+      double* Lp = L;
+      const int nl = K * P * n;
+      int item = tid;
+      for (; item + 3 * kThreads < nl; item += 4 * kThreads) {
+        int idx[4]; double dv[4], lv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int it = item + u * kThreads, s = it / (P * n), rem = it - s * (P * n), i = rem / n, a = rem - i * n;
+          idx[u] = (i * K + s) * n + a; dv[u] = R[s * b + OX + rem];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) lv[u] = Lp[idx[u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) Lp[idx[u]] = fma(alpha, dv[u], lv[u]);
+      }
+      for (; item < nl; item += kThreads) {
+        const int s = item / (P * n), rem = item - s * (P * n), i = rem / n, a = rem - i * n;
+        double* t = &Lp[(i * K + s) * n + a]; *t = fma(alpha, R[s * b + OX + rem], *t);
+      }
+    }
+    // primals: u_s += α·Δu_s, x_{s+1} += α·Δx_{s+1}; Δ_step accumulates |Δu| + |Δx| (primal_dual_traj.jl:130-147)
+    for (int item = tid; item < K * (m + n); item += kThreads) {
+      const int s = item / (m + n), q = item - s * (m + n);
+      const double dv = R[s * b + OU + q];
+      if (q < m) { double* t = &U[s * m + q]; *t = fma(alpha, dv, *t); }
+      else { double* t = &X[(s + 1) * n + (q - m)]; *t = fma(alpha, dv, *t); }
+      loc += fabs(dv);
     }
     Acc a = {loc, 0.0, 0.0, 0.0, 0.0, 0.0};
     a = block_reduce(a);
