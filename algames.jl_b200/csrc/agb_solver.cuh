@@ -1026,13 +1026,14 @@ struct Inst {
           const double* hm = Hm + (s & 1) * P * HmS + i * HmS;            // H^x_{i,s}, laid out during the previous stage
           const double hd = hm[4 * P * P + a];
           const double* hrow = hm + (c < 2 ? a : 0) * (2 * P);
+          const double hmask = (c < 2) ? 1.0 : 0.0;                       // position rows only (branch-free below)
 #pragma unroll
           for (int i3 = 0; i3 < P; i3++) {
             double At3[8], Bt3[8]; loadAB(s, i3, At3, Bt3);
             const double x0 = X[i3], x1 = X[P + i3], x2 = X[2 * P + i3], x3 = X[3 * P + i3];
             double o0 = x0, o1 = x1;
             double o2 = x2 + at_dot<0>(At3, x0, x1, x2, x3), o3 = x3 + at_dot<1>(At3, x0, x1, x2, x3);
-            if (c < 2) { o0 += hrow[i3]; o1 += hrow[P + i3]; }
+            o0 = fma(hmask, hrow[i3], o0); o1 = fma(hmask, hrow[P + i3], o1);
             brow[i3] = o0; brow[P + i3] = o1; brow[2 * P + i3] = o2; brow[3 * P + i3] = o3;
             wrow[i3] = bt_dot<0>(Bt3, x0, x1, x2, x3);
             wrow[P + i3] = bt_dot<1>(Bt3, x0, x1, x2, x3);
