@@ -33,6 +33,7 @@ class ProblemDesc(C.Structure):
         ("walls", ((C.c_double * 6) * MAX_WALLS) * MAX_P),
         ("n_circles", C.c_int * MAX_P),
         ("circles", ((C.c_double * 3) * MAX_CIRCLES) * MAX_P),
+        ("x_max_con", (C.c_int * MAX_N) * MAX_P), ("x_min_con", (C.c_int * MAX_N) * MAX_P),
     ]
 
 

@@ -140,12 +140,22 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     }
     o->sb_shift[i] = row - ncw;                 // this player's state-bound rows (if any) start here
     if (d->has_state_bound[i]) {
+      const int ncon = d->has_state_bound[i];
+      if (ncon < 0 || ncon > 2 * AGB_MAX_N) { *why = "has_state_bound: conval count out of range"; return AGB_EINVAL; }
       for (int a = 0; a < n; a++) {
-        if (!(d->x_max[i][a] >= d->x_min[i][a])) { *why = "Upper bounds must be greater than or equal to lower bounds"; return AGB_EINVAL; }
+        const bool fmx = isfinite(d->x_max[i][a]), fmn = isfinite(d->x_min[i][a]);
+        if ((fmx && (d->x_max_con[i][a] < 0 || d->x_max_con[i][a] >= ncon)) || (fmn && (d->x_min_con[i][a] < 0 || d->x_min_con[i][a] >= ncon))) {
+          *why = "x_max_con / x_min_con: conval index out of range"; return AGB_EINVAL;
+        }
+        // the reference checks x_max >= x_min inside one StateBoundConstraint (state_bound_constraint.jl:62-68)
+        const bool same = !(fmx && fmn) || d->x_max_con[i][a] == d->x_min_con[i][a];
+        if (same && !(d->x_max[i][a] >= d->x_min[i][a])) { *why = "Upper bounds must be greater than or equal to lower bounds"; return AGB_EINVAL; }
       }
       const int row0 = row;
-      for (int a = 0; a < n; a++) if (isfinite(d->x_max[i][a])) { o->x_max[i][a] = d->x_max[i][a]; o->sbmax_row[i][a] = row++; }
-      for (int a = 0; a < n; a++) if (isfinite(d->x_min[i][a])) { o->x_min[i][a] = d->x_min[i][a]; o->sbmin_row[i][a] = row++; }
+      for (int g = 0; g < ncon; g++) {           // conval order, each: finite x_max rows then finite x_min rows
+        for (int a = 0; a < n; a++) if (isfinite(d->x_max[i][a]) && d->x_max_con[i][a] == g) { o->x_max[i][a] = d->x_max[i][a]; o->sbmax_row[i][a] = row++; }
+        for (int a = 0; a < n; a++) if (isfinite(d->x_min[i][a]) && d->x_min_con[i][a] == g) { o->x_min[i][a] = d->x_min[i][a]; o->sbmin_row[i][a] = row++; }
+      }
       ncw += row - row0;
     }
     if (d->n_walls[i] < 0 || d->n_walls[i] > AGB_MAX_WALLS || d->n_circles[i] < 0 || d->n_circles[i] > AGB_MAX_CIRCLES) {

@@ -33,6 +33,7 @@ struct AgbProblemDesc
     walls::NTuple{MAX_P * MAX_WALLS * 6,Cdouble}
     n_circles::NTuple{MAX_P,Cint}
     circles::NTuple{MAX_P * MAX_CIRCLES * 3,Cdouble}
+    x_max_con::NTuple{MAX_P * MAX_N,Cint}; x_min_con::NTuple{MAX_P * MAX_N,Cint}   # owning conval of each finite bound
 end
 
 # ---- agb_options: live fields of Algames.Options (src/struct/options.jl) ------------------------------------------
@@ -86,6 +87,7 @@ function make_desc(prob::GameProblem)
     end
     col = zeros(MAX_P, MAX_P); hsb = zeros(Cint, MAX_P)
     xmax = fill(Inf, MAX_N, MAX_P); xmin = fill(-Inf, MAX_N, MAX_P)
+    xmaxc = zeros(Cint, MAX_N, MAX_P); xminc = zeros(Cint, MAX_N, MAX_P)
     nw = zeros(Cint, MAX_P); walls = zeros(6, MAX_WALLS, MAX_P)
     nc = zeros(Cint, MAX_P); circ = zeros(3, MAX_CIRCLES, MAX_P)
     for i in 1:p, con in gc.state_conlist[i].constraints
@@ -93,7 +95,19 @@ function make_desc(prob::GameProblem)
             j = findfirst(q -> ps.px[q] == con.x2, 1:p)
             col[j, i] = con.radius                      # stored transposed: tuple below is row-major [i][j]
         elseif con isa Algames.StateBoundConstraint
-            hsb[i] = 1; xmax[1:n, i] .= con.x_max; xmin[1:n, i] .= con.x_min
+            # several StateBound convals per player (add_velocity_bound!, velocity_constraint.jl:13-28) are merged
+            # component-wise; xmaxc / xminc keep the 0-based conval that owns each finite entry
+            g = hsb[i]; hsb[i] += 1
+            for a in 1:n
+                if isfinite(con.x_max[a])
+                    isfinite(xmax[a, i]) && error("AlgamesB200: two state bounds of player $i on component $a (upper)")
+                    xmax[a, i] = con.x_max[a]; xmaxc[a, i] = g
+                end
+                if isfinite(con.x_min[a])
+                    isfinite(xmin[a, i]) && error("AlgamesB200: two state bounds of player $i on component $a (lower)")
+                    xmin[a, i] = con.x_min[a]; xminc[a, i] = g
+                end
+            end
         elseif con isa Algames.WallConstraint
             for q in 1:length(con.x1)
                 nw[i] += 1
@@ -119,7 +133,8 @@ function make_desc(prob::GameProblem)
         pad(Q, MAX_N), pad(R, MAX_M), pad(xf, MAX_N), pad(uf, MAX_M), has_cc, pad(ccr, MAX_P), pad(ccm, MAX_P),
         pad(vec(col), MAX_P * MAX_P), hcb, pad(umax, MAX_M), pad(umin, MAX_M), padi(hsb, MAX_P),
         pad(vec(xmax), MAX_P * MAX_N), pad(vec(xmin), MAX_P * MAX_N), padi(nw, MAX_P),
-        pad(vec(walls), MAX_P * MAX_WALLS * 6), padi(nc, MAX_P), pad(vec(circ), MAX_P * MAX_CIRCLES * 3))
+        pad(vec(walls), MAX_P * MAX_WALLS * 6), padi(nc, MAX_P), pad(vec(circ), MAX_P * MAX_CIRCLES * 3),
+        padi(vec(xmaxc), MAX_P * MAX_N), padi(vec(xminc), MAX_P * MAX_N))
 end
 
 check(rc, h) = rc == 0 || error("libalgames_b200 ($rc): " *

@@ -21,7 +21,7 @@ from . import _capi
 
 __all__ = [
     "DoubleIntegratorGame", "UnicycleGame", "BicycleGame", "ProblemSize", "Options", "GameObjective",
-    "add_collision_cost", "GameConstraintValues", "add_collision_avoidance", "add_control_bound", "add_state_bound",
+    "add_collision_cost", "GameConstraintValues", "add_collision_avoidance", "add_control_bound", "add_state_bound", "add_velocity_bound", "velocity_index",
     "add_circle_constraint", "add_wall_constraint", "Wall", "GameProblem", "GameBatch", "newton_solve",
     "residual", "residual_jacobian", "kkt_solve", "line_search", "update_traj", "rollout", "dual_update",
     "penalty_update", "reset", "evaluate", "active_set", "Statistics", "spec_of", "IBROptions", "ibr_newton_solve",
@@ -204,7 +204,7 @@ class GameConstraintValues:
         p = probsize.p
         self.col_radius = np.zeros((p, p))
         self.control_bound = None                  # (u_max[m], u_min[m])
-        self.state_bound = [None] * p              # (x_max[n], x_min[n]) owned by player i
+        self.state_bound: List[List[tuple]] = [[] for _ in range(p)]   # StateBound convals (x_max[n], x_min[n]) of player i
         self.walls: List[List[Wall]] = [[] for _ in range(p)]
         self.circles: List[List[tuple]] = [[] for _ in range(p)]
 
@@ -237,10 +237,66 @@ def add_control_bound(game_con: GameConstraintValues, u_max, u_min):
     game_con.control_bound = _check_bounds(u_max, u_min, game_con.probsize.m)
 
 
+def _merge_state_bounds(bounds, n):
+    """Component-wise union of one player's StateBound convals: (x_max, x_min, owner_of_max, owner_of_min).
+    The device keeps one max and one min row per (player, component); a second conval bounding the same
+    component from the same side has no slot there."""
+    hi, lo = np.full(n, np.inf), np.full(n, -np.inf)
+    hi_con, lo_con = np.zeros(n, int), np.zeros(n, int)
+    for g, (h, l) in enumerate(bounds):
+        for a in range(n):
+            if np.isfinite(h[a]):
+                if np.isfinite(hi[a]):
+                    raise NotImplementedError("two state bounds of one player on the same component and side")
+                hi[a], hi_con[a] = h[a], g
+            if np.isfinite(l[a]):
+                if np.isfinite(lo[a]):
+                    raise NotImplementedError("two state bounds of one player on the same component and side")
+                lo[a], lo_con[a] = l[a], g
+    return hi, lo, hi_con, lo_con
+
+
 def add_state_bound(game_con: GameConstraintValues, i: int, x_max, x_min):
-    if game_con.state_bound[i] is not None:
-        raise NotImplementedError("one state bound per player")
-    game_con.state_bound[i] = _check_bounds(x_max, x_min, game_con.probsize.n)
+    """add_state_bound!(game_con, i, x_max, x_min) (constraints_methods.jl:87-98): one more StateBoundConstraint
+    conval on knots 2:N for player i (0-based here)."""
+    n = game_con.probsize.n
+    bound = _check_bounds(x_max, x_min, n)
+    _merge_state_bounds(game_con.state_bound[i] + [bound], n)       # raises if the schema has no device form
+    game_con.state_bound[i].append(bound)
+
+
+def velocity_index(model: _GameModel, i: int) -> int:
+    """velocity_index(model, i) (velocity_constraint.jl:30-43), 0-based joint state index of player i's speed."""
+    if not 0 <= i < model.p:
+        raise AssertionError("player out of range")
+    if isinstance(model, UnicycleGame):
+        return model.pz[i][3]
+    if isinstance(model, BicycleGame):
+        return model.pz[i][2]
+    raise NotImplementedError(f"Velocity Index is not implemented for {type(model).__name__}.")
+
+
+def add_velocity_bound(model: _GameModel, game_con: GameConstraintValues, v_max, v_min, i: Optional[int] = None):
+    """add_velocity_bound!(model, game_con, v_max, v_min) / (model, game_con, i, v_max, v_min)
+    (velocity_constraint.jl:1-28).  Bounding player i's speed adds one StateBoundConstraint on that joint
+    component to EVERY player's state constraint list; the vector form skips players whose bounds are both
+    infinite."""
+    p, n = model.p, model.n
+    if i is None:
+        v_max, v_min = np.asarray(v_max, float), np.asarray(v_min, float)
+        if not (len(v_max) == len(v_min) == p):
+            raise AssertionError("v_max and v_min need one entry per player")
+        for a in range(p):
+            if v_max[a] != np.inf or v_min[a] != -np.inf:
+                add_velocity_bound(model, game_con, float(v_max[a]), float(v_min[a]), i=a)
+        return
+    if not (v_max != np.inf or v_min != -np.inf):
+        raise AssertionError("at least one of v_max, v_min must be finite")
+    x_max, x_min = np.full(n, np.inf), np.full(n, -np.inf)
+    vi = velocity_index(model, i)
+    x_max[vi], x_min[vi] = v_max, v_min
+    for j in range(p):
+        add_state_bound(game_con, j, x_max, x_min)
 
 
 def add_circle_constraint(game_con: GameConstraintValues, xc, yc, radius, i: Optional[int] = None):
@@ -286,10 +342,12 @@ def _make_desc(model, N, dt, game_obj: GameObjective, game_con: GameConstraintVa
     for i in range(p):
         for j in range(p):
             d.col_radius[i][j] = game_con.col_radius[i, j]
-        if game_con.state_bound[i] is not None:
-            d.has_state_bound[i] = 1
+        if game_con.state_bound[i]:
+            d.has_state_bound[i] = len(game_con.state_bound[i])
+            hi, lo, hi_con, lo_con = _merge_state_bounds(game_con.state_bound[i], n)
             for a in range(n):
-                d.x_max[i][a], d.x_min[i][a] = game_con.state_bound[i][0][a], game_con.state_bound[i][1][a]
+                d.x_max[i][a], d.x_min[i][a] = hi[a], lo[a]
+                d.x_max_con[i][a], d.x_min_con[i][a] = int(hi_con[a]), int(lo_con[a])
         d.n_walls[i] = len(game_con.walls[i])
         for q, w in enumerate(game_con.walls[i]):
             for e, v in enumerate([w.p1[0], w.p1[1], w.p2[0], w.p2[1], w.v[0], w.v[1]]):
@@ -305,6 +363,11 @@ def _make_desc(model, N, dt, game_obj: GameObjective, game_con: GameConstraintVa
     return d
 
 
+def _sb_spec(bounds):
+    items = [{"x_max": hi.tolist(), "x_min": lo.tolist()} for hi, lo in bounds]
+    return None if not items else (items[0] if len(items) == 1 else items)
+
+
 def spec_of(prob: "GameProblem") -> dict:
     """Neutral plain-dict description of a problem (what the tests hand to the oracle's problem_from_spec)."""
     model, obj, con = prob.model, prob.game_obj, prob.game_con
@@ -317,7 +380,8 @@ def spec_of(prob: "GameProblem") -> dict:
         "collision_cost": None if obj.collision_cost is None else
         {"radius": obj.collision_cost[0].tolist(), "mu": obj.collision_cost[1].tolist()},
         "collision_radius": con.col_radius.tolist() if con.col_radius.any() else None,
-        "state_bounds": [None if sb is None else {"x_max": sb[0].tolist(), "x_min": sb[1].tolist()} for sb in con.state_bound],
+        # per player: None, one {"x_max", "x_min"} dict, or the list of them in the order they were added
+        "state_bounds": [_sb_spec(sbs) for sbs in con.state_bound],
         "walls": [[[w.p1[0], w.p1[1], w.p2[0], w.p2[1], w.v[0], w.v[1]] for w in con.walls[i]] for i in range(p)],
         "circles": [[list(c) for c in con.circles[i]] for i in range(p)],
         "control_bounds": None if con.control_bound is None else

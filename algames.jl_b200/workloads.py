@@ -8,7 +8,7 @@ import numpy as np
 
 from .problem import (BicycleGame, DoubleIntegratorGame, GameConstraintValues, GameObjective, Options, ProblemSize,
                       UnicycleGame, Wall, add_circle_constraint, add_collision_avoidance, add_collision_cost,
-                      add_control_bound, add_state_bound, add_wall_constraint)
+                      add_control_bound, add_state_bound, add_velocity_bound, add_wall_constraint)
 
 
 def config_a():
@@ -132,4 +132,14 @@ def config_e(batch=65536, seed=4567, N=60):
     return _lane_game(batch, seed, N, ramp=False)
 
 
-CONFIGS = {"A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}
+def config_v(batch=64, seed=5678, N=20):
+    """Highway lane game of config E with speed limits: add_velocity_bound! (velocity_constraint.jl:1-28) gives every
+    player one StateBound conval per limited player — both sides for player 1, an upper limit for player 2, a lower
+    limit for player 3 — next to the collision, wall and control-bound rows.  Desired speeds above the limit keep
+    some of the rows active at the solution."""
+    model, N, dt, obj, con, opts, x0, xf = _lane_game(batch, seed, N, ramp=False)
+    add_velocity_bound(model, con, [1.1, 1.0, np.inf], [0.6, -np.inf, 0.7])
+    return model, N, dt, obj, con, opts, x0, xf
+
+
+CONFIGS = {"V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}

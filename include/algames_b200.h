@@ -26,7 +26,7 @@
  *      res   [B][S]           KKT residual, reference row ("vertical") order        (core/newton_core.jl:40-63)
  *      dtraj [B][S]           Newton step, reference column ("horizontal") order    (core/newton_core.jl:65-89)
  *      conlam/conmu [B][N-1][nrow]  AL multipliers/penalties: stage k holds the state-constraint
- *                 rows of knot k+1 — per player [collision j≠i ascending | state bound max rows, min rows |
+ *                 rows of knot k+1 — per player [collision j≠i ascending | state bounds: per conval max rows, min rows |
  *                 walls | circles] — followed by the control-bound rows of knot k [u_max rows, u_min rows]
  *                 (finite bounds only, reference component order; control_bound_constraint.jl:33-35).
  */
@@ -78,7 +78,12 @@ typedef struct agb_problem_desc {
   /* add_control_bound!: ±INFINITY = no bound                                          */
   int has_control_bound;
   double u_max[AGB_MAX_M], u_min[AGB_MAX_M];
-  /* add_state_bound!(game_con, i, x_max, x_min): bound on the JOINT state, owned by player i */
+  /* add_state_bound!(game_con, i, x_max, x_min): bound on the JOINT state, owned by player i.
+   * has_state_bound[i] = number of StateBoundConstraint convals of player i (0 = none); several convals
+   * (add_velocity_bound! gives every player one per bounded velocity, velocity_constraint.jl:13-28) are
+   * merged component-wise into x_max / x_min, x_max_con / x_min_con (end of this struct) naming the
+   * 0-based conval that owns each finite entry.  Two convals of one player bounding the same component
+   * from the same side cannot be expressed (the host layers reject that schema).                      */
   int has_state_bound[AGB_MAX_P];
   double x_max[AGB_MAX_P][AGB_MAX_N], x_min[AGB_MAX_P][AGB_MAX_N];
   /* add_wall_constraint!: (x1,y1,x2,y2,xv,yv) per wall per player                      */
@@ -87,6 +92,10 @@ typedef struct agb_problem_desc {
   /* add_circle_constraint!: (xc,yc,r)                                                  */
   int n_circles[AGB_MAX_P];
   double circles[AGB_MAX_P][AGB_MAX_CIRCLES][3];
+  /* owning conval (0 .. has_state_bound[i]-1) of each finite x_max / x_min entry; all zero for a single
+   * add_state_bound! per player.  Rows follow the reference's conval order: for each conval in the order
+   * it was added, its finite x_max rows then its finite x_min rows (state_bound_constraint.jl:33-35).   */
+  int x_max_con[AGB_MAX_P][AGB_MAX_N], x_min_con[AGB_MAX_P][AGB_MAX_N];
 } agb_problem_desc;
 
 /* Live fields of Options (src/struct/options.jl:5-116; dead fields omitted). */

@@ -129,9 +129,9 @@ static int con_rows(const Work* w, const double* X, const double* U, int s, ConR
       q->idx[0] = i; q->g[0] = -2 * dx; q->idx[1] = p + i; q->g[1] = -2 * dy;
       q->idx[2] = j; q->g[2] = 2 * dx;  q->idx[3] = p + j; q->g[3] = 2 * dy;
     }
-    if (d->has_state_bound[i]) {                                                   /* StateBoundConstraint */
-      for (int a = 0; a < n; a++) if (isfinite(d->x_max[i][a])) { ConRow* q = &out[r++]; q->is_control = 0; q->c = x[a] - d->x_max[i][a]; q->nnz = 1; q->idx[0] = a; q->g[0] = 1; }
-      for (int a = 0; a < n; a++) if (isfinite(d->x_min[i][a])) { ConRow* q = &out[r++]; q->is_control = 0; q->c = d->x_min[i][a] - x[a]; q->nnz = 1; q->idx[0] = a; q->g[0] = -1; }
+    for (int g = 0; g < d->has_state_bound[i]; g++) {                              /* StateBoundConstraint convals, in the order added */
+      for (int a = 0; a < n; a++) if (isfinite(d->x_max[i][a]) && d->x_max_con[i][a] == g) { ConRow* q = &out[r++]; q->is_control = 0; q->c = x[a] - d->x_max[i][a]; q->nnz = 1; q->idx[0] = a; q->g[0] = 1; }
+      for (int a = 0; a < n; a++) if (isfinite(d->x_min[i][a]) && d->x_min_con[i][a] == g) { ConRow* q = &out[r++]; q->is_control = 0; q->c = d->x_min[i][a] - x[a]; q->nnz = 1; q->idx[0] = a; q->g[0] = -1; }
     }
     double px = x[i], py = x[p + i];
     for (int t = 0; t < d->n_walls[i]; t++) {                                      /* WallConstraint */

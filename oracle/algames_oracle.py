@@ -522,6 +522,16 @@ class ALConVal:
             self.c_max[j] = max(0.0, float(np.max(self.vals[j]))) if self.vals.shape[1] else 0.0
 
 
+def velocity_index(model, i):
+    """src/constraints/velocity_constraint.jl:30-43 (0-based player and index here)."""
+    assert 0 <= i < model.p
+    if model.name == "unicycle":
+        return model.pz[i][3]
+    if model.name == "bicycle":
+        return model.pz[i][2]
+    raise NotImplementedError("Velocity Index is not implemented for DoubleIntegratorGame.")
+
+
 class GameConstraintValues:
     """src/constraints/game_constraints.jl:5-53 + adders of constraints_methods.jl."""
 
@@ -552,6 +562,23 @@ class GameConstraintValues:
 
     def add_state_bound(self, i, x_max, x_min):
         self._add_state(i, StateBoundConstraint(self.probsize.n, x_max, x_min))       # :87-98
+
+    def add_velocity_bound(self, model, v_max, v_min, i=None):
+        """src/constraints/velocity_constraint.jl:1-28: a bound on player i's speed becomes one StateBoundConstraint
+        on that joint component in EVERY player's list; the vector form skips players with both bounds infinite."""
+        p, n = model.p, model.n
+        if i is None:
+            assert len(v_max) == len(v_min) == p                                       # :4
+            for a in range(p):
+                if v_max[a] != np.inf or v_min[a] != -np.inf:                          # :6
+                    self.add_velocity_bound(model, v_max[a], v_min[a], i=a)
+            return
+        assert v_max != np.inf or v_min != -np.inf                                     # :14
+        x_max, x_min = np.full(n, np.inf), np.full(n, -np.inf)
+        vi = velocity_index(model, i)
+        x_max[vi], x_min[vi] = v_max, v_min                                            # :18-22
+        for j in range(p):                                                             # :24-26
+            self.add_state_bound(j, x_max, x_min)
 
     def add_control_bound(self, u_max, u_min):
         ps = self.probsize
@@ -1118,8 +1145,8 @@ def problem_from_spec(spec: dict, x0=None, xf=None, opts: Optional[Options] = No
             for j in range(p):
                 if j != i and rad[i][j] > 0:
                     gc.add_collision_avoidance(rad[i][j], i, j)
-        if sb[i] is not None:
-            gc.add_state_bound(i, sb[i]["x_max"], sb[i]["x_min"])
+        for bound in ([] if sb[i] is None else [sb[i]] if isinstance(sb[i], dict) else sb[i]):
+            gc.add_state_bound(i, bound["x_max"], bound["x_min"])
         if len(walls[i]):
             gc.add_wall_constraint([Wall(np.array(w[0:2]), np.array(w[2:4]), np.array(w[4:6])) for w in walls[i]], i)
         if len(circles[i]):

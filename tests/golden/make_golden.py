@@ -1,6 +1,7 @@
 """Generates the golden fixtures in this directory with the NumPy oracle (the Julia reference cannot run in the build
 image — SURVEY F2 — so these are outputs of the pinned restatement, not of Algames.jl itself).
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # all cases
+    python tests/golden/make_golden.py V          # only the named ones
 """
 import os
 import sys
@@ -13,9 +14,11 @@ sys.path.insert(0, os.path.join(HERE, ".."))
 import oracle.algames_oracle as O  # noqa: E402
 import parity  # noqa: E402
 
-CASES = [("A", 1, None, 100), ("A'", 1, None, 101), ("B", 3, 40, 102), ("C", 2, 12, 103), ("E", 2, 14, 104)]
+CASES = [("A", 1, None, 100), ("A'", 1, None, 101), ("B", 3, 40, 102), ("C", 2, 12, 103), ("E", 2, 14, 104), ("V", 2, 14, 105)]
 
 for name, B, N, seed in CASES:
+    if len(sys.argv) > 1 and name not in sys.argv[1:]:
+        continue
     model, N, dt, obj, con, opts, x0, xf = parity.small_config(name, B, N)
     rng = np.random.default_rng(seed)
     Z0 = opts.amplitude_init * rng.random((B, N, model.n + model.m))

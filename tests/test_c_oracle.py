@@ -8,7 +8,7 @@ import parity
 from oracle import c_oracle
 
 
-@pytest.mark.parametrize("name,B,N", [("A", 1, None), ("A'", 1, None), ("B", 3, 40), ("C", 2, 12), ("D", 2, 12)])
+@pytest.mark.parametrize("name,B,N", [("A", 1, None), ("A'", 1, None), ("B", 3, 40), ("C", 2, 12), ("D", 2, 12), ("V", 2, 12)])
 def test_c_oracle_matches_numpy_oracle(name, B, N):
     model, N, dt, obj, con, opts, x0, xf = parity.small_config(name, B, N)
     if x0.shape[0] < B:

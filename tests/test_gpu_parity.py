@@ -22,7 +22,7 @@ def _built():
     g.build()
 
 
-@pytest.mark.parametrize("name,N", [("A", None), ("A'", None), ("B", None), ("C", None), ("D", None), ("E", 30), ("B", 2), ("C", 3)])
+@pytest.mark.parametrize("name,N", [("A", None), ("A'", None), ("B", None), ("C", None), ("D", None), ("E", 30), ("B", 2), ("C", 3), ("V", None), ("V", 40)])
 def test_per_function_parity(name, N):
     parity.check_per_function(LIB, name, seed=2, N=N)
 
@@ -69,6 +69,12 @@ def test_solve_config_c_short_horizon():
 
 def test_solve_config_d_short_horizon():
     parity.check_solve_vs_oracle(LIB, "D", B=2, N=16, which=[0])
+
+
+def test_solve_config_v_velocity_bounds():
+    # several StateBound convals per player (add_velocity_bound!, velocity_constraint.jl:1-28)
+    out = parity.check_solve_vs_oracle(LIB, "V", B=4, which=[0, 3])
+    assert (out["conlam"][:, :, [2, 3, 4, 5]] > 0).any()          # player 1's copies of the speed-limit rows
 
 
 def test_golden_fixtures():
