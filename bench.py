@@ -90,7 +90,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "newton_steps_per_s": newton_tot / t_tot,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -150,8 +150,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     # weak-scaling control: every rank solves the same 1024-instance set, so per-GPU work is identical by construction
@@ -315,11 +313,14 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
                                     "sample": f"{args.cpu_sample} config-B instances in {dt_s:.1f} s; oracle/algames_oracle.c (C restatement of "
                                               "Algames.jl newton_solve!: explicit KKT Jacobian + band LU per Newton step), one pthread per core"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     gb.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_OUT = sys.stdout
 
 
 def main():
@@ -333,6 +334,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the all-gather at N>1")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything any library writes to fd 1 (NCCL prints its version banner there at
+    # NCCL_DEBUG=VERSION and WARN) goes to stderr instead, and the line itself is written to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args)
     else:
