@@ -83,7 +83,8 @@ struct agb_handle {
   DevDesc hd;
   DevDesc* dd = nullptr;
   cudaStream_t stream = nullptr;
-  cudaStream_t chunk_stream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // agb_solve_from_host pipeline
+  static constexpr int kMaxChunks = 32;
+  cudaStream_t chunk_stream[kMaxChunks] = {};   // agb_solve_from_host pipeline
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // device buffers
@@ -703,7 +704,11 @@ int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, c
   AGB_CUDA(h, cudaStreamSynchronize(h->stream));
   const int B = h->batch, n = h->hd.n;
   const size_t zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n, cs = (size_t)h->hd.K * h->hd.nrow;
-  const int chunks = B >= 1024 ? 8 : (B >= 512 ? 4 : 1);   // each chunk: H2D -> solve -> D2H on its own stream
+  int chunks = B >= 1024 ? 8 : (B >= 512 ? 4 : 1);   // each chunk: H2D -> solve -> D2H on its own stream
+  if (const char* e = getenv("AGB_HOST_CHUNKS")) {    // tuning hook
+    const int v = atoi(e);
+    if (v >= 1 && v <= agb_handle::kMaxChunks) chunks = v < B ? v : B;
+  }
   for (int c = 0; c < chunks; c++) {
     if (!h->chunk_stream[c]) AGB_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
     cudaStream_t st = h->chunk_stream[c];
