@@ -657,6 +657,10 @@ class Statistics:
         self.newton_steps = 0
         self.residual_evals = 0
 
+    def reset(self):
+        """reset!(stats) (struct/statistics.jl:74-80)."""
+        self.__init__()
+
     def record_history(self, hist):
         """hist [count, 8] rows of agb_get_history."""
         for h in hist:

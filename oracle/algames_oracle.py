@@ -216,6 +216,14 @@ class ProblemSize:
         self.pu, self.px, self.pz = model.pu, model.px, model.pz
         self.S = self.n * self.p * (N - 1) + self.m * (N - 1) + self.n * (N - 1)  # :22
 
+    def __eq__(self, other):   # :37-46, field by field
+        if not isinstance(other, ProblemSize):
+            return NotImplemented
+        f = lambda v: [list(e) if hasattr(e, "__len__") else e for e in v] if hasattr(v, "__len__") else v
+        return all(f(getattr(self, k)) == f(getattr(other, k)) for k in ("N", "n", "m", "p", "ni", "mi", "pu", "px", "pz", "S"))
+
+    __hash__ = None
+
 
 def valid_v(prob, i0, n1, i1, v1, N, p):
     """src/core/stamp.jl:199-214 (VStamp validity); players/knots 1-based like the reference."""
@@ -304,6 +312,9 @@ class Regularizer:
 
     def set(self, v):          # regularizer.jl:25-29
         self.x = self.u = self.lam = v
+
+    def mult(self, v):         # regularizer.jl:31-35
+        self.x, self.u, self.lam = self.x * v, self.u * v, self.lam * v
 
 
 @dataclass
