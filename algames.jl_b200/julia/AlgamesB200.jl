@@ -137,6 +137,70 @@ function make_desc(prob::GameProblem)
         padi(vec(xmaxc), MAX_P * MAX_N), padi(vec(xminc), MAX_P * MAX_N))
 end
 
+# ---- agb_sizes ---------------------------------------------------------------------------------------------------
+struct AgbSizes
+    n::Cint; m::Cint; p::Cint; N::Cint; S::Cint; nrow::Cint; nrow_state::Cint; nrow_control::Cint
+end
+
+"""
+    canonical_convals(prob) -> Vector of (conval, is_control)
+
+The convals of `prob.game_con` in the row order of the ABI's `conlam` / `conmu` arrays (include/algames_b200.h): per
+player the collision convals by ascending opponent, then the state bounds, walls and circles each in the order they were
+added; then the control bound.  Rows inside a conval keep the conval's own order (finite upper bounds then finite lower
+bounds for the bound constraints, control_bound_constraint.jl:33-35; one row per wall / circle).
+"""
+function canonical_convals(prob::GameProblem)
+    ps, gc = prob.probsize, prob.game_con
+    out = Tuple{Any,Bool}[]
+    for i in 1:ps.p
+        cvs = gc.state_conval[i]
+        col = [cv for cv in cvs if cv.con isa TrajectoryOptimization.CollisionConstraint]
+        sort!(col, by = cv -> findfirst(q -> ps.px[q] == cv.con.x2, 1:ps.p))
+        append!(out, [(cv, false) for cv in col])
+        for T in (Algames.StateBoundConstraint, Algames.WallConstraint, TrajectoryOptimization.CircleConstraint)
+            append!(out, [(cv, false) for cv in cvs if cv.con isa T])
+        end
+    end
+    append!(out, [(cv, true) for cv in gc.control_conval])
+    return out
+end
+
+"""
+    scatter_multipliers!(prob, lam, mu)
+
+Writes the solver's AL multipliers and penalties (`lam`, `mu`: nrow × (N-1), stage s = state rows of knot s+1 followed by
+the control-bound rows of knot s) back into `conval.λ[l]`, `conval.μ[l]` as `newton_solve!` leaves them in the reference
+(dual_update! / penalty_update!, constraints_methods.jl:329-365, :421-430).
+"""
+function scatter_multipliers!(prob::GameProblem, lam::AbstractMatrix, mu::AbstractMatrix)
+    row = 0
+    for (cv, is_control) in canonical_convals(prob)
+        len = length(cv.λ[1])
+        for (l, k) in enumerate(cv.inds)                 # state convals: knots 2:N; control conval: knots 1:N-1
+            s = is_control ? k : k - 1
+            cv.λ[l] = typeof(cv.λ[l])(lam[row+1:row+len, s])
+            cv.μ[l] = typeof(cv.μ[l])(mu[row+1:row+len, s])
+        end
+        row += len
+    end
+    return nothing
+end
+
+"Inverse of `scatter_multipliers!`: the convals' λ, μ in the ABI's row order (warm starts with `dual_reset = false`)."
+function gather_multipliers!(lam::AbstractMatrix, mu::AbstractMatrix, prob::GameProblem)
+    row = 0
+    for (cv, is_control) in canonical_convals(prob)
+        len = length(cv.λ[1])
+        for (l, k) in enumerate(cv.inds)
+            s = is_control ? k : k - 1
+            lam[row+1:row+len, s] .= cv.λ[l]; mu[row+1:row+len, s] .= cv.μ[l]
+        end
+        row += len
+    end
+    return nothing
+end
+
 check(rc, h) = rc == 0 || error("libalgames_b200 ($rc): " *
     unsafe_string(ccall((:agb_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
 
@@ -168,18 +232,26 @@ function newton_solve!(probs::AbstractVector{<:GameProblem}; device::Integer=0)
         end
         check(ccall((:agb_set_instance_params, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
             h[], x0, xf, Q, R, uf), h[])
-        check(ccall((:agb_set_initial, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            h[], Z0, L0, C_NULL, C_NULL), h[])
+        sz = Ref(AgbSizes(0, 0, 0, 0, 0, 0, 0, 0))
+        check(ccall((:agb_get_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{AgbSizes}), h[], sz), h[])
+        nrow = Int(sz[].nrow)
+        conλ = Array{Float64}(undef, nrow, N - 1, B); conμ = similar(conλ)     # [B][N-1][nrow] in C order
+        warm = nrow > 0 && !opts.dual_reset            # dual_reset = false keeps the convals' λ, μ (solver_methods.jl:25)
+        if warm
+            for (b, q) in enumerate(probs); gather_multipliers!(view(conλ, :, :, b), view(conμ, :, :, b), q); end
+        end
+        GC.@preserve conλ conμ check(ccall((:agb_set_initial, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h[], Z0, L0, warm ? pointer(conλ) : C_NULL, warm ? pointer(conμ) : C_NULL), h[])
         Z = similar(Z0); L = similar(L0); stats = Array{Float64}(undef, NSTATS, B); status = Vector{Cint}(undef, B)
         # one log entry per record!(stats, …) of the reference loop (statistics.jl:44-57)
         maxrec = opts.outer_iter * opts.inner_iter + 1
         check(ccall((:agb_set_history, LIB), Cint, (Ptr{Cvoid}, Cint), h[], maxrec), h[])
         hist = Array{Float64}(undef, 8, maxrec, B); nrec = Vector{Cint}(undef, B)
         o = Ref(AgbOptions(opts))
-        GC.@preserve Z L stats status hist nrec begin
+        GC.@preserve Z L conλ conμ stats status hist nrec begin
             check(ccall((:agb_newton_solve_batch, LIB), Cint,
                 (Ptr{Cvoid}, Ref{AgbOptions}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
-                h[], o, Z, L, C_NULL, C_NULL, stats, status), h[])
+                h[], o, Z, L, nrow > 0 ? pointer(conλ) : C_NULL, nrow > 0 ? pointer(conμ) : C_NULL, stats, status), h[])
             check(ccall((:agb_get_history, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cint}), h[], hist, nrec), h[])
         end
         for (b, q) in enumerate(probs)
@@ -188,6 +260,8 @@ function newton_solve!(probs::AbstractVector{<:GameProblem}; device::Integer=0)
                 k < N && Algames.RobotDynamics.set_control!(q.pdtraj.pr[k], SVector{m}(Z[n+1:n+m, k, b]))
             end
             for i in 1:p, k in 1:N-1; q.pdtraj.du[i][k] = SVector{n}(L[:, k, i, b]); end
+            scatter_multipliers!(q, view(conλ, :, :, b), view(conμ, :, :, b))
+            evaluate!(q.game_con, q.pdtraj.pr)             # conval.vals at the returned iterate
             residual!(q)                                   # prob.core.res, as the reference leaves it
             reset!(q.stats)                                # the device log replays every record! of the solve
             for r in 1:min(nrec[b], maxrec)
