@@ -142,4 +142,41 @@ def config_v(batch=64, seed=5678, N=20):
     return model, N, dt, obj, con, opts, x0, xf
 
 
-CONFIGS = {"V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}
+def config_s(batch=8, seed=6789, N=12):
+    """Row-order stress for several StateBound convals per player (add_state_bound! called repeatedly,
+    constraints_methods.jl:87-98): 2-player unicycle, player 1 with three convals whose finite entries interleave
+    (components out of order across convals, both sides, one conval without rows), player 2 with two; plus collision
+    avoidance and control bounds so the bound rows sit between other row kinds."""
+    p, dt = 2, 0.1
+    model = UnicycleGame(p=p)
+    ps = ProblemSize(N, model)
+    n, inf = model.n, np.inf
+    obj = GameObjective([np.ones(4)] * p, [0.5 * np.ones(2)] * p, [np.array([2.0, 0.3, 0.0, 1.0]), np.array([2.0, -0.3, 0.0, 1.0])],
+                        [np.zeros(2)] * p, N, model)
+    con = GameConstraintValues(ps)
+    add_collision_avoidance(con, 0.1)
+    add_control_bound(con, 3 * np.ones(model.m), -3 * np.ones(model.m))
+
+    def bound(hi=(), lo=()):
+        x_max, x_min = np.full(n, inf), np.full(n, -inf)
+        for a, v in hi:
+            x_max[a] = v
+        for a, v in lo:
+            x_min[a] = v
+        return x_max, x_min
+
+    # joint state (component-major): 0,1 = x; 2,3 = y; 4,5 = heading; 6,7 = speed
+    add_state_bound(con, 0, *bound(hi=[(6, 1.2), (2, 0.5)], lo=[(2, -0.1)]))
+    add_state_bound(con, 0, *bound())                                   # a conval without rows
+    add_state_bound(con, 0, *bound(hi=[(0, 1.5), (7, 1.1)], lo=[(6, 0.7), (3, -0.5)]))
+    add_state_bound(con, 1, *bound(lo=[(7, 0.6), (0, -1.0)]))
+    add_state_bound(con, 1, *bound(hi=[(7, 1.1), (3, 0.1)], lo=[(4, -0.4)]))
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((batch, n))
+    x0[:, 0:2] = rng.uniform(0.0, 0.3, (batch, 2))
+    x0[:, 2:4] = np.array([0.25, -0.25]) + rng.uniform(-0.05, 0.05, (batch, 2))
+    x0[:, 6:8] = rng.uniform(0.8, 1.4, (batch, 2))
+    return model, N, dt, obj, con, Options(), x0, None
+
+
+CONFIGS = {"S": config_s, "V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}

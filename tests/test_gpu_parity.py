@@ -22,7 +22,7 @@ def _built():
     g.build()
 
 
-@pytest.mark.parametrize("name,N", [("A", None), ("A'", None), ("B", None), ("C", None), ("D", None), ("E", 30), ("B", 2), ("C", 3), ("V", None), ("V", 40)])
+@pytest.mark.parametrize("name,N", [("A", None), ("A'", None), ("B", None), ("C", None), ("D", None), ("E", 30), ("B", 2), ("C", 3), ("V", None), ("V", 40), ("S", None), ("S", 30)])
 def test_per_function_parity(name, N):
     parity.check_per_function(LIB, name, seed=2, N=N)
 
@@ -75,6 +75,11 @@ def test_solve_config_v_velocity_bounds():
     # several StateBound convals per player (add_velocity_bound!, velocity_constraint.jl:1-28)
     out = parity.check_solve_vs_oracle(LIB, "V", B=4, which=[0, 3])
     assert (out["conlam"][:, :, [2, 3, 4, 5]] > 0).any()          # player 1's copies of the speed-limit rows
+
+
+def test_solve_config_s_interleaved_state_bounds():
+    out = parity.check_solve_vs_oracle(LIB, "S", B=4, which=[0, 2])
+    assert (out["status"] == 0).all()
 
 
 def test_golden_fixtures():

@@ -119,3 +119,11 @@ def test_velocity_bound_solve_emulated(emu_lib):  # noqa: F811
     nrow_player = 2 + 4 + 2                                                   # collision | 4 speed-limit rows | walls
     sb = np.concatenate([out["conlam"][0][:, i * nrow_player + 2:i * nrow_player + 6] for i in range(3)], axis=1)
     assert (sb > 0).any()
+
+
+def test_interleaved_state_bound_convals_emulated(emu_lib):  # noqa: F811
+    # config S: three / two StateBound convals per player with interleaved components and sides, one without rows;
+    # the AL rows must follow the reference's conval order (oracle: one ALConVal per add_state_bound!)
+    parity.check_per_function(emu_lib, "S", seed=5)
+    out = parity.check_solve_vs_oracle(emu_lib, "S", B=2)
+    assert (out["status"] == 0).all() and (out["conlam"] > 0).any(axis=(0, 1)).sum() >= 3
