@@ -167,7 +167,94 @@ class BicycleGame(_GameModel):
         return F
 
 
+class QuadrotorGame(_GameModel):
+    """src/dynamics/quadrotor.jl:2-208 — ORACLE ONLY this round (the device kernels are specialised for
+    4-state / 2-control players and `agb_create` has no model id for it).
+
+    Per player 12 states [r(3), q(3) = MRP attitude, v(3), ω(3)] and 4 rotor commands, joint layout component-major
+    (:31-33, pinned by test/dynamics/quadrotor.jl:4-23).  forces / moments / dynamics follow :48-108.  The MRP rotation
+    matrix and kinematics come from Rotations.jl (third party, absent from /root/reference, exercised by no reference
+    test): restated from the package's published formulas — PARITY UNPINNED.
+    Jacobians: the reference differentiates with ForwardDiff (exact); here complex-step differentiation (exact to
+    round-off for this polynomial/rational right-hand side), with max(0, ·) following the real part.
+    """
+
+    name = "quadrotor"
+
+    def __init__(self, p: int = 2, mass: float = 0.5):
+        assert p <= 4                                                   # :21
+        super().__init__(p, 12, 4)
+        self.mass = mass
+        self.J = np.array([0.0023, 0.0023, 0.004])                      # :22
+        self.gravity = np.array([0.0, 0.0, -9.81])                      # :24
+        self.motor_dist, self.kf, self.km = 0.1750, 1.245, 1.0          # :25-29
+
+    @staticmethod
+    def _mrp_rotation(q):
+        """RotMatrix(MRP(q)) [3P Rotations.jl]: I + (8 S² + 4 (1 − |q|²) S) / (1 + |q|²)², S = skew(q)."""
+        S = np.array([[0, -q[2], q[1]], [q[2], 0, -q[0]], [-q[1], q[0], 0]], dtype=q.dtype)
+        n2 = q @ q
+        return np.eye(3, dtype=q.dtype) + (8.0 * (S @ S) + 4.0 * (1.0 - n2) * S) / (1.0 + n2) ** 2
+
+    @staticmethod
+    def _mrp_kinematics(q, w):
+        """Rotations.kinematics(MRP(q), ω) [3P Rotations.jl]: q̇ = ¼ ((1 − |q|²) I + 2 S + 2 q qᵀ) ω (body rates)."""
+        S = np.array([[0, -q[2], q[1]], [q[2], 0, -q[0]], [-q[1], q[0], 0]], dtype=q.dtype)
+        A = (1.0 - q @ q) * np.eye(3, dtype=q.dtype) + 2.0 * S + 2.0 * np.outer(q, q)
+        return 0.25 * (A @ w)
+
+    def _rotor_forces(self, u, i):
+        w = np.array([u[j * self.p + i] for j in range(4)])
+        F = np.where((self.kf * w).real > 0, self.kf * w, 0.0 * w)      # max(0, kf·w), :58-61
+        return w, F
+
+    def forces(self, x, u, i):                                          # :48-69
+        P = self.p
+        q = np.array([x[3 * P + i], x[4 * P + i], x[5 * P + i]])
+        _, F = self._rotor_forces(u, i)
+        body = np.array([0.0 * F[0], 0.0 * F[0], F.sum()])
+        return self.mass * self.gravity + self._mrp_rotation(q) @ body
+
+    def moments(self, x, u, i):                                         # :71-92
+        w, F = self._rotor_forces(u, i)
+        L = self.motor_dist
+        return np.array([L * (F[1] - F[3]), L * (F[2] - F[0]), self.km * (w[0] - w[1] + w[2] - w[3])])
+
+    def player_dynamics(self, x, u, i):                                 # :100-119
+        P = self.p
+        q = np.array([x[3 * P + i], x[4 * P + i], x[5 * P + i]])
+        v = np.array([x[6 * P + i], x[7 * P + i], x[8 * P + i]])
+        om = np.array([x[9 * P + i], x[10 * P + i], x[11 * P + i]])
+        F, tau = self.forces(x, u, i), self.moments(x, u, i)
+        return v, self._mrp_kinematics(q, om), F / self.mass, (tau - np.cross(om, self.J * om)) / self.J
+
+    def f(self, x, u):                                                  # :121-205 (component-major interleave)
+        x, u = np.asarray(x), np.asarray(u)
+        out = np.zeros(self.n, dtype=np.result_type(x.dtype, u.dtype, float))
+        for i in range(self.p):
+            parts = np.concatenate(self.player_dynamics(x, u, i))
+            out[[i + c * self.p for c in range(12)]] = parts
+        return out
+
+    def _cstep(self, x, u, wrt):
+        h = 1e-30
+        base = np.asarray(x if wrt == "x" else u, float)
+        cols = []
+        for a in range(len(base)):
+            z = base.astype(complex); z[a] += 1j * h
+            cols.append(self.f(z, np.asarray(u, float)).imag / h if wrt == "x" else self.f(np.asarray(x, float), z).imag / h)
+        return np.array(cols).T
+
+    def fx(self, x, u):
+        return self._cstep(x, u, "x")
+
+    def fu(self, x, u):
+        return self._cstep(x, u, "u")
+
+
 def make_model(name: str, p: int, d: int = 2, lf: float = 0.05, lr: float = 0.05):
+    if name == "quadrotor":
+        return QuadrotorGame(p=p)
     if name == "double_integrator":
         return DoubleIntegratorGame(p=p, d=d)
     if name == "unicycle":
