@@ -11,7 +11,8 @@ against every known-answer vector the reference's own test-suite holds for the p
 (tests/test_oracle_golden.py cites each one).  Arithmetic that lives in the third-party
 packages and is pinned by NO reference test is marked "parity unpinned" below:
   * RK2 (explicit midpoint) / RK3 tableaux of RobotDynamics 0.3.1,
-  * CollisionConstraint / CircleConstraint formulas of TrajectoryOptimization 0.4.1.
+  * CollisionConstraint / CircleConstraint formulas of TrajectoryOptimization 0.4.1,
+  * MRP rotation matrix / kinematics of Rotations.jl used by QuadrotorGame (an oracle-only model this round).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).  Indices are 0-based here, 1-based in the reference.
