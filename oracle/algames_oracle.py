@@ -579,6 +579,90 @@ class WallConstraint(_Con):
         return J
 
 
+@dataclass
+class Wall3D:
+    """src/constraints/constraints_methods.jl:201-206: corner points p1, p2, p3 of the rectangle, outward normal v."""
+    p1: np.ndarray
+    p2: np.ndarray
+    p3: np.ndarray
+    v: np.ndarray
+
+
+class Wall3DConstraint(_Con):
+    """src/constraints/wall_constraint.jl:141-233 (ORACLE ONLY, SURVEY §8 f3): ((X−p1)·v) · 1[left]·1[right]·1[bottom]·1[top];
+    pinned by test/constraints/wall_constraint.jl:33-70."""
+
+    def __init__(self, n, x1, y1, z1, x2, y2, z2, x3, y3, z3, xv, yv, zv, x=0, y=1, z=2):
+        self.n = n
+        (self.x1, self.y1, self.z1, self.x2, self.y2, self.z2, self.x3, self.y3, self.z3, self.xv, self.yv, self.zv) = (
+            np.asarray(v, float) for v in (x1, y1, z1, x2, y2, z2, x3, y3, z3, xv, yv, zv))
+        self.x, self.y, self.z = x, y, z
+
+    def length(self):
+        return len(self.x1)
+
+    def _mask(self, X):
+        x, y, z = X[self.x], X[self.y], X[self.z]
+        dot = lambda ax, ay, az, bx, by, bz, cx, cy, cz: (x - ax) * (bx - cx) + (y - ay) * (by - cy) + (z - az) * (bz - cz)
+        left = dot(self.x1, self.y1, self.z1, self.x2, self.y2, self.z2, self.x1, self.y1, self.z1) > 0       # :203
+        right = dot(self.x2, self.y2, self.z2, self.x1, self.y1, self.z1, self.x2, self.y2, self.z2) > 0      # :204
+        bottom = dot(self.x3, self.y3, self.z3, self.x2, self.y2, self.z2, self.x3, self.y3, self.z3) > 0     # :205
+        top = dot(self.x2, self.y2, self.z2, self.x3, self.y3, self.z3, self.x2, self.y2, self.z2) > 0        # :206
+        return x, y, z, (left & right & bottom & top).astype(float)
+
+    def evaluate(self, X, u):
+        x, y, z, msk = self._mask(X)
+        return ((x - self.x1) * self.xv + (y - self.y1) * self.yv + (z - self.z1) * self.zv) * msk           # :207-208
+
+    def jacobian(self, X, u):
+        _, _, _, msk = self._mask(X)
+        J = np.zeros((len(self.x1), self.n))
+        J[:, self.x], J[:, self.y], J[:, self.z] = msk * self.xv, msk * self.yv, msk * self.zv                # :231-235
+        return J
+
+
+@dataclass
+class CylinderWall:
+    """src/constraints/constraints_methods.jl:249-254: base point p, axis v in {"x","y","z"}, length l, radius r."""
+    p: np.ndarray
+    v: str
+    l: float
+    r: float
+
+
+class CylinderConstraint(_Con):
+    """src/constraints/cylinder_constraint.jl:33-129 (ORACLE ONLY): r² − (squared distance to the axis), active
+    only between the end caps; pinned by test/constraints/cylinder_constraint.jl:4-22."""
+
+    def __init__(self, n, p1, p2, p3, v, l, r, x=0, y=1, z=2):
+        self.n = n
+        self.p1, self.p2, self.p3, self.l, self.r = (np.asarray(a, float) for a in (p1, p2, p3, l, r))
+        self.v = [str(a) for a in v]
+        assert all(a in ("x", "y", "z") for a in self.v)
+        self.axis = np.array([[a == "x", a == "y", a == "z"] for a in self.v], dtype=float)     # one-hot axis per cylinder
+        self.x, self.y, self.z = x, y, z
+
+    def length(self):
+        return len(self.p1)
+
+    def _terms(self, X):
+        t = np.stack([X[self.x] - self.p1, X[self.y] - self.p2, X[self.z] - self.p3], axis=1)  # t0 = X − p, :76-79
+        along = (t * self.axis).sum(axis=1)
+        valid = ((along > 0.0) & (along < self.l)).astype(float)                              # :81-84
+        return t, valid
+
+    def evaluate(self, X, u):
+        t, valid = self._terms(X)
+        return (self.r ** 2 - (t ** 2 * (1.0 - self.axis)).sum(axis=1)) * valid               # :86-91
+
+    def jacobian(self, X, u):
+        t, valid = self._terms(X)
+        J = np.zeros((len(self.p1), self.n))
+        g = -2.0 * t * (1.0 - self.axis) * valid[:, None]                                     # :122-126
+        J[:, self.x], J[:, self.y], J[:, self.z] = g[:, 0], g[:, 1], g[:, 2]
+        return J
+
+
 class ALConVal:
     """[3P Altro 0.3.0 ALConVal] per-knot vals/jac/λ/μ/grad/hess; formulas pinned by
     test/constraints/constraint_derivatives.jl:22-34 and test/constraints/constraints_methods.jl:176-229."""
@@ -658,6 +742,33 @@ class GameConstraintValues:
             for b in range(ps.p):
                 if b != a:
                     self._add_state(a, CollisionConstraint(ps.n, ps.px[a], ps.px[b], rad[a] + rad[b]))
+
+    def add_spherical_collision_avoidance(self, radius, i=None, j=None):
+        """constraints_methods.jl:45-81 (ORACLE ONLY): CollisionConstraint on the first three state components."""
+        ps = self.probsize
+        if i is not None:
+            self._add_state(i, CollisionConstraint(ps.n, ps.pz[i][:3], ps.pz[j][:3], radius))       # :52-55
+            return
+        rad = np.broadcast_to(np.asarray(radius, float), (ps.p,))
+        for a in range(ps.p):
+            for b in range(ps.p):
+                if b != a:
+                    self._add_state(a, CollisionConstraint(ps.n, ps.pz[a][:3], ps.pz[b][:3], rad[a] + rad[b]))
+
+    def add_wall3d_constraint(self, walls, i=None):
+        """add_wall_constraint!(game_con, i, walls::Vector{Wall3D}) (constraints_methods.jl:208-247, ORACLE ONLY)."""
+        ps = self.probsize
+        for a in (range(ps.p) if i is None else [i]):
+            cols = [[getattr(w, f)[c] for w in walls] for f in ("p1", "p2", "p3", "v") for c in range(3)]
+            self._add_state(a, Wall3DConstraint(ps.n, *cols, ps.pz[a][0], ps.pz[a][1], ps.pz[a][2]))
+
+    def add_cylinder_constraint(self, walls, i=None):
+        """add_wall_constraint!(game_con, i, walls::Vector{CylinderWall}) (constraints_methods.jl:256-285, ORACLE ONLY)."""
+        ps = self.probsize
+        for a in (range(ps.p) if i is None else [i]):
+            self._add_state(a, CylinderConstraint(ps.n, [w.p[0] for w in walls], [w.p[1] for w in walls], [w.p[2] for w in walls],
+                                                  [w.v for w in walls], [w.l for w in walls], [w.r for w in walls],
+                                                  ps.pz[a][0], ps.pz[a][1], ps.pz[a][2]))
 
     def add_state_bound(self, i, x_max, x_min):
         self._add_state(i, StateBoundConstraint(self.probsize.n, x_max, x_min))       # :87-98

@@ -91,3 +91,68 @@ def test_quadrotor_game_kkt_jacobian_matches_residual_differences():
     rp = O.residual(prob, plus).copy(); rm = O.residual(prob, minus).copy()
     fd = (rp - rm) / (2 * h)
     assert np.abs(J @ d - fd).max() < 1e-6 * max(1.0, np.abs(fd).max())
+
+
+# ---------------------------------------------------------------- 3-D constraints (oracle only)
+S2 = 1.0 / np.sqrt(2.0)
+
+
+def _wall3d():
+    # test/constraints/wall_constraint.jl:33-62 (x = 4, y = 2, z = 1 there; 0-based here)
+    return O.Wall3DConstraint(6, [0] * 5, [0] * 5, [0] * 5, [1] * 5, [0] * 5, [0, 0, 1, 0, 0], [1, 1, 1, 0, 0], [1] * 5, [0, 1, 1, 0, 1],
+                              [0, 0, -S2, 0, 0], [0, -S2, 0, 0, -S2], [1, S2, S2, 1, S2], 3, 1, 0)
+
+
+def test_wall3d_constraint_values():
+    con = _wall3d()
+    cases = [([0.0, 0.10, -12.0, 0.10, 12.0, 11.0], [0.0, -0.1 * S2, -0.1 * S2, 0.0, -0.1 * S2]),       # :63
+             ([1.0, 0.55, -12.0, 0.55, 12.0, 11.0], [1.0, 0.45 * S2, 0.45 * S2, 1.0, 0.45 * S2]),       # :64
+             ([1.0, 1.25, -12.0, 0.75, 12.0, 11.0], [0.0, 0.0, 0.0, 1.0, -0.25 * S2])]                  # :65
+    for X, want in cases:
+        assert np.abs(con.evaluate(np.array(X), None) - np.array(want)).sum() < 1e-10
+    # :68-71: jacobian! equals the derivative of evaluate (away from the mask edges)
+    X = np.array([0.4, 0.55, -12.0, 0.55, 12.0, 11.0]); h = 1e-7
+    fd = np.array([(con.evaluate(X + h * np.eye(6)[a], None) - con.evaluate(X - h * np.eye(6)[a], None)) / (2 * h) for a in range(6)]).T
+    assert np.abs(con.jacobian(X, None) - fd).sum() < 1e-7
+
+
+def test_cylinder_constraint_values():
+    # test/constraints/cylinder_constraint.jl:4-35 (x = 2, y = 3, z = 4 there)
+    con = O.CylinderConstraint(4, [1, 1, 1, 0, 1], [0, 0, 0, 1, 0], [1, 1, 3, 1, 2], ["z", "z", "z", "x", "y"],
+                               [5, 2, 0.5, 2, 10], [3, 2, 7, 3, 1], 1, 2, 3)
+    X0 = np.array([13.0, 1.0, 1.0, 2.0])
+    assert np.abs(con.evaluate(X0, None) - np.array([8.0, 3.0, 0.0, 8.0, 1.0])).sum() < 1e-10               # :21
+    h = 1e-7
+    fd = np.array([(con.evaluate(X0 + h * np.eye(4)[a], None) - con.evaluate(X0 - h * np.eye(4)[a], None)) / (2 * h) for a in range(4)]).T
+    assert np.abs(con.jacobian(X0, None) - fd).sum() < 1e-6                                                 # :30-34
+
+
+def test_spherical_collision_avoidance_indices():
+    # test/constraints/constraints_methods.jl:30-57: 3-player, 3-D double integrator; the collision convals of player i
+    # pair its first three state components with each opponent's (pu == pz[:3] for this model)
+    p = 3
+    model = O.make_model("double_integrator", p, d=3)
+    gc = O.GameConstraintValues(O.ProblemSize(20, model))
+    gc.add_spherical_collision_avoidance(1.0)
+    for i in range(p):
+        others = [j for j in range(p) if j != i]
+        assert len(gc.state_conval[i]) == 2
+        for cv, j in zip(gc.state_conval[i], others):
+            assert list(cv.con.x1) == list(model.pu[i]) and list(cv.con.x2) == list(model.pu[j])
+            assert cv.con.radius == 2.0 and list(cv.inds) == list(range(2, 21))
+
+
+def test_3d_adders_build_one_conval_per_player_on_position_components():
+    # add_wall_constraint!(…, Vector{Wall3D}) / (…, Vector{CylinderWall}) (constraints_methods.jl:208-285) for a quadrotor game
+    model = O.make_model("quadrotor", 2)
+    gc = O.GameConstraintValues(O.ProblemSize(5, model))
+    gc.add_wall3d_constraint([O.Wall3D(np.zeros(3), np.array([1.0, 0, 0]), np.array([1.0, 1, 0]), np.array([0, 0, 1.0]))])
+    gc.add_cylinder_constraint([O.CylinderWall(np.array([0.5, 0.5, 0.0]), "z", 2.0, 0.3)], i=1)
+    assert [len(c) for c in gc.state_conval] == [1, 2]
+    w = gc.state_conval[1][0].con
+    assert (w.x, w.y, w.z) == tuple(model.pz[1][:3]) and w.length() == 1
+    cyl = gc.state_conval[1][1].con
+    x = np.zeros(model.n); x[model.pz[1][:3]] = [0.6, 0.5, 1.0]            # inside the cylinder, 0.1 from its axis
+    assert np.isclose(cyl.evaluate(x, None)[0], 0.3 ** 2 - 0.1 ** 2)
+    x[model.pz[1][2]] = 2.5                                                 # above the top cap: inactive
+    assert cyl.evaluate(x, None)[0] == 0.0
