@@ -847,6 +847,10 @@ class GameConstraintValues:
         for _, _, cv in self.all_convals():
             cv.evaluate(X, U)
 
+    def jacobian(self, X, U):                 # :382-394
+        for _, _, cv in self.all_convals():
+            cv.jacobian(X, U)
+
     def dual_update(self):
         """:349-365 and :421-440 (all in-scope constraints are Inequality ⇒ clamp to [0, λ_max])."""
         for kind, i, cv in self.all_convals():
@@ -1657,3 +1661,154 @@ def ibr_newton_solve(prob: GameProblem, Z0=None, L0=None, ibr_iter=100, ordering
         if all(not c for c in change):
             break
     return prob
+
+
+# --------------------------------------------------------------------------------------
+# Active-set analysis  (src/active_set/*.jl) — ORACLE ONLY (host-side analysis, off the solve path)
+# --------------------------------------------------------------------------------------
+def valid_c(dim, con, i, j, k, N, p):
+    """valid(::CStamp, N, p) (active_set_stamp.jl:64-81; pinned test/active_set/active_set_stamp.jl:6-36), 1-based."""
+    if dim == "v":
+        return i < j and 1 <= i <= p and 1 <= j <= p and 2 <= k <= N
+    if dim == "h":
+        return 1 <= i <= p and 1 <= j <= p and 2 <= k <= N and i != j
+    return False
+
+
+class ActiveSetCore:
+    """active_set_core.jl:57-160: the Newton system augmented with one row per unordered collision pair and knot
+    (`("v","col",i,j,k)`, i < j) and one column per ordered pair (`("h","col",i,j,k)`): Sv = S + p(p−1)(N−1)/2 rows,
+    Sh = S + p(p−1)(N−1) columns.  The first S rows / columns are NewtonCore's."""
+
+    def __init__(self, ps: ProblemSize):
+        self.ps = ps
+        N, p, S = ps.N, ps.p, ps.S
+        self.Sv, self.Sh = S + p * (p - 1) * (N - 1) // 2, S + p * (p - 1) * (N - 1)     # :81-82
+        self.vert, self.horiz = {}, {}
+        off = S
+        for k in range(2, N + 1):                                                        # :118-126
+            for i in range(1, p + 1):
+                for j in range(i + 1, p + 1):
+                    self.vert[("v", "col", i, j, k)] = off; off += 1
+        assert off == self.Sv
+        off = S
+        for k in range(2, N + 1):                                                        # :151-159
+            for i in range(1, p + 1):
+                for j in range(1, p + 1):
+                    if j != i:
+                        self.horiz[("h", "col", i, j, k)] = off; off += 1
+        assert off == self.Sh
+        self.res = np.zeros(self.Sv)
+        self.jac = np.zeros((self.Sv, self.Sh))
+        self.vmask = np.arange(self.Sv)                                                  # :91-92
+        self.hmask = np.arange(self.Sh)
+        self.null_mat = np.zeros((0, 0))
+        self.null_vec, self.null_dtraj, self.null_dlam = [], [], []                      # NullSpace, :5-27
+
+
+def _collision_conval(game_con, i, j):
+    """get_collision_conval (active_set_methods.jl:80-94), players 1-based."""
+    px = game_con.probsize.px
+    for cv in game_con.state_conval[i - 1]:
+        if isinstance(cv.con, CollisionConstraint) and np.array_equal(cv.con.x2, px[j - 1]):
+            return cv
+    return None
+
+
+def as_active(game_con, dim, i, j, k, tol=None):
+    """active(game_con, stamp) (active_set_methods.jl:5-26): the `active` flag Altro keeps for the (i,j) collision row of knot k."""
+    ps = game_con.probsize
+    if not valid_c(dim, "col", i, j, k, ps.N, ps.p):
+        return False
+    cv = _collision_conval(game_con, i, j)
+    l = cv.inds.index(k)
+    tol = game_con.active_set_tolerance if tol is None else tol
+    return bool((cv.vals[l, 0] >= -tol) | (cv.lam[l, 0] > 0))
+
+
+def active_vertical_mask(ascore, game_con):
+    """active_set_methods.jl:28-50: rows of the Newton system + the rows of the active collision pairs."""
+    ps = ascore.ps
+    keep = list(range(ps.S))
+    for k in range(2, ps.N + 1):
+        for i in range(1, ps.p + 1):
+            for j in range(i + 1, ps.p + 1):
+                if as_active(game_con, "v", i, j, k):
+                    keep.append(ascore.vert[("v", "col", i, j, k)])
+    ascore.vmask = np.array(keep)
+
+
+def active_horizontal_mask(ascore, game_con):
+    """active_set_methods.jl:52-74."""
+    ps = ascore.ps
+    keep = list(range(ps.S))
+    for k in range(2, ps.N + 1):
+        for i in range(1, ps.p + 1):
+            for j in range(1, ps.p + 1):
+                if j != i and as_active(game_con, "h", i, j, k):
+                    keep.append(ascore.horiz[("h", "col", i, j, k)])
+    ascore.hmask = np.array(keep)
+
+
+def as_residual(ascore, prob, pd=None):
+    """residual!(ascore, prob, pdtraj) (active_set_methods.jl:96-124): [KKT residual; collision values of the pairs i < j]."""
+    pd = pd or prob.pdtraj
+    ps = ascore.ps
+    ascore.res[:] = 0.0
+    ascore.res[:ps.S] = residual(prob, pd)
+    prob.game_con.evaluate(pd.X, pd.U)
+    for i in range(1, ps.p + 1):
+        for j in range(i + 1, ps.p + 1):
+            cv = _collision_conval(prob.game_con, i, j)
+            if cv is not None:
+                for l, k in enumerate(cv.inds):
+                    ascore.res[ascore.vert[("v", "col", i, j, k)]] += cv.vals[l, 0]
+    return ascore.res
+
+
+def as_residual_jacobian(ascore, prob, pd=None):
+    """residual_jacobian!(ascore, prob, pdtraj) (active_set_methods.jl:131-170): the KKT Jacobian bordered by ∇cᵀ in the
+    column of the ordered pair (i,j) on player i's opt-x rows, and by ∇c in the row of the unordered pair on the x columns."""
+    pd = pd or prob.pdtraj
+    ps, core = ascore.ps, prob.core
+    ascore.jac[:] = 0.0
+    residual(prob, pd)
+    ascore.jac[:ps.S, :ps.S] = residual_jacobian(prob, pd)
+    prob.game_con.jacobian(pd.X, pd.U)
+    for i in range(1, ps.p + 1):
+        for j in range(1, ps.p + 1):
+            if j == i:
+                continue
+            cv = _collision_conval(prob.game_con, i, j)
+            if cv is None:
+                continue
+            for l, k in enumerate(cv.inds):
+                ascore.jac[core.vert[("opt", i, "x", k)], ascore.horiz[("h", "col", i, j, k)]] += cv.jac[l, 0]       # :154-156
+                if valid_c("v", "col", i, j, k, ps.N, ps.p):                                                        # :157-161
+                    ascore.jac[ascore.vert[("v", "col", i, j, k)], core.horiz[("x", k)]] += cv.jac[l, 0]
+    return ascore.jac
+
+
+def update_nullspace(ascore, prob, pd=None, atol=1e-20):
+    """update_nullspace! (active_set_methods.jl:173-184) + add_matrix! (active_set_core.jl:29-52): null space of the
+    active-set Jacobian (LinearAlgebra.nullspace = right singular vectors of the singular values ≤ atol), each vector
+    scattered to the full column set and scaled to unit mean absolute value."""
+    pd = pd or prob.pdtraj
+    ps = ascore.ps
+    prob.game_con.evaluate(pd.X, pd.U)                       # update_active_set!(game_con, traj)
+    active_vertical_mask(ascore, prob.game_con)
+    active_horizontal_mask(ascore, prob.game_con)
+    as_residual_jacobian(ascore, prob, pd)
+    djac = ascore.jac[np.ix_(ascore.vmask, ascore.hmask)]
+    _, sv, Vt = np.linalg.svd(djac, full_matrices=True)
+    rank = int((sv > atol).sum())
+    mat = Vt[rank:].T                                       # columns span the null space
+    assert ps.S <= mat.shape[0] <= ascore.Sh                # active_set_core.jl:37
+    ascore.null_mat = mat
+    ascore.null_vec, ascore.null_dtraj, ascore.null_dlam = [], [], []
+    for c in range(mat.shape[1]):
+        vec = np.zeros(ascore.Sh)
+        vec[ascore.hmask] = mat[:, c]
+        vec /= np.mean(np.abs(vec))
+        ascore.null_vec.append(vec); ascore.null_dtraj.append(vec[:ps.S]); ascore.null_dlam.append(vec[ps.S:])
+    return ascore.null_mat
