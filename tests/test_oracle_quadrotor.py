@@ -156,3 +156,22 @@ def test_3d_adders_build_one_conval_per_player_on_position_components():
     assert np.isclose(cyl.evaluate(x, None)[0], 0.3 ** 2 - 0.1 ** 2)
     x[model.pz[1][2]] = 2.5                                                 # above the top cap: inactive
     assert cyl.evaluate(x, None)[0] == 0.0
+
+
+@pytest.mark.parametrize("p,N", [(1, 6), (2, 5)])
+def test_quadrotor_game_solves_on_the_oracle(p, N):
+    # the generic newton_solve! loop (solver_methods.jl:5-65) with 12-state / 4-control players: hover-to-waypoint LQ game,
+    # for p = 2 with spherical collision avoidance (inactive along the way); same convergence test as every other model
+    model = O.make_model("quadrotor", p)
+    hover = model.mass * 9.81 / 4 / model.kf
+    xf = [np.r_[0.3 * (1 - 2 * i), 0.2, 1.1, np.zeros(9)] for i in range(p)]
+    obj = O.GameObjective([np.ones(12)] * p, [0.1 * np.ones(4)] * p, xf, [hover * np.ones(4)] * p, N, model)
+    gc = O.GameConstraintValues(O.ProblemSize(N, model))
+    if p > 1:
+        gc.add_spherical_collision_avoidance(0.1)
+    x0 = np.zeros(model.n); x0[2 * p:3 * p] = 1.0; x0[0:p] = np.linspace(-0.5, 0.5, p) if p > 1 else 0.0
+    prob = O.GameProblem(N, 0.1, x0, model, O.Options(), obj, gc)
+    O.newton_solve(prob)
+    last = prob.stats[-1]
+    assert prob.converged and max(last.dyn, last.con, last.sta, last.opt) < 1e-3
+    assert prob.pdtraj.X[-1][2 * p] > 1.0                                  # climbing towards z = 1.1
