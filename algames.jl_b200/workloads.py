@@ -179,4 +179,28 @@ def config_s(batch=8, seed=6789, N=12):
     return model, N, dt, obj, con, Options(), x0, None
 
 
+def config_s_random(layout_seed, batch=4, seed=6789, N=8):
+    """Config S with a random StateBound layout: every (component, side) of the joint state is given, with probability
+    1/2, to one of up to four convals of each player (bounds wide enough to stay feasible, tight enough that some are
+    active on a random iterate).  Used by the randomized row-order tests."""
+    model, N, dt, obj, con, opts, x0, xf = config_s(batch=batch, seed=seed, N=N)
+    con.state_bound = [[] for _ in range(model.p)]
+    rng = np.random.default_rng(layout_seed)
+    n = model.n
+    for i in range(model.p):
+        ncon = int(rng.integers(1, 5))
+        his = [np.full(n, np.inf) for _ in range(ncon)]
+        los = [np.full(n, -np.inf) for _ in range(ncon)]
+        for a in range(n):
+            if rng.random() < 0.5:
+                his[int(rng.integers(ncon))][a] = float(rng.uniform(0.5, 3.0))
+            if rng.random() < 0.5:
+                los[int(rng.integers(ncon))][a] = float(rng.uniform(-3.0, -0.5))
+        for hi, lo in zip(his, los):
+            add_state_bound(con, i, hi, lo)
+    return model, N, dt, obj, con, opts, x0, xf
+
+
 CONFIGS = {"S": config_s, "V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}
+for _ls in range(1, 5):                                   # "S1" … "S4": random StateBound layouts
+    CONFIGS["S%d" % _ls] = (lambda ls: (lambda batch=4, N=8: config_s_random(ls, batch=batch, N=N)))(_ls)

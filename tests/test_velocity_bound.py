@@ -127,3 +127,10 @@ def test_interleaved_state_bound_convals_emulated(emu_lib):  # noqa: F811
     parity.check_per_function(emu_lib, "S", seed=5)
     out = parity.check_solve_vs_oracle(emu_lib, "S", B=2)
     assert (out["status"] == 0).all() and (out["conlam"] > 0).any(axis=(0, 1)).sum() >= 3
+
+
+@pytest.mark.parametrize("name", ["S1", "S2", "S3", "S4"])
+def test_random_state_bound_layouts_emulated(emu_lib, name):  # noqa: F811
+    # random assignment of (component, side) pairs to up to four convals per player: values, AL rows, multiplier updates
+    # and the Newton step must follow the oracle's conval-by-conval row order
+    parity.check_per_function(emu_lib, name, seed=7)
