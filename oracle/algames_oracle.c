@@ -44,6 +44,7 @@ typedef struct {
   /* state */
   double *X, *U, *L, *Xt, *Ut, *Lt, *dX, *dU, *dL, *lam, *mu, *res, *band, *rhs;
   int n_newton, n_eval;
+  double* hist; int hist_max, n_rec;   /* optional record!(stats, …) log of this instance (statistics.jl:44-57) */
 } Work;
 
 /* ---- models (src/dynamics/*.jl), per player: s[4], u[2] ---------------------------------------------------- */
@@ -335,6 +336,14 @@ static void setup_rows(Work* w) {
 }
 
 /* newton_solve!(prob) for one instance.  stats[10] as in include/algames_b200.h; returns the status code. */
+static void log_rec(Work* w, const Norms* r, double delta, int kout, int l) {
+  if (w->hist && w->n_rec < w->hist_max) {
+    double* h = w->hist + (size_t)w->n_rec * AGB_NHIST;
+    h[0] = kout; h[1] = r->sum / (double)w->S; h[2] = r->dyn; h[3] = r->con; h[4] = r->sta; h[5] = r->opt; h[6] = delta; h[7] = l;
+  }
+  w->n_rec++;
+}
+
 static int solve_one(Work* w, double* stats) {
   const agb_options* o = w->o;
   const int n = w->n, m = w->m, p = w->p, K = w->K;
@@ -349,7 +358,7 @@ static int solve_one(Work* w, double* stats) {
   if (o->dual_reset) for (int q = 0; q < K * w->nrow; q++) { w->lam[q] = 0; w->mu[q] = o->rho_0; }
   Norms rec = {0, 0, 0, 0, 0};
   double delta = 0; int outer = 0, failed = 0;
-  w->n_newton = 0; w->n_eval = 0;
+  w->n_newton = 0; w->n_eval = 0; w->n_rec = 0;
   ConRow rows[MAXROW];
   for (int kout = 1; kout <= o->outer_iter; kout++) {
     outer = kout;
@@ -358,6 +367,7 @@ static int solve_one(Work* w, double* stats) {
       double l2 = (double)l * l, reg = o->reg_0 * (l2 * l2);
       rec = assemble(w, w->X, w->U, w->L, w->X, w->U, 0.0, 1, reg);              /* residual! + residual_jacobian! */
       double res_norm = rec.sum / Sd;
+      log_rec(w, &rec, delta, kout, l);                                          /* record!(stats, …) (:75) */
       delta = 0;
       if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
       if (rec.opt < o->eps_opt) break;
@@ -395,6 +405,7 @@ static int solve_one(Work* w, double* stats) {
     }
   }
   rec = assemble(w, w->X, w->U, w->L, w->X, w->U, 0.0, 0, 0.0);
+  log_rec(w, &rec, delta, outer, 0);                                             /* :63 */
   int finite = (rec.sum == rec.sum) && !isinf(rec.sum);
   int conv = finite && rec.dyn < o->eps_dyn && rec.con < o->eps_con && rec.sta < o->eps_sta && rec.opt < o->eps_opt;
   stats[0] = rec.sum / Sd; stats[1] = rec.dyn; stats[2] = rec.con; stats[3] = rec.sta; stats[4] = rec.opt; stats[5] = delta;
@@ -407,6 +418,9 @@ typedef struct {
   const agb_problem_desc* d; const agb_options* o; int batch;
   const double *x0, *xf, *Q, *R, *uf, *Z0, *L0; double *Z, *L, *stats; int* status;
   atomic_int next;
+  const double *lam0, *mu0;      /* [B][K][nrow] initial AL multipliers / penalties (used when !dual_reset), or NULL */
+  double *lam_out, *mu_out;      /* [B][K][nrow] or NULL */
+  double* hist; int* hist_count; int hist_max;   /* [B][hist_max][AGB_NHIST], [B], or NULL */
 } Job;
 
 static void* worker(void* arg) {
@@ -432,7 +446,13 @@ static void* worker(void* arg) {
     memcpy(w.L, jb->L0 + (size_t)inst * p * K * n, (size_t)p * K * n * sizeof(double));
     memcpy(w.X, jb->x0 + (size_t)inst * n, n * sizeof(double));
     for (int t = 0; t < K * w.nrow; t++) { w.lam[t] = 0; w.mu[t] = o->rho_0; }
+    if (jb->lam0) memcpy(w.lam, jb->lam0 + (size_t)inst * K * w.nrow, (size_t)K * w.nrow * sizeof(double));
+    if (jb->mu0) memcpy(w.mu, jb->mu0 + (size_t)inst * K * w.nrow, (size_t)K * w.nrow * sizeof(double));
+    w.hist = jb->hist ? jb->hist + (size_t)inst * jb->hist_max * AGB_NHIST : NULL; w.hist_max = jb->hist_max;
     jb->status[inst] = solve_one(&w, jb->stats + (size_t)inst * AGB_NSTATS);
+    if (jb->hist_count) jb->hist_count[inst] = w.n_rec;
+    if (jb->lam_out) memcpy(jb->lam_out + (size_t)inst * K * w.nrow, w.lam, (size_t)K * w.nrow * sizeof(double));
+    if (jb->mu_out) memcpy(jb->mu_out + (size_t)inst * K * w.nrow, w.mu, (size_t)K * w.nrow * sizeof(double));
     double* z = jb->Z + (size_t)inst * N * (n + m);
     for (int k = 0; k < N; k++) { memcpy(z + k * (n + m), w.X + k * n, n * sizeof(double)); memcpy(z + k * (n + m) + n, w.U + k * m, m * sizeof(double)); }
     memcpy(jb->L + (size_t)inst * p * K * n, w.L, (size_t)p * K * n * sizeof(double));
@@ -441,17 +461,39 @@ static void* worker(void* arg) {
   return NULL;
 }
 
-int ago_newton_solve(const agb_problem_desc* d, const agb_options* o, int batch, int nthreads,
-                     const double* x0, const double* xf, const double* Q, const double* R, const double* uf,
-                     const double* Z0, const double* L0, double* Z, double* L, double* stats, int* status) {
+static int run_job(Job* jb, int nthreads) {
   if (nthreads <= 0) nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
-  if (nthreads > batch) nthreads = batch;
+  if (nthreads > jb->batch) nthreads = jb->batch;
   if (nthreads < 1) nthreads = 1;
-  Job jb = {d, o, batch, x0, xf, Q, R, uf, Z0, L0, Z, L, stats, status, 0};
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
-  for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, worker, &jb);
-  worker(&jb);
+  for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, worker, jb);
+  worker(jb);
   for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
   free(th);
   return nthreads;
+}
+
+int ago_newton_solve(const agb_problem_desc* d, const agb_options* o, int batch, int nthreads,
+                     const double* x0, const double* xf, const double* Q, const double* R, const double* uf,
+                     const double* Z0, const double* L0, double* Z, double* L, double* stats, int* status) {
+  Job jb = {d, o, batch, x0, xf, Q, R, uf, Z0, L0, Z, L, stats, status, 0, NULL, NULL, NULL, NULL, NULL, NULL, 0};
+  return run_job(&jb, nthreads);
+}
+
+/* Same, with the AL multipliers / penalties going in (warm start, dual_reset = false) and coming out, and the optional
+ * per-record history; any of lam0, mu0, lam_out, mu_out, hist, hist_count may be NULL. */
+int ago_newton_solve_ex(const agb_problem_desc* d, const agb_options* o, int batch, int nthreads,
+                        const double* x0, const double* xf, const double* Q, const double* R, const double* uf,
+                        const double* Z0, const double* L0, const double* lam0, const double* mu0,
+                        double* Z, double* L, double* lam_out, double* mu_out, double* stats, int* status,
+                        double* hist, int* hist_count, int hist_max) {
+  Job jb = {d, o, batch, x0, xf, Q, R, uf, Z0, L0, Z, L, stats, status, 0, lam0, mu0, lam_out, mu_out, hist, hist_count, hist_max};
+  return run_job(&jb, nthreads);
+}
+
+int ago_nrow(const agb_problem_desc* d) {
+  Work w; memset(&w, 0, sizeof w);
+  w.d = d; w.p = d->p; w.n = 4 * d->p; w.m = 2 * d->p;
+  setup_rows(&w);
+  return w.nrow;
 }

@@ -43,9 +43,10 @@ def random_state(oprob, x0, rng, mu_exp=(0, 3)):
     return Z, pd.du.copy(), lam, mu
 
 
-def check_per_function(lib_path, name, seed=0, reg=1e-3, N=None):
+def check_per_function(lib_path, name, seed=0, reg=1e-3, N=None, mu_exp=(0, 3)):
     """residual!, residual_jacobian!, Δtraj solve, line search, update_traj!, Δ_step, evaluate!, dual/penalty update,
-    active set — one random (far from converged) iterate with random multipliers and penalties up to 1e3."""
+    active set — one random (far from converged) iterate with random multipliers and penalties 10^mu_exp (the reference
+    runs its penalties up to ρ_max = 1e7, options.jl:59)."""
     model, N, dt, obj, con, opts, x0, xf = small_config(name, 2, N)
     B = 2
     x0 = np.tile(x0[:1], (B, 1)) if x0.shape[0] < B else x0[:B]
@@ -56,7 +57,7 @@ def check_per_function(lib_path, name, seed=0, reg=1e-3, N=None):
     oprobs, Zs, Ls, lams, mus = [], [], [], [], []
     for b in range(B):
         op = oracle_problem(model, N, dt, obj, con, opts, x0[b], None if xf is None else xf[b])
-        Z, L, lam, mu = random_state(op, x0[b], rng)
+        Z, L, lam, mu = random_state(op, x0[b], rng, mu_exp)
         oprobs.append(op); Zs.append(Z); Ls.append(L); lams.append(lam); mus.append(mu)
     has_con = lams[0].size > 0
     gb.set_initial(np.stack(Zs), np.stack(Ls), np.stack(lams) if has_con else None, np.stack(mus) if has_con else None)
@@ -78,7 +79,10 @@ def check_per_function(lib_path, name, seed=0, reg=1e-3, N=None):
         Jo = O.residual_jacobian(op, pd)
         assert np.abs(J[b] - Jo).max() <= TOL_FUNC * np.abs(Jo).max()
         ref = -np.linalg.solve(Jo, ores)
-        assert np.abs(d[b] - ref).max() <= 1e-9 * np.abs(ref).max()
+        # forward error: 1e-9 relative; beyond cond(J) ~ 1e10 (penalties >= 1e4) dense LU itself is only good to
+        # cond·ε, so the bound becomes 1e-4·cond(J)·ε — four orders below what backward stability guarantees
+        tol_fwd = 1e-9 if mu_exp[1] <= 3 else max(1e-9, 1e-4 * np.linalg.cond(Jo) * np.finfo(float).eps)
+        assert np.abs(d[b] - ref).max() <= tol_fwd * np.abs(ref).max()
         # the step solves the reference's linear system at least as well as dense LU does
         assert np.abs(Jo @ d[b] + ores).max() <= 10 * max(np.abs(Jo @ ref + ores).max(), 1e-12 * scale)
         # line search from the same step
@@ -329,3 +333,136 @@ def check_ibr_solve(lib_path, name, B=1, N=None, ibr_iter=3, opts_override=None)
         assert abs(out["stats"][b, 0] - np.abs(op.core.res).sum() / op.probsize.S) < TOL_SOLVE
     gb.close()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bulk parity at BASELINE sizes: every instance of a batch against the C restatement of the reference algorithm
+# (oracle/algames_oracle.c: explicit KKT Jacobian + pivoted band LU per Newton step, cross-checked against the NumPy
+# oracle in tests/test_c_oracle.py)
+# ---------------------------------------------------------------------------------------------------------------
+def c_oracle_solve(cfg, x0, xf, Z0, L0, opts, conlam=None, conmu=None, hist_max=0, nthreads=0):
+    from oracle import c_oracle
+    model, N, dt, obj, con = cfg[0], cfg[1], cfg[2], cfg[3], cfg[4]
+    p, J, B = model.p, ab.problem._joint, x0.shape[0]
+    desc = ab.problem._make_desc(model, N, dt, obj, con)
+    tile = lambda v: np.tile(v, (B, 1))
+    xfj = tile(J(obj.xf, p, 4)) if xf is None else xf
+    out, _ = c_oracle.newton_solve(desc, opts.to_c(), x0, xfj, tile(J(obj.Q, p, 4)), tile(J(obj.R, p, 2)), tile(J(obj.uf, p, 2)),
+                                   Z0, L0, nthreads=nthreads, conlam=conlam, conmu=conmu, hist_max=hist_max)
+    return out
+
+
+def compare_bulk(dev, ref, tol=TOL_SOLVE):
+    """Instance-by-instance comparison of a device solve with the C oracle's on the same inputs.  An instance FORKS when
+    its iteration trace differs (status, Newton steps, outer iterations or number of records): round-off differences
+    between the two linear solvers flipped a discrete decision (line-search step, active set, exit test), after which the
+    two runs are different — equally valid — executions of the same algorithm.  Non-forked instances must agree to `tol`:
+    converged ones on trajectories, duals and multipliers; the others on their final record (relative)."""
+    B = dev["status"].shape[0]
+    st_d, st_r = dev["stats"], ref["stats"]
+    fork = (dev["status"] != ref["status"]) | (st_d[:, 6] != st_r[:, 6]) | (st_d[:, 7] != st_r[:, 7])
+    if "hist_count" in dev and "hist_count" in ref:
+        fork |= dev["hist_count"] != ref["hist_count"]
+    same = ~fork
+    conv = (ref["status"] == 0) & same
+    nonc = (ref["status"] != 0) & same
+    rep = {"n": int(B), "forked": int(fork.sum()), "converged": int((dev["status"] == 0).sum()), "ref_converged": int((ref["status"] == 0).sum()),
+           "nonconverged_compared": int(nonc.sum()), "fork_idx": np.nonzero(fork)[0][:16].tolist()}
+    ax = tuple(range(1, dev["Z"].ndim))
+    zerr = np.abs(dev["Z"] - ref["Z"]).max(axis=ax)
+    lscale = np.maximum(1.0, np.abs(ref["L"]).max(axis=(1, 2, 3)))
+    lerr = np.abs(dev["L"] - ref["L"]).max(axis=(1, 2, 3)) / lscale
+    rec_rel = (np.abs(st_d[:, :5] - st_r[:, :5]) / np.maximum(np.abs(st_r[:, :5]), 1e-9)).max(axis=1)
+    rec_abs = np.abs(st_d[:, :5] - st_r[:, :5]).max(axis=1)
+    if dev["conlam"].size:
+        cscale = np.maximum(1.0, np.abs(ref["conlam"]).max(axis=(1, 2)))
+        cerr = np.abs(dev["conlam"] - ref["conlam"]).max(axis=(1, 2)) / cscale
+        mu_same = np.all(np.isclose(dev["conmu"], ref["conmu"], rtol=1e-12, atol=0), axis=(1, 2))
+    else:
+        cerr, mu_same = np.zeros(B), np.ones(B, bool)
+    pick = lambda v, msk: float(v[msk].max()) if msk.any() else 0.0
+    rep.update(worst_Z_converged=pick(zerr, conv), worst_L_converged=pick(lerr, conv), worst_conlam_converged=pick(cerr, conv),
+               worst_record_abs_converged=pick(rec_abs, conv), worst_record_rel_nonconverged=pick(rec_rel, nonc),
+               worst_Z_nonconverged=pick(zerr, nonc), worst_Z_forked=pick(zerr, fork))
+    if "hist" in dev and "hist" in ref:               # whole convergence trace of the non-forked instances
+        worst = 0.0
+        for b in np.nonzero(same)[0]:
+            c = int(ref["hist_count"][b]); c = min(c, dev["hist"].shape[1], ref["hist"].shape[1])
+            hd, hr = dev["hist"][b, :c], ref["hist"][b, :c]
+            assert np.array_equal(hd[:, [0, 7]], hr[:, [0, 7]]), b
+            worst = max(worst, float((np.abs(hd[:, 1:7] - hr[:, 1:7]) / np.maximum(np.abs(hr[:, 1:7]), 1e-6)).max()))
+        rep["worst_history_rel"] = worst
+    rep["ok_converged"] = bool((zerr[conv] < tol).all() and (lerr[conv] < tol).all() and (cerr[conv] < tol).all() and mu_same[conv].all()
+                               and (rec_abs[conv] < tol).all())
+    rep["ok_nonconverged"] = bool(((rec_rel[nonc] < tol) | (rec_abs[nonc] < tol)).all() and mu_same[nonc].all())
+    return rep
+
+
+def check_bulk_vs_c_oracle(lib_path, name, B, N=None, resolves=0, max_fork_frac=0.0, disturbance_std=1e-3, report=print):
+    """Cold solve of every instance of config `name` on the device and with the C oracle from the same initial iterate;
+    then `resolves` MPC re-solves (shift = 1, multipliers carried, dual_reset = false), each compared on the device's own
+    shifted iterate so that re-solve r is checked on identical inputs whatever happened before."""
+    cfg = small_config(name, B, N)
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    n = model.n
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path)
+    gb.set_instance_params(x0=x0, xf=xf)
+    Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+    hmax = opts.outer_iter * opts.inner_iter + 1
+    gb.set_history(hmax)
+    cold = ab.Options(**{**opts.to_dict(), "dual_reset": True})
+    dev = gb.newton_solve(cold)
+    dev["hist"], dev["hist_count"] = gb.get_history()
+    ref = c_oracle_solve(cfg, x0, xf, Z0, L0, cold, hist_max=hmax)
+    reps = [compare_bulk(dev, ref)]
+    reps[0]["what"] = f"{name} cold B={B} N={N}"
+    rng = np.random.default_rng(11)
+    warm = ab.Options(**{**opts.to_dict(), "dual_reset": False, "shift": 1})
+    for r in range(resolves):
+        d = disturbance_std * rng.standard_normal((B, n))
+        x0 = dev["Z"][:, 1, :n] + d
+        gb.mpc_advance(1, d)
+        Zs, Ls, cl, cm = gb.get_state()
+        dev = gb.newton_solve(warm)
+        dev["hist"], dev["hist_count"] = gb.get_history()
+        ref = c_oracle_solve(cfg, x0, xf, Zs, Ls, warm, conlam=cl, conmu=cm, hist_max=hmax)
+        reps.append(compare_bulk(dev, ref))
+        reps[-1]["what"] = f"{name} warm re-solve {r + 1} B={B} N={N}"
+    gb.close()
+    for rep in reps:
+        report("bulk parity: " + ", ".join(f"{k}={v if not isinstance(v, float) else format(v, '.2e')}" for k, v in rep.items()))
+        assert rep["ok_converged"], rep
+        assert rep["ok_nonconverged"], rep
+        assert rep["forked"] <= max_fork_frac * rep["n"], rep
+    return reps
+
+
+def check_edge_shape(lib_path, model_name, p, N):
+    """Smallest horizons (N = 2: one stage, no backward recursion), single player, and a 4-player bicycle game carrying every
+    constraint type: full solve vs the NumPy oracle."""
+    model = {"double_integrator": ab.DoubleIntegratorGame, "unicycle": ab.UnicycleGame, "bicycle": ab.BicycleGame}[model_name](p=p)
+    rng = np.random.default_rng(p * 10 + N)
+    obj = ab.GameObjective([1 + rng.random(4) for _ in range(p)], [0.1 + rng.random(2) for _ in range(p)],
+                           [rng.normal(size=4) for _ in range(p)], [0.1 * rng.normal(size=2) for _ in range(p)], N, model)
+    con = ab.GameConstraintValues(ab.ProblemSize(N, model))
+    if p > 1:
+        ab.add_collision_cost(obj, 0.5 * np.ones(p), 2.0 * np.ones(p))
+        ab.add_collision_avoidance(con, 0.05)
+    if model_name == "bicycle":
+        ab.add_control_bound(con, np.r_[2 * np.ones(p), 0.5 * np.ones(p)], np.r_[-2 * np.ones(p), -np.inf * np.ones(p)])
+        ab.add_state_bound(con, 1, 5 * np.ones(model.n), np.r_[-5 * np.ones(model.n - 2), -np.inf, -np.inf])
+        ab.add_wall_constraint(con, [ab.Wall([0.0, -0.4], [1.0, -0.4], [0.0, -1.0])], 2)
+        ab.add_circle_constraint(con, [1.0], [1.0], [0.2])
+    x0 = rng.normal(size=model.n)
+    opts = ab.Options()
+    gb = ab.GameBatch(model, N, 0.1, obj, con, 1, lib_path=lib_path)
+    gb.set_instance_params(x0=x0[None])
+    Z0, L0 = gb.random_initial()
+    out = gb.newton_solve(opts)
+    prob = ab.GameProblem(N, 0.1, x0, model, opts, obj, con, lib_path=lib_path)
+    op = O.problem_from_spec(ab.spec_of(prob))
+    O.newton_solve(op, Z0=Z0[0], L0=L0[0])
+    Zo = np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1)
+    assert np.abs(out["Z"][0] - Zo).max() < TOL_SOLVE
+    assert int(out["stats"][0, 6]) == op.n_newton and (out["status"][0] == 0) == op.converged
+    gb.close()

@@ -175,36 +175,18 @@ def test_solve_from_host_matches_staged_calls_emulated(emu_lib):
 
 @pytest.mark.parametrize("model_name,p,N", [("double_integrator", 1, 2), ("unicycle", 1, 3), ("bicycle", 4, 5), ("unicycle", 2, 2)])
 def test_edge_shapes_emulated(emu_lib, model_name, p, N):
-    """Smallest horizons (N = 2: one stage, no backward recursion), single player, and a 4-player bicycle game carrying every
-    constraint type: full solve vs oracle."""
-    import algames_b200 as ab
-    import oracle.algames_oracle as O
-    model = {"double_integrator": ab.DoubleIntegratorGame, "unicycle": ab.UnicycleGame, "bicycle": ab.BicycleGame}[model_name](p=p)
-    rng = np.random.default_rng(p * 10 + N)
-    obj = ab.GameObjective([1 + rng.random(4) for _ in range(p)], [0.1 + rng.random(2) for _ in range(p)],
-                           [rng.normal(size=4) for _ in range(p)], [0.1 * rng.normal(size=2) for _ in range(p)], N, model)
-    con = ab.GameConstraintValues(ab.ProblemSize(N, model))
-    if p > 1:
-        ab.add_collision_cost(obj, 0.5 * np.ones(p), 2.0 * np.ones(p))
-        ab.add_collision_avoidance(con, 0.05)
-    if model_name == "bicycle":
-        ab.add_control_bound(con, np.r_[2 * np.ones(p), 0.5 * np.ones(p)], np.r_[-2 * np.ones(p), -np.inf * np.ones(p)])
-        ab.add_state_bound(con, 1, 5 * np.ones(model.n), np.r_[-5 * np.ones(model.n - 2), -np.inf, -np.inf])
-        ab.add_wall_constraint(con, [ab.Wall([0.0, -0.4], [1.0, -0.4], [0.0, -1.0])], 2)
-        ab.add_circle_constraint(con, [1.0], [1.0], [0.2])
-    x0 = rng.normal(size=model.n)
-    opts = ab.Options()
-    gb = ab.GameBatch(model, N, 0.1, obj, con, 1, lib_path=emu_lib)
-    gb.set_instance_params(x0=x0[None])
-    Z0, L0 = gb.random_initial()
-    out = gb.newton_solve(opts)
-    prob = ab.GameProblem(N, 0.1, x0, model, opts, obj, con, lib_path=emu_lib)
-    op = O.problem_from_spec(ab.spec_of(prob))
-    O.newton_solve(op, Z0=Z0[0], L0=L0[0])
-    Zo = np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1)
-    assert np.abs(out["Z"][0] - Zo).max() < parity.TOL_SOLVE
-    assert int(out["stats"][0, 6]) == op.n_newton and (out["status"][0] == 0) == op.converged
-    gb.close()
+    parity.check_edge_shape(emu_lib, model_name, p, N)
+
+
+@pytest.mark.parametrize("name,N", [("B", 10), ("D", 8)])
+def test_per_function_parity_high_penalties_emulated(emu_lib, name, N):
+    parity.check_per_function(emu_lib, name, seed=5, N=N, mu_exp=(4, 7))
+
+
+def test_bulk_parity_vs_c_oracle_emulated(emu_lib):
+    """The bulk comparison of tests/test_gpu_parity.py::test_bulk_parity_vs_c_oracle on a handful of instances."""
+    parity.check_bulk_vs_c_oracle(emu_lib, "B", 6, 20, report=lambda s: None)
+    parity.check_bulk_vs_c_oracle(emu_lib, "D", 2, 12, resolves=2, report=lambda s: None)
 
 
 def test_working_set_too_large_is_rejected_emulated(emu_lib):
