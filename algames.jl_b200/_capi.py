@@ -9,9 +9,11 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST = 4, 16, 8, 8, 8, 10, 8
+MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST, IPC_BYTES, MAX_RANKS = 4, 16, 8, 8, 8, 10, 10, 64, 64
 MODEL_IDS = {"double_integrator": 0, "unicycle": 1, "bicycle": 2}
-STATUS_NAMES = {0: "converged", 1: "not_converged", 2: "numerical_failure"}
+# per-instance status (include/algames_b200.h): 1-3 = not converged (how the last inner loop ended), 4-5 = numerical failure
+CONVERGED, MAX_OUTER, LINE_SEARCH_FAILED, STALLED, SINGULAR, NONFINITE = range(6)
+STATUS_NAMES = {0: "converged", 1: "max_outer", 2: "line_search_failed", 3: "stalled", 4: "singular", 5: "nonfinite"}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libalgames_b200.so")
@@ -76,6 +78,8 @@ SYMBOLS = {
     "agb_get_state": (C.c_int, [_H, _DP, _DP, _DP, _DP]),
     "agb_shift_initial": (C.c_int, [_H, C.c_int, _DP, _DP]),
     "agb_mpc_advance": (C.c_int, [_H, C.c_int, _DP, _DP, _DP]),
+    "agb_mpc_advance_async": (C.c_int, [_H, C.c_int, C.c_void_p]),
+    "agb_join_stream": (C.c_int, [_H, C.c_void_p]),
     "agb_rollout": (C.c_int, [_H]),
     "agb_residual": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, _DP, _DP]),
     "agb_residual_jacobian_dense": (C.c_int, [_H, C.c_double, C.c_double, _DP]),
@@ -97,11 +101,34 @@ SYMBOLS = {
     "agb_get_device_view": (C.c_int, [_H, C.POINTER(DeviceView)]),
     "agb_set_history": (C.c_int, [_H, C.c_int]),
     "agb_get_history": (C.c_int, [_H, _DP, _IP]),
+    "agb_abi_check": (C.c_int, [_IP, C.c_int]),
+    "agb_abi_layout": (C.c_int, [_IP, C.c_int]),
+    "agb_violations": (C.c_int, [_H, _DP, _DP, _DP, _DP]),
+    "agb_peer_init": (C.c_int, [_H, C.c_int, C.c_int, _IP]),
+    "agb_peer_export": (C.c_int, [_H, C.POINTER(C.c_ubyte)]),
+    "agb_peer_connect": (C.c_int, [_H, C.POINTER(C.c_ubyte)]),
+    "agb_peer_connect_local": (C.c_int, [C.POINTER(_H), C.c_int]),
+    "agb_allgather": (C.c_int, [_H, C.c_void_p]),
+    "agb_allgather_wait": (C.c_int, [_H]),
+    "agb_gathered_view": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_ulonglong)]),
+    "agb_unpack_gathered": (C.c_int, [_H, C.c_int, _DP, _DP, _DP, _IP]),
+    "agb_create_sharded": (C.c_int, [C.POINTER(ProblemDesc), C.c_int, C.c_int, _IP, C.POINTER(_H), _IP]),
+    "agb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _DP, C.POINTER(C.c_float)]),
     "agb_launch_count": (C.c_longlong, [_H]),
     "agb_last_solve_ms": (C.c_float, [_H]),
 }
 
 _cache = {}
+
+
+def abi_layout():
+    """The AGB_ABI_WORDS values agb_abi_check expects, computed from the ctypes mirrors above."""
+    off = lambda st, f: getattr(st, f).offset
+    return [C.sizeof(ProblemDesc), off(ProblemDesc, "dt"), off(ProblemDesc, "Q"), off(ProblemDesc, "col_radius"),
+            off(ProblemDesc, "has_state_bound"), off(ProblemDesc, "walls"), off(ProblemDesc, "circles"), off(ProblemDesc, "x_max_con"),
+            C.sizeof(OptionsC), off(OptionsC, "alphax_dual"), off(OptionsC, "eps_dyn"), off(OptionsC, "dual_reset"),
+            C.sizeof(IBROptionsC), off(IBROptionsC, "delta_min"), C.sizeof(Sizes), C.sizeof(DeviceView),
+            MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST, IPC_BYTES]
 
 
 class LibraryMissing(RuntimeError):
@@ -121,6 +148,10 @@ def load(path: str | None = None) -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
         fn.restype, fn.argtypes = res, args
+    # the structs above are hand-written mirrors of include/algames_b200.h: let the library compare sizes and offsets
+    words = (C.c_int * len(abi_layout()))(*abi_layout())
+    if lib.agb_abi_check(words, len(words)) != 0:
+        raise RuntimeError(f"{path}: {lib.agb_last_error(None).decode()}")
     _cache[path] = lib
     return lib
 

@@ -5,6 +5,7 @@
 #include <string.h>
 #include <new>
 #include <cstdlib>
+#include <stddef.h>
 #include <string>
 #include "agb_kernels.cuh"
 
@@ -74,6 +75,21 @@ __global__ void agb_fill_kernel(double* dst, double v, size_t total) {
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) dst[t] = v;
 }
 
+// FP64 vector peak: 8 independent DFMA chains per thread, everything in registers (agb_measure_fp64_peak)
+__global__ void __launch_bounds__(1024, 2) agb_fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3, x4 = x0 + 4e-3, x5 = x0 + 5e-3, x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+#pragma unroll 1
+  for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 12345.678) out[0] = r;          // never true: keeps the chains alive
+}
+
 // =============================================================================================================
 // Host side
 // =============================================================================================================
@@ -99,6 +115,16 @@ struct agb_handle {
   double* stage3 = nullptr;                            // disturbance staging of agb_mpc_advance
   long long launches = 0;
   size_t smem_bytes = 0;
+  cudaEvent_t ev_async = nullptr;                      // orders agb_newton_solve_async (caller stream) against h->stream
+  // multi-GPU gather (agb_peer_* / agb_allgather)
+  int nranks = 0, rank = -1;
+  size_t slab_off[AGB_MAX_RANKS + 1] = {};             // byte offset of every rank's result slab in a gather buffer
+  unsigned char* gather = nullptr;                     // this rank's gather buffer [slab_off[nranks]]
+  unsigned char* peer_gather[AGB_MAX_RANKS] = {};      // every rank's gather buffer as seen from this process / device
+  int peer_device[AGB_MAX_RANKS] = {};                 // in-process peers: their device ordinal; -1 = IPC-mapped pointer
+  bool peer_ipc_opened[AGB_MAX_RANKS] = {};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr;
   std::string err;
 };
 
@@ -280,6 +306,11 @@ void agb_destroy(agb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count, h->Hpg};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int r = 0; r < h->nranks; r++) if (h->peer_ipc_opened[r]) cudaIpcCloseMemHandle(h->peer_gather[r]);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->gather) cudaFree(h->gather);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->ev_async) cudaEventDestroy(h->ev_async);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaStream_t cs : h->chunk_stream) if (cs) cudaStreamDestroy(cs);
@@ -320,10 +351,13 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
     snprintf(buf, sizeof buf, "instance needs %zu B of shared memory per CTA, device allows %d B", h->smem_bytes, max_smem);
     g_create_err = buf; agb_destroy(h); return AGB_EUNSUPPORTED;
   }
-  CKC(agb::set_attr(t.p, t.big, t.model, h->smem_bytes));
+  // the opt-in limit is a per-kernel attribute shared by every handle using the same template instance: always raise it to
+  // the device maximum, so a later handle with a smaller footprint can never lower it under an earlier one's launches
+  CKC(agb::set_attr(t.p, t.big, t.model, (size_t)max_smem));
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
+  CKC(cudaEventCreateWithFlags(&h->ev_async, cudaEventDisableTiming));
   CKC(cudaMalloc((void**)&h->dd, sizeof(DevDesc)));
   CKC(cudaMemcpyAsync(h->dd, &h->hd, sizeof(DevDesc), cudaMemcpyHostToDevice, h->stream));
   const size_t B = batch, n = t.n, m = t.m, N = t.N, K = t.K, p = t.p;
@@ -459,6 +493,31 @@ int agb_mpc_advance(agb_handle* h, int s, const double* disturbance, const doubl
   AGB_LAUNCH(agb_advance_kernel, grid_for(B * n), 256, 0, h->stream, h->Z, dd, h->x0, h->batch, h->hd.p, h->hd.N, s);
   h->launches++;
   return agb_shift_initial(h, s, Zfresh, Lfresh);
+}
+
+// Device-resident variant: disturbance_dev is a DEVICE pointer [B][n] (or NULL), the tail of the shifted iterate is zero;
+// nothing is copied from the host and nothing synchronises — 200 × (agb_newton_solve_async + agb_mpc_advance_async) is one
+// uninterrupted stream of kernels.
+int agb_mpc_advance_async(agb_handle* h, int s, const double* disturbance_dev) {
+  if (!h || s < 1 || s >= h->hd.N) return fail(h, AGB_EINVAL, "shift must be in 1..N-1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, n = h->hd.n, zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n;
+  AGB_LAUNCH(agb_advance_kernel, grid_for(B * n), 256, 0, h->stream, h->Z, disturbance_dev, h->x0, h->batch, h->hd.p, h->hd.N, s);
+  AGB_LAUNCH(agb_shift_kernel, grid_for(B * (zs + ls)), 256, 0, h->stream, h->Z, h->L, (const double*)nullptr, (const double*)nullptr, h->Z0, h->L0, h->batch, h->hd.p, h->hd.N, s);
+  h->launches += 2;
+  AGB_CUDA(h, cudaMemcpyAsync(h->Z, h->Z0, B * zs * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  AGB_CUDA(h, cudaMemcpyAsync(h->L, h->L0, B * ls * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  AGB_CUDA(h, cudaGetLastError());
+  return AGB_OK;
+}
+
+int agb_join_stream(agb_handle* h, void* stream) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  if ((cudaStream_t)stream == h->stream) return AGB_OK;
+  AGB_CUDA(h, cudaEventRecord(h->ev_async, h->stream));
+  AGB_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->ev_async, 0));
+  return AGB_OK;
 }
 
 static int launch_op(agb_handle* h, const agb_options* o, const OpArgs& a) {
@@ -625,7 +684,17 @@ int agb_newton_solve_async(agb_handle* h, const agb_options* o, void* stream) {
   if (!h || !o) return AGB_EINVAL;
   if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1) return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter must be >= 1");
   AGB_CUDA(h, cudaSetDevice(h->device));
-  return launch_solve(h, o, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (st != h->stream) {                 // the solve reads what earlier calls enqueued on the handle's stream …
+    AGB_CUDA(h, cudaEventRecord(h->ev_async, h->stream));
+    AGB_CUDA(h, cudaStreamWaitEvent(st, h->ev_async, 0));
+  }
+  AGB_TRY(launch_solve(h, o, st));
+  if (st != h->stream) {                 // … and every later call on the handle sees its results
+    AGB_CUDA(h, cudaEventRecord(h->ev_async, st));
+    AGB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_async, 0));
+  }
+  return AGB_OK;
 }
 
 int agb_newton_solve_batch(agb_handle* h, const agb_options* o, double* Z_out, double* L_out, double* conlam_out,
@@ -782,6 +851,243 @@ float agb_last_solve_ms(agb_handle* h) {
   float ms = -1.0f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
   return ms;
+}
+
+// ---- ABI layout check (bindings mirror the structs by hand) ------------------------------------------------------
+static void abi_words(int* w) {
+  int k = 0;
+  w[k++] = (int)sizeof(agb_problem_desc); w[k++] = (int)offsetof(agb_problem_desc, dt); w[k++] = (int)offsetof(agb_problem_desc, Q);
+  w[k++] = (int)offsetof(agb_problem_desc, col_radius); w[k++] = (int)offsetof(agb_problem_desc, has_state_bound);
+  w[k++] = (int)offsetof(agb_problem_desc, walls); w[k++] = (int)offsetof(agb_problem_desc, circles); w[k++] = (int)offsetof(agb_problem_desc, x_max_con);
+  w[k++] = (int)sizeof(agb_options); w[k++] = (int)offsetof(agb_options, alphax_dual); w[k++] = (int)offsetof(agb_options, eps_dyn);
+  w[k++] = (int)offsetof(agb_options, dual_reset);
+  w[k++] = (int)sizeof(agb_ibr_options); w[k++] = (int)offsetof(agb_ibr_options, delta_min);
+  w[k++] = (int)sizeof(agb_sizes); w[k++] = (int)sizeof(agb_device_view);
+  w[k++] = AGB_MAX_P; w[k++] = AGB_MAX_N; w[k++] = AGB_MAX_M; w[k++] = AGB_MAX_WALLS; w[k++] = AGB_MAX_CIRCLES;
+  w[k++] = AGB_NSTATS; w[k++] = AGB_NHIST; w[k++] = AGB_IPC_BYTES;
+  static_assert(AGB_ABI_WORDS == 24, "update abi_words");
+}
+static const char* const kAbiNames[AGB_ABI_WORDS] = {
+  "sizeof(agb_problem_desc)", "offsetof(agb_problem_desc, dt)", "offsetof(agb_problem_desc, Q)", "offsetof(agb_problem_desc, col_radius)",
+  "offsetof(agb_problem_desc, has_state_bound)", "offsetof(agb_problem_desc, walls)", "offsetof(agb_problem_desc, circles)",
+  "offsetof(agb_problem_desc, x_max_con)", "sizeof(agb_options)", "offsetof(agb_options, alphax_dual)", "offsetof(agb_options, eps_dyn)",
+  "offsetof(agb_options, dual_reset)", "sizeof(agb_ibr_options)", "offsetof(agb_ibr_options, delta_min)", "sizeof(agb_sizes)",
+  "sizeof(agb_device_view)", "AGB_MAX_P", "AGB_MAX_N", "AGB_MAX_M", "AGB_MAX_WALLS", "AGB_MAX_CIRCLES", "AGB_NSTATS", "AGB_NHIST", "AGB_IPC_BYTES"};
+
+int agb_abi_layout(int* layout_out, int count) {
+  if (!layout_out || count < AGB_ABI_WORDS) return fail(nullptr, AGB_EINVAL, "agb_abi_layout: need room for AGB_ABI_WORDS ints");
+  abi_words(layout_out);
+  return AGB_OK;
+}
+int agb_abi_check(const int* layout, int count) {
+  if (!layout || count != AGB_ABI_WORDS) return fail(nullptr, AGB_EINVAL, "agb_abi_check: expected AGB_ABI_WORDS = 24 entries (binding built against another header?)");
+  int mine[AGB_ABI_WORDS];
+  abi_words(mine);
+  for (int k = 0; k < AGB_ABI_WORDS; k++) {
+    if (layout[k] != mine[k]) {
+      char buf[200];
+      snprintf(buf, sizeof buf, "ABI mismatch: %s is %d in the library, %d in the binding", kAbiNames[k], mine[k], layout[k]);
+      return fail(nullptr, AGB_EINVAL, buf);
+    }
+  }
+  return AGB_OK;
+}
+
+// ---- per-knot violation vectors ----------------------------------------------------------------------------------
+int agb_violations(agb_handle* h, double* dyn_out, double* con_out, double* sta_out, double* opt_out) {
+  if (!h) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, N = h->hd.N, K = h->hd.K, per = 4 * N - 2;
+  AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, B * per * sizeof(double)));
+  OpArgs a = op_args(OP_VIOLATIONS);
+  a.out0 = h->stage;
+  AGB_TRY(launch_op(h, nullptr, a));
+  const size_t pitch = per * sizeof(double);
+  if (dyn_out) AGB_CUDA(h, cudaMemcpy2DAsync(dyn_out, K * sizeof(double), h->stage, pitch, K * sizeof(double), B, cudaMemcpyDeviceToHost, h->stream));
+  if (con_out) AGB_CUDA(h, cudaMemcpy2DAsync(con_out, K * sizeof(double), h->stage + K, pitch, K * sizeof(double), B, cudaMemcpyDeviceToHost, h->stream));
+  if (sta_out) AGB_CUDA(h, cudaMemcpy2DAsync(sta_out, N * sizeof(double), h->stage + 2 * K, pitch, N * sizeof(double), B, cudaMemcpyDeviceToHost, h->stream));
+  if (opt_out) AGB_CUDA(h, cudaMemcpy2DAsync(opt_out, N * sizeof(double), h->stage + 2 * K + N, pitch, N * sizeof(double), B, cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+// ---- multi-GPU: result slabs of all ranks on every rank, pushed over peer memory by the copy engines ----------------
+static size_t slab_bytes_for(const agb_handle* h, size_t B) {
+  const size_t zs = B * h->hd.N * (h->hd.n + h->hd.m), ls = B * h->hd.p * h->hd.K * h->hd.n, ss = B * AGB_NSTATS, is = (B + 1) / 2;
+  return (zs + ls + ss + is) * sizeof(double);
+}
+
+int agb_peer_init(agb_handle* h, int nranks, int rank, const int* batches) {
+  if (!h || !batches || nranks < 1 || nranks > AGB_MAX_RANKS || rank < 0 || rank >= nranks) return fail(h, AGB_EINVAL, "agb_peer_init: bad rank layout");
+  if (batches[rank] != h->batch) return fail(h, AGB_EINVAL, "agb_peer_init: batches[rank] must equal this handle's batch");
+  if (h->gather) return fail(h, AGB_EINVAL, "agb_peer_init: already initialised");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  h->slab_off[0] = 0;
+  for (int r = 0; r < nranks; r++) {
+    if (batches[r] < 1) return fail(h, AGB_EINVAL, "agb_peer_init: every rank needs at least one instance");
+    h->slab_off[r + 1] = h->slab_off[r] + slab_bytes_for(h, (size_t)batches[r]);
+  }
+  if (h->slab_off[rank + 1] - h->slab_off[rank] != h->results_doubles * sizeof(double)) return fail(h, AGB_EINVAL, "agb_peer_init: slab size mismatch");
+  AGB_CUDA(h, cudaMalloc((void**)&h->gather, h->slab_off[nranks]));
+  AGB_CUDA(h, cudaMemsetAsync(h->gather, 0, h->slab_off[nranks], h->stream));
+  AGB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  AGB_CUDA(h, cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->nranks = nranks; h->rank = rank;
+  for (int r = 0; r < nranks; r++) { h->peer_gather[r] = nullptr; h->peer_device[r] = -1; h->peer_ipc_opened[r] = false; }
+  h->peer_gather[rank] = h->gather; h->peer_device[rank] = h->device;
+  return AGB_OK;
+}
+
+int agb_peer_export(agb_handle* h, unsigned char* ipc_out) {
+  if (!h || !ipc_out || !h->gather) return fail(h, AGB_EINVAL, "agb_peer_export: call agb_peer_init first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == AGB_IPC_BYTES, "AGB_IPC_BYTES");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  AGB_CUDA(h, cudaIpcGetMemHandle(&mh, h->gather));
+  memcpy(ipc_out, &mh, AGB_IPC_BYTES);
+  return AGB_OK;
+}
+
+int agb_peer_connect(agb_handle* h, const unsigned char* ipc_all) {
+  if (!h || !ipc_all || !h->gather) return fail(h, AGB_EINVAL, "agb_peer_connect: call agb_peer_init first");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  for (int r = 0; r < h->nranks; r++) {
+    if (r == h->rank || h->peer_gather[r]) continue;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, ipc_all + (size_t)r * AGB_IPC_BYTES, AGB_IPC_BYTES);
+    void* p = nullptr;
+    AGB_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_gather[r] = (unsigned char*)p; h->peer_device[r] = -1; h->peer_ipc_opened[r] = true;
+  }
+  return AGB_OK;
+}
+
+int agb_peer_connect_local(agb_handle* const* handles, int nranks) {
+  if (!handles || nranks < 1 || nranks > AGB_MAX_RANKS) return fail(nullptr, AGB_EINVAL, "agb_peer_connect_local: bad arguments");
+  for (int r = 0; r < nranks; r++)
+    if (!handles[r] || handles[r]->nranks != nranks || handles[r]->rank != r || !handles[r]->gather)
+      return fail(nullptr, AGB_EINVAL, "agb_peer_connect_local: handles[r] must be rank r of an nranks layout (agb_peer_init)");
+  for (int r = 0; r < nranks; r++) {
+    agb_handle* h = handles[r];
+    AGB_CUDA(h, cudaSetDevice(h->device));
+    for (int q = 0; q < nranks; q++) {
+      if (q == r) continue;
+      if (handles[q]->device != h->device) {
+        int can = 0;
+        AGB_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, handles[q]->device));
+        if (can) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(handles[q]->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, AGB_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+          (void)cudaGetLastError();
+        }
+      }
+      h->peer_gather[q] = handles[q]->gather; h->peer_device[q] = handles[q]->device;
+    }
+  }
+  return AGB_OK;
+}
+
+int agb_allgather(agb_handle* h, void* stream) {
+  if (!h || !h->gather) return fail(h, AGB_EINVAL, "agb_allgather: call agb_peer_init and connect the peers first");
+  for (int r = 0; r < h->nranks; r++) if (!h->peer_gather[r]) return fail(h, AGB_EINVAL, "agb_allgather: peers not connected");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t after = stream ? (cudaStream_t)stream : h->stream;
+  AGB_CUDA(h, cudaEventRecord(h->ev_ready, after));
+  AGB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+  const size_t bytes = h->results_doubles * sizeof(double), off = h->slab_off[h->rank];
+  for (int q = 0; q < h->nranks; q++) {
+    const int r = (h->rank + q) % h->nranks;             // start with the own copy, then ring order: spreads the link load
+    unsigned char* dst = h->peer_gather[r] + off;
+    if (h->peer_device[r] >= 0 && h->peer_device[r] != h->device)
+      AGB_CUDA(h, cudaMemcpyPeerAsync(dst, h->peer_device[r], h->results, h->device, bytes, h->copy_stream));
+    else
+      AGB_CUDA(h, cudaMemcpyAsync(dst, h->results, bytes, cudaMemcpyDeviceToDevice, h->copy_stream));
+  }
+  return AGB_OK;
+}
+
+int agb_allgather_wait(agb_handle* h) {
+  if (!h || !h->gather) return fail(h, AGB_EINVAL, "agb_allgather_wait: call agb_peer_init first");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  AGB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  return AGB_OK;
+}
+
+int agb_gathered_view(agb_handle* h, void** gathered_dev, unsigned long long* offsets_out) {
+  if (!h || !h->gather) return fail(h, AGB_EINVAL, "agb_gathered_view: call agb_peer_init first");
+  if (gathered_dev) *gathered_dev = h->gather;
+  if (offsets_out) for (int r = 0; r <= h->nranks; r++) offsets_out[r] = (unsigned long long)h->slab_off[r];
+  return AGB_OK;
+}
+
+int agb_unpack_gathered(agb_handle* h, int src_rank, double* Z, double* L, double* stats, int* status) {
+  if (!h || !h->gather || src_rank < 0 || src_rank >= h->nranks) return fail(h, AGB_EINVAL, "agb_unpack_gathered: bad rank");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  // batch of the source rank from its slab size: slab(B) = 8·(B·(zs+ls+NSTATS) + ceil(B/2))
+  const size_t zs1 = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls1 = (size_t)h->hd.p * h->hd.K * h->hd.n;
+  const size_t bytes = h->slab_off[src_rank + 1] - h->slab_off[src_rank];
+  size_t B = bytes / (8 * (zs1 + ls1 + AGB_NSTATS));
+  while (B > 0 && slab_bytes_for(h, B) > bytes) B--;
+  if (B == 0 || slab_bytes_for(h, B) != bytes) return fail(h, AGB_EINVAL, "agb_unpack_gathered: inconsistent slab size");
+  const double* base = (const double*)(h->gather + h->slab_off[src_rank]);
+  AGB_TRY(d2h(h, Z, base, B * zs1)); AGB_TRY(d2h(h, L, base + B * zs1, B * ls1));
+  AGB_TRY(d2h(h, stats, base + B * (zs1 + ls1), B * AGB_NSTATS));
+  if (status) AGB_CUDA(h, cudaMemcpyAsync(status, base + B * (zs1 + ls1 + AGB_NSTATS), B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+int agb_create_sharded(const agb_problem_desc* desc, int batch, int ndev, const int* devices, agb_handle** handles_out, int* ndev_out) {
+  if (!desc || !handles_out || !ndev_out) return fail(nullptr, AGB_EINVAL, "null argument");
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) return fail(nullptr, AGB_ECUDA, "no CUDA device: libalgames_b200 has no CPU fallback");
+  if (ndev <= 0) { ndev = have; devices = nullptr; }
+  if (ndev > AGB_MAX_RANKS) return fail(nullptr, AGB_EINVAL, "too many devices");
+  if (batch < ndev) return fail(nullptr, AGB_EINVAL, "agb_create_sharded: batch must be >= the number of devices");
+  int batches[AGB_MAX_RANKS];
+  for (int r = 0; r < ndev; r++) batches[r] = batch / ndev + (r < batch % ndev ? 1 : 0);      // ranks < batch % ndev get one extra
+  int rc = AGB_OK, made = 0;
+  for (int r = 0; r < ndev && rc == AGB_OK; r++) {
+    rc = agb_create(desc, batches[r], devices ? devices[r] : r, &handles_out[r]);
+    if (rc == AGB_OK) { made++; rc = agb_peer_init(handles_out[r], ndev, r, batches); if (rc) g_create_err = handles_out[r]->err; }
+  }
+  if (rc == AGB_OK) rc = agb_peer_connect_local(handles_out, ndev);
+  if (rc != AGB_OK) { for (int r = 0; r < made; r++) { agb_destroy(handles_out[r]); handles_out[r] = nullptr; } return rc; }
+  *ndev_out = ndev;
+  return AGB_OK;
+}
+
+// ---- measured FP64 vector peak -------------------------------------------------------------------------------------
+int agb_measure_fp64_peak(int device, int iters, double* tflops_out, float* ms_out) {
+  if (!tflops_out || iters < 8) return fail(nullptr, AGB_EINVAL, "agb_measure_fp64_peak: bad arguments");
+#ifdef AGB_EMULATE
+  return fail(nullptr, AGB_EUNSUPPORTED, "agb_measure_fp64_peak: needs a CUDA device");
+#endif
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(nullptr, AGB_ECUDA, "no such CUDA device");
+  AGB_CUDA(nullptr, cudaSetDevice(device));
+  int sms = 0;
+  AGB_CUDA(nullptr, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  double* out = nullptr;
+  AGB_CUDA(nullptr, cudaMalloc((void**)&out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  AGB_CUDA(nullptr, cudaEventCreate(&e0)); AGB_CUDA(nullptr, cudaEventCreate(&e1));
+  iters = (iters + 7) & ~7;
+  const int grid = sms * 2, block = 1024;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {                      // first repetition warms up; best of the rest
+    cudaEventRecord(e0, 0);
+    AGB_LAUNCH(agb_fp64_peak_kernel, grid, block, 0, 0, out, iters, 0.999999, 1e-7);
+    cudaEventRecord(e1, 0);
+    AGB_CUDA(nullptr, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  AGB_CUDA(nullptr, cudaGetLastError());
+  *tflops_out = 2.0 * 8.0 * (double)iters * (double)block * (double)grid / ((double)best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return AGB_OK;
 }
 
 }  // extern "C"

@@ -77,7 +77,7 @@ struct Buffers {
 
 enum Op {
   OP_ROLLOUT = 0, OP_RESIDUAL, OP_JAC_DENSE, OP_KKT_SOLVE, OP_LINE_SEARCH, OP_UPDATE,
-  OP_DUAL_UPDATE, OP_PENALTY_UPDATE, OP_RESET, OP_EVAL_CON, OP_ACTIVE_SET, OP_GAIN_SOLVE
+  OP_DUAL_UPDATE, OP_PENALTY_UPDATE, OP_RESET, OP_EVAL_CON, OP_ACTIVE_SET, OP_GAIN_SOLVE, OP_VIOLATIONS
 };
 
 struct OpArgs {

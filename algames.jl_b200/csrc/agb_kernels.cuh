@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         if (n_rec < g.hist_max) {
           double* hrec = g.hist + ((size_t)inst * g.hist_max + n_rec) * AGB_NHIST;
           hrec[0] = (double)kk; hrec[1] = r.sum / S; hrec[2] = r.dyn; hrec[3] = r.con; hrec[4] = r.sta; hrec[5] = r.opt;
-          hrec[6] = dlt; hrec[7] = (double)ll;
+          hrec[6] = dlt; hrec[7] = (double)ll; hrec[8] = -1.0; hrec[9] = 0.0;
         }
       }
       n_rec++;
@@ -51,9 +51,11 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     Acc kept_rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double delta = 0.0;
     Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int last_exit = AGB_MAX_OUTER;   // how the last inner loop ended (status of a non-converged instance)
     for (int kout = 1; kout <= o.outer_iter; kout++) {                                  // :30
       outer_done = kout;
       int ls_count = 0;
+      last_exit = AGB_MAX_OUTER;
       for (int l = 1; l <= o.inner_iter; l++) {                                         // :38
         const double l2 = (double)l * (double)l;
         const double reg = o.reg_0 * (l2 * l2);                                         // :39
@@ -63,17 +65,17 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         const double res_norm = rec.sum / S;                                            // :76
         log_record(rec, delta, kout, l);                                                // :75
         delta = 0.0;
-        if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
+        if (!(rec.sum == rec.sum) || isinf(rec.sum)) { if (!failed) failed = AGB_NONFINITE; break; }
         if (rec.opt < o.eps_opt) break;                                                 // :80-82
-        if (!I.kkt_solve(reg, reg)) failed = 1;                                         // :84-88
+        if (!I.kkt_solve(reg, reg)) { if (!failed) failed = AGB_SINGULAR; }             // :84-88
         n_newton++;
         double alpha; int j;
         kept = I.line_search(o, reg, res_norm, alpha, j, n_eval, &kept_rec);            // :91
         ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;                                 // :92-93
         delta = I.update_traj(alpha);                                                   // :94-95 (taken even when the search failed)
-        if (delta < o.delta_min) break;                                                 // :96-98
-        if (ls_count >= 1) break;                                                       // :43
-        if (!(delta == delta)) { failed = 1; break; }
+        if (delta < o.delta_min) { last_exit = AGB_STALLED; break; }                    // :96-98
+        if (ls_count >= 1) { last_exit = AGB_LINE_SEARCH_FAILED; break; }               // :43
+        if (!(delta == delta)) { if (!failed) failed = AGB_NONFINITE; break; }
       }
       if (failed) break;
       if (kout == o.outer_iter || (rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt))
@@ -93,8 +95,8 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     if (I.tid == 0) {
       double* st = g.stats + (size_t)inst * AGB_NSTATS;
       st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;
-      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)outer_done; st[8] = (double)n_eval; st[9] = (double)failed;
-      g.status[inst] = conv ? AGB_CONVERGED : ((failed || !finite) ? AGB_NUMERICAL_FAILURE : AGB_NOT_CONVERGED);
+      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)outer_done; st[8] = (double)n_eval; st[9] = (double)(failed != 0);
+      g.status[inst] = conv ? AGB_CONVERGED : (failed ? failed : (!finite ? AGB_NONFINITE : last_exit));
     }
   }
 }
@@ -118,7 +120,21 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];
     __syncthreads();
     I.rollout();                                                                        // :145
-    int n_newton = 0, n_eval = 0, failed = 0, sweeps = 0;
+    int n_newton = 0, n_eval = 0, failed = 0, sweeps = 0, n_rec = 0;
+    // record!(stats, prob, model, game_con, pdtraj, t_elap, Δ, k, i) (statistics.jl:59-72): player-i violations next to the
+    // FULL-game residual norm; that extra residual! is evaluated only while a history buffer is set
+    auto log_record = [&](const Acc& r, double dlt, int kk, int ll, int player, int sweep) {
+      if (g.hist == nullptr) return;
+      I.pl = -1;
+      const Acc full = I.template residual<false>(0.0, 0.0, 0.0, nullptr);    // rows are not stored (R keeps player i's)
+      I.pl = player;
+      if (I.tid == 0 && n_rec < g.hist_max) {
+        double* hrec = g.hist + ((size_t)inst * g.hist_max + n_rec) * AGB_NHIST;
+        hrec[0] = (double)kk; hrec[1] = full.sum / (double)(K * Inst<P, MODEL, (LAY != 0)>::b); hrec[2] = r.dyn; hrec[3] = r.con; hrec[4] = r.sta;
+        hrec[5] = r.opt; hrec[6] = dlt; hrec[7] = (double)ll; hrec[8] = (double)player; hrec[9] = (double)sweep;
+      }
+      n_rec++;
+    };
     unsigned change = (1u << P) - 1u;                                                   // Δ_change = trues(p) (:150)
     double delta = 0.0, dmax = 0.0;                                                     // dmax = maximum(stats.Δ_traj)
     for (int q = 0; q < io.ibr_iter && !failed; q++) {                                  // :151
@@ -135,8 +151,10 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         const double S = I.res_size();
         delta = 0.0;
         bool kept = false;
+        int out = 0;
         Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, kept_rec = rec;
         for (int kout = 1; kout <= o.outer_iter; kout++) {
+          out = kout;
           int ls_count = 0;
           for (int l = 1; l <= o.inner_iter; l++) {
             const double l2 = (double)l * (double)l;
@@ -144,10 +162,11 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
             if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; }
             else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }    // ibr_inner_iteration (:226-265)
             const double res_norm = rec.sum / S;
+            log_record(rec, delta, kout, l, i, q + 1);                                  // :237
             delta = 0.0;
-            if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
+            if (!(rec.sum == rec.sum) || isinf(rec.sum)) { if (!failed) failed = AGB_NONFINITE; break; }
             if (rec.opt < o.eps_opt) break;
-            if (!I.kkt_solve(reg, reg)) failed = 1;
+            if (!I.kkt_solve(reg, reg)) { if (!failed) failed = AGB_SINGULAR; }
             n_newton++;
             double alpha; int j;
             kept = I.line_search(o, reg, res_norm, alpha, j, n_eval, &kept_rec);
@@ -156,7 +175,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
             dmax = fmax(dmax, delta);
             if (delta < o.delta_min) break;
             if (ls_count >= 1) break;
-            if (!(delta == delta)) { failed = 1; break; }
+            if (!(delta == delta)) { if (!failed) failed = AGB_NONFINITE; break; }
           }
           if (failed) break;
           if (kout == o.outer_iter || (rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt))
@@ -164,6 +183,11 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
           I.dual_update(o);
           I.penalty_update(o);
           kept = false;
+        }
+        if (g.hist != nullptr && !failed) {                                             // final record!(…, out, i) (:222)
+          if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; }
+          else rec = I.template residual<false>(0.0, 0.0, 0.0, I.R);
+          log_record(rec, delta, out, 0, i, q + 1);
         }
         if (!(io.delta_min > dmax)) change |= (1u << i); else change &= ~(1u << i);     // :156
       }
@@ -180,9 +204,10 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     if (I.tid == 0) {
       double* st = g.stats + (size_t)inst * AGB_NSTATS;
       st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;
-      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)sweeps; st[8] = (double)n_eval; st[9] = (double)failed;
-      g.status[inst] = conv ? AGB_CONVERGED : ((failed || !finite) ? AGB_NUMERICAL_FAILURE : AGB_NOT_CONVERGED);
+      st[5] = delta; st[6] = (double)n_newton; st[7] = (double)sweeps; st[8] = (double)n_eval; st[9] = (double)(failed != 0);
+      g.status[inst] = conv ? AGB_CONVERGED : (failed ? failed : (!finite ? AGB_NONFINITE : AGB_MAX_OUTER));
     }
+    if (g.hist != nullptr && I.tid == 0) g.hist_count[inst] = n_rec;
   }
 }
 
@@ -297,6 +322,32 @@ __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* _
         for (int q = I.tid; q < K * nrow; q += kThreads) {
           const double c = I.con_value(q / nrow, q % nrow);
           a.bout[(size_t)inst * K * nrow + q] = ((c >= -a.tol) || (I.CL[q] > 0.0)) ? 1 : 0;
+        }
+      } break;
+      case OP_VIOLATIONS: {                 // per-knot vectors of struct/violations.jl (full game, or player a.player)
+        I.template residual<false>(0.0, 0.0, 0.0, I.R);
+        __syncthreads();
+        const int N = K + 1;
+        double* o_dyn = a.out0 + (size_t)inst * (4 * N - 2);
+        double* o_con = o_dyn + K; double* o_sta = o_con + K; double* o_opt = o_sta + N;
+        const int pl = I.pl;
+        for (int s = I.tid; s < K; s += kThreads) {
+          double v = 0.0;
+          for (int q = 0; q < n; q++) if (pl < 0 || q % P == pl) v = fmax(v, fabs(I.R[s * b + Inst<P, MODEL, (LAY != 0)>::OD + q]));
+          o_dyn[s] = v;
+          double c = 0.0;
+          if (pl < 0) { for (int r = I.d->nrow_state; r < nrow; r++) c = fmax(c, I.con_value(s, r)); }
+          else { for (int j = 0; j < 2; j++) { const int local = j * P + pl; if (local < I.d->nrow_control) c = fmax(c, I.con_value(s, I.d->nrow_state + local)); } }
+          o_con[s] = c;
+        }
+        for (int k = I.tid; k < N; k += kThreads) {
+          double v = 0.0, w = 0.0;
+          if (k > 0) {
+            for (int r = 0; r < I.d->nrow_state; r++) if (pl < 0 || I.row_player(r) == pl) v = fmax(v, I.con_value(k - 1, r));
+            for (int q = 0; q < P * n; q++) if (pl < 0 || q / n == pl) w = fmax(w, fabs(I.R[(k - 1) * b + q]));
+          }
+          if (k < K) for (int q = 0; q < m; q++) if (pl < 0 || q % P == pl) w = fmax(w, fabs(I.R[k * b + P * n + q]));
+          o_sta[k] = v; o_opt[k] = w;
         }
       } break;
       case OP_GAIN_SOLVE: {

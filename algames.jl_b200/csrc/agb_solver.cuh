@@ -581,12 +581,18 @@ struct Inst {
       acc.opt = fmax(acc.opt, fabs(v));
       if (Rout) Rout[s * b + OU + idx] = v;
     }
-    if (pl >= 0 && has_cb && !TRIAL) {
+    if (pl >= 0 && has_cb && (!TRIAL || keep)) {
       // control_violation(game_con, pdtraj, i) (violations.jl:69-82) indexes the stacked bound rows with pu[i]: rows
-      // pu[i] of the control-bound conval, whatever bound they belong to — restated as is
+      // pu[i] of the control-bound conval, whatever bound they belong to — restated as is (at the trial point too when
+      // its record is kept for the next inner iteration)
       for (int item = tid; item < K * 2; item += kThreads) {
-        const int j = item & 1, s = item >> 1, local = j * P + pl;
-        if (local < d->nrow_control) acc.con = fmax(acc.con, con_value(s, d->nrow_state + local));
+        const int j = item & 1, s = item >> 1, local = j * P + pl, row = d->nrow_state + local;
+        if (local < d->nrow_control) {
+          for (int idx = 0; idx < m; idx++) {
+            if (d->ub_row[idx] == row) acc.con = fmax(acc.con, ug<TRIAL>(s, idx, alpha) - d->u_max[idx]);
+            if (d->lb_row[idx] == row) acc.con = fmax(acc.con, d->u_min[idx] - ug<TRIAL>(s, idx, alpha));
+          }
+        }
       }
     }
     Acc t = block_reduce(acc);

@@ -480,6 +480,14 @@ class GameBatch:
         a = [self._arr(disturbance, (self.batch, self.n)), self._arr(Zfresh, self._z()), self._arr(Lfresh, self._l())]
         self._ck(self.lib.agb_mpc_advance(self.h, int(s), *[_capi.dptr(v) for v in a]))
 
+    def mpc_advance_async(self, s: int = 1, disturbance_dev: int = 0):
+        """agb_mpc_advance_async: the same step with a DEVICE pointer for the disturbance (0 = none) and no host sync."""
+        self._ck(self.lib.agb_mpc_advance_async(self.h, int(s), C.c_void_p(disturbance_dev) if disturbance_dev else None))
+
+    def join_stream(self, stream: int):
+        """agb_join_stream: `stream` waits (on the device) for everything enqueued on the handle's own stream."""
+        self._ck(self.lib.agb_join_stream(self.h, C.c_void_p(stream) if stream else None))
+
     def get_state(self):
         Z, L = np.empty(self._z()), np.empty(self._l())
         cl, cm = np.empty(self._c()), np.empty(self._c())
@@ -625,6 +633,62 @@ class GameBatch:
         self._ck(self.lib.agb_get_device_view(self.h, C.byref(v)))
         return v
 
+    def violations(self):
+        """agb_violations: per-knot vectors of dynamics_violation / control_violation / state_violation / optimality_violation
+        at the resident iterate (struct/violations.jl): dyn [B,N-1], con [B,N-1], sta [B,N], opt [B,N]."""
+        B, N = self.batch, self.N
+        dyn, con, sta, opt = np.empty((B, N - 1)), np.empty((B, N - 1)), np.empty((B, N)), np.empty((B, N))
+        self._ck(self.lib.agb_violations(self.h, _capi.dptr(dyn), _capi.dptr(con), _capi.dptr(sta), _capi.dptr(opt)))
+        return dyn, con, sta, opt
+
+    # ---- multi-GPU: the path's single all-gather, pushed over peer memory by the copy engines (agb_peer_* / agb_allgather)
+    def peer_init(self, nranks: int, rank: int, batches):
+        b = np.ascontiguousarray(batches, dtype=np.int32)
+        assert b.shape == (nranks,)
+        self._ck(self.lib.agb_peer_init(self.h, int(nranks), int(rank), _capi.iptr(b)))
+        self._peer = (int(nranks), int(rank), b.copy())
+
+    def peer_export(self) -> bytes:
+        buf = (C.c_ubyte * _capi.IPC_BYTES)()
+        self._ck(self.lib.agb_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_connect(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == self._peer[0] * _capi.IPC_BYTES
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.agb_peer_connect(self.h, buf))
+
+    @staticmethod
+    def peer_connect_local(batches: Sequence["GameBatch"]):
+        lib = batches[0].lib
+        arr = (C.c_void_p * len(batches))(*[b.h for b in batches])
+        rc = lib.agb_peer_connect_local(arr, len(batches))
+        if rc != 0:
+            raise AlgamesError(f"agb_peer_connect_local failed ({rc}): {lib.agb_last_error(None).decode()}")
+
+    def allgather(self, stream: Optional[int] = None):
+        self._ck(self.lib.agb_allgather(self.h, C.c_void_p(stream) if stream else None))
+
+    def allgather_wait(self):
+        self._ck(self.lib.agb_allgather_wait(self.h))
+
+    def gathered_view(self):
+        """(device pointer of this rank's gather buffer, byte offsets [nranks+1] of the ranks' slabs)."""
+        ptr = C.c_void_p()
+        offs = (C.c_ulonglong * (self._peer[0] + 1))()
+        self._ck(self.lib.agb_gathered_view(self.h, C.byref(ptr), offs))
+        return ptr.value, list(offs)
+
+    def unpack_gathered(self, src_rank: int):
+        """Rank `src_rank`'s results as they arrived in this rank's gather buffer."""
+        Bs = int(self._peer[2][src_rank])
+        out = {"Z": np.empty((Bs, self.N, self.n + self.m)), "L": np.empty((Bs, self.p, self.N - 1, self.n)),
+               "stats": np.empty((Bs, _capi.NSTATS)), "status": np.empty(Bs, dtype=np.int32)}
+        self._ck(self.lib.agb_unpack_gathered(self.h, int(src_rank), _capi.dptr(out["Z"]), _capi.dptr(out["L"]),
+                                              _capi.dptr(out["stats"]), _capi.iptr(out["status"])))
+        return out
+
     def launch_count(self) -> int:
         return int(self.lib.agb_launch_count(self.h))
 
@@ -637,7 +701,10 @@ class GameBatch:
 # ------------------------------------------------------------------------------------------------------------
 @dataclass
 class Violation:
+    """DynamicsViolation / ControlViolation / StateViolation / OptimalityViolation (struct/violations.jl:5-16, …): `.max`
+    for every record; `.vio` (the per-knot vector) for the final record of a solve (agb_violations)."""
     max: float
+    vio: Optional[np.ndarray] = None
 
 
 class Statistics:
@@ -710,7 +777,9 @@ class GameProblem:
     def batch(self) -> GameBatch:
         if self._batch is None:
             self._batch = GameBatch(self.model, self.N, self.dt, self.game_obj, self.game_con, 1, self._device, self._lib_path)
-        self._batch.set_instance_params(x0=self.x0[None, :])
+        o, p = self.game_obj, self.probsize.p      # the objective may have been edited since the handle was created
+        self._batch.set_instance_params(x0=self.x0[None, :], xf=_joint(o.xf, p, 4)[None], Q=_joint(o.Q, p, 4)[None],
+                                        R=_joint(o.R, p, 2)[None], uf=_joint(o.uf, p, 2)[None])
         return self._batch
 
     def _push(self):
@@ -732,6 +801,16 @@ def _same_schema(a: GameProblem, b: GameProblem) -> bool:
     for k in ("x0", "xf", "Q", "R", "uf", "opts"):
         sa.pop(k); sb.pop(k)
     return sa == sb
+
+
+def _check_batch(plist):
+    """One schema and ONE set of solver options per batch: the kernel takes a single agb_options for all instances."""
+    p0 = plist[0]
+    for q in plist[1:]:
+        if not _same_schema(p0, q):
+            raise ValueError("all problems of a batch must share model, sizes and constraint schema")
+        if q.opts.to_dict() != p0.opts.to_dict():
+            raise ValueError("all problems of a batch must share the same Options (one agb_options per launch)")
 
 
 def init_traj(prob: GameProblem, rng=None):
@@ -759,9 +838,7 @@ def newton_solve(probs, init: bool = True):
     if not plist:
         return None
     p0 = plist[0]
-    for q in plist[1:]:
-        if not _same_schema(p0, q):
-            raise ValueError("all problems of a batch must share model, sizes and constraint schema")
+    _check_batch(plist)
     B, ps = len(plist), p0.probsize
     batch = p0.batch() if B == 1 else GameBatch(p0.model, p0.N, p0.dt, p0.game_obj, p0.game_con, B, p0._device, p0._lib_path)
     try:
@@ -783,10 +860,14 @@ def newton_solve(probs, init: bool = True):
         out = batch.newton_solve(p0.opts)
         hist, count = batch.get_history()
         res, _ = batch.residual()
+        vio = batch.violations()
         for b, q in enumerate(plist):
             q.pdtraj.X[:], q.pdtraj.U[:], q.pdtraj.du[:] = out["Z"][b, :, :ps.n], out["Z"][b, :, ps.n:], out["L"][b]
             q.conlam, q.conmu = out["conlam"][b], out["conmu"][b]
             q.stats = Statistics(); q.stats.record_history(hist[b, :min(int(count[b]), max_rec)])
+            for lst, v in zip((q.stats.dyn_vio, q.stats.con_vio, q.stats.sta_vio, q.stats.opt_vio), vio):
+                if lst:
+                    lst[-1].vio = v[b].copy()             # per-knot vectors of the final record (struct/violations.jl)
             q.stats.newton_steps, q.stats.residual_evals = int(out["stats"][b, 6]), int(out["stats"][b, 8])
             q.status = _capi.STATUS_NAMES[int(out["status"][b])]
             q.core.res[:] = res[b]
@@ -803,9 +884,7 @@ def ibr_newton_solve(probs, ibr_opts: Optional[IBROptions] = None, init: bool = 
     if not plist:
         return None
     p0 = plist[0]
-    for q in plist[1:]:
-        if not _same_schema(p0, q):
-            raise ValueError("all problems of a batch must share model, sizes and constraint schema")
+    _check_batch(plist)
     B, ps = len(plist), p0.probsize
     batch = p0.batch() if B == 1 else GameBatch(p0.model, p0.N, p0.dt, p0.game_obj, p0.game_con, B, p0._device, p0._lib_path)
     try:
@@ -819,12 +898,19 @@ def ibr_newton_solve(probs, ibr_opts: Optional[IBROptions] = None, init: bool = 
             R=np.stack([_joint(o.R, ps.p, 2) for o in obj]), uf=np.stack([_joint(o.uf, ps.p, 2) for o in obj]))
         batch.set_initial(np.stack([np.concatenate([q.pdtraj.X, q.pdtraj.U], axis=1) for q in plist]),
                           np.stack([q.pdtraj.du for q in plist]))
+        io = ibr_opts or IBROptions()
+        # every record!(stats, …, k, i) of the sweeps (statistics.jl:59-72); capped so that ibr_iter = 100 stays cheap
+        max_rec = min(io.ibr_iter * ps.p * (p0.opts.outer_iter * p0.opts.inner_iter + 1), 4096)
+        batch.set_history(max_rec)
         out = batch.ibr_newton_solve(p0.opts, ibr_opts)
+        hist, count = batch.get_history()
+        batch.set_history(0)
         res, _ = batch.residual()
         for b, q in enumerate(plist):
             q.pdtraj.X[:], q.pdtraj.U[:], q.pdtraj.du[:] = out["Z"][b, :, :ps.n], out["Z"][b, :, ps.n:], out["L"][b]
             q.conlam, q.conmu = out["conlam"][b], out["conmu"][b]
-            q.stats = Statistics(); q.stats.record(out["stats"][b])
+            q.stats = Statistics(); q.stats.record_history(hist[b, :min(int(count[b]), max_rec)])
+            q.stats.record(out["stats"][b])              # + the full-game record at the returned iterate
             q.status = _capi.STATUS_NAMES[int(out["status"][b])]
             q.core.res[:] = res[b]
     finally:

@@ -29,6 +29,11 @@
  *                 rows of knot k+1 — per player [collision j≠i ascending | state bounds: per conval max rows, min rows |
  *                 walls | circles] — followed by the control-bound rows of knot k [u_max rows, u_min rows]
  *                 (finite bounds only, reference component order; control_bound_constraint.jl:33-35).
+ *
+ * Environment variables read by the library (test / tuning hooks, never needed in production):
+ *   AGB_FORCE_BIG_LAYOUT=1|2|3  agb_create: force a big-storage shared-memory layout on 3-player instances (parity tests
+ *                               run every layout on small games with it)
+ *   AGB_HOST_CHUNKS=1..32       agb_solve_from_host: number of copy/solve pipeline chunks (default 8 for batch >= 1024)
  */
 #ifndef ALGAMES_B200_H
 #define ALGAMES_B200_H
@@ -46,12 +51,19 @@ extern "C" {
 
 enum { AGB_MODEL_DOUBLE_INTEGRATOR = 0, AGB_MODEL_UNICYCLE = 1, AGB_MODEL_BICYCLE = 2 };
 
-/* per-instance status written by agb_newton_solve_batch */
+/* per-instance status written by agb_newton_solve_batch.  Codes 1-3 all mean "outer_iter exhausted with a
+ * tolerance unmet" (the reference keeps iterating through failed line searches and stalls, solver_methods.jl:38-55); they
+ * tell how the LAST inner loop ended.  AGB_IS_NOT_CONVERGED / AGB_IS_NUMERICAL_FAILURE group them. */
 enum {
-  AGB_CONVERGED = 0,      /* final record: dyn, con, sta, opt maxima all below their ϵ (solver_methods.jl:49-53) */
-  AGB_NOT_CONVERGED = 1,  /* outer_iter exhausted / line search failed / Δ<Δ_min with tolerances unmet       */
-  AGB_NUMERICAL_FAILURE = 2 /* singular pivot or non-finite residual                                       */
+  AGB_CONVERGED = 0,          /* final record: dyn, con, sta, opt maxima all below their ϵ (solver_methods.jl:49-53)     */
+  AGB_MAX_OUTER = 1,          /* not converged; last inner loop ran out of inner_iter or stopped on opt < ϵ_opt (:80-82)  */
+  AGB_LINE_SEARCH_FAILED = 2, /* not converged; last inner loop ended on a failed line search, j == ls_iter (:43, :92-93) */
+  AGB_STALLED = 3,            /* not converged; last inner loop ended on Δ_traj < Δ_min (:96-98)                          */
+  AGB_SINGULAR = 4,           /* zero / non-finite pivot in the structured KKT factorisation and in its pivoted fallback  */
+  AGB_NONFINITE = 5           /* non-finite residual or step (NaN / Inf inputs)                                           */
 };
+#define AGB_IS_NOT_CONVERGED(s) ((s) >= AGB_MAX_OUTER && (s) <= AGB_STALLED)
+#define AGB_IS_NUMERICAL_FAILURE(s) ((s) >= AGB_SINGULAR)
 
 /* error codes */
 enum { AGB_OK = 0, AGB_EINVAL = -1, AGB_ECUDA = -2, AGB_ENOMEM = -3, AGB_EUNSUPPORTED = -4 };
@@ -134,6 +146,18 @@ void agb_default_options(agb_options* o);
 typedef struct agb_sizes { int n, m, p, N, S, nrow, nrow_state, nrow_control; } agb_sizes;
 int agb_sizes_of(const agb_problem_desc* d, agb_sizes* out);
 
+/* Layout check for bindings that mirror the structs above by hand (ctypes, Julia): `layout` lists, in this order,
+ *   sizeof(agb_problem_desc), offsetof(.., dt), offsetof(.., Q), offsetof(.., col_radius), offsetof(.., has_state_bound),
+ *   offsetof(.., walls), offsetof(.., circles), offsetof(.., x_max_con),
+ *   sizeof(agb_options), offsetof(.., alphax_dual), offsetof(.., eps_dyn), offsetof(.., dual_reset),
+ *   sizeof(agb_ibr_options), offsetof(.., delta_min), sizeof(agb_sizes), sizeof(agb_device_view),
+ *   AGB_MAX_P, AGB_MAX_N, AGB_MAX_M, AGB_MAX_WALLS, AGB_MAX_CIRCLES, AGB_NSTATS, AGB_NHIST, AGB_IPC_BYTES
+ * (AGB_ABI_WORDS values).  Returns AGB_OK when every entry equals the library's own, else AGB_EINVAL with
+ * agb_last_error(NULL) naming the first mismatch.  agb_abi_layout writes the library's values (for diagnostics). */
+#define AGB_ABI_WORDS 24
+int agb_abi_check(const int* layout, int count);
+int agb_abi_layout(int* layout_out, int count);
+
 /* GameProblem(...) for a batch: allocates all device state.  device = CUDA ordinal.   */
 int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle** out);
 void agb_destroy(agb_handle* h);
@@ -160,6 +184,12 @@ int agb_shift_initial(agb_handle* h, int s, const double* Zfresh, const double* 
  * NULL), then agb_shift_initial(s, Zfresh, Lfresh).  Together with agb_newton_solve_async(dual_reset = 0) this is the MPC
  * loop Options.shift / Options.dual_reset exist for (struct/options.jl:16-17, :114-115); no host round trip per step. */
 int agb_mpc_advance(agb_handle* h, int s, const double* disturbance, const double* Zfresh, const double* Lfresh);
+/* The same step with no host involvement at all: disturbance_dev is a DEVICE pointer [B][n] (or NULL), the tail knots are
+ * zero, nothing synchronises.  agb_newton_solve_async + agb_mpc_advance_async, repeated, is one uninterrupted stream of
+ * kernels (the ordering rules of agb_newton_solve_async apply). */
+int agb_mpc_advance_async(agb_handle* h, int s, const double* disturbance_dev);
+/* Makes `stream` (a cudaStream_t) wait, on the device, for everything enqueued so far on the handle's own stream. */
+int agb_join_stream(agb_handle* h, void* stream);
 
 /* ---- per-function entry points (operate on the resident batch; parity tests) -------- */
 /* rollout!(RK3, model, traj)                                  solver_methods.jl:17     */
@@ -227,7 +257,10 @@ int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, c
                         double* stats_out, int* status_out);
 
 /* Device-resident form: enqueue the solve on `stream` (a cudaStream_t, 0 = legacy default)
- * with no host copies and no synchronisation; results stay in the handle's device buffers. */
+ * with no host copies and no host synchronisation; results stay in the handle's device buffers.  Ordering: the solve
+ * waits (on the device) for everything already enqueued on the handle's own stream, and every later call on the handle
+ * (agb_get_state, agb_mpc_advance, agb_shift_initial, agb_residual, …, agb_allgather with a NULL stream) waits for the
+ * solve — so agb_newton_solve_async + agb_mpc_advance is a correct device-resident MPC loop without host syncs. */
 int agb_newton_solve_async(agb_handle* h, const agb_options* o, void* stream);
 
 /* Raw device pointers of the resident results (for NCCL all-gather / zero-copy consumers). */
@@ -253,11 +286,59 @@ int agb_get_device_view(agb_handle* h, agb_device_view* out);
  * agb_set_history(h, max_records) makes every later agb_newton_solve_batch / agb_solve_from_host keep up to max_records
  * records per instance on the device (0 switches the log off and frees it); agb_get_history copies them out:
  * hist_out [B][max_records][AGB_NHIST] = {outer iteration k, res = ‖res‖₁/S, dyn_vio.max, con_vio.max, sta_vio.max,
- * opt_vio.max, Δ_traj, inner iteration l (0 for the final record)}, count_out [B] = records the solve produced
- * (may exceed max_records: later records were dropped).  The iterative-best-response solver keeps no history. */
-#define AGB_NHIST 8
+ * opt_vio.max, Δ_traj, inner iteration l (0 for the final record), player, sweep}, count_out [B] = records the solve
+ * produced (may exceed max_records: later records were dropped).  newton_solve: player = -1, sweep = 0.
+ * agb_ibr_newton_solve_batch logs record!(stats, …, k, i) (statistics.jl:59-72, called at solver_methods.jl:222 and :237):
+ * res = FULL-game ‖res‖₁/S, the four maxima restricted to player i (violations.jl:28-37, 69-82, 116-134, 170-183),
+ * player = i (0-based), sweep = IBR iteration q (1-based); the extra full-game residual is evaluated only while a
+ * history buffer is set. */
+#define AGB_NHIST 10
 int agb_set_history(agb_handle* h, int max_records);
 int agb_get_history(agb_handle* h, double* hist_out, int* count_out);
+
+/* Per-knot violation vectors of the resident iterate (struct/violations.jl:5-16, 44-55, 84-96, 136-148): what
+ * dynamics_violation / control_violation / state_violation / optimality_violation return in `.vio`:
+ * dyn_out [B][N-1], con_out [B][N-1], sta_out [B][N], opt_out [B][N] (knot 1 of sta is always 0; opt of knot 1 holds the
+ * u rows only, of knot N the x rows only).  Any pointer may be NULL.  The maxima are stats[1..4] of the solve. */
+int agb_violations(agb_handle* h, double* dyn_out, double* con_out, double* sta_out, double* opt_out);
+
+/* ---- multi-GPU: the batch is split contiguously over ranks — one agb_handle per GPU, in one process or in
+ * one process per GPU — solves need no communication, and ONE all-gather collects every rank's result slab
+ * [Z | L | stats | status] (agb_device_view.results_dev) on every rank.  The gather is a push over NVLink peer memory on
+ * the copy engines (cudaMemcpyPeerAsync / IPC-mapped peer buffers): it takes no SM from solves that are still running.
+ *   agb_peer_init        rank layout: batches[r] = instances of rank r (this handle's batch must equal batches[rank]);
+ *                        allocates this rank's gather buffer [sum_r slab(r)].
+ *   agb_peer_export      64-byte CUDA IPC handle of that buffer (one process per GPU; exchange them out of band,
+ *                        e.g. torch.distributed.all_gather) — then agb_peer_connect with all ranks' handles.
+ *   agb_peer_connect_local  all ranks live in THIS process: pass their handles (enables peer access between the devices).
+ *   agb_allgather        enqueue: push this rank's slab into every rank's gather buffer, ordered after `stream`
+ *                        (NULL = the handle's own stream, i.e. after every solve enqueued through the handle).
+ *   agb_allgather_wait   host-blocks until this rank's pushes have landed.  A barrier between the ranks (or waiting on
+ *                        every local handle) then makes every gather buffer complete.
+ *   agb_gathered_view    device pointer of the gather buffer and the byte offset of every rank's slab in it.
+ *   agb_unpack_gathered  copies rank r's slab out of the local gather buffer into host arrays (any may be NULL).
+ *   agb_create_sharded   convenience for a single-process host (Julia): splits `batch` over `ndev` devices
+ *                        (devices == NULL: ordinals 0..ndev-1; ndev <= 0: all visible devices), creates the handles and
+ *                        runs agb_peer_init + agb_peer_connect_local.  handles_out must hold ndev (or device-count)
+ *                        pointers; *ndev_out receives the count.  Destroy every handle with agb_destroy. */
+#define AGB_IPC_BYTES 64
+#define AGB_MAX_RANKS 64
+int agb_peer_init(agb_handle* h, int nranks, int rank, const int* batches);
+int agb_peer_export(agb_handle* h, unsigned char* ipc_out /* [AGB_IPC_BYTES] */);
+int agb_peer_connect(agb_handle* h, const unsigned char* ipc_all /* [nranks][AGB_IPC_BYTES] */);
+int agb_peer_connect_local(agb_handle* const* handles, int nranks);
+int agb_allgather(agb_handle* h, void* stream);
+int agb_allgather_wait(agb_handle* h);
+int agb_gathered_view(agb_handle* h, void** gathered_dev, unsigned long long* offsets_out /* [nranks+1] bytes */);
+int agb_unpack_gathered(agb_handle* h, int src_rank, double* Z, double* L, double* stats, int* status);
+int agb_create_sharded(const agb_problem_desc* desc, int batch, int ndev, const int* devices,
+                       agb_handle** handles_out, int* ndev_out);
+
+/* FP64 vector peak of the device, measured: a register-resident kernel of independent DFMA chains (8 per thread, 1024
+ * threads per CTA, 2 CTAs per SM), `iters` FMAs per chain; returns TFLOP/s (2 flops per DFMA) through *tflops_out and
+ * the kernel time through *ms_out.  bench.py uses it as the denominator of roofline.frac (the solve is FP64-issue
+ * bound, not HBM bound). */
+int agb_measure_fp64_peak(int device, int iters, double* tflops_out, float* ms_out);
 
 /* Number of kernels this library has launched on the handle since creation. */
 long long agb_launch_count(const agb_handle* h);

@@ -339,7 +339,7 @@ static void setup_rows(Work* w) {
 static void log_rec(Work* w, const Norms* r, double delta, int kout, int l) {
   if (w->hist && w->n_rec < w->hist_max) {
     double* h = w->hist + (size_t)w->n_rec * AGB_NHIST;
-    h[0] = kout; h[1] = r->sum / (double)w->S; h[2] = r->dyn; h[3] = r->con; h[4] = r->sta; h[5] = r->opt; h[6] = delta; h[7] = l;
+    h[0] = kout; h[1] = r->sum / (double)w->S; h[2] = r->dyn; h[3] = r->con; h[4] = r->sta; h[5] = r->opt; h[6] = delta; h[7] = l; h[8] = -1; h[9] = 0;
   }
   w->n_rec++;
 }
@@ -357,21 +357,22 @@ static int solve_one(Work* w, double* stats) {
   }
   if (o->dual_reset) for (int q = 0; q < K * w->nrow; q++) { w->lam[q] = 0; w->mu[q] = o->rho_0; }
   Norms rec = {0, 0, 0, 0, 0};
-  double delta = 0; int outer = 0, failed = 0;
+  double delta = 0; int outer = 0, failed = 0, last_exit = AGB_MAX_OUTER;
   w->n_newton = 0; w->n_eval = 0; w->n_rec = 0;
   ConRow rows[MAXROW];
   for (int kout = 1; kout <= o->outer_iter; kout++) {
     outer = kout;
     int ls_count = 0;
+    last_exit = AGB_MAX_OUTER;
     for (int l = 1; l <= o->inner_iter; l++) {
       double l2 = (double)l * l, reg = o->reg_0 * (l2 * l2);
       rec = assemble(w, w->X, w->U, w->L, w->X, w->U, 0.0, 1, reg);              /* residual! + residual_jacobian! */
       double res_norm = rec.sum / Sd;
       log_rec(w, &rec, delta, kout, l);                                          /* record!(stats, …) (:75) */
       delta = 0;
-      if (!(rec.sum == rec.sum) || isinf(rec.sum)) { failed = 1; break; }
+      if (!(rec.sum == rec.sum) || isinf(rec.sum)) { if (!failed) failed = AGB_NONFINITE; break; }
       if (rec.opt < o->eps_opt) break;
-      if (band_solve(w)) failed = 1;
+      if (band_solve(w)) { if (!failed) failed = AGB_SINGULAR; }
       w->n_newton++;
       scatter_step(w);
       double alpha = 1.0; int j = 1;                                             /* line_search (:105-125) */
@@ -387,9 +388,9 @@ static int solve_one(Work* w, double* stats) {
       for (int q = 0; q < K * m; q++) acc += fabs(w->dU[q]);
       axpy_traj(w, alpha, w->X, w->U, w->L);
       delta = alpha * acc / (double)(K * (n + m));
-      if (delta < o->delta_min) break;
-      if (ls_count >= 1) break;
-      if (!(delta == delta)) { failed = 1; break; }
+      if (delta < o->delta_min) { last_exit = AGB_STALLED; break; }
+      if (ls_count >= 1) { last_exit = AGB_LINE_SEARCH_FAILED; break; }
+      if (!(delta == delta)) { if (!failed) failed = AGB_NONFINITE; break; }
     }
     if (failed) break;
     if (kout == o->outer_iter || (rec.dyn < o->eps_dyn && rec.con < o->eps_con && rec.sta < o->eps_sta && rec.opt < o->eps_opt)) break;
@@ -409,8 +410,8 @@ static int solve_one(Work* w, double* stats) {
   int finite = (rec.sum == rec.sum) && !isinf(rec.sum);
   int conv = finite && rec.dyn < o->eps_dyn && rec.con < o->eps_con && rec.sta < o->eps_sta && rec.opt < o->eps_opt;
   stats[0] = rec.sum / Sd; stats[1] = rec.dyn; stats[2] = rec.con; stats[3] = rec.sta; stats[4] = rec.opt; stats[5] = delta;
-  stats[6] = w->n_newton; stats[7] = outer; stats[8] = w->n_eval; stats[9] = failed;
-  return conv ? AGB_CONVERGED : ((failed || !finite) ? AGB_NUMERICAL_FAILURE : AGB_NOT_CONVERGED);
+  stats[6] = w->n_newton; stats[7] = outer; stats[8] = w->n_eval; stats[9] = failed != 0;
+  return conv ? AGB_CONVERGED : (failed ? failed : (!finite ? AGB_NONFINITE : last_exit));
 }
 
 /* Batched entry point (ctypes).  Layouts as in include/algames_b200.h; nthreads <= 0 → all cores. Returns threads used. */

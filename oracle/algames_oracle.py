@@ -1218,6 +1218,36 @@ def optimality_violation(core: NewtonCore):
     return best
 
 
+def violation_vectors(prob, pd):
+    """The `.vio` vectors of dynamics_violation / control_violation / state_violation / optimality_violation
+    (struct/violations.jl:18-26, 57-67, 101-114, 153-168): dyn [N-1], con [N-1], sta [N], opt [N].  Leaves residual!(prob, pd)
+    in core.res like record! does."""
+    ps, core = prob.probsize, prob.core
+    residual(prob, pd)
+    dyn = np.array([np.max(np.abs(dynamics_residual(prob.model, pd, k))) for k in range(1, prob.N)])
+    con = np.zeros(prob.N - 1)
+    for cv in prob.game_con.control_conval:
+        cv.evaluate(pd.X, pd.U)
+        cv.max_violation()
+        idx = np.array(cv.inds) - 1
+        con[idx] = np.maximum(con[idx], cv.c_max)
+    sta = np.zeros(prob.N)
+    for i in range(ps.p):
+        for cv in prob.game_con.state_conval[i]:
+            cv.evaluate(pd.X, pd.U)
+            cv.max_violation()
+            idx = np.array(cv.inds) - 1
+            sta[idx] = np.maximum(sta[idx], cv.c_max)
+    opt = np.zeros(prob.N)
+    for i in range(1, ps.p + 1):
+        for k in range(1, ps.N + 1):
+            if k >= 2:
+                opt[k - 1] = max(opt[k - 1], float(np.max(np.abs(core.res[core.vert[("opt", i, "x", k)]]))))
+            if k <= ps.N - 1:
+                opt[k - 1] = max(opt[k - 1], float(np.max(np.abs(core.res[core.vert[("opt", i, "u", k)]]))))
+    return dyn, con, sta, opt
+
+
 def record(prob, pd, delta, k_out):
     """statistics.jl:44-57: residual! is re-run WITHOUT regularisation before the norms are taken."""
     residual(prob, pd)

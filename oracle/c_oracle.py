@@ -8,7 +8,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libalgames_oracle.so")
-NHIST = 8
+NHIST = 10
 
 
 def load():

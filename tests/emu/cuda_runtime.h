@@ -85,9 +85,20 @@ enum { cudaSuccess = 0 };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-enum { cudaStreamNonBlocking = 1, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaStreamNonBlocking = 1, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaFuncAttributeMaxDynamicSharedMemorySize = 8,
+       cudaEventDisableTiming = 2, cudaDevAttrMultiProcessorCount = 16, cudaErrorPeerAccessAlreadyEnabled = 704,
+       cudaIpcMemLazyEnablePeerAccess = 1 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+// AGB_EMU_DEVICES=n makes the shim report n (identical, host-memory) devices, for the in-process multi-GPU gather tests
+inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = getenv("AGB_EMU_DEVICES"); *n = e ? atoi(e) : 1; if (*n < 1) *n = 1; return 0; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return 801; }      // no inter-process mapping on the shim
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return 801; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
+inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return 0; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
+inline cudaError_t cudaEventCreateWithFlags(void** e, unsigned) { *e = nullptr; return 0; }
+inline cudaError_t cudaStreamWaitEvent(void*, void*, unsigned) { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 232448; return 0; }
 inline cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
@@ -104,3 +115,8 @@ inline cudaError_t cudaMalloc(void** p, size_t bytes) { *p = malloc(bytes ? byte
 inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(d, s, bytes); return 0; }
+inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t bytes, cudaStream_t) { memmove(d, s, bytes); return 0; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < height; r++) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+  return 0;
+}

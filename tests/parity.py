@@ -466,3 +466,113 @@ def check_edge_shape(lib_path, model_name, p, N):
     assert np.abs(out["Z"][0] - Zo).max() < TOL_SOLVE
     assert int(out["stats"][0, 6]) == op.n_newton and (out["status"][0] == 0) == op.converged
     gb.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Round-2 boundary features
+# ---------------------------------------------------------------------------------------------------------------
+def check_violation_vectors(lib_path, name, N=None):
+    """agb_violations vs the oracle's restatement of struct/violations.jl on a random iterate."""
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, 1, N)
+    rng = np.random.default_rng(9)
+    gb = ab.GameBatch(model, N, dt, obj, con, 1, lib_path=lib_path)
+    gb.set_instance_params(x0=x0[:1], xf=None if xf is None else xf[:1])
+    op = oracle_problem(model, N, dt, obj, con, opts, x0[0], None if xf is None else xf[0])
+    Z, L, lam, mu = random_state(op, x0[0], rng)
+    gb.set_initial(Z[None], L[None], lam[None] if lam.size else None, mu[None] if lam.size else None)
+    got = gb.violations()
+    want = O.violation_vectors(op, op.pdtraj)
+    for g, w, nm in zip(got, want, ("dyn", "con", "sta", "opt")):
+        assert g.shape == (1,) + w.shape, nm
+        assert np.allclose(g[0], w, rtol=1e-12, atol=1e-12), (nm, np.abs(g[0] - w).max())
+    _, norms = gb.residual(want_res=False)
+    assert np.allclose([g.max() for g in got], norms[0, 1:5], rtol=1e-13, atol=0)      # .max of every vector = the record's maxima
+    gb.close()
+
+
+def check_ibr_history(lib_path, name="B", N=10, ibr_iter=2):
+    """IBR history (statistics.jl:59-72): every record!(stats, …, k, i) of the sweeps, against the oracle's."""
+    model, N, dt, obj, con, opts, x0, xf = small_config(name, 1, N)
+    gb = ab.GameBatch(model, N, dt, obj, con, 1, lib_path=lib_path)
+    gb.set_instance_params(x0=x0[:1], xf=None if xf is None else xf[:1])
+    Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+    gb.set_history(2048)
+    out = gb.ibr_newton_solve(opts, ab.IBROptions(ibr_iter=ibr_iter))
+    hist, count = gb.get_history()
+    op = oracle_problem(model, N, dt, obj, con, opts, x0[0], None if xf is None else xf[0])
+    O.ibr_newton_solve(op, Z0=Z0[0], L0=L0[0], ibr_iter=ibr_iter)
+    cnt = int(count[0])
+    assert cnt == len(op.stats), (cnt, len(op.stats))
+    ho = np.array([[r.outer, r.res, r.dyn, r.con, r.sta, r.opt, r.delta] for r in op.stats])
+    hd = hist[0, :cnt]
+    assert np.array_equal(hd[:, 0], ho[:, 0])
+    assert np.allclose(hd[:, 1:7], ho[:, 1:], rtol=1e-6, atol=TOL_SOLVE), np.abs(hd[:, 1:7] - ho[:, 1:]).max(axis=0)
+    assert set(hd[:, 8].astype(int)) == set(range(model.p)) and hd[:, 9].max() <= ibr_iter
+    # switching the log off changes nothing in the result
+    gb.set_history(0)
+    gb.set_initial(Z0, L0)
+    out2 = gb.ibr_newton_solve(opts, ab.IBROptions(ibr_iter=ibr_iter))
+    assert np.array_equal(out["Z"], out2["Z"]) and np.array_equal(out["stats"][:, :8], out2["stats"][:, :8])
+    gb.close()
+
+
+def check_status_codes(lib_path):
+    """The six per-instance outcomes of include/algames_b200.h, on the device and in the C oracle."""
+    S = ab._capi
+    model, N, dt, obj, con, opts, x0, xf = small_config("B", 4, 12)
+    cfg = (model, N, dt, obj, con, opts, x0, xf)
+
+    def run(o, x):
+        gb = ab.GameBatch(model, N, dt, obj, con, x.shape[0], lib_path=lib_path)
+        gb.set_instance_params(x0=x)
+        Z0, L0 = gb.random_initial()
+        out = gb.newton_solve(o)
+        gb.close()
+        ref = c_oracle_solve(cfg, x, None, Z0, L0, o)
+        assert np.array_equal(out["status"], ref["status"]), (out["status"], ref["status"])
+        return out["status"]
+
+    assert (run(opts, x0) == S.CONVERGED).all()
+    tight = ab.Options(**{**opts.to_dict(), "eps_opt": 1e-300, "eps_dyn": 1e-300, "outer_iter": 2, "inner_iter": 3, "delta_min": 0.0, "ls_iter": 40})
+    assert (run(tight, x0) == S.MAX_OUTER).all()                       # inner_iter exhausted, tolerances unreachable
+    stall = ab.Options(**{**opts.to_dict(), "eps_opt": 1e-300, "outer_iter": 1, "delta_min": 1e30})
+    assert (run(stall, x0) == S.STALLED).all()                         # first step is "too small"
+    nols = ab.Options(**{**opts.to_dict(), "eps_opt": 1e-300, "outer_iter": 1, "ls_iter": 1, "delta_min": 0.0})
+    assert (run(nols, x0) == S.LINE_SEARCH_FAILED).all()               # no trial allowed: j == ls_iter at once
+    xn = x0.copy(); xn[2, 1] = np.inf
+    st = run(opts, xn)
+    assert st[2] == S.NONFINITE and (np.delete(st, 2) == S.CONVERGED).all()
+
+
+def check_local_gather(lib_path, ndev=2, total=5):
+    """Single-process multi-GPU path of the C ABI (agb_create_sharded-style layout built from GameBatch handles): uneven
+    contiguous shards, one push all-gather, every rank's buffer holds every rank's results."""
+    model, N, dt, obj, con, opts, x0, xf = small_config("B", total, 10)
+    from algames_b200 import distributed as D
+    bounds = [D.shard_bounds(total, ndev, r) for r in range(ndev)]
+    batches = [hi - lo for lo, hi in bounds]
+    gbs, outs = [], []
+    rng = np.random.default_rng(opts.seed)
+    Z0 = opts.amplitude_init * rng.random((total, N, model.n + model.m)); L0 = opts.amplitude_init * rng.random((total, model.p, N - 1, model.n))
+    for r, (lo, hi) in enumerate(bounds):
+        gb = ab.GameBatch(model, N, dt, obj, con, hi - lo, device=r, lib_path=lib_path)
+        gb.set_instance_params(x0=x0[lo:hi]); gb.set_initial(Z0[lo:hi], L0[lo:hi])
+        gb.peer_init(ndev, r, batches)
+        gbs.append(gb)
+    ab.GameBatch.peer_connect_local(gbs)
+    for gb in gbs:
+        gb.newton_solve_async(opts, 0)
+        gb.allgather()
+    for gb in gbs:
+        gb.allgather_wait()
+    for gb in gbs:
+        outs.append(gb.newton_solve(opts, want=("Z", "L", "stats", "status")))      # same solve again, host copies: the reference result
+    for gb in gbs:
+        ptr, offs = gb.gathered_view()
+        assert ptr and len(offs) == ndev + 1 and offs[0] == 0
+        for r in range(ndev):
+            got = gb.unpack_gathered(r)
+            for k in ("Z", "L", "stats", "status"):
+                assert np.array_equal(got[k], outs[r][k]), (r, k)
+    for gb in gbs:
+        gb.close()

@@ -41,7 +41,8 @@ import pytest  # noqa: E402
 
 @pytest.mark.gpu
 def test_gpu_arm_prints_one_json_line():
-    r = _run("--steps", "3", "--warmup", "3", "--no-cpu-baseline")
+    r = _run("--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--other-batch", "256", "--mpc-streams", "64", "--mpc-resolves", "5",
+             "--cpu-sample-other", "16")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
@@ -51,3 +52,10 @@ def test_gpu_arm_prints_one_json_line():
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["roofline"]["bound"] == "fp64-issue" and d["roofline"]["unit"] == "TFLOP/s" and d["roofline"]["peak"] > 10.0
+    assert 0.0 < d["roofline"]["hbm"]["frac"] < 0.05          # real DRAM traffic: a fraction of a per cent of the HBM peak
+    oc = d["other_configs"]
+    assert isinstance(oc, list) and [o["workload"][0] for o in oc] == ["E", "D", "C"], oc
+    for o in oc:
+        assert o["value"] > 0 and o["e2e"]["value"] > 0 and 0.5 < o["converged_fraction"] <= 1.0
+        assert o["cpu_baseline"]["value"] > 0 and o["cpu_baseline"]["kind"] == "port"

@@ -20,12 +20,27 @@ def built():
 
 def test_library_exports_every_declared_symbol(built):
     header = open(os.path.join(ROOT, "include", "algames_b200.h")).read()
-    declared = set(re.findall(r"\b(agb_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(agb_[a-z0-9_]+)\s*\(", header))
     import algames_b200 as ab
     assert declared == set(ab._capi.SYMBOLS), declared ^ set(ab._capi.SYMBOLS)
     lib = C.CDLL(built)
     for name in declared:
         assert hasattr(lib, name), name
+
+
+def test_abi_layout_check(built):
+    """agb_abi_check: the hand-written ctypes mirrors agree with the header the library was built from, and a drifted
+    binding (one more field in a struct, another AGB_NHIST) is refused with a message naming the entry."""
+    import algames_b200 as ab
+    lib = ab._capi.load()                       # load() itself runs the check
+    words = ab._capi.abi_layout()
+    mine = (C.c_int * len(words))()
+    assert lib.agb_abi_layout(mine, len(words)) == 0 and list(mine) == words
+    for k, name in ((0, "sizeof(agb_problem_desc)"), (11, "offsetof(agb_options, dual_reset)"), (22, "AGB_NHIST")):
+        bad = list(words); bad[k] += 4
+        assert lib.agb_abi_check((C.c_int * len(bad))(*bad), len(bad)) != 0
+        assert name in lib.agb_last_error(None).decode()
+    assert lib.agb_abi_check((C.c_int * 3)(1, 2, 3), 3) != 0
 
 
 def test_sizes_of_descriptor(built):

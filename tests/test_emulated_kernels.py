@@ -198,3 +198,43 @@ def test_working_set_too_large_is_rejected_emulated(emu_lib):
     ab.add_collision_avoidance(con, 0.1)
     with pytest.raises(ab.AlgamesError, match="shared memory"):
         ab.GameBatch(model, N, 0.1, obj, con, 1, lib_path=emu_lib)
+
+
+# ---- round-2 boundary features on the emulator -------------------------------------------------------------------------
+@pytest.mark.parametrize("name,N", [("A", None), ("A'", 10), ("B", 8), ("E", 8)])
+def test_violation_vectors_emulated(emu_lib, name, N):
+    parity.check_violation_vectors(emu_lib, name, N)
+
+
+def test_ibr_history_emulated(emu_lib):
+    parity.check_ibr_history(emu_lib, "B", N=8, ibr_iter=2)
+    parity.check_ibr_history(emu_lib, "A", N=None, ibr_iter=1)
+
+
+def test_status_codes_emulated(emu_lib):
+    parity.check_status_codes(emu_lib)
+
+
+def test_local_gather_emulated(emu_lib, monkeypatch):
+    monkeypatch.setenv("AGB_EMU_DEVICES", "3")
+    parity.check_local_gather(emu_lib, ndev=3, total=7)
+
+
+def test_batch_requires_equal_options_emulated(emu_lib):
+    import algames_b200 as ab
+    model, N, dt, obj, con, opts, x0, _ = ab.workloads.config_b(batch=2, N=6)
+    a = ab.GameProblem(N, dt, x0[0], model, ab.Options(), obj, con, lib_path=emu_lib)
+    b = ab.GameProblem(N, dt, x0[1], model, ab.Options(inner_iter=3), obj, con, lib_path=emu_lib)
+    with pytest.raises(ValueError, match="Options"):
+        ab.newton_solve([a, b])
+    b.opts = ab.Options()
+    ab.newton_solve([a, b])
+    assert a.status == b.status == "converged"
+    assert a.stats.dyn_vio[-1].vio.shape == (N - 1,) and a.stats.opt_vio[-1].vio.shape == (N,)
+    assert a.stats.dyn_vio[-1].vio.max() == a.stats.dyn_vio[-1].max
+    # the cached single-problem handle re-pushes the objective (xf edited after the first solve)
+    ab.newton_solve(a)
+    z_before = a.pdtraj.X[-1].copy()
+    a.game_obj.xf[0][:] = [0.3, 0.3, 0.0, 0.0]
+    ab.newton_solve(a)
+    assert np.abs(a.pdtraj.X[-1] - z_before).max() > 1e-3
