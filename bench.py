@@ -557,9 +557,9 @@ def run_mpc_config(ctx, streams, resolves, cpu_streams, cpu_resolves):
     conv, newton = ctx.allreduce([conv_l, newton_l])
     # e2e: every re-solve's trajectories, stats and status copied to the host, disturbance supplied from the host
     t0 = time.perf_counter()
-    stats, status, xs = ab.mpc.mpc_run(gb, opts, x0, max(resolves // 10, 1), xf=xf, disturbance_std=1e-3, seed=3456 + rank)
+    e2e_n = resolves
+    stats, status, xs = ab.mpc.mpc_run(gb, opts, x0, e2e_n, xf=xf, disturbance_std=1e-3, seed=3456 + rank)
     ctx.sync_all()
-    e2e_n = max(resolves // 10, 1)
     e2e_t = ctx.allreduce([time.perf_counter() - t0], "max")[0]
     e2e_conv = ctx.allreduce([float((status == 0).sum())])[0]
     rec = {"workload": "D: MPC ramp merge, 3-player UnicycleGame N=40, shift=1, dual_reset=false, x0 <- x_2 + N(0,1e-3) after every solve",

@@ -450,8 +450,8 @@ def check_edge_shape(lib_path, model_name, p, N):
         ab.add_collision_avoidance(con, 0.05)
     if model_name == "bicycle":
         ab.add_control_bound(con, np.r_[2 * np.ones(p), 0.5 * np.ones(p)], np.r_[-2 * np.ones(p), -np.inf * np.ones(p)])
-        ab.add_state_bound(con, 1, 5 * np.ones(model.n), np.r_[-5 * np.ones(model.n - 2), -np.inf, -np.inf])
-        ab.add_wall_constraint(con, [ab.Wall([0.0, -0.4], [1.0, -0.4], [0.0, -1.0])], 2)
+        ab.add_state_bound(con, min(1, p - 1), 5 * np.ones(model.n), np.r_[-5 * np.ones(model.n - 2), -np.inf, -np.inf])
+        ab.add_wall_constraint(con, [ab.Wall([0.0, -0.4], [1.0, -0.4], [0.0, -1.0])], min(2, p - 1))
         ab.add_circle_constraint(con, [1.0], [1.0], [0.2])
     x0 = rng.normal(size=model.n)
     opts = ab.Options()
