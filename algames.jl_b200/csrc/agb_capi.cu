@@ -109,7 +109,6 @@ struct agb_handle {
   int* status = nullptr;
   double* hist = nullptr; int* hist_count = nullptr; int hist_max = 0;   // agb_set_history
   double* Hpg = nullptr; int hpg_stride = 0;                              // big layout: pair / self Hessian blocks
-  int* sm_slots = nullptr;                                                // warp-role rotation counters (Buffers::sm_slots)
   double* results = nullptr; size_t results_doubles = 0;   // owns Z, L, stats, status
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
@@ -305,7 +304,7 @@ void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count, h->Hpg, h->sm_slots};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count, h->Hpg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int r = 0; r < h->nranks; r++) if (h->peer_ipc_opened[r]) cudaIpcCloseMemHandle(h->peer_gather[r]);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -374,13 +373,6 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
   CK(alloc_d(h, &h->conlam, B * K * t.nrow)); CK(alloc_d(h, &h->conmu, B * K * t.nrow));
   CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 2)));       // rows padded to n+2 (Inst::n1p)
   if (t.big) { h->hpg_stride = N * t.npairs * 3 + N * p * 3; CK(alloc_d(h, &h->Hpg, B * (size_t)h->hpg_stride)); }
-  {
-    const char* e = getenv("AGB_ROLE_ROTATION");         // tuning hook: "0" pins the warp roles (round-1 behaviour)
-    if (!(e && e[0] == '0')) {
-      CKC(cudaMalloc((void**)&h->sm_slots, 256 * 4 * sizeof(int)));
-      CKC(cudaMemsetAsync(h->sm_slots, 0, 256 * 4 * sizeof(int), h->stream));
-    }
-  }
   // descriptor defaults broadcast to every instance; μ starts at 1 (Altro ALConVal default)
   double tmp[2 * AGB_MAX_N + 2 * AGB_MAX_M];
   double* dtmp = nullptr;
@@ -416,7 +408,6 @@ static Buffers buffers_of(agb_handle* h) {
   g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.KUg = h->KUg; g.stats = h->stats; g.status = h->status;
   g.hist = h->hist; g.hist_count = h->hist_count; g.hist_max = h->hist_max;
   g.Hpg = h->Hpg; g.hpg_stride = h->hpg_stride;
-  g.sm_slots = h->sm_slots;
   return g;
 }
 

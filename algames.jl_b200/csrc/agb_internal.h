@@ -73,7 +73,6 @@ struct Buffers {
   int hist_max;
   double* Hpg;        // big layout only: [B][N·p(p-1)·3 + N·p·3] pair / self Hessian blocks
   int hpg_stride;
-  int* sm_slots;      // [256][4] live CTAs per (SM, warp-role rotation), or nullptr = no rotation (agb_kernels.cuh pick_role)
 };
 
 enum Op {

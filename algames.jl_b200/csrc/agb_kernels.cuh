@@ -15,53 +15,12 @@ namespace agb {
 // =============================================================================================================
 // Kernels
 // =============================================================================================================
-// Warp-role rotation.  The hardware pins warp w of every CTA to sub-partition (scheduler) w mod 4, and the solve gives its
-// warps very different loads: warp 0 alone runs the Gauss-Jordan of every stage and the forward sweep, warps 0..P-1 the
-// costate recursions.  With four co-resident CTAs all four heavy warps would share ONE scheduler while the other three
-// idle at the barriers.  Each CTA therefore takes the role offset that is least used on its SM (four counters per SM in
-// global memory), and every loop indexes work by the rotated thread id (Inst::tid).
-__device__ __forceinline__ int pick_role(int* sm_slots) {
-#ifdef AGB_EMULATE
-  (void)sm_slots;
-  return (int)(blockIdx.x & 3);                       // the emulator exercises every rotation
-#else
-  __shared__ int rot_s;
-  if (threadIdx.x == 0) {
-    int rot = 0;
-    if (sm_slots != nullptr) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      int* c = sm_slots + 4 * (smid & 255u);
-      int best = atomicAdd(&c[0], 0);
-#pragma unroll
-      for (int r = 1; r < 4; r++) { const int v = atomicAdd(&c[r], 0); if (v < best) { best = v; rot = r; } }
-      atomicAdd(&c[rot], 1);
-    }
-    rot_s = rot;
-  }
-  __syncthreads();
-  return rot_s;
-#endif
-}
-__device__ __forceinline__ void release_role(int* sm_slots, int rot) {
-#ifndef AGB_EMULATE
-  if (sm_slots != nullptr && threadIdx.x == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    atomicSub(&sm_slots[4 * (smid & 255u) + rot], 1);
-  }
-#else
-  (void)sm_slots; (void)rot;
-#endif
-}
-
 // newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
 template <int P, int MODEL, int LAY>
 __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 : 4))) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;
-  const int rot = pick_role(g.sm_slots);
-  I.bind(dd, sm, rot);
+  I.bind(dd, sm);
   constexpr int n = Inst<P, MODEL, (LAY != 0)>::n, kThreads = threads_for(P);
   const int K = I.K;
   const double S = (double)(K * Inst<P, MODEL, (LAY != 0)>::b);
@@ -140,7 +99,6 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
       g.status[inst] = conv ? AGB_CONVERGED : (failed ? failed : (!finite ? AGB_NONFINITE : last_exit));
     }
   }
-  release_role(g.sm_slots, rot);
 }
 
 // ibr_newton_solve!(prob; ibr_opts) for every instance (solver_methods.jl:133-224); one CTA per instance.
@@ -149,8 +107,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
                                                                                           agb_ibr_options io, Buffers g, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;
-  const int rot = pick_role(g.sm_slots);
-  I.bind(dd, sm, rot);
+  I.bind(dd, sm);
   constexpr int n = Inst<P, MODEL, (LAY != 0)>::n, kThreads = threads_for(P);
   const int K = I.K;
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
@@ -252,7 +209,6 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     }
     if (g.hist != nullptr && I.tid == 0) g.hist_count[inst] = n_rec;
   }
-  release_role(g.sm_slots, rot);
 }
 
 // Per-function entry points on the resident batch (parity tests and stand-alone use of the exported reference API).
@@ -260,7 +216,7 @@ template <int P, int MODEL, int LAY>
 __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;
-  I.bind(dd, sm, (int)(blockIdx.x & 3));              // per-function entry points: every rotation gets parity coverage
+  I.bind(dd, sm);
   constexpr int n = Inst<P, MODEL, (LAY != 0)>::n, m = Inst<P, MODEL, (LAY != 0)>::m, b = Inst<P, MODEL, (LAY != 0)>::b, kThreads = threads_for(P);
   const int K = I.K, Sz = K * b, nrow = I.nrow;
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {

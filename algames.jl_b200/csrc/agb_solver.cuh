@@ -239,9 +239,7 @@ struct Inst {
   int pl;                 // iterative best response: the player whose problem is being solved (-1: the full game)
   int tid, lane, warp;
 
-  // `rot` rotates the warp roles (which warp runs the Gauss-Jordan, the forward sweep, …): tid is the VIRTUAL thread index
-  // every loop of this file is written against, lane the physical lane; see pick_role() in agb_kernels.cuh.
-  __device__ void bind(const DevDesc* dd, double* sm, int rot = 0) {
+  __device__ void bind(const DevDesc* dd, double* sm) {
     d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; ncw = dd->ncw; has_cc = dd->has_cc; has_sb = dd->has_sb; has_cb = dd->has_cb;
     has_pairs = dd->has_pairs; has_self = dd->has_self; dt = dd->dt;
     (void)sm;
@@ -251,8 +249,7 @@ struct Inst {
     else { L.p = nullptr; CL.p = nullptr; CM.p = nullptr; Hp.p = nullptr; Hs.p = nullptr; }
     Pm.off = dd->o_P; Sv.off = dd->o_Sv; Ym.off = dd->o_Y; Aug.off = dd->o_Aug; Base.off = dd->o_Base;
     Wm.off = dd->o_W; Hm.off = dd->o_Ta; xf.off = dd->o_par; Q.off = xf.off + n; Rw.off = Q.off + n; uf.off = Rw.off + m; red.off = dd->o_red;
-    lane = threadIdx.x & 31; warp = ((threadIdx.x >> 5) + rot) % (kThreads / 32); tid = warp * 32 + lane;
-    KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
+    tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
   }
   __device__ void bind_instance(const Buffers& g, int inst) {
     KUg = g.KUg + (size_t)inst * K * KUSP; Rtrial = g.D + (size_t)inst * K * b;

@@ -34,7 +34,6 @@
  *   AGB_FORCE_BIG_LAYOUT=1|2|3  agb_create: force a big-storage shared-memory layout on 3-player instances (parity tests
  *                               run every layout on small games with it)
  *   AGB_HOST_CHUNKS=1..32       agb_solve_from_host: number of copy/solve pipeline chunks (default 8 for batch >= 1024)
- *   AGB_ROLE_ROTATION=0         agb_create: pin the warp roles of the solve kernels instead of rotating them per SM
  */
 #ifndef ALGAMES_B200_H
 #define ALGAMES_B200_H
