@@ -233,8 +233,12 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
       if (need > have) take(need - have);
       o->o_Gp = o->o_P; o->o_Gs = o->o_P + (o->has_pairs ? N * o->npairs * 2 : 0);
     }
-    // the forward sweep lays a 4-stage ring of padded gain blocks (Inst::KUSP = m*(n+2)) over [o_P, end of Hm)
-    if (off - o->o_P < 4 * m * (n + 2)) take(4 * m * (n + 2) - (off - o->o_P));
+    // the forward sweep lays a ring of fwd_ring_depth(p) closed-loop blocks (Inst::ACS = n*(n+2) doubles) and its flags
+    // over [o_P, end of Hm)
+    {
+      const int need = fwd_ring_depth(p) * n * (n + 2) + 8;
+      if (off - o->o_P < need) take(need - (off - o->o_P));
+    }
     o->o_par = take(2 * n + 2 * m); o->o_red = take(6 * kMaxWarps);
     o->smem_doubles = off;
     o->big = big ? 1 : 0;

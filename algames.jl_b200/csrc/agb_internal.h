@@ -14,6 +14,9 @@ namespace agb {
 #define AGB_HD
 #endif
 AGB_HD constexpr int threads_for(int) { return 128; }
+// stages of closed-loop blocks in the forward sweep's shared-memory ring (laid over the factorisation scratch, which
+// build_dev_desc sizes for it): as deep as the scratch of a p-player game allows
+AGB_HD constexpr int fwd_ring_depth(int p) { return p == 1 ? 3 : (p == 2 ? 6 : (p == 3 ? 8 : 12)); }
 constexpr int kMaxWarps = 8;
 
 // Flattened, index-resolved form of agb_problem_desc, lives in device global memory (read through L1).

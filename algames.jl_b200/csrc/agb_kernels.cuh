@@ -35,6 +35,12 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     __syncthreads();
     I.rollout();                                                                        // :17
     if (o.dual_reset) I.reset_duals_penalties(o);                                       // :25
+#ifdef AGB_PHASE_TIMING
+#define AGB_PROFK(k) do { const long long t_ = clock64(); I.prof[k] += t_ - I.prof_t; I.prof_t = t_; } while (0)
+#else
+#define AGB_PROFK(k) do { } while (0)
+#endif
+    AGB_PROFK(11);
     int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0, n_rec = 0;
     // record!(stats, …) (statistics.jl:44-57): optional per-instance log of every record of the solve
     auto log_record = [&](const Acc& r, double dlt, int kk, int ll) {
@@ -60,8 +66,8 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         const double l2 = (double)l * (double)l;
         const double reg = o.reg_0 * (l2 * l2);                                         // :39
         // ---- inner_iteration (:67-103)
-        if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; }             // accepted trial point: already evaluated
-        else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }        // :73-75 (the reg terms vanish at Z)
+        if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; AGB_PROFK(10); }   // accepted trial point: already evaluated
+        else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; AGB_PROFK(0); }   // :73-75 (the reg terms vanish at Z)
         const double res_norm = rec.sum / S;                                            // :76
         log_record(rec, delta, kout, l);                                                // :75
         delta = 0.0;
@@ -71,8 +77,10 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         n_newton++;
         double alpha; int j;
         kept = I.line_search(o, reg, res_norm, alpha, j, n_eval, &kept_rec);            // :91
+        AGB_PROFK(1);
         ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;                                 // :92-93
         delta = I.update_traj(alpha);                                                   // :94-95 (taken even when the search failed)
+        AGB_PROFK(9);
         if (delta < o.delta_min) { last_exit = AGB_STALLED; break; }                    // :96-98
         if (ls_count >= 1) { last_exit = AGB_LINE_SEARCH_FAILED; break; }               // :43
         if (!(delta == delta)) { if (!failed) failed = AGB_NONFINITE; break; }
@@ -92,6 +100,11 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
     I.store_iterate(g.Z, g.L, inst);
     I.store_duals(g, inst);
+    AGB_PROFK(11);
+#ifdef AGB_PHASE_TIMING
+    if (g.hist != nullptr && g.hist_max >= 2 && I.tid == 0)
+      for (int q = 0; q < 16; q++) g.hist[(size_t)inst * g.hist_max * AGB_NHIST + q] = (double)I.prof[q];
+#endif
     if (I.tid == 0) {
       double* st = g.stats + (size_t)inst * AGB_NSTATS;
       st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;

@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <string.h>
 #include "agb_internal.h"
 
 namespace agb {
@@ -58,6 +59,26 @@ struct GPh {
 };
 template <bool BIG> struct SpillSel { typedef SP type; };
 template <> struct SpillSel<true> { typedef GPh type; };
+
+// Flags between the warps of one CTA (producer / consumer forward sweep): release-store, acquire-load, and a spin hint
+// (the fiber emulator must yield inside a spin loop; the GPU backs off a little so that pollers leave issue slots free).
+#ifndef AGB_EMULATE
+__device__ __forceinline__ void flag_store(int* p, int v) { asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
+__device__ __forceinline__ int flag_load(const int* p) { int v; asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory"); return v; }
+__device__ __forceinline__ void spin_hint(bool relaxed) { if (relaxed) __nanosleep(64); }
+#else
+inline void flag_store(int* p, int v) { *(volatile int*)p = v; }
+inline int flag_load(const int* p) { return *(volatile const int*)p; }
+inline void spin_hint(bool) { emu::yield(emu::RUN); }
+#endif
+
+// Optional critical-path profile (-DAGB_PHASE_TIMING, profiling builds only): thread 0 accumulates clock64() deltas per
+// phase between block barriers; the solve kernel writes the 16 counters over the instance's history log.
+#ifdef AGB_PHASE_TIMING
+#define AGB_PROF(k) do { const long long t_ = clock64(); prof[k] += t_ - prof_t; prof_t = t_; } while (0)
+#else
+#define AGB_PROF(k) do { } while (0)
+#endif
 
 struct Acc {            // norms of one residual evaluation (statistics.jl:44-57, violations.jl:18-168)
   double sum, opt, dyn, con, sta;
@@ -179,6 +200,8 @@ struct Inst {
   static constexpr int n = 4 * P, m = 2 * P, b = P * n + m + n, W = m + n + 1, KUS = m * (n + 1), n1 = n + 1;
   // rows of the gain scratch in global memory are padded to an even length (16-byte row alignment for 128-bit loads)
   static constexpr int n1p = n + 2, KUSP = m * n1p;
+  // forward sweep: closed-loop blocks [A − B K | rd − B κ] (n rows of n1p) staged through a shared-memory ring of FWD_D stages
+  static constexpr int ACS = n * n1p, FWD_D = fwd_ring_depth(P);
   // per-stage H^x_{i,s} in compact form: dense 2P x 2P position block + diagonal, per player (kkt_solve phases 2/3)
   static constexpr int HmS = 4 * P * P + n;
   static constexpr int HB = 32 + ((P * n + 31) / 32) * 32;      // first thread of the H builders (after GJ warp + row threads)
@@ -238,6 +261,9 @@ struct Inst {
   bool keep;              // trial evaluation also produces what the next inner iteration needs (rows, Hessian blocks)
   int pl;                 // iterative best response: the player whose problem is being solved (-1: the full game)
   int tid, lane, warp;
+#ifdef AGB_PHASE_TIMING
+  long long prof_t, prof[16];
+#endif
 
   __device__ void bind(const DevDesc* dd, double* sm) {
     d = dd; N = dd->N; K = dd->K; nrow = dd->nrow; ncw = dd->ncw; has_cc = dd->has_cc; has_sb = dd->has_sb; has_cb = dd->has_cb;
@@ -250,6 +276,10 @@ struct Inst {
     Pm.off = dd->o_P; Sv.off = dd->o_Sv; Ym.off = dd->o_Y; Aug.off = dd->o_Aug; Base.off = dd->o_Base;
     Wm.off = dd->o_W; Hm.off = dd->o_Ta; xf.off = dd->o_par; Q.off = xf.off + n; Rw.off = Q.off + n; uf.off = Rw.off + m; red.off = dd->o_red;
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
+#ifdef AGB_PHASE_TIMING
+    for (int q = 0; q < 16; q++) prof[q] = 0;
+    prof_t = clock64();
+#endif
   }
   __device__ void bind_instance(const Buffers& g, int inst) {
     KUg = g.KUg + (size_t)inst * K * KUSP; Rtrial = g.D + (size_t)inst * K * b;
@@ -664,11 +694,22 @@ struct Inst {
 #endif
   }
 
+  // |x| as an ordered integer: the high word of a non-negative double is monotone in its value, so magnitude tests run on
+  // the integer pipe — the FP64 pipe of the scheduler that hosts this warp is the scarce resource of the whole solve
+  // (measured: every variant of this routine that issued more FP64 instructions was slower, whatever its dependency chain).
+  static __device__ __forceinline__ int abs_hi(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x) & 0x7fffffff;
+#else
+    long long u; memcpy(&u, &x, 8); return (int)((u >> 32) & 0x7fffffff);
+#endif
+  }
+
   // Gauss-Jordan on the m x W augmented gain system, one column per lane (warp 0).  Threshold pivoting like the
-  // reference's UMFPACK: the diagonal pivot is kept while |a_tt| >= 0.01·max_r |a_rt| (no row exchange, no index
+  // reference's UMFPACK: the diagonal pivot is kept while |a_tt| >= 2^-7·max_r |a_rt| (no row exchange, no index
   // shuffles); only if some step violates the threshold is the system re-solved from shared memory with full partial
   // pivoting.  Returns false on a zero / non-finite pivot.
-  __device__ bool gj_warp(double* aug) {
+  __device__ bool gj_warp(double* aug, double* kg = nullptr) {
     double a[m];
     const bool act = lane < W;
 #pragma unroll
@@ -688,10 +729,11 @@ struct Inst {
       for (int r = 0; r < m; r += 2) { const double2 v = piv[r / 2]; f[r] = v.x; f[r + 1] = v.y; }
       const double pv = f[t];
       f[t] = 0.0;
-      const double apv = fabs(pv), tpv = 100.0 * apv;
-      if (!(apv > 0.0 && apv <= 1.7976931348623157e308)) weak = true;
+      const int hp = abs_hi(pv);
+      if ((unsigned)(hp - 0x00100000) >= 0x7fe00000u) weak = true;          // zero / subnormal / inf / NaN pivot
+      const int lim = hp + (7 << 20);                                       // 2^7·|pv|
 #pragma unroll
-      for (int r = t + 1; r < m; r++) if (!(tpv >= fabs(f[r]))) weak = true;
+      for (int r = t + 1; r < m; r++) if (abs_hi(f[r]) > lim) weak = true;
       const double at = a[t] * fast_rcp(pv);
 #pragma unroll
       for (int r = 0; r < m; r++) if (r != t) a[r] = fma(-f[r], at, a[r]);
@@ -701,14 +743,26 @@ struct Inst {
       if (act) {
 #pragma unroll
         for (int r = 0; r < m; r++) aug[r * W + lane] = a[r];
+        if (kg != nullptr && lane >= m) {                                   // K | κ → the L2-resident gain scratch, from registers
+#pragma unroll
+          for (int r = 0; r < m; r++) kg[r * n1p + (lane - m)] = a[r];
+        }
       }
       return true;
     }
-    return gj_warp_pivoted(aug);
+    const bool ok = gj_warp_pivoted(aug);
+    if (kg != nullptr && lane >= m && act) {
+#pragma unroll
+      for (int r = 0; r < m; r++) kg[r * n1p + (lane - m)] = aug[r * W + lane];
+    }
+    return ok;
   }
 
   // full partial pivoting (row exchanges), used when the threshold test above fails
   __device__ bool gj_warp_pivoted(double* aug) {
+#ifdef AGB_DEBUG_COUNT_FALLBACK
+    { static long cnt = 0; if (lane == 0) { cnt++; if ((cnt & (cnt - 1)) == 0) fprintf(stderr, "gj_warp_pivoted call #%ld\n", cnt); } }
+#endif
     double a[m];
     const bool act = lane < W;
 #pragma unroll
@@ -926,6 +980,7 @@ struct Inst {
   __device__ bool kkt_solve(double reg_x, double reg_u) {
     if (pl >= 0) return kkt_solve_ibr(reg_x, reg_u);
     int ok = 1;
+    AGB_PROF(11);
     // terminal knot: P_i = H_{i,N}, s_i = r^x_{i,N}
     for (int item = tid; item < P * n * n; item += kThreads) {
       int bq = item % n, r = item / n;
@@ -940,6 +995,7 @@ struct Inst {
     __syncthreads();
     compute_Y(K - 1);
     __syncthreads();
+    AGB_PROF(2);
     for (int s = K - 1; s >= 0; s--) {
       const double* Rs = R + s * b;
       // ---- phase 1: Aug = [Hu + Y B | Y A | Y rd + (Bᵀ s) + ru], items grouped by kind so that warps stay convergent
@@ -977,14 +1033,16 @@ struct Inst {
         Aug[r * W + col] = v;
       }
       __syncthreads();
+      AGB_PROF(3);
       // ---- phase 2
       if (warp == 0) {
-        if (!gj_warp(Aug)) ok = 0;
-        if (lane >= m && lane < W) {
-          double* kg = KUg + s * KUSP;
-#pragma unroll
-          for (int r = 0; r < m; r++) kg[r * n1p + (lane - m)] = Aug[r * W + lane];      // K, κ stay in Aug for phase 3
-        }
+#ifdef AGB_PHASE_TIMING
+        const long long gj0 = clock64();
+#endif
+        if (!gj_warp(Aug, KUg + s * KUSP)) ok = 0;                           // K, κ stay in Aug for phase 3
+#ifdef AGB_PHASE_TIMING
+        prof[12] += clock64() - gj0;
+#endif
       } else if (s > 0) {
         // one thread per row a = (c,i2) of player i's Base_i = H_{i,s} + Aᵀ P_i A, W_i = Aᵀ P_i B and base_i:
         // X = (Aᵀ P_i)[a,:] is a combination of at most four rows of P_i held in registers; A and B are block diagonal
@@ -1050,6 +1108,7 @@ struct Inst {
         if (s - 1 > 0) build_hm(Hm + ((s - 1) & 1) * P * HmS, s - 1, reg_x, tid - HB, kThreads - HB);
       }
       __syncthreads();
+      AGB_PROF(4);
       if (s == 0) break;
       // ---- phase 3
       {
@@ -1079,6 +1138,7 @@ struct Inst {
         }
       }
       __syncthreads();
+      AGB_PROF(5);
     }
     ok = __syncthreads_and(ok);
     forward_and_costate(reg_x);
@@ -1112,91 +1172,103 @@ struct Inst {
 
   // forward sweep + costate recursion shared by the game and the best-response factorisations
   __device__ void forward_and_costate(double reg_x) {
-    // ---- forward sweep (warp 0): Δu_s = −Ku Δx_s − ku,  Δx_{s+1} = A Δx_s + B Δu_s + rd.  Δx_s lives in registers (lane a
-    // owns component a and recomputes its player's two controls), so the only dependent chain per stage is
-    // shuffle-broadcast → dot product → A/B update.  The gains come back from the L2-resident scratch with cp.async into
-    // a 4-stage shared-memory ring laid over the factorisation's scratch (P, s, Y, Aug, Base …: free at this point).
-    if (warp == 0) {
-      constexpr int DEPTH = 4, NV = KUSP / 2;             // 16-byte vectors per stage
-      constexpr int NI = (NV + 31) / 32;
+    // ---- forward sweep.  The recurrence Δx_{s+1} = (A − B K_s) Δx_s + (rd_s − B κ_s) is a serial chain over the stages, and a
+    // dependent FP64 operation costs ≈ 20 cycles, so the chain is kept as short as it can be: the closed-loop blocks
+    // Acl_s = [A − B K_s | rd_s − B κ_s] are PRODUCED by warps 1.. (gains back from the L2-resident scratch, one warp per
+    // stage, round robin) into a shared-memory ring laid over the factorisation's scratch (P, s, Y, Aug, Base …: free at this
+    // point), and CONSUMED by warp 0, whose lane a owns component a: one row · Δx_s product in four accumulators, one store,
+    // one warp barrier per stage.  ready[slot] = s + 1 publishes stage s, done = s + 1 frees its slot (release / acquire
+    // flags in shared memory).  The controls Δu_s = −K_s Δx_s − κ_s do not feed the chain: they are formed afterwards by all
+    // threads in parallel.
+    {
       double* const ring = Pm;
-      const SmemAddr ring_s = smem_off(smem_addr(ring), 2 * lane);
-      const double* gsrc = KUg + 2 * lane;                // next stage to fetch
-      int s_fetch = 0;
-      __syncwarp();
+      int* const flags = reinterpret_cast<int*>(ring + FWD_D * ACS);      // ready[FWD_D], done
+      if (tid <= FWD_D) flags[tid] = 0;
+      __syncthreads();
+      constexpr int NW = kThreads / 32 - 1;                               // producer warps
+      if (warp > 0) {
+        for (int s = warp - 1; s < K; s += NW) {
+          const int slot = s % FWD_D;
+          const double* kg = KUg + s * KUSP;
+          // gains first (L2 latency), then wait for the slot
+          constexpr int NQ = (P * n1 + 31) / 32;
+          double k0[NQ], k1[NQ];
+          int it[NQ];
 #pragma unroll
-      for (int dd = 0; dd < DEPTH - 1; dd++) {
-        if (s_fetch < K) {
+          for (int q = 0; q < NQ; q++) {
+            it[q] = lane + 32 * q;
+            const int i = it[q] / n1, col = it[q] - i * n1;
+            const bool on = it[q] < P * n1;
+            k0[q] = on ? kg[(0 * P + i) * n1p + col] : 0.0;
+            k1[q] = on ? kg[(1 * P + i) * n1p + col] : 0.0;
+          }
+          while (s - flag_load(flags + FWD_D) >= FWD_D) spin_hint(true);
+          double* dst = ring + slot * ACS;
 #pragma unroll
-          for (int q = 0; q < NI; q++)
-            if (lane + 32 * q < NV) cp_async16(smem_off(ring_s, dd * KUSP + 64 * q), gsrc + 64 * q);
-        }
-        cp_async_commit();
-        gsrc += KUSP; s_fetch++;
-      }
-      const bool act = lane < n;
-      const int c = act ? lane / P : 0, i = act ? lane - c * P : 0;
-      double at0 = 0.0, at1 = 0.0, bt0 = 0.0, bt1 = 0.0;   // row c of [At | Bt] of player i (constant for the double integrator)
-      if constexpr (MODEL == AGB_MODEL_DOUBLE_INTEGRATOR) {
-        double At[8], Bt[8]; loadAB(0, i, At, Bt);
+          for (int q = 0; q < NQ; q++) {
+            if (it[q] < P * n1) {
+              const int i = it[q] / n1, col = it[q] - i * n1;
+              double At[8], Bt[8]; loadAB(s, i, At, Bt);
+              const int c2 = col / P, i2 = col - c2 * P;
+              const bool own = (col < n) && (i2 == i);
 #pragma unroll
-        for (int q = 0; q < 4; q++) if (q == c) { at0 = At[2 * q]; at1 = At[2 * q + 1]; bt0 = Bt[2 * q]; bt1 = Bt[2 * q + 1]; }
-      }
-      const double* krow0 = ring + i * n1p;               // gain rows of player i's two controls inside a ring slot
-      const double* krow1 = ring + (P + i) * n1p;
-      double* rdp = R + OD + (act ? lane : 0);            // rd_s[lane] / Δx_{s+1}[lane]
-      double* up = R + OU + (c == 0 ? i : P + i);         // Δu slot written by the lanes of component rows 0 and 1
-      const double2* dxp = reinterpret_cast<const double2*>(R + OD) ;   // Δx_s = row s-1 (unused at s = 0)
-      const double* abp = AB + i * 16;
-      for (int s0 = 0; s0 < K; s0 += DEPTH) {
-#pragma unroll
-        for (int dd = 0; dd < DEPTH; dd++) {
-          const int s = s0 + dd;
-          if (s < K) {
-            cp_async_wait<DEPTH - 2>();                   // this lane's pieces of stage s have landed …
-            __syncwarp();                                 // … everyone's have, Δx_s is visible, and slot (dd+3)%4 is free
-            if (s_fetch < K) {
-#pragma unroll
-              for (int q = 0; q < NI; q++)
-                if (lane + 32 * q < NV) cp_async16(smem_off(ring_s, ((dd + DEPTH - 1) % DEPTH) * KUSP + 64 * q), gsrc + 64 * q);
-            }
-            cp_async_commit();
-            gsrc += KUSP; s_fetch++;
-            const double2* k0 = reinterpret_cast<const double2*>(krow0 + dd * KUSP);
-            const double2* k1 = reinterpret_cast<const double2*>(krow1 + dd * KUSP);
-            if constexpr (MODEL != AGB_MODEL_DOUBLE_INTEGRATOR) {
-              const double2* ab = reinterpret_cast<const double2*>(abp);
-              const double2 ar = ab[c], br = ab[4 + c];
-              at0 = ar.x; at1 = ar.y; bt0 = br.x; bt1 = br.y;
-              abp += P * 16;
-            }
-            const double rd = act ? *rdp : 0.0;           // (idle lanes must not touch row s: lane 0 rewrites it below)
-            const double2 kap0 = k0[n / 2], kap1 = k1[n / 2];
-            double a0 = kap0.x, a1 = 0.0, b0 = kap1.x, b1 = 0.0, dxl = 0.0, y0 = 0.0, y1 = 0.0;
-            if (s > 0) {
-              const double2* dx = dxp - b / 2;            // row s-1
-              dxl = act ? rdp[-b] : 0.0;
-              y0 = (R + OD + 2 * P + i)[(s - 1) * b]; y1 = (R + OD + 3 * P + i)[(s - 1) * b];
-#pragma unroll
-              for (int a = 0; a < n / 2; a += 2) {
-                const double2 x0 = dx[a], x1 = dx[a + 1], p0 = k0[a], p1 = k0[a + 1], q0 = k1[a], q1 = k1[a + 1];
-                a0 += p0.x * x0.x; a1 += p0.y * x0.y; a0 += p1.x * x1.x; a1 += p1.y * x1.y;
-                b0 += q0.x * x0.x; b1 += q0.y * x0.y; b0 += q1.x * x1.x; b1 += q1.y * x1.y;
+              for (int c = 0; c < 4; c++) {
+                const int a = c * P + i;
+                double base;
+                if (col == n) base = R[s * b + OD + a];
+                else {
+                  base = (own && c2 == c) ? 1.0 : 0.0;
+                  if (own && c2 == 2) base += At[c * 2];
+                  if (own && c2 == 3) base += At[c * 2 + 1];
+                }
+                dst[a * n1p + col] = (base - Bt[c * 2] * k0[q]) - Bt[c * 2 + 1] * k1[q];
               }
             }
-            const double u0 = -(a0 + a1), u1 = -(b0 + b1);
-            const double v = (rd + dxl) + ((at0 * y0 + at1 * y1) + (bt0 * u0 + bt1 * u1));
-            if (act) {
-              *rdp = v;
-              if (c < 2) *up = (c == 0) ? u0 : u1;
-            }
-            rdp += b; up += b; dxp += b / 2;
           }
+          __syncwarp();
+          if (lane == 0) flag_store(flags + slot, s + 1);
+        }
+      } else {
+        const bool act = lane < n;
+        const int a = act ? lane : 0;
+        for (int s = 0; s < K; s++) {
+          const int slot = s % FWD_D;
+          while (flag_load(flags + slot) != s + 1) spin_hint(false);
+          const double2* row = reinterpret_cast<const double2*>(ring + slot * ACS + a * n1p);
+          double v0 = row[n / 2].x, v1 = 0.0, v2 = 0.0, v3 = 0.0;          // affine column
+          if (s > 0) {
+            const double2* dx = reinterpret_cast<const double2*>(R + (s - 1) * b + OD);
+#pragma unroll
+            for (int q = 0; q < n / 2; q += 2) {
+              const double2 r0 = row[q], r1 = row[q + 1], x0 = dx[q], x1 = dx[q + 1];
+              v0 = fma(r0.x, x0.x, v0); v1 = fma(r0.y, x0.y, v1); v2 = fma(r1.x, x1.x, v2); v3 = fma(r1.y, x1.y, v3);
+            }
+          }
+          const double v = (v0 + v1) + (v2 + v3);
+          if (act) R[s * b + OD + a] = v;                                  // rd_s → Δx_{s+1} (its producer has read rd_s)
+          __syncwarp();                                                    // Δx_{s+1} visible; every lane is done with the slot
+          if (lane == 0) flag_store(flags + FWD_D, s + 1);
         }
       }
-      cp_async_wait<0>();
+      __syncthreads();
+      // Δu_s = −K_s Δx_s − κ_s for every stage (Δx_0 = 0: x_1 is not a variable)
+      for (int item = tid; item < K * m; item += kThreads) {
+        const int s = item / m, r = item - s * m;
+        const double2* kr = reinterpret_cast<const double2*>(KUg + s * KUSP + r * n1p);
+        double u0 = kr[n / 2].x, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+        if (s > 0) {
+          const double2* dx = reinterpret_cast<const double2*>(R + (s - 1) * b + OD);
+#pragma unroll
+          for (int q = 0; q < n / 2; q += 2) {
+            const double2 g0 = kr[q], g1 = kr[q + 1], x0 = dx[q], x1 = dx[q + 1];
+            u0 = fma(g0.x, x0.x, u0); u1 = fma(g0.y, x0.y, u1); u2 = fma(g1.x, x1.x, u2); u3 = fma(g1.y, x1.y, u3);
+          }
+        }
+        R[s * b + OU + r] = -((u0 + u1) + (u2 + u3));
+      }
     }
     __syncthreads();
+    AGB_PROF(6);
     // ---- costate: Δλ_{i,k−1} = g_{i,k} + A_kᵀ Δλ_{i,k} with g_{i,k} = H_{i,k} Δx_k + r^x_{i,k} (exactly the opt-x rows).
     // One warp per player, Δλ in registers (lane a owns component a); g of the next step is evaluated ahead of the
     // dependent shuffle → Aᵀ chain.
@@ -1211,31 +1283,38 @@ struct Inst {
       }
     }
     __syncthreads();
-    if (warp < P && (pl < 0 || warp == pl)) {
-      const int i = warp;
-      const bool act = lane < n;
-      const int a = act ? lane : 0, c = a / P, ia = a - c * P;
-      const double* gi = R + OX + i * n + a;
-      double ln = 0.0;
-      double g = act ? gi[(K - 1) * b] : 0.0;
+    AGB_PROF(7);
+    // One thread per (player i, state block of player j): the four components of Δλ_i on player j's states stay in
+    // registers (A is block diagonal per player), so a step is load g → add → at most two dependent FMAs → store, with
+    // no shuffles; the next step's g is fetched ahead of the chain.
+    if (tid < P * P && (pl < 0 || tid / P == pl)) {
+      const int i = tid / P, j = tid - i * P;
+      double* gi = R + OX + i * n + j;                   // component c of the block: gi[s·b + c·P]
+      double ln[4] = {0.0, 0.0, 0.0, 0.0}, g[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) g[c] = gi[(K - 1) * b + c * P];
       for (int s = K - 1; s >= 0; s--) {
-        const double gn = (act && s > 0) ? gi[(s - 1) * b] : 0.0;     // (idle lanes must not read rows lane 0 rewrites)
-        double v = g;
-        if (s < K - 1) {
-          const double l0 = __shfl_sync(AGB_FULL, ln, ia), l1 = __shfl_sync(AGB_FULL, ln, P + ia);
-          const double l2 = __shfl_sync(AGB_FULL, ln, 2 * P + ia), l3 = __shfl_sync(AGB_FULL, ln, 3 * P + ia);
-          v += ln;
-          if (c >= 2) {
-            double At[8], Bt[8]; loadAB(s + 1, ia, At, Bt);
-            v += at_dot_sel(c - 2, At, l0, l1, l2, l3);
-          }
+        double gn[4] = {0.0, 0.0, 0.0, 0.0};
+        if (s > 0) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) gn[c] = gi[(s - 1) * b + c * P];
         }
-        if (act) R[s * b + OX + i * n + lane] = v;
-        ln = v;
-        g = gn;
+        double v[4];
+        if (s < K - 1) {
+          double At[8], Bt[8]; loadAB(s + 1, j, At, Bt);
+          v[0] = g[0] + ln[0]; v[1] = g[1] + ln[1];
+          v[2] = (g[2] + ln[2]) + at_dot<0>(At, ln[0], ln[1], ln[2], ln[3]);
+          v[3] = (g[3] + ln[3]) + at_dot<1>(At, ln[0], ln[1], ln[2], ln[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; c++) v[c] = g[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) { gi[s * b + c * P] = v[c]; ln[c] = v[c]; g[c] = gn[c]; }
       }
     }
     __syncthreads();
+    AGB_PROF(8);
   }
 
 

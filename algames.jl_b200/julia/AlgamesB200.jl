@@ -5,7 +5,7 @@
 #     newton_solve!(probs)                      # all instances on the GPU; each `prob` is mutated like Algames.newton_solve!
 #
 # NOTE: no Julia toolchain exists in the build image (SURVEY.md F2), so this file has never been executed; it is kept
-# deliberately thin — descriptor packing + `ccall`s that mirror, one for one, the ctypes binding in ../_capi.py that the
+# deliberately thin (its struct layouts are checked against the library by agb_abi_check in __init__) — descriptor packing + `ccall`s that mirror, one for one, the ctypes binding in ../_capi.py that the
 # test-suite exercises.  Struct layouts below must match include/algames_b200.h field for field.
 module AlgamesB200
 
@@ -15,7 +15,10 @@ using LinearAlgebra
 import Algames: newton_solve!
 
 const LIB = get(ENV, "ALGAMES_B200_LIB", joinpath(@__DIR__, "..", "libalgames_b200.so"))
-const MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS = 4, 16, 8, 8, 8, 10
+const MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST, IPC_BYTES = 4, 16, 8, 8, 8, 10, 10, 64
+
+# per-instance status codes (include/algames_b200.h)
+const CONVERGED, MAX_OUTER, LINE_SEARCH_FAILED, STALLED, SINGULAR, NONFINITE = 0, 1, 2, 3, 4, 5
 
 # ---- include/algames_b200.h : agb_problem_desc (isbits, C layout) --------------------------------------------------
 struct AgbProblemDesc
@@ -204,79 +207,182 @@ end
 check(rc, h) = rc == 0 || error("libalgames_b200 ($rc): " *
     unsafe_string(ccall((:agb_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
 
-"""
-    newton_solve!(probs::AbstractVector{<:GameProblem}; device=0)
+# agb_device_view (only its size is needed here: 10 pointers + one UInt64)
+struct AgbDeviceView
+    ptrs::NTuple{10,Ptr{Cvoid}}; results_bytes::Culonglong
+end
+struct AgbIBROptions
+    ibr_iter::Cint; ordering::NTuple{MAX_P,Cint}; delta_min::Cdouble
+end
 
-Batched replacement of `Algames.newton_solve!` (src/problem/solver_methods.jl:5-65).  All problems must share the
-model, sizes and constraint schema of `probs[1]`; x0 and the LQR weights/targets may differ per instance.
-C arrays are row-major: a Julia `Array{Float64}` with reversed dims has exactly the layout the ABI expects.
+"The AGB_ABI_WORDS values agb_abi_check compares with the header the library was built from (include/algames_b200.h)."
+abi_layout() = Cint[sizeof(AgbProblemDesc), fieldoffset(AgbProblemDesc, 5), fieldoffset(AgbProblemDesc, 8),
+    fieldoffset(AgbProblemDesc, 15), fieldoffset(AgbProblemDesc, 19), fieldoffset(AgbProblemDesc, 23), fieldoffset(AgbProblemDesc, 25),
+    fieldoffset(AgbProblemDesc, 26), sizeof(AgbOptions), fieldoffset(AgbOptions, 12), fieldoffset(AgbOptions, 14), fieldoffset(AgbOptions, 20),
+    sizeof(AgbIBROptions), fieldoffset(AgbIBROptions, 3), sizeof(AgbSizes), sizeof(AgbDeviceView),
+    MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST, IPC_BYTES]
+
+function __init__()
+    # the structs above mirror the C header by hand: refuse to run against a library built from another layout
+    w = abi_layout()
+    rc = ccall((:agb_abi_check, LIB), Cint, (Ptr{Cint}, Cint), w, length(w))
+    rc == 0 || error("AlgamesB200: " * unsafe_string(ccall((:agb_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+end
+
 """
-function newton_solve!(probs::AbstractVector{<:GameProblem}; device::Integer=0)
-    B = length(probs); prob = probs[1]; opts = prob.opts
-    ps = prob.probsize; n, m, p, N = ps.n, ps.m, ps.p, ps.N
+    Batch(probs; device=0)
+
+Persistent device state for a vector of GameProblems sharing one schema: ONE agb_handle (device buffers, streams, the loaded
+kernels) and page-locked host staging arrays, created once and reused by every `newton_solve!(batch)` / `mpc_step!(batch)`.
+`close(batch)` (or the finalizer) releases it.  `batch.status[b]` holds the per-instance status code of the last solve.
+"""
+mutable struct Batch
+    h::Ptr{Cvoid}
+    probs::Vector
+    n::Int; m::Int; p::Int; N::Int; nrow::Int
+    x0::Matrix{Float64}; Z0::Array{Float64,3}; L0::Array{Float64,4}
+    Z::Array{Float64,3}; L::Array{Float64,4}; conλ::Array{Float64,3}; conμ::Array{Float64,3}
+    stats::Matrix{Float64}; status::Vector{Cint}
+end
+
+function Batch(probs::AbstractVector{<:GameProblem}; device::Integer=0)
+    prob = probs[1]; ps = prob.probsize; n, m, p, N = ps.n, ps.m, ps.p, ps.N; B = length(probs)
     desc = Ref(make_desc(prob)); h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:agb_create, LIB), Cint, (Ref{AgbProblemDesc}, Cint, Cint, Ref{Ptr{Cvoid}}), desc, B, device, h)
     rc == 0 || error("agb_create ($rc): " * unsafe_string(ccall((:agb_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    sz = Ref(AgbSizes(0, 0, 0, 0, 0, 0, 0, 0))
+    check(ccall((:agb_get_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{AgbSizes}), h[], sz), h[])
+    nrow = Int(sz[].nrow)
+    b = Batch(h[], collect(probs), n, m, p, N, nrow, zeros(n, B), zeros(n + m, N, B), zeros(n, N - 1, p, B),
+              zeros(n + m, N, B), zeros(n, N - 1, p, B), zeros(nrow, N - 1, B), zeros(nrow, N - 1, B), zeros(NSTATS, B), zeros(Cint, B))
+    # page-lock the staging arrays so that agb_solve_from_host's chunked copy/solve pipeline overlaps (CUDA.jl: Mem.register;
+    # without CUDA.jl the copies still work, just without overlap)
+    finalizer(close, b)
+    return b
+end
+
+function Base.close(b::Batch)
+    b.h == C_NULL && return
+    ccall((:agb_destroy, LIB), Cvoid, (Ptr{Cvoid},), b.h); b.h = C_NULL
+    return nothing
+end
+
+"""
+    newton_solve!(batch::Batch)  ->  nothing
+
+One call of the hot path (`agb_solve_from_host`: x0 + initial iterate in, trajectories / duals / multipliers / stats out,
+copies pipelined with the solve in chunks) for every problem of the batch; mutates each `prob` like Algames.newton_solve!.
+Returns `nothing` like the reference; per-instance outcomes are in `batch.status`.
+"""
+function newton_solve!(b::Batch)
+    probs = b.probs; opts = probs[1].opts; n, m, p, N = b.n, b.m, b.p, b.N
+    for (k, q) in enumerate(probs)
+        Algames.Random.seed!(q.opts.seed)                  # Julia's RNG semantics for the initial iterate (solver_methods.jl:12-15)
+        init_traj!(q.pdtraj; x0=q.x0, f=q.opts.f_init, amplitude=q.opts.amplitude_init, s=q.opts.shift)
+        b.x0[:, k] .= q.x0
+        for t in 1:N; b.Z0[:, t, k] .= q.pdtraj.pr[t].z; end
+        for i in 1:p, t in 1:N-1; b.L0[:, t, i, k] .= q.pdtraj.du[i][t]; end
+    end
+    if b.nrow > 0 && !opts.dual_reset                       # warm start: the convals' λ, μ go in through agb_set_initial
+        for (k, q) in enumerate(probs); gather_multipliers!(view(b.conλ, :, :, k), view(b.conμ, :, :, k), q); end
+        check(ccall((:agb_set_initial, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            b.h, C_NULL, C_NULL, b.conλ, b.conμ), b.h)
+    end
+    o = Ref(AgbOptions(opts))
+    check(ccall((:agb_solve_from_host, LIB), Cint,
+        (Ptr{Cvoid}, Ref{AgbOptions}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        b.h, o, b.x0, b.Z0, b.L0, b.Z, b.L, b.nrow > 0 ? pointer(b.conλ) : C_NULL, b.nrow > 0 ? pointer(b.conμ) : C_NULL, b.stats, b.status), b.h)
+    scatter_results!(b)
+    return nothing
+end
+
+"Per-knot violation vectors of the resident iterate (agb_violations; struct/violations.jl `.vio`)."
+function violations(b::Batch)
+    B = length(b.probs); N = b.N
+    dyn = zeros(N - 1, B); con = zeros(N - 1, B); sta = zeros(N, B); opt = zeros(N, B)
+    check(ccall((:agb_violations, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), b.h, dyn, con, sta, opt), b.h)
+    return dyn, con, sta, opt
+end
+
+function scatter_results!(b::Batch)
+    n, m, p, N = b.n, b.m, b.p, b.N
+    dyn, con, sta, opt = violations(b)
+    for (k, q) in enumerate(b.probs)
+        for t in 1:N
+            Algames.RobotDynamics.set_state!(q.pdtraj.pr[t], SVector{n}(b.Z[1:n, t, k]))
+            t < N && Algames.RobotDynamics.set_control!(q.pdtraj.pr[t], SVector{m}(b.Z[n+1:n+m, t, k]))
+        end
+        for i in 1:p, t in 1:N-1; q.pdtraj.du[i][t] = SVector{n}(b.L[:, t, i, k]); end
+        b.nrow > 0 && scatter_multipliers!(q, view(b.conλ, :, :, k), view(b.conμ, :, :, k))
+        evaluate!(q.game_con, q.pdtraj.pr); residual!(q)
+        reset!(q.stats)
+        dv = DynamicsViolation(N); dv.vio .= dyn[:, k]; dv.max = b.stats[2, k]
+        cv = ControlViolation(N); cv.vio .= con[:, k]; cv.max = b.stats[3, k]
+        sv = StateViolation(N); sv.vio .= sta[:, k]; sv.max = b.stats[4, k]
+        ov = OptimalityViolation(N); ov.vio .= opt[:, k]; ov.max = b.stats[5, k]
+        record!(q.stats, 0.0, b.stats[1, k], b.stats[6, k], dv, cv, sv, ov, Int(b.stats[8, k]))   # the final record (:63)
+    end
+end
+
+"""
+    mpc_step!(batch::Batch; disturbance=nothing)
+
+One receding-horizon step on the device (`agb_mpc_advance`): x0 ← x₂ of the resident solution (+ disturbance n×B), the
+solution is shifted by one knot as the warm start (Options.shift = 1, primal_dual_traj.jl:34-41), then re-solved with the
+multipliers carried (dual_reset = false).  Only x₂…, stats and status come back to the host.
+"""
+function mpc_step!(b::Batch; disturbance::Union{Nothing,Matrix{Float64}}=nothing)
+    check(ccall((:agb_mpc_advance, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        b.h, 1, disturbance === nothing ? C_NULL : pointer(disturbance), C_NULL, C_NULL), b.h)
+    o = AgbOptions(b.probs[1].opts)
+    warm = Ref(AgbOptions(o.reg_0, o.regularize, o.alpha_decrease, o.beta, o.ls_iter, o.delta_min, o.rho_0, o.rho_increase, o.rho_max,
+        o.lambda_max, o.alpha_dual, o.alphax_dual, o.active_set_tolerance, o.eps_dyn, o.eps_sta, o.eps_con, o.eps_opt, o.outer_iter, o.inner_iter, Cint(0)))
+    check(ccall((:agb_newton_solve_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ref{AgbOptions}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        b.h, warm, b.Z, C_NULL, C_NULL, C_NULL, b.stats, b.status), b.h)
+    return nothing
+end
+
+"""
+    ShardedBatch(probs; devices=nothing)
+
+Single-process multi-GPU form (agb_create_sharded): the problems are split contiguously over the visible GPUs, every shard
+is solved by its own handle with no communication, and `allgather!(sb)` pushes every shard's result slab into every GPU's
+gather buffer over NVLink peer memory (the path's single collective, SURVEY §8e).
+"""
+mutable struct ShardedBatch
+    handles::Vector{Ptr{Cvoid}}
+    shards::Vector{Batch}
+end
+
+function allgather!(hs::Vector{Ptr{Cvoid}})
+    for h in hs; check(ccall((:agb_allgather, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h, C_NULL), h); end
+    for h in hs; check(ccall((:agb_allgather_wait, LIB), Cint, (Ptr{Cvoid},), h), h); end
+    return nothing
+end
+
+"""
+    newton_solve!(probs::AbstractVector{<:GameProblem}; device=0)  ->  nothing
+
+Batched replacement of `Algames.newton_solve!` (src/problem/solver_methods.jl:5-65) for a one-off batch: builds a `Batch`,
+solves, releases it.  All problems must share the model, sizes, constraint schema and Options of `probs[1]`; x0 and the LQR
+weights/targets may differ per instance.  In a loop (MPC, Monte-Carlo sweeps) create the `Batch` once instead.
+C arrays are row-major: a Julia `Array{Float64}` with reversed dims has exactly the layout the ABI expects.
+"""
+function newton_solve!(probs::AbstractVector{<:GameProblem}; device::Integer=0)
+    b = Batch(probs; device=device)
     try
-        x0 = Array{Float64}(undef, n, B); xf = similar(x0); Q = similar(x0)
-        R = Array{Float64}(undef, m, B); uf = similar(R)
-        Z0 = Array{Float64}(undef, n + m, N, B); L0 = Array{Float64}(undef, n, N - 1, p, B)
-        for (b, q) in enumerate(probs)
-            # host keeps Julia's RNG semantics for the initial iterate (solver_methods.jl:12-15)
-            Algames.Random.seed!(q.opts.seed)
-            init_traj!(q.pdtraj; x0=q.x0, f=q.opts.f_init, amplitude=q.opts.amplitude_init, s=q.opts.shift)
-            x0[:, b] .= q.x0
-            Q[:, b], R[:, b], xf[:, b], uf[:, b] = joint_lqr(q.game_obj, q.model)
-            for k in 1:N; Z0[:, k, b] .= q.pdtraj.pr[k].z; end
-            for i in 1:p, k in 1:N-1; L0[:, k, i, b] .= q.pdtraj.du[i][k]; end
+        xf = zeros(b.n, length(probs)); Q = similar(xf); R = zeros(b.m, length(probs)); uf = similar(R)
+        for (k, q) in enumerate(probs)
+            Q[:, k], R[:, k], xf[:, k], uf[:, k] = joint_lqr(q.game_obj, q.model)
         end
         check(ccall((:agb_set_instance_params, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            h[], x0, xf, Q, R, uf), h[])
-        sz = Ref(AgbSizes(0, 0, 0, 0, 0, 0, 0, 0))
-        check(ccall((:agb_get_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{AgbSizes}), h[], sz), h[])
-        nrow = Int(sz[].nrow)
-        conλ = Array{Float64}(undef, nrow, N - 1, B); conμ = similar(conλ)     # [B][N-1][nrow] in C order
-        warm = nrow > 0 && !opts.dual_reset            # dual_reset = false keeps the convals' λ, μ (solver_methods.jl:25)
-        if warm
-            for (b, q) in enumerate(probs); gather_multipliers!(view(conλ, :, :, b), view(conμ, :, :, b), q); end
-        end
-        GC.@preserve conλ conμ check(ccall((:agb_set_initial, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            h[], Z0, L0, warm ? pointer(conλ) : C_NULL, warm ? pointer(conμ) : C_NULL), h[])
-        Z = similar(Z0); L = similar(L0); stats = Array{Float64}(undef, NSTATS, B); status = Vector{Cint}(undef, B)
-        # one log entry per record!(stats, …) of the reference loop (statistics.jl:44-57)
-        maxrec = opts.outer_iter * opts.inner_iter + 1
-        check(ccall((:agb_set_history, LIB), Cint, (Ptr{Cvoid}, Cint), h[], maxrec), h[])
-        hist = Array{Float64}(undef, 8, maxrec, B); nrec = Vector{Cint}(undef, B)
-        o = Ref(AgbOptions(opts))
-        GC.@preserve Z L conλ conμ stats status hist nrec begin
-            check(ccall((:agb_newton_solve_batch, LIB), Cint,
-                (Ptr{Cvoid}, Ref{AgbOptions}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
-                h[], o, Z, L, nrow > 0 ? pointer(conλ) : C_NULL, nrow > 0 ? pointer(conμ) : C_NULL, stats, status), h[])
-            check(ccall((:agb_get_history, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cint}), h[], hist, nrec), h[])
-        end
-        for (b, q) in enumerate(probs)
-            for k in 1:N
-                Algames.RobotDynamics.set_state!(q.pdtraj.pr[k], SVector{n}(Z[1:n, k, b]))
-                k < N && Algames.RobotDynamics.set_control!(q.pdtraj.pr[k], SVector{m}(Z[n+1:n+m, k, b]))
-            end
-            for i in 1:p, k in 1:N-1; q.pdtraj.du[i][k] = SVector{n}(L[:, k, i, b]); end
-            scatter_multipliers!(q, view(conλ, :, :, b), view(conμ, :, :, b))
-            evaluate!(q.game_con, q.pdtraj.pr)             # conval.vals at the returned iterate
-            residual!(q)                                   # prob.core.res, as the reference leaves it
-            reset!(q.stats)                                # the device log replays every record! of the solve
-            for r in 1:min(nrec[b], maxrec)
-                k, res, dyn, con, sta, opt, Δ = hist[1:7, r, b]
-                dv = DynamicsViolation(N); dv.max = dyn        # violations.jl:11-16 (per-knot vectors stay zero)
-                cv = ControlViolation(N); cv.max = con
-                sv = StateViolation(N); sv.max = sta
-                ov = OptimalityViolation(N); ov.max = opt
-                record!(q.stats, 0.0, res, Δ, dv, cv, sv, ov, Int(k))      # statistics.jl:30-42
-            end
-        end
-        return status
+            b.h, C_NULL, xf, Q, R, uf), b.h)
+        newton_solve!(b)
     finally
-        ccall((:agb_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+        close(b)
     end
+    return nothing
 end
 
 end # module

@@ -11,7 +11,7 @@ rows = []
 for item in todo:
     cfg, B = item.split(":"); B = int(B)
     model, N, dt, obj, con, opts, x0, xf = ab.workloads.CONFIGS[cfg](batch=B)
-    gb = ab.GameBatch(model, N, dt, obj, con, B, device=0)
+    gb = ab.GameBatch(model, N, dt, obj, con, B, device=0, lib_path=os.environ.get("AGB_LIB"))
     gb.set_instance_params(x0=x0, xf=xf)
     gb.random_initial(opts.amplitude_init, opts.seed)
     o = ab.Options(**{**opts.to_dict(), "dual_reset": True})
