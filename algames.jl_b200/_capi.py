@@ -9,8 +9,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST, IPC_BYTES, MAX_RANKS = 4, 16, 8, 8, 8, 10, 10, 64, 64
-MODEL_IDS = {"double_integrator": 0, "unicycle": 1, "bicycle": 2}
+MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST, IPC_BYTES, MAX_RANKS = 4, 48, 16, 8, 8, 10, 10, 64, 64
+MODEL_IDS = {"double_integrator": 0, "unicycle": 1, "bicycle": 2, "quadrotor": 3}
+SOLVER_AUTO, SOLVER_BAND = 0, 1
 # per-instance status (include/algames_b200.h): 1-3 = not converged (how the last inner loop ended), 4-5 = numerical failure
 CONVERGED, MAX_OUTER, LINE_SEARCH_FAILED, STALLED, SINGULAR, NONFINITE = range(6)
 STATUS_NAMES = {0: "converged", 1: "max_outer", 2: "line_search_failed", 3: "stalled", 4: "singular", 5: "nonfinite"}
@@ -36,6 +37,10 @@ class ProblemDesc(C.Structure):
         ("n_circles", C.c_int * MAX_P),
         ("circles", ((C.c_double * 3) * MAX_CIRCLES) * MAX_P),
         ("x_max_con", (C.c_int * MAX_N) * MAX_P), ("x_min_con", (C.c_int * MAX_N) * MAX_P),
+        ("quad_mass", C.c_double), ("spherical_collision", C.c_int),
+        ("n_walls3d", C.c_int * MAX_P), ("walls3d", ((C.c_double * 12) * MAX_WALLS) * MAX_P),
+        ("n_cylinders", C.c_int * MAX_P), ("cylinders", ((C.c_double * 6) * MAX_WALLS) * MAX_P),
+        ("solver", C.c_int),
     ]
 
 
@@ -126,6 +131,7 @@ def abi_layout():
     off = lambda st, f: getattr(st, f).offset
     return [C.sizeof(ProblemDesc), off(ProblemDesc, "dt"), off(ProblemDesc, "Q"), off(ProblemDesc, "col_radius"),
             off(ProblemDesc, "has_state_bound"), off(ProblemDesc, "walls"), off(ProblemDesc, "circles"), off(ProblemDesc, "x_max_con"),
+            off(ProblemDesc, "quad_mass"), off(ProblemDesc, "solver"),
             C.sizeof(OptionsC), off(OptionsC, "alphax_dual"), off(OptionsC, "eps_dyn"), off(OptionsC, "dual_reset"),
             C.sizeof(IBROptionsC), off(IBROptionsC, "delta_min"), C.sizeof(Sizes), C.sizeof(DeviceView),
             MAX_P, MAX_N, MAX_M, MAX_WALLS, MAX_CIRCLES, NSTATS, NHIST, IPC_BYTES]

@@ -11,6 +11,12 @@
 
 using namespace agb;
 
+namespace agb {   // agb_band.cu
+void launch_band_solve(const DevDesc* dd, const agb_options& o, const Buffers& g, int inst0, int batch, int only_status, int grid, cudaStream_t st);
+void launch_band_op(const DevDesc* dd, const agb_options& o, const Buffers& g, const OpArgs& a, int batch, int grid, cudaStream_t st);
+size_t band_scratch_doubles(const DevDesc& d);
+}
+
 // internal stage-major layout → reference row ("vertical", mode 0) or column ("horizontal", mode 1) order
 __global__ void agb_export_kernel(const double* __restrict__ in, double* __restrict__ out, int batch, int P, int K, int mode) {
   const int n = 4 * P, m = 2 * P, b = P * n + m + n, Sz = K * b;
@@ -38,8 +44,8 @@ __global__ void agb_export_kernel(const double* __restrict__ in, double* __restr
 // the tail comes from the fresh arrays (zeros if null).
 __global__ void agb_shift_kernel(const double* __restrict__ Z, const double* __restrict__ L, const double* __restrict__ Zf,
                                  const double* __restrict__ Lf, double* __restrict__ Z0, double* __restrict__ L0,
-                                 int batch, int P, int N, int shift) {
-  const int n = 4 * P, m = 2 * P, K = N - 1, zs = N * (n + m), ls = P * K * n;
+                                 int batch, int P, int n, int m, int N, int shift) {
+  const int K = N - 1, zs = N * (n + m), ls = P * K * n;
   const size_t total = (size_t)batch * (zs + ls);
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const size_t inst = t / (zs + ls);
@@ -58,8 +64,7 @@ __global__ void agb_shift_kernel(const double* __restrict__ Z, const double* __r
 
 // x0 <- x_{1+shift} of the resident solution (+ disturbance)
 __global__ void agb_advance_kernel(const double* __restrict__ Z, const double* __restrict__ dist, double* __restrict__ x0,
-                                   int batch, int P, int N, int shift) {
-  const int n = 4 * P, m = 2 * P;
+                                   int batch, int n, int m, int N, int shift) {
   const size_t total = (size_t)batch * n;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const size_t inst = t / n; const int a = (int)(t % n);
@@ -110,6 +115,12 @@ struct agb_handle {
   double* hist = nullptr; int* hist_count = nullptr; int hist_max = 0;   // agb_set_history
   double* Hpg = nullptr; int hpg_stride = 0;                              // big layout: pair / self Hessian blocks
   double* results = nullptr; size_t results_doubles = 0;   // owns Z, L, stats, status
+  // band solver (agb_band.cuh): scratch slots (one per resident CTA); conlam0 / conmu0 keep the multipliers a warm-started
+  // solve began with, for the fallback re-solve of AGB_SINGULAR instances
+  double* band = nullptr; size_t band_stride = 0; int band_slots = 0;
+  double *conlam0 = nullptr, *conmu0 = nullptr;
+  bool fallback = true;
+  int force_singular = 0;
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
   double* stage3 = nullptr;                            // disturbance staging of agb_mpc_advance
@@ -143,12 +154,22 @@ static int fail(agb_handle* h, int code, const std::string& msg) {
 static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* why) {
   memset(o, 0, sizeof(*o));
   if (d->p < 1 || d->p > AGB_MAX_P) { *why = "p must be in 1..4"; return AGB_EINVAL; }
-  if (d->model < 0 || d->model > 2) { *why = "unknown model"; return AGB_EINVAL; }
+  if (d->model < 0 || d->model > 3) { *why = "unknown model"; return AGB_EINVAL; }
+  if (d->solver != AGB_SOLVER_AUTO && d->solver != AGB_SOLVER_BAND) { *why = "unknown solver"; return AGB_EINVAL; }
   if (d->model == AGB_MODEL_DOUBLE_INTEGRATOR && d->d != 2) { *why = "DoubleIntegratorGame: only d = 2 is supported"; return AGB_EUNSUPPORTED; }
   if (d->N < 2) { *why = "N must be >= 2"; return AGB_EINVAL; }
   if (!(d->dt > 0)) { *why = "dt must be positive"; return AGB_EINVAL; }
-  const int p = d->p, n = 4 * p, m = 2 * p;
+  const int ni = d->model == AGB_MODEL_QUADROTOR ? 12 : 4, mi = d->model == AGB_MODEL_QUADROTOR ? 4 : 2;
+  const int p = d->p, n = ni * p, m = mi * p;
+  o->ni = ni; o->mi = mi;
   o->model = d->model; o->p = p; o->n = n; o->m = m; o->N = d->N; o->K = d->N - 1;
+  o->quad_mass = d->quad_mass; o->spherical = d->spherical_collision ? 1 : 0;
+  if (d->model == AGB_MODEL_QUADROTOR && !(d->quad_mass > 0)) { *why = "QuadrotorGame: mass must be positive"; return AGB_EINVAL; }
+  o->use_band = (d->model == AGB_MODEL_QUADROTOR || d->spherical_collision || d->solver == AGB_SOLVER_BAND) ? 1 : 0;
+  for (int i = 0; i < p; i++) if (d->n_walls3d[i] > 0 || d->n_cylinders[i] > 0) o->use_band = 1;
+  o->kl = (2 * n - 1 > n + m) ? 2 * n - 1 : n + m;
+  o->ku = (p * n + n - 1 > p * n + m) ? p * n + n - 1 : p * n + m;
+  o->wd = 2 * o->kl + o->ku + 1;
   o->b = p * n + m + n; o->S = o->K * o->b;
   o->dt = d->dt; o->lf = d->lf; o->lr = d->lr;
   if (d->model == AGB_MODEL_BICYCLE && !(d->lr > 0)) { *why = "BicycleGame: lr must be positive"; return AGB_EINVAL; }
@@ -178,6 +199,11 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
         const bool same = !(fmx && fmn) || d->x_max_con[i][a] == d->x_min_con[i][a];
         if (same && !(d->x_max[i][a] >= d->x_min[i][a])) { *why = "Upper bounds must be greater than or equal to lower bounds"; return AGB_EINVAL; }
       }
+      o->sb_ncon[i] = ncon;
+      for (int a = 0; a < n; a++) {
+        o->has_x_max[i][a] = isfinite(d->x_max[i][a]) ? 1 : 0; o->has_x_min[i][a] = isfinite(d->x_min[i][a]) ? 1 : 0;
+        o->x_max_con[i][a] = d->x_max_con[i][a]; o->x_min_con[i][a] = d->x_min_con[i][a];
+      }
       const int row0 = row;
       for (int g = 0; g < ncon; g++) {           // conval order, each: finite x_max rows then finite x_min rows
         for (int a = 0; a < n; a++) if (isfinite(d->x_max[i][a]) && d->x_max_con[i][a] == g) { o->x_max[i][a] = d->x_max[i][a]; o->sbmax_row[i][a] = row++; }
@@ -192,6 +218,18 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     for (int q = 0; q < d->n_walls[i]; q++) for (int e = 0; e < 6; e++) o->walls[i][q][e] = d->walls[i][q][e];
     o->n_circles[i] = d->n_circles[i]; o->circle_row[i] = row; row += d->n_circles[i];
     for (int q = 0; q < d->n_circles[i]; q++) for (int e = 0; e < 3; e++) o->circles[i][q][e] = d->circles[i][q][e];
+    if (d->n_walls3d[i] < 0 || d->n_walls3d[i] > AGB_MAX_WALLS || d->n_cylinders[i] < 0 || d->n_cylinders[i] > AGB_MAX_WALLS) {
+      *why = "too many 3-D walls / cylinders"; return AGB_EINVAL;
+    }
+    if ((d->n_walls3d[i] > 0 || d->n_cylinders[i] > 0) && ni < 3) { *why = "3-D walls and cylinders need three position components"; return AGB_EINVAL; }
+    o->n_walls3d[i] = d->n_walls3d[i]; o->wall3d_row[i] = row; row += d->n_walls3d[i];
+    for (int q = 0; q < d->n_walls3d[i]; q++) for (int e = 0; e < 12; e++) o->walls3d[i][q][e] = d->walls3d[i][q][e];
+    o->n_cyl[i] = d->n_cylinders[i]; o->cyl_row[i] = row; row += d->n_cylinders[i];
+    for (int q = 0; q < d->n_cylinders[i]; q++) {
+      for (int e = 0; e < 6; e++) o->cyl[i][q][e] = d->cylinders[i][q][e];
+      const int ax = (int)d->cylinders[i][q][3];
+      if (ax < 0 || ax > 2 || (double)ax != d->cylinders[i][q][3]) { *why = "cylinder axis must be 0, 1 or 2"; return AGB_EINVAL; }
+    }
   }
   for (int i = p; i <= AGB_MAX_P; i++) o->srow_off[i] = row;
   o->nrow_state = row;
@@ -243,6 +281,7 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
     o->smem_doubles = off;
     o->big = big ? 1 : 0;
   };
+  if (o->use_band) { o->smem_doubles = 0; o->big = 0; return AGB_OK; }     // no structured-kernel form: band solver only
   layout(false);
   // layout choice (DevDesc::big: 0 small / big storage with 1: 2, 2: 4, 3: 3 CTAs per SM):
   //   small if it gives 4 CTAs per SM; else big storage with as many CTAs per SM as its footprint allows (4 at 128
@@ -308,7 +347,7 @@ void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count, h->Hpg};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count, h->Hpg, h->band, h->conlam0, h->conmu0};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int r = 0; r < h->nranks; r++) if (h->peer_ipc_opened[r]) cudaIpcCloseMemHandle(h->peer_gather[r]);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -350,14 +389,14 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
   CKC(cudaSetDevice(device));
   int max_smem = 0;
   CKC(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  if ((int)h->smem_bytes > max_smem) {
+  if (!t.use_band && (int)h->smem_bytes > max_smem) {
     char buf[160];
     snprintf(buf, sizeof buf, "instance needs %zu B of shared memory per CTA, device allows %d B", h->smem_bytes, max_smem);
     g_create_err = buf; agb_destroy(h); return AGB_EUNSUPPORTED;
   }
   // the opt-in limit is a per-kernel attribute shared by every handle using the same template instance: always raise it to
   // the device maximum, so a later handle with a smaller footprint can never lower it under an earlier one's launches
-  CKC(agb::set_attr(t.p, t.big, t.model, (size_t)max_smem));
+  if (!t.use_band) CKC(agb::set_attr(t.p, t.big, t.model, (size_t)max_smem));
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
@@ -377,6 +416,20 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
   CK(alloc_d(h, &h->conlam, B * K * t.nrow)); CK(alloc_d(h, &h->conmu, B * K * t.nrow));
   CK(alloc_d(h, &h->D, B * t.S)); CK(alloc_d(h, &h->KUg, B * K * m * (n + 2)));       // rows padded to n+2 (Inst::n1p)
   if (t.big) { h->hpg_stride = N * t.npairs * 3 + N * p * 3; CK(alloc_d(h, &h->Hpg, B * (size_t)h->hpg_stride)); }
+  {  // band solver scratch: one slot per resident CTA — the whole device for band-only schemas, a few slots for the fallback
+    const char* e = getenv("AGB_BAND_FALLBACK");         // "0": AGB_SINGULAR instances of the structured kernels are returned as they are
+    h->fallback = !(e && e[0] == '0');
+    if (const char* f = getenv("AGB_TEST_FORCE_SINGULAR")) h->force_singular = atoi(f);
+    if (t.use_band || h->fallback) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      const int want = t.use_band ? 2 * sms : 32;
+      h->band_slots = batch < want ? batch : want;
+      h->band_stride = (agb::band_scratch_doubles(t) + 1) & ~(size_t)1;
+      CK(alloc_d(h, &h->band, (size_t)h->band_slots * h->band_stride));
+      if (!t.use_band) { CK(alloc_d(h, &h->conlam0, B * K * t.nrow)); CK(alloc_d(h, &h->conmu0, B * K * t.nrow)); }
+    }
+  }
   // descriptor defaults broadcast to every instance; μ starts at 1 (Altro ALConVal default)
   double tmp[2 * AGB_MAX_N + 2 * AGB_MAX_M];
   double* dtmp = nullptr;
@@ -412,6 +465,8 @@ static Buffers buffers_of(agb_handle* h) {
   g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.KUg = h->KUg; g.stats = h->stats; g.status = h->status;
   g.hist = h->hist; g.hist_count = h->hist_count; g.hist_max = h->hist_max;
   g.Hpg = h->Hpg; g.hpg_stride = h->hpg_stride;
+  g.band = h->band; g.band_stride = h->band_stride; g.band_slots = h->band_slots; g.conlam0 = nullptr; g.conmu0 = nullptr;
+  g.force_singular = h->force_singular;
   return g;
 }
 
@@ -475,7 +530,7 @@ int agb_shift_initial(agb_handle* h, int s, const double* Zfresh, const double* 
   double *zf = nullptr, *lf = nullptr;
   if (Zfresh) { AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, B * zs * sizeof(double))); zf = h->stage; AGB_TRY(h2d(h, zf, Zfresh, B * zs)); }
   if (Lfresh) { AGB_TRY(ensure_stage(h, &h->stage2, &h->stage2_bytes, B * ls * sizeof(double))); lf = h->stage2; AGB_TRY(h2d(h, lf, Lfresh, B * ls)); }
-  AGB_LAUNCH(agb_shift_kernel, grid_for(B * (zs + ls)), 256, 0, h->stream, h->Z, h->L, zf, lf, h->Z0, h->L0, h->batch, h->hd.p, h->hd.N, s);
+  AGB_LAUNCH(agb_shift_kernel, grid_for(B * (zs + ls)), 256, 0, h->stream, h->Z, h->L, zf, lf, h->Z0, h->L0, h->batch, h->hd.p, h->hd.n, h->hd.m, h->hd.N, s);
   h->launches++;
   AGB_CUDA(h, cudaMemcpyAsync(h->Z, h->Z0, B * zs * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   AGB_CUDA(h, cudaMemcpyAsync(h->L, h->L0, B * ls * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -494,7 +549,7 @@ int agb_mpc_advance(agb_handle* h, int s, const double* disturbance, const doubl
     dd = h->stage3;
     AGB_TRY(h2d(h, dd, disturbance, B * n));
   }
-  AGB_LAUNCH(agb_advance_kernel, grid_for(B * n), 256, 0, h->stream, h->Z, dd, h->x0, h->batch, h->hd.p, h->hd.N, s);
+  AGB_LAUNCH(agb_advance_kernel, grid_for(B * n), 256, 0, h->stream, h->Z, dd, h->x0, h->batch, h->hd.n, h->hd.m, h->hd.N, s);
   h->launches++;
   return agb_shift_initial(h, s, Zfresh, Lfresh);
 }
@@ -506,8 +561,8 @@ int agb_mpc_advance_async(agb_handle* h, int s, const double* disturbance_dev) {
   if (!h || s < 1 || s >= h->hd.N) return fail(h, AGB_EINVAL, "shift must be in 1..N-1");
   AGB_CUDA(h, cudaSetDevice(h->device));
   const size_t B = h->batch, n = h->hd.n, zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n;
-  AGB_LAUNCH(agb_advance_kernel, grid_for(B * n), 256, 0, h->stream, h->Z, disturbance_dev, h->x0, h->batch, h->hd.p, h->hd.N, s);
-  AGB_LAUNCH(agb_shift_kernel, grid_for(B * (zs + ls)), 256, 0, h->stream, h->Z, h->L, (const double*)nullptr, (const double*)nullptr, h->Z0, h->L0, h->batch, h->hd.p, h->hd.N, s);
+  AGB_LAUNCH(agb_advance_kernel, grid_for(B * n), 256, 0, h->stream, h->Z, disturbance_dev, h->x0, h->batch, h->hd.n, h->hd.m, h->hd.N, s);
+  AGB_LAUNCH(agb_shift_kernel, grid_for(B * (zs + ls)), 256, 0, h->stream, h->Z, h->L, (const double*)nullptr, (const double*)nullptr, h->Z0, h->L0, h->batch, h->hd.p, h->hd.n, h->hd.m, h->hd.N, s);
   h->launches += 2;
   AGB_CUDA(h, cudaMemcpyAsync(h->Z, h->Z0, B * zs * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   AGB_CUDA(h, cudaMemcpyAsync(h->L, h->L0, B * ls * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -527,6 +582,16 @@ int agb_join_stream(agb_handle* h, void* stream) {
 static int launch_op(agb_handle* h, const agb_options* o, const OpArgs& a) {
   agb_options od;
   if (o) od = *o; else agb_default_options(&od);
+  if (h->hd.use_band) {
+    if (a.player >= 0 || !(a.op == OP_ROLLOUT || a.op == OP_RESIDUAL || a.op == OP_JAC_DENSE || a.op == OP_KKT_SOLVE || a.op == OP_EVAL_CON))
+      return fail(h, AGB_EUNSUPPORTED, "this entry point is not available for schemas solved by the band solver (QuadrotorGame, 3-D constraints, AGB_SOLVER_BAND): "
+                                       "use agb_rollout / agb_residual / agb_residual_jacobian_dense / agb_kkt_solve / agb_evaluate_constraints and the solves");
+    const int grid = h->batch < h->band_slots ? h->batch : h->band_slots;
+    agb::launch_band_op(h->dd, od, buffers_of(h), a, h->batch, grid, h->stream);
+    h->launches++;
+    AGB_CUDA(h, cudaGetLastError());
+    return AGB_OK;
+  }
   LaunchArgs L;
   L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = h->stream; L.dd = h->dd; L.o = od;
   memset(&L.io, 0, sizeof L.io);
@@ -566,7 +631,7 @@ int agb_residual(agb_handle* h, double reg_x, double reg_u, double alpha, double
   OpArgs a = op_args(OP_RESIDUAL);
   a.reg_x = reg_x; a.reg_u = reg_u; a.alpha = alpha; a.out0 = h->stage; a.out1 = h->stage + B * S;
   AGB_TRY(launch_op(h, nullptr, a));
-  if (res_out) AGB_TRY(export_to_host(h, h->stage, res_out, 0));
+  if (res_out) { if (h->hd.use_band) AGB_TRY(d2h(h, res_out, h->stage, B * S)); else AGB_TRY(export_to_host(h, h->stage, res_out, 0)); }
   AGB_TRY(d2h(h, norms_out, h->stage + B * S, B * 5));
   return finish(h);
 }
@@ -591,6 +656,14 @@ int agb_kkt_solve(agb_handle* h, double reg_x, double reg_u, double* dtraj_out) 
   AGB_CUDA(h, cudaSetDevice(h->device));
   OpArgs a = op_args(OP_KKT_SOLVE);
   a.reg_x = reg_x; a.reg_u = reg_u;
+  if (h->hd.use_band) {                              // the band solver writes the step in the reference's column order itself
+    const size_t B = h->batch, S = h->hd.S;
+    AGB_TRY(ensure_stage(h, &h->stage2, &h->stage2_bytes, B * S * sizeof(double)));
+    a.out0 = h->stage2;
+    AGB_TRY(launch_op(h, nullptr, a));
+    AGB_TRY(d2h(h, dtraj_out, h->stage2, B * S));
+    return finish(h);
+  }
   AGB_TRY(launch_op(h, nullptr, a));
   if (dtraj_out) AGB_TRY(export_to_host(h, h->D, dtraj_out, 1));
   return finish(h);
@@ -673,15 +746,44 @@ int agb_debug_gain_solve(agb_handle* h, const double* aug, double* aug_out, int*
   return finish(h);
 }
 
-static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
+// newton_solve! of instances [lo, hi) on stream st: the band solver for band-only schemas; otherwise the structured kernel,
+// followed (fallback) by a band-solver launch that re-solves, from the same initial iterate, the instances it left
+// AGB_SINGULAR.  `slot0 / nslots`: the band scratch slots this launch may use (concurrent chunks get disjoint slots).
+static int launch_solve_range(agb_handle* h, const agb_options* o, cudaStream_t st, int lo, int hi, int slot0, int nslots) {
+  Buffers g = buffers_of(h);
+  if (h->hd.use_band) {
+    const int grid = (hi - lo) < nslots ? (hi - lo) : nslots;
+    g.band = h->band + (size_t)slot0 * h->band_stride; g.band_slots = nslots;
+    agb::launch_band_solve(h->dd, *o, g, lo, hi, -1, grid, st);
+    h->launches++;
+    AGB_CUDA(h, cudaGetLastError());
+    return AGB_OK;
+  }
+  const size_t cs = (size_t)h->hd.K * h->hd.nrow;
+  const bool fb = h->fallback && h->band != nullptr;
+  if (fb && !o->dual_reset && cs)  {                        // warm start: keep what the solve began with for the fallback
+    AGB_CUDA(h, cudaMemcpyAsync(h->conlam0 + lo * cs, h->conlam + lo * cs, (size_t)(hi - lo) * cs * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    AGB_CUDA(h, cudaMemcpyAsync(h->conmu0 + lo * cs, h->conmu + lo * cs, (size_t)(hi - lo) * cs * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
   LaunchArgs L;
-  L.model = h->hd.model; L.grid = h->batch; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
+  L.model = h->hd.model; L.grid = hi - lo; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
   memset(&L.io, 0, sizeof L.io);
-  L.g = buffers_of(h); memset(&L.a, 0, sizeof L.a); L.batch = h->batch; L.inst0 = 0;
+  L.g = g; memset(&L.a, 0, sizeof L.a); L.batch = hi; L.inst0 = lo;
   agb::launch_solve(h->hd.p, h->hd.big, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
+  if (fb) {
+    g.band = h->band + (size_t)slot0 * h->band_stride; g.band_slots = nslots;
+    if (!o->dual_reset && cs) { g.conlam0 = h->conlam0; g.conmu0 = h->conmu0; }
+    const int grid = (hi - lo) < nslots ? (hi - lo) : nslots;
+    agb::launch_band_solve(h->dd, *o, g, lo, hi, AGB_SINGULAR, grid, st);
+    h->launches++;
+    AGB_CUDA(h, cudaGetLastError());
+  }
   return AGB_OK;
+}
+static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st) {
+  return launch_solve_range(h, o, st, 0, h->batch, 0, h->band_slots);
 }
 
 int agb_newton_solve_async(agb_handle* h, const agb_options* o, void* stream) {
@@ -721,6 +823,7 @@ int agb_newton_solve_batch(agb_handle* h, const agb_options* o, double* Z_out, d
 int agb_ibr_newton_solve_batch(agb_handle* h, const agb_options* o, const agb_ibr_options* io, double* Z_out, double* L_out,
                                double* conlam_out, double* conmu_out, double* stats_out, int* status_out) {
   if (!h || !o || !io) return AGB_EINVAL;
+  if (h->hd.use_band) return fail(h, AGB_EUNSUPPORTED, "iterative best response is not available for schemas solved by the band solver");
   if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1 || io->ibr_iter < 1)
     return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter, ibr_iter must be >= 1");
   unsigned seen = 0;
@@ -782,6 +885,7 @@ int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, c
     const int v = atoi(e);
     if (v >= 1 && v <= agb_handle::kMaxChunks) chunks = v < B ? v : B;
   }
+  if (h->band_slots > 0 && chunks > h->band_slots) chunks = h->band_slots;           // every chunk needs its own band scratch slot
   for (int c = 0; c < chunks; c++) {
     if (!h->chunk_stream[c]) AGB_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
     cudaStream_t st = h->chunk_stream[c];
@@ -790,13 +894,10 @@ int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, c
     AGB_CUDA(h, cudaMemcpyAsync(h->x0 + (size_t)lo * n, x0 + (size_t)lo * n, (size_t)cnt * n * sizeof(double), cudaMemcpyHostToDevice, st));
     AGB_CUDA(h, cudaMemcpyAsync(h->Z0 + lo * zs, Z0 + lo * zs, cnt * zs * sizeof(double), cudaMemcpyHostToDevice, st));
     AGB_CUDA(h, cudaMemcpyAsync(h->L0 + lo * ls, L0 + lo * ls, cnt * ls * sizeof(double), cudaMemcpyHostToDevice, st));
-    LaunchArgs L;
-    L.model = h->hd.model; L.grid = cnt; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
-    memset(&L.io, 0, sizeof L.io); memset(&L.a, 0, sizeof L.a);
-    L.g = buffers_of(h); L.batch = hi; L.inst0 = lo;
-    agb::launch_solve(h->hd.p, h->hd.big, L);
-    h->launches++;
-    AGB_CUDA(h, cudaGetLastError());
+    {
+      const int per = h->band_slots / chunks > 0 ? h->band_slots / chunks : 1;        // disjoint band scratch slots per chunk
+      AGB_TRY(launch_solve_range(h, o, st, lo, hi, (c * per) % (h->band_slots > 0 ? h->band_slots : 1), per));
+    }
     if (Z_out) AGB_CUDA(h, cudaMemcpyAsync(Z_out + lo * zs, h->Z + lo * zs, cnt * zs * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (L_out) AGB_CUDA(h, cudaMemcpyAsync(L_out + lo * ls, h->L + lo * ls, cnt * ls * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (conlam_out && cs) AGB_CUDA(h, cudaMemcpyAsync(conlam_out + lo * cs, h->conlam + lo * cs, cnt * cs * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -863,18 +964,19 @@ static void abi_words(int* w) {
   w[k++] = (int)sizeof(agb_problem_desc); w[k++] = (int)offsetof(agb_problem_desc, dt); w[k++] = (int)offsetof(agb_problem_desc, Q);
   w[k++] = (int)offsetof(agb_problem_desc, col_radius); w[k++] = (int)offsetof(agb_problem_desc, has_state_bound);
   w[k++] = (int)offsetof(agb_problem_desc, walls); w[k++] = (int)offsetof(agb_problem_desc, circles); w[k++] = (int)offsetof(agb_problem_desc, x_max_con);
+  w[k++] = (int)offsetof(agb_problem_desc, quad_mass); w[k++] = (int)offsetof(agb_problem_desc, solver);
   w[k++] = (int)sizeof(agb_options); w[k++] = (int)offsetof(agb_options, alphax_dual); w[k++] = (int)offsetof(agb_options, eps_dyn);
   w[k++] = (int)offsetof(agb_options, dual_reset);
   w[k++] = (int)sizeof(agb_ibr_options); w[k++] = (int)offsetof(agb_ibr_options, delta_min);
   w[k++] = (int)sizeof(agb_sizes); w[k++] = (int)sizeof(agb_device_view);
   w[k++] = AGB_MAX_P; w[k++] = AGB_MAX_N; w[k++] = AGB_MAX_M; w[k++] = AGB_MAX_WALLS; w[k++] = AGB_MAX_CIRCLES;
   w[k++] = AGB_NSTATS; w[k++] = AGB_NHIST; w[k++] = AGB_IPC_BYTES;
-  static_assert(AGB_ABI_WORDS == 24, "update abi_words");
+  static_assert(AGB_ABI_WORDS == 26, "update abi_words");
 }
 static const char* const kAbiNames[AGB_ABI_WORDS] = {
   "sizeof(agb_problem_desc)", "offsetof(agb_problem_desc, dt)", "offsetof(agb_problem_desc, Q)", "offsetof(agb_problem_desc, col_radius)",
   "offsetof(agb_problem_desc, has_state_bound)", "offsetof(agb_problem_desc, walls)", "offsetof(agb_problem_desc, circles)",
-  "offsetof(agb_problem_desc, x_max_con)", "sizeof(agb_options)", "offsetof(agb_options, alphax_dual)", "offsetof(agb_options, eps_dyn)",
+  "offsetof(agb_problem_desc, x_max_con)", "offsetof(agb_problem_desc, quad_mass)", "offsetof(agb_problem_desc, solver)", "sizeof(agb_options)", "offsetof(agb_options, alphax_dual)", "offsetof(agb_options, eps_dyn)",
   "offsetof(agb_options, dual_reset)", "sizeof(agb_ibr_options)", "offsetof(agb_ibr_options, delta_min)", "sizeof(agb_sizes)",
   "sizeof(agb_device_view)", "AGB_MAX_P", "AGB_MAX_N", "AGB_MAX_M", "AGB_MAX_WALLS", "AGB_MAX_CIRCLES", "AGB_NSTATS", "AGB_NHIST", "AGB_IPC_BYTES"};
 
@@ -884,7 +986,7 @@ int agb_abi_layout(int* layout_out, int count) {
   return AGB_OK;
 }
 int agb_abi_check(const int* layout, int count) {
-  if (!layout || count != AGB_ABI_WORDS) return fail(nullptr, AGB_EINVAL, "agb_abi_check: expected AGB_ABI_WORDS = 24 entries (binding built against another header?)");
+  if (!layout || count != AGB_ABI_WORDS) return fail(nullptr, AGB_EINVAL, "agb_abi_check: expected AGB_ABI_WORDS = 26 entries (binding built against another header?)");
   int mine[AGB_ABI_WORDS];
   abi_words(mine);
   for (int k = 0; k < AGB_ABI_WORDS; k++) {

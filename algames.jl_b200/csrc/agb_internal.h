@@ -24,7 +24,20 @@ constexpr int kMaxWarps = 8;
 // state comp c of player i -> c*p+i, control comp j of player i -> j*p+i.
 struct DevDesc {
   int model, p, n, m, N, K, b, S;      // K = N-1 stages, b = p*n+m+n rows per stage, S = K*b (problem_size.jl:22)
+  int ni, mi;                          // states / controls per player (4, 2; QuadrotorGame 12, 4)
+  int use_band;                        // 1: the schema has no structured-kernel form (band solver only)
   double dt, lf, lr;
+  double quad_mass;                    // QuadrotorGame
+  int spherical;                       // collision avoidance on three position components
+  int n_walls3d[AGB_MAX_P], wall3d_row[AGB_MAX_P];
+  double walls3d[AGB_MAX_P][AGB_MAX_WALLS][12];
+  int n_cyl[AGB_MAX_P], cyl_row[AGB_MAX_P];
+  double cyl[AGB_MAX_P][AGB_MAX_WALLS][6];
+  int sb_ncon[AGB_MAX_P];              // StateBound convals of player i (band solver: rows enumerated conval by conval)
+  int x_max_con[AGB_MAX_P][AGB_MAX_N], x_min_con[AGB_MAX_P][AGB_MAX_N];
+  int has_x_max[AGB_MAX_P][AGB_MAX_N], has_x_min[AGB_MAX_P][AGB_MAX_N];
+  // band solver: KKT band in time-major order, rows [dyn_s | opt u_s | opt x_{s+1}], columns [λ_s | u_s | x_{s+1}]
+  int kl, ku, wd;                      // lower / upper bandwidth, stored row width 2·kl + ku + 1 (room for the pivoting fill)
   // objective (objective.jl:84-100)
   int has_cc, npairs;
   int has_pairs, has_self, has_sb, has_cb;  // + any state bound; any control bound                  // any pair term (collision cost / avoidance); any wall / circle
@@ -74,6 +87,12 @@ struct Buffers {
   double* hist;       // [B][hist_max][AGB_NHIST] record!(stats, …) log, or nullptr
   int* hist_count;    // [B]
   int hist_max;
+  double* band;       // band solver scratch: [slots][band_stride]
+  size_t band_stride;
+  int band_slots;
+  const double* conlam0;   // multipliers / penalties the solve started from (fallback re-solves with dual_reset = 0), or nullptr
+  const double* conmu0;
+  int force_singular; // test hook (AGB_TEST_FORCE_SINGULAR=k): the structured solve kernel reports every k-th instance as AGB_SINGULAR
   double* Hpg;        // big layout only: [B][N·p(p-1)·3 + N·p·3] pair / self Hessian blocks
   int hpg_stride;
 };

@@ -26,6 +26,10 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
   const double S = (double)(K * Inst<P, MODEL, (LAY != 0)>::b);
   for (int inst = inst0 + blockIdx.x; inst < batch; inst += gridDim.x) {   // instances [inst0, batch)
     __syncthreads();
+    if (g.force_singular > 0 && inst % g.force_singular == 0) {                          // test hook of the band fallback
+      if (I.tid == 0) { g.status[inst] = AGB_SINGULAR; for (int q = 0; q < AGB_NSTATS; q++) g.stats[(size_t)inst * AGB_NSTATS + q] = 0.0; }
+      continue;
+    }
     I.bind_instance(g, inst);
     I.load_params(g, inst);
     I.load_iterate(g.Z0, g.L0, inst);

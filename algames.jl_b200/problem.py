@@ -20,7 +20,7 @@ import numpy as np
 from . import _capi
 
 __all__ = [
-    "DoubleIntegratorGame", "UnicycleGame", "BicycleGame", "ProblemSize", "Options", "GameObjective",
+    "DoubleIntegratorGame", "UnicycleGame", "BicycleGame", "QuadrotorGame", "Wall3D", "CylinderWall", "add_spherical_collision_avoidance", "ProblemSize", "Options", "GameObjective",
     "add_collision_cost", "GameConstraintValues", "add_collision_avoidance", "add_control_bound", "add_state_bound", "add_velocity_bound", "velocity_index",
     "add_circle_constraint", "add_wall_constraint", "Wall", "GameProblem", "GameBatch", "newton_solve",
     "residual", "residual_jacobian", "kkt_solve", "line_search", "update_traj", "rollout", "dual_update",
@@ -34,14 +34,14 @@ __all__ = [
 class _GameModel:
     name = "abstract"
 
-    def __init__(self, p: int):
+    def __init__(self, p: int, ni: int = 4, mi: int = 2):
         if not 1 <= p <= _capi.MAX_P:
             raise ValueError(f"p must be in 1..{_capi.MAX_P}")
-        self.p, self.n, self.m = p, 4 * p, 2 * p
-        self.ni, self.mi = [4] * p, [2] * p
-        self.pu = [[i + j * p for j in range(2)] for i in range(p)]       # 0-based
+        self.p, self.n, self.m = p, ni * p, mi * p
+        self.ni, self.mi = [ni] * p, [mi] * p
+        self.pu = [[i + j * p for j in range(mi)] for i in range(p)]      # 0-based
         self.px = [[i + j * p for j in range(2)] for i in range(p)]
-        self.pz = [[i + j * p for j in range(4)] for i in range(p)]
+        self.pz = [[i + j * p for j in range(ni)] for i in range(p)]
 
 
 class DoubleIntegratorGame(_GameModel):
@@ -70,6 +70,16 @@ class BicycleGame(_GameModel):
     def __init__(self, p: int = 2, lf: float = 0.05, lr: float = 0.05):
         super().__init__(p)
         self.lf, self.lr = lf, lr
+
+
+class QuadrotorGame(_GameModel):
+    """dynamics/quadrotor.jl:2-208: 12 states [r, q (MRP attitude), v, ω] and 4 rotor commands per player, component-major
+    joint layout.  Solved by the library's band solver (the structured kernels are specialised for planar players)."""
+    name = "quadrotor"
+
+    def __init__(self, p: int = 2, mass: float = 0.5):
+        super().__init__(p, 12, 4)
+        self.mass = mass
 
 
 class ProblemSize:
@@ -171,10 +181,11 @@ class GameObjective:
         if not (len(Q) == len(R) == len(xf) == len(uf) == p):
             raise ValueError("Q, R, xf, uf must have one entry per player")
         self.p, self.N, self.model = p, N, model
-        self.Q = [_diag(Q[i], 4) for i in range(p)]
-        self.R = [_diag(R[i], 2) for i in range(p)]
-        self.xf = [np.asarray(xf[i], float).reshape(4).copy() for i in range(p)]
-        self.uf = [np.asarray(uf[i], float).reshape(2).copy() for i in range(p)]
+        ni, mi = model.ni[0], model.mi[0]
+        self.Q = [_diag(Q[i], ni) for i in range(p)]
+        self.R = [_diag(R[i], mi) for i in range(p)]
+        self.xf = [np.asarray(xf[i], float).reshape(ni).copy() for i in range(p)]
+        self.uf = [np.asarray(uf[i], float).reshape(mi).copy() for i in range(p)]
         self.collision_cost = None     # (radius[p], mu[p])
 
 
@@ -196,6 +207,24 @@ class Wall:
     v: Sequence[float]
 
 
+@dataclass
+class Wall3D:
+    """constraints_methods.jl:201-206: corner points p1, p2, p3 of the rectangle and its outward normal v."""
+    p1: Sequence[float]
+    p2: Sequence[float]
+    p3: Sequence[float]
+    v: Sequence[float]
+
+
+@dataclass
+class CylinderWall:
+    """constraints_methods.jl:249-254: base point p, axis v in {"x", "y", "z"}, length l, radius r."""
+    p: Sequence[float]
+    v: str
+    l: float
+    r: float
+
+
 class GameConstraintValues:
     """Constraint schema of a game.  Row order of the AL multipliers is canonical (see include/algames_b200.h)."""
 
@@ -207,6 +236,9 @@ class GameConstraintValues:
         self.state_bound: List[List[tuple]] = [[] for _ in range(p)]   # StateBound convals (x_max[n], x_min[n]) of player i
         self.walls: List[List[Wall]] = [[] for _ in range(p)]
         self.circles: List[List[tuple]] = [[] for _ in range(p)]
+        self.spherical = False                     # add_spherical_collision_avoidance: col_radius acts on three components
+        self.walls3d: List[List[Wall3D]] = [[] for _ in range(p)]
+        self.cylinders: List[List[CylinderWall]] = [[] for _ in range(p)]
 
 
 def add_collision_avoidance(game_con: GameConstraintValues, radius, i: Optional[int] = None, j: Optional[int] = None):
@@ -221,6 +253,15 @@ def add_collision_avoidance(game_con: GameConstraintValues, radius, i: Optional[
         for b in range(p):
             if a != b:
                 game_con.col_radius[a, b] = r[a] + r[b]
+
+
+def add_spherical_collision_avoidance(game_con: GameConstraintValues, radius, i: Optional[int] = None, j: Optional[int] = None):
+    """add_spherical_collision_avoidance!(game_con, radius) / (game_con, i, j, radius) (constraints_methods.jl:45-81): the same
+    CollisionConstraint on the first three state components.  One game uses either the planar or the spherical form."""
+    if game_con.col_radius.any() and not game_con.spherical:
+        raise NotImplementedError("planar and spherical collision avoidance in one game")
+    game_con.spherical = True
+    add_collision_avoidance(game_con, radius, i, j)
 
 
 def _check_bounds(hi, lo, k):
@@ -307,10 +348,13 @@ def add_circle_constraint(game_con: GameConstraintValues, xc, yc, radius, i: Opt
             raise ValueError(f"at most {_capi.MAX_CIRCLES} circles per player")
 
 
-def add_wall_constraint(game_con: GameConstraintValues, walls: Sequence[Wall], i: Optional[int] = None):
+def add_wall_constraint(game_con: GameConstraintValues, walls: Sequence, i: Optional[int] = None):
+    """add_wall_constraint!(game_con, [i,] walls) for Vector{Wall} (constraints_methods.jl:161-195), Vector{Wall3D} (:208-247)
+    or Vector{CylinderWall} (:256-285)."""
+    kind = {Wall: "walls", Wall3D: "walls3d", CylinderWall: "cylinders"}[type(walls[0])]
     for a in (range(game_con.probsize.p) if i is None else [i]):
-        game_con.walls[a].extend(walls)
-        if len(game_con.walls[a]) > _capi.MAX_WALLS:
+        getattr(game_con, kind)[a].extend(walls)
+        if len(getattr(game_con, kind)[a]) > _capi.MAX_WALLS:
             raise ValueError(f"at most {_capi.MAX_WALLS} walls per player")
 
 
@@ -325,13 +369,24 @@ def _joint(per_player, p, k):
     return out
 
 
-def _make_desc(model, N, dt, game_obj: GameObjective, game_con: GameConstraintValues) -> _capi.ProblemDesc:
+def _make_desc(model, N, dt, game_obj: GameObjective, game_con: GameConstraintValues, solver: int = 0) -> _capi.ProblemDesc:
     d = _capi.ProblemDesc()
     p, n, m = model.p, model.n, model.m
+    ni, mi = model.ni[0], model.mi[0]
     d.model, d.p, d.d, d.N, d.dt = _capi.MODEL_IDS[model.name], p, getattr(model, "d", 2), N, dt
     d.lf, d.lr = getattr(model, "lf", 0.05), getattr(model, "lr", 0.05)
-    for name, vec in (("Q", _joint(game_obj.Q, p, 4)), ("xf", _joint(game_obj.xf, p, 4)),
-                      ("R", _joint(game_obj.R, p, 2)), ("uf", _joint(game_obj.uf, p, 2))):
+    d.quad_mass, d.solver, d.spherical_collision = getattr(model, "mass", 0.5), int(solver), int(game_con.spherical)
+    for i in range(p):
+        d.n_walls3d[i] = len(game_con.walls3d[i])
+        for q, w in enumerate(game_con.walls3d[i]):
+            for e, v in enumerate([*w.p1, *w.p2, *w.p3, *w.v]):
+                d.walls3d[i][q][e] = float(v)
+        d.n_cylinders[i] = len(game_con.cylinders[i])
+        for q, w in enumerate(game_con.cylinders[i]):
+            for e, v in enumerate([*w.p, "xyz".index(w.v), w.l, w.r]):
+                d.cylinders[i][q][e] = float(v)
+    for name, vec in (("Q", _joint(game_obj.Q, p, ni)), ("xf", _joint(game_obj.xf, p, ni)),
+                      ("R", _joint(game_obj.R, p, mi)), ("uf", _joint(game_obj.uf, p, mi))):
         arr = getattr(d, name)
         for a, v in enumerate(vec):
             arr[a] = v
@@ -373,7 +428,10 @@ def spec_of(prob: "GameProblem") -> dict:
     model, obj, con = prob.model, prob.game_obj, prob.game_con
     p = model.p
     return {
-        "model": model.name, "p": p, "d": getattr(model, "d", 2), "lf": getattr(model, "lf", 0.05),
+        "model": model.name, "p": p, "d": getattr(model, "d", 2), "lf": getattr(model, "lf", 0.05), "mass": getattr(model, "mass", 0.5),
+        "spherical": bool(con.spherical),
+        "walls3d": [[[*map(float, w.p1), *map(float, w.p2), *map(float, w.p3), *map(float, w.v)] for w in con.walls3d[i]] for i in range(p)],
+        "cylinders": [[[*map(float, w.p), w.v, float(w.l), float(w.r)] for w in con.cylinders[i]] for i in range(p)],
         "lr": getattr(model, "lr", 0.05), "N": prob.probsize.N, "dt": prob.dt, "x0": np.asarray(prob.x0, float).tolist(),
         "Q": [q.tolist() for q in obj.Q], "R": [r.tolist() for r in obj.R],
         "xf": [x.tolist() for x in obj.xf], "uf": [u.tolist() for u in obj.uf],
@@ -403,11 +461,14 @@ class GameBatch:
     Arrays use the ABI layouts: x0 [B,n], Z [B,N,n+m], L [B,p,N-1,n], conlam/conmu [B,N-1,nrow], res/dtraj [B,S].
     """
 
-    def __init__(self, model, N, dt, game_obj, game_con, batch: int, device: int = 0, lib_path: Optional[str] = None):
+    def __init__(self, model, N, dt, game_obj, game_con, batch: int, device: int = 0, lib_path: Optional[str] = None,
+                 solver: int = _capi.SOLVER_AUTO):
+        """`solver`: _capi.SOLVER_AUTO (structured kernels where the schema allows, band solver otherwise and as the fallback
+        for singular stage systems) or _capi.SOLVER_BAND (explicit KKT band + pivoted LU for every instance)."""
         self.lib = _capi.load(lib_path)
         self.model, self.N, self.dt, self.batch, self.device = model, N, dt, batch, device
         self.probsize = ProblemSize(N, model)
-        self.desc = _make_desc(model, N, dt, game_obj, game_con)
+        self.desc = _make_desc(model, N, dt, game_obj, game_con, solver)
         h = C.c_void_p()
         rc = self.lib.agb_create(C.byref(self.desc), batch, device, C.byref(h))
         if rc != 0:
@@ -778,8 +839,9 @@ class GameProblem:
         if self._batch is None:
             self._batch = GameBatch(self.model, self.N, self.dt, self.game_obj, self.game_con, 1, self._device, self._lib_path)
         o, p = self.game_obj, self.probsize.p      # the objective may have been edited since the handle was created
-        self._batch.set_instance_params(x0=self.x0[None, :], xf=_joint(o.xf, p, 4)[None], Q=_joint(o.Q, p, 4)[None],
-                                        R=_joint(o.R, p, 2)[None], uf=_joint(o.uf, p, 2)[None])
+        ni, mi = self.probsize.ni[0], self.probsize.mi[0]
+        self._batch.set_instance_params(x0=self.x0[None, :], xf=_joint(o.xf, p, ni)[None], Q=_joint(o.Q, p, ni)[None],
+                                        R=_joint(o.R, p, mi)[None], uf=_joint(o.uf, p, mi)[None])
         return self._batch
 
     def _push(self):
@@ -848,8 +910,8 @@ def newton_solve(probs, init: bool = True):
         obj = [q.game_obj for q in plist]
         batch.set_instance_params(
             x0=np.stack([q.x0 for q in plist]),
-            xf=np.stack([_joint(o.xf, ps.p, 4) for o in obj]), Q=np.stack([_joint(o.Q, ps.p, 4) for o in obj]),
-            R=np.stack([_joint(o.R, ps.p, 2) for o in obj]), uf=np.stack([_joint(o.uf, ps.p, 2) for o in obj]))
+            xf=np.stack([_joint(o.xf, ps.p, ps.ni[0]) for o in obj]), Q=np.stack([_joint(o.Q, ps.p, ps.ni[0]) for o in obj]),
+            R=np.stack([_joint(o.R, ps.p, ps.mi[0]) for o in obj]), uf=np.stack([_joint(o.uf, ps.p, ps.mi[0]) for o in obj]))
         Z0 = np.stack([np.concatenate([q.pdtraj.X, q.pdtraj.U], axis=1) for q in plist])
         L0 = np.stack([q.pdtraj.du for q in plist])
         have_duals = all(q.conlam is not None for q in plist)
@@ -860,7 +922,10 @@ def newton_solve(probs, init: bool = True):
         out = batch.newton_solve(p0.opts)
         hist, count = batch.get_history()
         res, _ = batch.residual()
-        vio = batch.violations()
+        try:
+            vio = batch.violations()
+        except AlgamesError:                      # band-solver schemas (QuadrotorGame, 3-D constraints): maxima only
+            vio = ()
         for b, q in enumerate(plist):
             q.pdtraj.X[:], q.pdtraj.U[:], q.pdtraj.du[:] = out["Z"][b, :, :ps.n], out["Z"][b, :, ps.n:], out["L"][b]
             q.conlam, q.conmu = out["conlam"][b], out["conmu"][b]
@@ -894,8 +959,8 @@ def ibr_newton_solve(probs, ibr_opts: Optional[IBROptions] = None, init: bool = 
         obj = [q.game_obj for q in plist]
         batch.set_instance_params(
             x0=np.stack([q.x0 for q in plist]),
-            xf=np.stack([_joint(o.xf, ps.p, 4) for o in obj]), Q=np.stack([_joint(o.Q, ps.p, 4) for o in obj]),
-            R=np.stack([_joint(o.R, ps.p, 2) for o in obj]), uf=np.stack([_joint(o.uf, ps.p, 2) for o in obj]))
+            xf=np.stack([_joint(o.xf, ps.p, ps.ni[0]) for o in obj]), Q=np.stack([_joint(o.Q, ps.p, ps.ni[0]) for o in obj]),
+            R=np.stack([_joint(o.R, ps.p, ps.mi[0]) for o in obj]), uf=np.stack([_joint(o.uf, ps.p, ps.mi[0]) for o in obj]))
         batch.set_initial(np.stack([np.concatenate([q.pdtraj.X, q.pdtraj.U], axis=1) for q in plist]),
                           np.stack([q.pdtraj.du for q in plist]))
         io = ibr_opts or IBROptions()

@@ -6,9 +6,9 @@ import math
 
 import numpy as np
 
-from .problem import (BicycleGame, DoubleIntegratorGame, GameConstraintValues, GameObjective, Options, ProblemSize,
-                      UnicycleGame, Wall, add_circle_constraint, add_collision_avoidance, add_collision_cost,
-                      add_control_bound, add_state_bound, add_velocity_bound, add_wall_constraint)
+from .problem import (BicycleGame, CylinderWall, DoubleIntegratorGame, GameConstraintValues, GameObjective, Options, ProblemSize,
+                      QuadrotorGame, UnicycleGame, Wall, Wall3D, add_circle_constraint, add_collision_avoidance, add_collision_cost,
+                      add_control_bound, add_spherical_collision_avoidance, add_state_bound, add_velocity_bound, add_wall_constraint)
 
 
 def config_a():
@@ -201,6 +201,32 @@ def config_s_random(layout_seed, batch=4, seed=6789, N=8):
     return model, N, dt, obj, con, opts, x0, xf
 
 
-CONFIGS = {"S": config_s, "V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}
+def config_q(batch=8, seed=7890, N=12, p=2, constraints=True):
+    """QuadrotorGame (dynamics/quadrotor.jl): p quadrotors fly from a hover at z = 1 to waypoints on the other side, crossing
+    each other; spherical collision avoidance (constraints_methods.jl:45-81), rotor-command bounds, a 3-D wall under the flight
+    corridor (wall_constraint.jl:141-249) and a vertical cylinder next to it (cylinder_constraint.jl:33-137).  The reference
+    ships no quadrotor example; shapes follow test/dynamics/quadrotor.jl and the oracle's test_oracle_quadrotor.py."""
+    dt = 0.1
+    model = QuadrotorGame(p=p)
+    ps = ProblemSize(N, model)
+    hover = model.mass * 9.81 / 4 / 1.245
+    xf = [np.r_[0.4 * (1 - 2 * (i % 2)), 0.2 * (i // 2) + 0.2 * (i % 2), 1.1, np.zeros(9)] for i in range(p)]      # lanes 0.2 apart
+    obj = GameObjective([np.ones(12)] * p, [1.0 * np.ones(4)] * p, xf, [hover * np.ones(4)] * p, N, model)
+    con = GameConstraintValues(ps)
+    if constraints:
+        if p > 1:
+            add_spherical_collision_avoidance(con, 0.15)
+        add_control_bound(con, 2.0 * np.ones(model.m), np.zeros(model.m))
+        add_wall_constraint(con, [Wall3D([-1.0, -1.0, 0.9], [1.0, -1.0, 0.9], [1.0, 1.0, 0.9], [0.0, 0.0, -1.0])])
+        add_wall_constraint(con, [CylinderWall([0.0, 0.6, 0.0], "z", 3.0, 0.2)], 0)
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((batch, model.n))
+    x0[:, 0:p] = np.array([-0.4 * (1 - 2 * (i % 2)) for i in range(p)]) + rng.uniform(-0.05, 0.05, (batch, p))
+    x0[:, p:2 * p] = np.array([0.2 * (i // 2) + 0.2 * (i % 2) for i in range(p)]) + rng.uniform(-0.05, 0.05, (batch, p))
+    x0[:, 2 * p:3 * p] = 1.0 + rng.uniform(-0.02, 0.02, (batch, p))
+    return model, N, dt, obj, con, Options(), x0, None
+
+
+CONFIGS = {"Q": config_q, "S": config_s, "V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}
 for _ls in range(1, 5):                                   # "S1" … "S4": random StateBound layouts
     CONFIGS["S%d" % _ls] = (lambda ls: (lambda batch=4, N=8: config_s_random(ls, batch=batch, N=N)))(_ls)

@@ -27,13 +27,15 @@
  *      dtraj [B][S]           Newton step, reference column ("horizontal") order    (core/newton_core.jl:65-89)
  *      conlam/conmu [B][N-1][nrow]  AL multipliers/penalties: stage k holds the state-constraint
  *                 rows of knot k+1 — per player [collision j≠i ascending | state bounds: per conval max rows, min rows |
- *                 walls | circles] — followed by the control-bound rows of knot k [u_max rows, u_min rows]
+ *                 walls | circles | 3-D walls | cylinders] — followed by the control-bound rows of knot k [u_max rows, u_min rows]
  *                 (finite bounds only, reference component order; control_bound_constraint.jl:33-35).
  *
  * Environment variables read by the library (test / tuning hooks, never needed in production):
  *   AGB_FORCE_BIG_LAYOUT=1|2|3  agb_create: force a big-storage shared-memory layout on 3-player instances (parity tests
  *                               run every layout on small games with it)
  *   AGB_HOST_CHUNKS=1..32       agb_solve_from_host: number of copy/solve pipeline chunks (default 8 for batch >= 1024)
+ *   AGB_BAND_FALLBACK=0         agb_create: do not re-solve AGB_SINGULAR instances of the structured kernels with the band solver
+ *   AGB_TEST_FORCE_SINGULAR=k   agb_create: the structured solve reports every k-th instance as AGB_SINGULAR (fallback tests)
  */
 #ifndef ALGAMES_B200_H
 #define ALGAMES_B200_H
@@ -42,14 +44,22 @@
 extern "C" {
 #endif
 
-#define AGB_MAX_P 4      /* players                       */
-#define AGB_MAX_N 16     /* joint state dim  n = 4p       */
-#define AGB_MAX_M 8      /* joint control dim m = 2p      */
+#define AGB_MAX_P 4      /* players                                                        */
+#define AGB_MAX_N 48     /* joint state dim   n = ni·p  (ni = 4; QuadrotorGame: 12)        */
+#define AGB_MAX_M 16     /* joint control dim m = mi·p  (mi = 2; QuadrotorGame: 4)         */
 #define AGB_MAX_WALLS 8  /* walls per player              */
 #define AGB_MAX_CIRCLES 8
 #define AGB_NSTATS 10
 
-enum { AGB_MODEL_DOUBLE_INTEGRATOR = 0, AGB_MODEL_UNICYCLE = 1, AGB_MODEL_BICYCLE = 2 };
+enum { AGB_MODEL_DOUBLE_INTEGRATOR = 0, AGB_MODEL_UNICYCLE = 1, AGB_MODEL_BICYCLE = 2, AGB_MODEL_QUADROTOR = 3 };
+
+/* Two solvers share the ABI.  The STRUCTURED kernels (stage-wise block elimination in shared memory) cover
+ * the planar models with 4 states / 2 controls per player and planar constraints.  The BAND solver (explicit KKT band in
+ * global memory, LU with partial pivoting — the reference's own formulation, solver_methods.jl:87) covers every schema:
+ * QuadrotorGame, the 3-D constraints, and it re-solves, transparently, any instance on which the structured elimination
+ * meets a singular stage system (status AGB_SINGULAR) although the KKT matrix itself is regular.  agb_problem_desc.solver
+ * picks: AGB_SOLVER_AUTO (structured where the schema allows, band as fallback / for the rest) or AGB_SOLVER_BAND. */
+enum { AGB_SOLVER_AUTO = 0, AGB_SOLVER_BAND = 1 };
 
 /* per-instance status written by agb_newton_solve_batch.  Codes 1-3 all mean "outer_iter exhausted with a
  * tolerance unmet" (the reference keeps iterating through failed line searches and stalls, solver_methods.jl:38-55); they
@@ -74,7 +84,7 @@ enum { AGB_OK = 0, AGB_EINVAL = -1, AGB_ECUDA = -2, AGB_ENOMEM = -3, AGB_EUNSUPP
  * GameConstraintValues + adders (constraints/constraints_methods.jl:5-195).           */
 typedef struct agb_problem_desc {
   int model;                 /* AGB_MODEL_*                                              */
-  int p;                     /* players (1..4); n = 4p, m = 2p                           */
+  int p;                     /* players (1..4); n = ni·p, m = mi·p (ni, mi = 4, 2; quadrotor 12, 4) */
   int d;                     /* DoubleIntegratorGame dimension — only d = 2 is supported */
   int N;                     /* knots                                                    */
   double dt;
@@ -108,6 +118,16 @@ typedef struct agb_problem_desc {
    * add_state_bound! per player.  Rows follow the reference's conval order: for each conval in the order
    * it was added, its finite x_max rows then its finite x_min rows (state_bound_constraint.jl:33-35).   */
   int x_max_con[AGB_MAX_P][AGB_MAX_N], x_min_con[AGB_MAX_P][AGB_MAX_N];
+  /* ---- QuadrotorGame and the 3-D constraints (dynamics/quadrotor.jl, constraints_methods.jl:45-81, :201-285) ---------- */
+  double quad_mass;          /* QuadrotorGame(mass = 0.5); inertia, rotor geometry and constants are the reference's (:22-29) */
+  int spherical_collision;   /* add_spherical_collision_avoidance!: col_radius acts on the first THREE state components  */
+  /* add_wall_constraint!(game_con, i, walls::Vector{Wall3D}): corner points p1, p2, p3 and outward normal v per wall      */
+  int n_walls3d[AGB_MAX_P];
+  double walls3d[AGB_MAX_P][AGB_MAX_WALLS][12];
+  /* add_wall_constraint!(game_con, i, walls::Vector{CylinderWall}): base point p(3), axis (0,1,2 = x,y,z), length, radius */
+  int n_cylinders[AGB_MAX_P];
+  double cylinders[AGB_MAX_P][AGB_MAX_WALLS][6];
+  int solver;                /* AGB_SOLVER_AUTO / AGB_SOLVER_BAND                                                          */
 } agb_problem_desc;
 
 /* Live fields of Options (src/struct/options.jl:5-116; dead fields omitted). */
@@ -148,13 +168,13 @@ int agb_sizes_of(const agb_problem_desc* d, agb_sizes* out);
 
 /* Layout check for bindings that mirror the structs above by hand (ctypes, Julia): `layout` lists, in this order,
  *   sizeof(agb_problem_desc), offsetof(.., dt), offsetof(.., Q), offsetof(.., col_radius), offsetof(.., has_state_bound),
- *   offsetof(.., walls), offsetof(.., circles), offsetof(.., x_max_con),
+ *   offsetof(.., walls), offsetof(.., circles), offsetof(.., x_max_con), offsetof(.., quad_mass), offsetof(.., solver),
  *   sizeof(agb_options), offsetof(.., alphax_dual), offsetof(.., eps_dyn), offsetof(.., dual_reset),
  *   sizeof(agb_ibr_options), offsetof(.., delta_min), sizeof(agb_sizes), sizeof(agb_device_view),
  *   AGB_MAX_P, AGB_MAX_N, AGB_MAX_M, AGB_MAX_WALLS, AGB_MAX_CIRCLES, AGB_NSTATS, AGB_NHIST, AGB_IPC_BYTES
- * (AGB_ABI_WORDS values).  Returns AGB_OK when every entry equals the library's own, else AGB_EINVAL with
+ * (AGB_ABI_WORDS = 26 values).  Returns AGB_OK when every entry equals the library's own, else AGB_EINVAL with
  * agb_last_error(NULL) naming the first mismatch.  agb_abi_layout writes the library's values (for diagnostics). */
-#define AGB_ABI_WORDS 24
+#define AGB_ABI_WORDS 26
 int agb_abi_check(const int* layout, int count);
 int agb_abi_layout(int* layout_out, int count);
 

@@ -1371,7 +1371,10 @@ def problem_from_spec(spec: dict, x0=None, xf=None, opts: Optional[Options] = No
     Constraint order is canonical: per player [collision pairs j≠i ascending | state bound | walls |
     circles]; one control-bound conval.  That is also the row order of the C-ABI's conλ/conμ arrays.
     """
-    model = make_model(spec["model"], spec["p"], spec.get("d", 2), spec.get("lf", 0.05), spec.get("lr", 0.05))
+    if spec["model"] == "quadrotor":
+        model = QuadrotorGame(p=spec["p"], mass=spec.get("mass", 0.5))
+    else:
+        model = make_model(spec["model"], spec["p"], spec.get("d", 2), spec.get("lf", 0.05), spec.get("lr", 0.05))
     N, dt, p = spec["N"], spec["dt"], spec["p"]
     ps = ProblemSize(N, model)
     xf_ = np.asarray(spec["xf"] if xf is None else xf, float).reshape(p, -1)
@@ -1388,7 +1391,7 @@ def problem_from_spec(spec: dict, x0=None, xf=None, opts: Optional[Options] = No
         if rad is not None:
             for j in range(p):
                 if j != i and rad[i][j] > 0:
-                    gc.add_collision_avoidance(rad[i][j], i, j)
+                    (gc.add_spherical_collision_avoidance if spec.get("spherical") else gc.add_collision_avoidance)(rad[i][j], i, j)
         for bound in ([] if sb[i] is None else [sb[i]] if isinstance(sb[i], dict) else sb[i]):
             gc.add_state_bound(i, bound["x_max"], bound["x_min"])
         if len(walls[i]):
@@ -1396,6 +1399,12 @@ def problem_from_spec(spec: dict, x0=None, xf=None, opts: Optional[Options] = No
         if len(circles[i]):
             c = np.asarray(circles[i], float)
             gc.add_circle_constraint(c[:, 0], c[:, 1], c[:, 2], i)
+        w3 = (spec.get("walls3d") or [[] for _ in range(p)])[i]
+        if len(w3):
+            gc.add_wall3d_constraint([Wall3D(np.array(w[0:3]), np.array(w[3:6]), np.array(w[6:9]), np.array(w[9:12])) for w in w3], i)
+        cy = (spec.get("cylinders") or [[] for _ in range(p)])[i]
+        if len(cy):
+            gc.add_cylinder_constraint([CylinderWall(np.array(w[0:3]), w[3], w[4], w[5]) for w in cy], i)
     if spec.get("control_bounds"):
         gc.add_control_bound(spec["control_bounds"]["u_max"], spec["control_bounds"]["u_min"])
     opts = opts or options_from_dict(spec.get("opts", {}))

@@ -13,7 +13,8 @@ NHIST = 10
 
 def load():
     src = os.path.join(HERE, "algames_oracle.c")
-    if not os.path.exists(LIB) or os.path.getmtime(src) > os.path.getmtime(LIB):
+    hdr = os.path.join(HERE, "..", "include", "algames_b200.h")
+    if not os.path.exists(LIB) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(LIB):
         subprocess.run(["make", "-s", "-C", HERE], check=True)
     lib = C.CDLL(LIB)
     lib.ago_newton_solve.restype = C.c_int

@@ -14,7 +14,7 @@ for u in "$@"; do
 done
 for p in $pids; do wait $p; done
 objs=""
-for u in agb_capi agb_kernels_p1 agb_kernels_p2 agb_kernels_p3 agb_kernels_p3b agb_kernels_p3m agb_kernels_p3t agb_kernels_p4; do
+for u in agb_capi agb_band agb_kernels_p1 agb_kernels_p2 agb_kernels_p3 agb_kernels_p3b agb_kernels_p3m agb_kernels_p3t agb_kernels_p4; do
   if [ -f "$out/$u.o" ]; then objs="$objs $out/$u.o"; else objs="$objs $root/algames.jl_b200/build/$u.o"; fi
 done
 /usr/local/cuda/bin/nvcc -shared -o "$out/libalgames_b200.so" $objs

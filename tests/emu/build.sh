@@ -6,7 +6,7 @@ root="$(cd "$here/../.." && pwd)"
 src="$root/algames.jl_b200/csrc"
 mkdir -p "$here/obj"
 pids=""
-for f in agb_capi agb_kernels_p1 agb_kernels_p2 agb_kernels_p3 agb_kernels_p3b agb_kernels_p3m agb_kernels_p3t agb_kernels_p4; do
+for f in agb_capi agb_band agb_kernels_p1 agb_kernels_p2 agb_kernels_p3 agb_kernels_p3b agb_kernels_p3m agb_kernels_p3t agb_kernels_p4; do
   g++ -O2 -std=c++17 -fPIC -DAGB_EMULATE -I "$here" -x c++ -c "$src/$f.cu" -o "$here/obj/$f.o" &
   pids="$pids $!"
 done

@@ -24,6 +24,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(x)
+#define __shared__ static      /* CTAs run one at a time on the emulator: a function-local static is the block's shared memory */
 
 struct emu_dim3 { unsigned x, y, z; };
 struct alignas(16) double2 { double x, y; };

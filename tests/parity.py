@@ -27,7 +27,7 @@ def oracle_problem(model, N, dt, obj, con, opts, x0, xf_joint=None):
     xfb = None
     if xf_joint is not None:
         p = model.p
-        xfb = np.stack([np.asarray(xf_joint)[[i + c * p for c in range(4)]] for i in range(p)])
+        xfb = np.stack([np.asarray(xf_joint)[[i + c * p for c in range(model.ni[0])]] for i in range(p)])
     return O.problem_from_spec(ab.spec_of(prob), xf=xfb)
 
 
@@ -576,3 +576,127 @@ def check_local_gather(lib_path, ndev=2, total=5):
                 assert np.array_equal(got[k], outs[r][k]), (r, k)
     for gb in gbs:
         gb.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Band solver (agb_band.cuh): QuadrotorGame / 3-D constraints, AGB_SOLVER_BAND on the planar configs, singular fallback
+# ---------------------------------------------------------------------------------------------------------------
+def check_band_per_function(lib_path, name, seed=0, reg=1e-3, N=None, **kw):
+    """residual!, residual_jacobian!, Δtraj and evaluate! of the band solver on a random iterate vs the NumPy oracle."""
+    W = ab.workloads
+    model, N, dt, obj, con, opts, x0, xf = W.CONFIGS[name](batch=2, **({"N": N} if N else {}), **kw)
+    B = 2
+    rng = np.random.default_rng(seed)
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path, solver=ab._capi.SOLVER_BAND)
+    gb.set_instance_params(x0=x0[:B], xf=None if xf is None else xf[:B])
+    oprobs, Zs, Ls, lams, mus = [], [], [], [], []
+    for b in range(B):
+        op = oracle_problem(model, N, dt, obj, con, opts, x0[b], None if xf is None else xf[b])
+        pd = op.pdtraj
+        Z, L, lam, mu = random_state(op, x0[b], rng)
+        if model.name == "quadrotor":                       # keep the random iterate in the model's sensible range
+            pd.X[:] *= 0.3; pd.U[:] = 1.0 + 0.3 * pd.U; pd.X[0] = x0[b]
+            Z = np.concatenate([pd.X, pd.U], axis=1)
+        oprobs.append(op); Zs.append(Z); Ls.append(L); lams.append(lam); mus.append(mu)
+    has_con = lams[0].size > 0
+    gb.set_initial(np.stack(Zs), np.stack(Ls), np.stack(lams) if has_con else None, np.stack(mus) if has_con else None)
+    res, norms = gb.residual()
+    J = gb.residual_jacobian_dense(reg, reg)
+    d = gb.kkt_solve(reg, reg)
+    c = gb.evaluate() if has_con else None
+    for b, op in enumerate(oprobs):
+        pd = op.pdtraj
+        ores = O.residual(op, pd).copy()
+        assert np.abs(res[b] - ores).max() <= TOL_FUNC * np.abs(ores).max(), np.abs(res[b] - ores).max()
+        rec = O.record(op, pd, 0.0, 1)
+        assert np.allclose(norms[b], [rec.res, rec.dyn, rec.con, rec.sta, rec.opt], rtol=1e-12, atol=1e-12)
+        op.opts.reg.set(reg)
+        O.residual(op, pd)
+        Jo = O.residual_jacobian(op, pd)
+        assert np.abs(J[b] - Jo).max() <= 1e-9 * np.abs(Jo).max(), np.abs(J[b] - Jo).max() / np.abs(Jo).max()
+        ref = -np.linalg.solve(Jo, ores)
+        assert np.abs(d[b] - ref).max() <= 1e-8 * np.abs(ref).max(), np.abs(d[b] - ref).max() / np.abs(ref).max()
+        if has_con:
+            op.game_con.evaluate(pd.X, pd.U)
+            vals, _ = pack_vals(op)
+            assert np.allclose(c[b], vals, rtol=1e-13, atol=1e-13)
+    # trial residual with the proximal term
+    rt, _ = gb.residual(reg, reg, 0.25)
+    for b, op in enumerate(oprobs):
+        O.set_traj(op.core, op.dpdtraj, d[b])
+        op.pdtraj_trial = op.pdtraj.copy()
+        O.update_traj(op.pdtraj_trial, op.pdtraj, 0.25, op.dpdtraj)
+        O.residual(op, op.pdtraj_trial)
+        O.regularize_residual(op, op.pdtraj_trial, op.pdtraj)
+        assert np.abs(rt[b] - op.core.res).max() <= TOL_FUNC * np.abs(op.core.res).max()
+    gb.close()
+
+
+def check_band_solve_vs_oracle(lib_path, name, B=2, N=None, which=None, **kw):
+    """Full newton_solve! through the band solver vs the NumPy oracle (trajectories, duals, multipliers, history)."""
+    W = ab.workloads
+    model, N, dt, obj, con, opts, x0, xf = W.CONFIGS[name](batch=B, **({"N": N} if N else {}), **kw)
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path, solver=ab._capi.SOLVER_BAND)
+    gb.set_instance_params(x0=x0, xf=xf)
+    Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+    gb.set_history(opts.outer_iter * opts.inner_iter + 1)
+    out = gb.newton_solve(opts)
+    hist, count = gb.get_history()
+    for b in (range(B) if which is None else which):
+        op = oracle_problem(model, N, dt, obj, con, opts, x0[b], None if xf is None else xf[b])
+        O.newton_solve(op, Z0=Z0[b], L0=L0[b])
+        Zo = np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1)
+        assert np.abs(out["Z"][b] - Zo).max() < TOL_SOLVE, np.abs(out["Z"][b] - Zo).max()
+        assert np.abs(out["L"][b] - op.pdtraj.du).max() < TOL_SOLVE * max(1.0, np.abs(op.pdtraj.du).max())
+        assert (out["status"][b] == 0) == op.converged and int(out["stats"][b, 6]) == op.n_newton
+        cnt = int(count[b])
+        assert cnt == len(op.stats)
+        ho = np.array([[r.outer, r.res, r.dyn, r.con, r.sta, r.opt, r.delta] for r in op.stats])
+        assert np.array_equal(hist[b, :cnt, 0], ho[:, 0])
+        assert np.allclose(hist[b, :cnt, 1:7], ho[:, 1:], rtol=1e-6, atol=TOL_SOLVE)
+        lam_o, mu_o = O.pack_multipliers(op)
+        if lam_o.size:
+            assert np.allclose(out["conlam"][b], lam_o, atol=TOL_SOLVE * max(1.0, np.abs(lam_o).max()))
+            assert np.allclose(out["conmu"][b], mu_o, rtol=1e-12)
+    gb.close()
+    return out
+
+
+def check_band_equals_structured(lib_path, name, B=4, N=None):
+    """The planar configs through both solvers of the library: same statuses and Newton counts, solutions within 1e-6."""
+    cfg = small_config(name, B, N)
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    if x0.shape[0] < B:
+        x0 = np.tile(x0[:1], (B, 1)); x0[:, :2 * model.p] += 0.01 * np.arange(B)[:, None]
+    outs = []
+    for solver in (ab._capi.SOLVER_AUTO, ab._capi.SOLVER_BAND):
+        gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path, solver=solver)
+        gb.set_instance_params(x0=x0, xf=xf)
+        gb.random_initial(opts.amplitude_init, opts.seed)
+        outs.append(gb.newton_solve(ab.Options(**{**opts.to_dict(), "dual_reset": True})))
+        gb.close()
+    a, b = outs
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["stats"][:, 6], b["stats"][:, 6])
+    conv = a["status"] == 0
+    assert np.abs(a["Z"][conv] - b["Z"][conv]).max() < TOL_SOLVE and np.allclose(a["stats"][:, :5], b["stats"][:, :5], rtol=1e-5, atol=TOL_SOLVE)
+    return a
+
+
+def check_singular_fallback(lib_path, monkeypatch):
+    """Plumbing of the fallback: with the test hook AGB_TEST_FORCE_SINGULAR=k the structured kernel reports every k-th
+    instance as AGB_SINGULAR after its first factorisation; the band solver must re-solve exactly those, from the same
+    initial iterate, and the batch must come out as if nothing had happened (stats[9] = 2 marks the re-solved ones)."""
+    model, N, dt, obj, con, opts, x0, xf = small_config("B", 6, 10)
+    res = {}
+    for hook in ("0", "3"):
+        monkeypatch.setenv("AGB_TEST_FORCE_SINGULAR", hook)
+        gb = ab.GameBatch(model, N, dt, obj, con, 6, lib_path=lib_path)
+        gb.set_instance_params(x0=x0)
+        gb.random_initial(opts.amplitude_init, opts.seed)
+        res[hook] = gb.newton_solve(opts)
+        gb.close()
+    monkeypatch.delenv("AGB_TEST_FORCE_SINGULAR")
+    a, b = res["0"], res["3"]
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert np.array_equal(b["stats"][:, 9] >= 2, np.arange(6) % 3 == 0), b["stats"][:, 9]
+    assert np.abs(a["Z"] - b["Z"]).max() < TOL_SOLVE and np.array_equal(a["stats"][:, 6], b["stats"][:, 6])

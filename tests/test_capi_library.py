@@ -36,7 +36,7 @@ def test_abi_layout_check(built):
     words = ab._capi.abi_layout()
     mine = (C.c_int * len(words))()
     assert lib.agb_abi_layout(mine, len(words)) == 0 and list(mine) == words
-    for k, name in ((0, "sizeof(agb_problem_desc)"), (11, "offsetof(agb_options, dual_reset)"), (22, "AGB_NHIST")):
+    for k, name in ((0, "sizeof(agb_problem_desc)"), (13, "offsetof(agb_options, dual_reset)"), (24, "AGB_NHIST")):
         bad = list(words); bad[k] += 4
         assert lib.agb_abi_check((C.c_int * len(bad))(*bad), len(bad)) != 0
         assert name in lib.agb_last_error(None).decode()

@@ -238,3 +238,28 @@ def test_batch_requires_equal_options_emulated(emu_lib):
     a.game_obj.xf[0][:] = [0.3, 0.3, 0.0, 0.0]
     ab.newton_solve(a)
     assert np.abs(a.pdtraj.X[-1] - z_before).max() > 1e-3
+
+
+# ---- band solver: QuadrotorGame, 3-D constraints, AGB_SOLVER_BAND, singular fallback -------------------------------------
+@pytest.mark.parametrize("name,N,kw", [("Q", 5, {"p": 1}), ("Q", 4, {"p": 2}), ("B", 6, {}), ("A", None, {}), ("E", 6, {})])
+def test_band_per_function_parity_emulated(emu_lib, name, N, kw):
+    if name == "A":
+        import algames_b200 as ab
+        ab.workloads.CONFIGS["A_"] = lambda batch=2: tuple(np.tile(v, (batch, 1)) if i == 6 else v for i, v in enumerate(ab.workloads.config_a()))
+        parity.check_band_per_function(emu_lib, "A_", seed=3)
+    else:
+        parity.check_band_per_function(emu_lib, name, seed=3, N=N, **kw)
+
+
+def test_band_quadrotor_solve_emulated(emu_lib):
+    parity.check_band_solve_vs_oracle(emu_lib, "Q", B=1, N=5, p=1)
+    parity.check_band_solve_vs_oracle(emu_lib, "Q", B=1, N=4, p=2)
+
+
+def test_band_equals_structured_emulated(emu_lib):
+    parity.check_band_equals_structured(emu_lib, "B", B=3, N=8)
+    parity.check_band_equals_structured(emu_lib, "D", B=2, N=8)
+
+
+def test_singular_fallback_emulated(emu_lib, monkeypatch):
+    parity.check_singular_fallback(emu_lib, monkeypatch)

@@ -321,3 +321,71 @@ def test_solve_from_host_matches_staged_calls():
         for k in ("Z", "L", "conlam", "conmu", "stats", "status"):
             assert np.array_equal(ref[k], got[k]), (B, k)
         gb.close()
+
+
+# ---- band solver (agb_band.cuh): QuadrotorGame + 3-D constraints, AGB_SOLVER_BAND on the planar configs, fallback ---------
+@pytest.mark.parametrize("name,N,kw", [("Q", 6, {"p": 1}), ("Q", 5, {"p": 2}), ("Q", 4, {"p": 3}), ("B", 10, {}), ("C", 6, {}), ("E", 8, {})])
+def test_band_per_function_parity(name, N, kw):
+    parity.check_band_per_function(LIB, name, seed=4, N=N, **kw)
+
+
+def test_band_quadrotor_solves_vs_oracle():
+    """QuadrotorGame on the device: 1 and 2 players, spherical collision avoidance, rotor bounds, a 3-D wall and
+    a cylinder — full newton_solve! vs the NumPy oracle: trajectories, duals, multipliers, the whole Statistics history."""
+    parity.check_band_solve_vs_oracle(LIB, "Q", B=2, N=8, p=1)
+    out = parity.check_band_solve_vs_oracle(LIB, "Q", B=2, N=6, p=2, which=[0])
+    assert np.isfinite(out["Z"]).all()
+
+
+def test_band_quadrotor_batch_properties():
+    """A batch of 2-player quadrotor games at N = 12: every instance converges, instance independence (a sub-batch alone
+    gives bit-identical results), determinism."""
+    import algames_b200 as ab
+    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_q(batch=48, N=12, p=2)
+    outs = []
+    for sl in (slice(0, 48), slice(8, 24)):
+        gb = ab.GameBatch(model, N, dt, obj, con, sl.stop - sl.start, lib_path=LIB)
+        gb.set_instance_params(x0=x0[sl])
+        Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+        if sl.start:
+            gb.set_initial(outs[0][1][sl], outs[0][2][sl])
+        out = gb.newton_solve(opts)
+        outs.append((out, Z0, L0))
+        if not sl.start:
+            out_b = gb.newton_solve(opts)
+            assert np.array_equal(out["Z"], out_b["Z"])
+        gb.close()
+    full, sub = outs[0][0], outs[1][0]
+    assert (full["status"] == 0).mean() > 0.9 and (full["stats"][:, 1:5] < 1e-3)[full["status"] == 0].all()
+    assert np.array_equal(sub["Z"], full["Z"][8:24]) and np.array_equal(sub["stats"][:, :9], full["stats"][8:24, :9])
+
+
+@pytest.mark.parametrize("name,B,N", [("B", 64, 40), ("D", 32, 40), ("E", 32, 30)])
+def test_band_equals_structured(name, B, N):
+    parity.check_band_equals_structured(LIB, name, B=B, N=N)
+
+
+def test_band_bulk_vs_c_oracle(capsys):
+    """The band solver is the device twin of the C oracle's formulation (explicit band + pivoted LU): every instance of a
+    config-B batch at N = 40 and a config-C batch at N = 20 must reproduce its traces."""
+    import algames_b200 as ab
+    for name, B, N in (("B", 128, 40), ("C", 32, 20)):
+        cfg = parity.small_config(name, B, N)
+        model, N, dt, obj, con, opts, x0, xf = cfg
+        gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=LIB, solver=ab._capi.SOLVER_BAND)
+        gb.set_instance_params(x0=x0, xf=xf)
+        Z0, L0 = gb.random_initial(opts.amplitude_init, opts.seed)
+        hmax = opts.outer_iter * opts.inner_iter + 1
+        gb.set_history(hmax)
+        dev = gb.newton_solve(opts)
+        dev["hist"], dev["hist_count"] = gb.get_history()
+        gb.close()
+        ref = parity.c_oracle_solve(cfg, x0, xf, Z0, L0, opts, hist_max=hmax)
+        rep = parity.compare_bulk(dev, ref)
+        with capsys.disabled():
+            print("\nband bulk parity %s: " % name + ", ".join(f"{k}={v if not isinstance(v, float) else format(v, '.2e')}" for k, v in rep.items()), flush=True)
+        assert rep["ok_converged"] and rep["ok_nonconverged"] and rep["forked"] <= 0.02 * B, rep
+
+
+def test_singular_fallback(monkeypatch):
+    parity.check_singular_fallback(LIB, monkeypatch)
