@@ -84,6 +84,7 @@ SYMBOLS = {
     "agb_shift_initial": (C.c_int, [_H, C.c_int, _DP, _DP]),
     "agb_mpc_advance": (C.c_int, [_H, C.c_int, _DP, _DP, _DP]),
     "agb_mpc_advance_async": (C.c_int, [_H, C.c_int, C.c_void_p]),
+    "agb_get_stream": (C.c_void_p, [_H]),
     "agb_join_stream": (C.c_int, [_H, C.c_void_p]),
     "agb_rollout": (C.c_int, [_H]),
     "agb_residual": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, _DP, _DP]),

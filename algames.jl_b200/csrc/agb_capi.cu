@@ -570,6 +570,8 @@ int agb_mpc_advance_async(agb_handle* h, int s, const double* disturbance_dev) {
   return AGB_OK;
 }
 
+void* agb_get_stream(agb_handle* h) { return h ? (void*)h->stream : nullptr; }
+
 int agb_join_stream(agb_handle* h, void* stream) {
   if (!h) return AGB_EINVAL;
   AGB_CUDA(h, cudaSetDevice(h->device));

@@ -32,8 +32,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     }
     I.bind_instance(g, inst);
     I.load_params(g, inst);
-    I.load_iterate(g.Z0, g.L0, inst);
-    I.load_duals(g, inst);
+    I.load_iterate(g.Z0, g.L0, inst, &g);
     __syncthreads();
     for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];     // x_1 ← x0 (primal_dual_traj.jl:42)
     __syncthreads();
@@ -131,8 +130,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     __syncthreads();
     I.bind_instance(g, inst);
     I.load_params(g, inst);
-    I.load_iterate(g.Z0, g.L0, inst);
-    I.load_duals(g, inst);
+    I.load_iterate(g.Z0, g.L0, inst, &g);
     __syncthreads();
     for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];
     __syncthreads();
@@ -240,8 +238,7 @@ __global__ void __launch_bounds__(threads_for(P)) agb_op_kernel(const DevDesc* _
     __syncthreads();
     I.bind_instance(g, inst);
     I.load_params(g, inst);
-    I.load_iterate(g.Z, g.L, inst);
-    I.load_duals(g, inst);
+    I.load_iterate(g.Z, g.L, inst, &g);
     __syncthreads();
     for (int q = I.tid; q < n; q += kThreads) I.X[q] = g.x0[(size_t)inst * n + q];
     __syncthreads();

@@ -60,6 +60,38 @@ struct GPh {
 template <bool BIG> struct SpillSel { typedef SP type; };
 template <> struct SpillSel<true> { typedef GPh type; };
 
+// 1-D bulk asynchronous copies (the TMA engine's cp.async.bulk, SASS UBLKCP): one elected thread moves a whole contiguous slab
+// global → shared, completion counted in bytes on an mbarrier every thread then waits on; shared → global as a bulk group.
+// Slabs must be 16-byte aligned multiples of 16 bytes (callers fall back to element loops otherwise).
+#ifndef AGB_EMULATE
+__device__ __forceinline__ unsigned smem32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(void* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem32(dst)), "l"(src), "r"(bytes), "r"(smem32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) { asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem32(src)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_commit_wait() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#else
+inline void mbar_init(void*) {}
+inline void mbar_expect(void*, unsigned) {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, void*) { memcpy(dst, src, bytes); }
+inline void mbar_wait(void*, unsigned) {}
+inline void bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
+inline void bulk_commit_wait() {}
+inline void fence_async_smem() {}
+#endif
+
 // Flags between the warps of one CTA (producer / consumer forward sweep): release-store, acquire-load, and a spin hint
 // (the fiber emulator must yield inside a spin loop; the GPU backs off a little so that pollers leave issue slots free).
 #ifndef AGB_EMULATE
@@ -261,6 +293,7 @@ struct Inst {
   bool keep;              // trial evaluation also produces what the next inner iteration needs (rows, Hessian blocks)
   int pl;                 // iterative best response: the player whose problem is being solved (-1: the full game)
   int tid, lane, warp;
+  unsigned bulk_phase;    // parity of the bulk-copy mbarrier (red[47]; the reductions use red[0..23])
 #ifdef AGB_PHASE_TIMING
   long long prof_t, prof[16];
 #endif
@@ -276,6 +309,8 @@ struct Inst {
     Pm.off = dd->o_P; Sv.off = dd->o_Sv; Ym.off = dd->o_Y; Aug.off = dd->o_Aug; Base.off = dd->o_Base;
     Wm.off = dd->o_W; Hm.off = dd->o_Ta; xf.off = dd->o_par; Q.off = xf.off + n; Rw.off = Q.off + n; uf.off = Rw.off + m; red.off = dd->o_red;
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; KUg = nullptr; pl = -1; Rtrial = nullptr; keep = false;
+    bulk_phase = 0;
+    if constexpr (!BIG) { if (tid == 0) mbar_init((double*)red + 47); }      // (the kernels' instance loops start with a block barrier)
 #ifdef AGB_PHASE_TIMING
     for (int q = 0; q < 16; q++) prof[q] = 0;
     prof_t = clock64();
@@ -1481,33 +1516,76 @@ struct Inst {
     for (int a = tid; a < n; a += kThreads) { xf[a] = g.xf[(size_t)inst * n + a]; Q[a] = g.Q[(size_t)inst * n + a]; }
     for (int a = tid; a < m; a += kThreads) { Rw[a] = g.R[(size_t)inst * m + a]; uf[a] = g.uf[(size_t)inst * m + a]; }
   }
-  __device__ void load_iterate(const double* Zg, const double* Lg, int inst) {
+  static __device__ __forceinline__ bool bulk_ok(const void* gp, unsigned bytes) { return bytes > 0 && (bytes & 15u) == 0 && (((size_t)gp) & 15u) == 0; }
+  // Instance slab → shared memory.  Λ, the AL multipliers and the penalties have the same layout in HBM and in shared
+  // memory: thread 0 issues them as bulk copies on ONE mbarrier phase (a phase must not complete twice before every waiter
+  // has seen it, so the three slabs share a transaction and the next phase starts an instance later, many block barriers
+  // away); z_k = [x_k; u_k] is de-interleaved by element loops that run beside the bulk copies.
+  __device__ void load_iterate(const double* Zg, const double* Lg, int inst, const Buffers* gd = nullptr) {
     const double* __restrict__ z = Zg + (size_t)inst * N * (n + m);
+    const double* __restrict__ l = Lg + (size_t)inst * P * K * n;
+    const size_t o = (size_t)inst * K * nrow;
+    const unsigned lbytes = (unsigned)(P * K * n) * 8u, cbytes = (unsigned)(K * nrow) * 8u;
+    bool lb = false, cb = false;
+    if constexpr (!BIG) {
+      lb = bulk_ok(l, lbytes);
+      cb = gd != nullptr && bulk_ok(gd->conlam + o, cbytes) && bulk_ok(gd->conmu + o, cbytes);
+      if ((lb || cb) && tid == 0) {
+        mbar_expect((double*)red + 47, (lb ? lbytes : 0u) + (cb ? 2u * cbytes : 0u));
+        if (lb) bulk_g2s((double*)L, l, lbytes, (double*)red + 47);
+        if (cb) { bulk_g2s((double*)CL, gd->conlam + o, cbytes, (double*)red + 47); bulk_g2s((double*)CM, gd->conmu + o, cbytes, (double*)red + 47); }
+      }
+    }
 #pragma unroll 4
     for (int item = tid; item < N * (n + m); item += kThreads) {
       const int q = item % (n + m), k = item / (n + m);
       const double v = __ldg(z + item);
       if (q < n) X[k * n + q] = v; else U[k * m + (q - n)] = v;
     }
-    const double* __restrict__ l = Lg + (size_t)inst * P * K * n;
+    if (!lb) {
 #pragma unroll 4
-    for (int item = tid; item < P * K * n; item += kThreads) L[item] = __ldg(l + item);
+      for (int item = tid; item < P * K * n; item += kThreads) L[item] = __ldg(l + item);
+    }
+    if (gd != nullptr && !cb) {
+      for (int item = tid; item < K * nrow; item += kThreads) { CL[item] = gd->conlam[o + item]; CM[item] = gd->conmu[o + item]; }
+    }
+    if (lb || cb) { mbar_wait((double*)red + 47, bulk_phase); bulk_phase ^= 1u; }
   }
-  __device__ void store_iterate(double* Zg, double* Lg, int inst) const {
+  __device__ void store_iterate(double* Zg, double* Lg, int inst) {
     double* z = Zg + (size_t)inst * N * (n + m);
+    double* l = Lg + (size_t)inst * P * K * n;
+    const unsigned lbytes = (unsigned)(P * K * n) * 8u;
+    bool bulk = false;
+    if constexpr (!BIG) {
+      bulk = bulk_ok(l, lbytes);
+      if (bulk) {                                            // writers order their shared-memory stores before the async proxy reads them
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) bulk_s2g(l, (double*)L, lbytes);
+      }
+    }
     for (int item = tid; item < N * (n + m); item += kThreads) {
       const int q = item % (n + m), k = item / (n + m);
       z[item] = (q < n) ? X[k * n + q] : U[k * m + (q - n)];
     }
-    double* l = Lg + (size_t)inst * P * K * n;
-    for (int item = tid; item < P * K * n; item += kThreads) l[item] = L[item];
+    if (bulk) { if (tid == 0) bulk_commit_wait(); }          // (Λ's shared copy is not rewritten before the next block barrier)
+    else for (int item = tid; item < P * K * n; item += kThreads) l[item] = L[item];
   }
   __device__ void load_duals(const Buffers& g, int inst) {
     const size_t o = (size_t)inst * K * nrow;
     for (int item = tid; item < K * nrow; item += kThreads) { CL[item] = g.conlam[o + item]; CM[item] = g.conmu[o + item]; }
   }
-  __device__ void store_duals(const Buffers& g, int inst) const {
+  __device__ void store_duals(const Buffers& g, int inst) {
     const size_t o = (size_t)inst * K * nrow;
+    const unsigned cbytes = (unsigned)(K * nrow) * 8u;
+    if constexpr (!BIG) {
+      if (bulk_ok(g.conlam + o, cbytes) && bulk_ok(g.conmu + o, cbytes)) {
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) { bulk_s2g(g.conlam + o, (double*)CL, cbytes); bulk_s2g(g.conmu + o, (double*)CM, cbytes); bulk_commit_wait(); }
+        return;
+      }
+    }
     for (int item = tid; item < K * nrow; item += kThreads) { g.conlam[o + item] = CL[item]; g.conmu[o + item] = CM[item]; }
   }
 };

@@ -545,6 +545,10 @@ class GameBatch:
         """agb_mpc_advance_async: the same step with a DEVICE pointer for the disturbance (0 = none) and no host sync."""
         self._ck(self.lib.agb_mpc_advance_async(self.h, int(s), C.c_void_p(disturbance_dev) if disturbance_dev else None))
 
+    def stream(self) -> int:
+        """agb_get_stream: the handle's own cudaStream_t (as an integer)."""
+        return int(self.lib.agb_get_stream(self.h) or 0)
+
     def join_stream(self, stream: int):
         """agb_join_stream: `stream` waits (on the device) for everything enqueued on the handle's own stream."""
         self._ck(self.lib.agb_join_stream(self.h, C.c_void_p(stream) if stream else None))

@@ -539,15 +539,15 @@ def run_mpc_config(ctx, streams, resolves, cpu_streams, cpu_resolves):
         newton = torch.zeros((), dtype=torch.float64, device=ctx.dev)
         torch.cuda.synchronize(ctx.dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(ctx.stream):
-            a.record(ctx.stream)
+        hs = torch.cuda.ExternalStream(gb.stream(), device=ctx.dev)      # the whole loop on the handle's own stream
+        with torch.cuda.stream(hs):
+            a.record(hs)
             for t in range(resolves):
-                gb.newton_solve_async(first if t == 0 else warm, ctx.sp)
+                gb.newton_solve_async(first if t == 0 else warm, hs.cuda_stream)
                 if collect:
                     conv += (v["status"] == 0).sum(); newton += v["stats"][:, 6].sum()
                 gb.mpc_advance_async(1, dist_dev[t].data_ptr())
-            gb.join_stream(ctx.sp)               # the last advance ran on the handle's stream: order the closing event after it
-            b.record(ctx.stream)
+            b.record(hs)
         torch.cuda.synchronize(ctx.dev)
         return a.elapsed_time(b), float(conv.item()), float(newton.item())
 
@@ -610,7 +610,50 @@ def run_other_configs(ctx, args):
         cfg = W.config_c(batch=per)
         out.append(run_cold_config(ctx, "C: %d x 4-player UnicycleGame N=50, collision avoidance + control bounds, seed 2345" % per, cfg,
                                    min(args.cpu_sample_other, 256), 1))
+        # Q: QuadrotorGame through the band solver; CPU arm = the NumPy oracle on ONE instance (the C port
+        # has no quadrotor model), so its figure is a single-core one
+        if args.quad_batch > 0:
+            out.append(run_quadrotor_config(ctx, args.quad_batch, args.quad_cpu))
     return out
+
+
+def run_quadrotor_config(ctx, B, cpu_n):
+    import algames_b200 as ab
+    torch = ctx.torch
+    cfg = ab.workloads.config_q(batch=B, N=12, p=2)
+    model, N, dt, obj, con, opts, x0, xf = cfg
+    n, m, p = model.n, model.m, model.p
+    gb = ab.GameBatch(model, N, dt, obj, con, B, device=ctx.local)
+    Z0, L0 = initial_iterate(opts, B, N, n, m, p)
+    gb.set_instance_params(x0=x0)
+    gb.set_initial(Z0, L0)
+    ms = time_solves(ctx, gb, opts, 1)
+    out = gb.solve_from_host(opts, x0, Z0, L0)          # warm-up of the chunked host pipeline
+    t0 = time.perf_counter()
+    out = gb.solve_from_host(opts, x0, Z0, L0)
+    e2e_t = time.perf_counter() - t0
+    conv = int((out["status"] == 0).sum())
+    rec = {"workload": "Q: %d x 2-player QuadrotorGame N=12 (12 states, 4 rotor commands per player), spherical collision avoidance, rotor bounds, 3-D wall, cylinder; band solver" % B,
+           "instances": B, "n_gpus": 1, "value": conv / (ms / 1e3), "unit": "converged instances/s", "ms_per_solve": ms,
+           "converged_fraction": conv / B, "newton_steps_per_instance": float(out["stats"][:, 6].mean()),
+           "e2e": {"value": conv / e2e_t, "unit": "converged instances/s"}}
+    gb.close()
+    if cpu_n > 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle.algames_oracle as O
+        import parity
+        t0 = time.perf_counter()
+        cc = 0
+        for b in range(cpu_n):
+            op = parity.oracle_problem(model, N, dt, obj, con, opts, x0[b])
+            O.newton_solve(op, Z0=Z0[b], L0=L0[b])
+            cc += int(op.converged)
+            agree = bool(op.converged == (out["status"][b] == 0)) and abs(float(np.abs(np.concatenate([op.pdtraj.X, op.pdtraj.U], axis=1) - out["Z"][b]).max())) < 1e-6
+        dt_s = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": cc / dt_s, "unit": "converged instances/s", "cores": 1, "kind": "port",
+                               "sample": f"{cpu_n} instance(s) of the same inputs in {dt_s:.1f} s (oracle/algames_oracle.py, NumPy, one core; the C port has no quadrotor model)",
+                               "agrees_with_device_to_1e-6": agree}
+    return rec
 
 
 def run_gpu(args):
@@ -657,6 +700,8 @@ def main():
     ap.add_argument("--other-batch", type=int, default=8192, help="instances per GPU of configs C and E")
     ap.add_argument("--mpc-streams", type=int, default=1024, help="config D streams per GPU")
     ap.add_argument("--mpc-resolves", type=int, default=200)
+    ap.add_argument("--quad-batch", type=int, default=512, help="config Q (QuadrotorGame, band solver) instances; 0 skips it")
+    ap.add_argument("--quad-cpu", type=int, default=1, help="instances of config Q solved by the NumPy oracle for its CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="headline only (profiling runs)")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the all-gather at N>1")

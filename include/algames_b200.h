@@ -208,6 +208,8 @@ int agb_mpc_advance(agb_handle* h, int s, const double* disturbance, const doubl
  * zero, nothing synchronises.  agb_newton_solve_async + agb_mpc_advance_async, repeated, is one uninterrupted stream of
  * kernels (the ordering rules of agb_newton_solve_async apply). */
 int agb_mpc_advance_async(agb_handle* h, int s, const double* disturbance_dev);
+/* The handle's own stream (a cudaStream_t): pass it to agb_newton_solve_async to keep a device-resident loop on ONE stream. */
+void* agb_get_stream(agb_handle* h);
 /* Makes `stream` (a cudaStream_t) wait, on the device, for everything enqueued so far on the handle's own stream. */
 int agb_join_stream(agb_handle* h, void* stream);
 

@@ -42,7 +42,7 @@ import pytest  # noqa: E402
 @pytest.mark.gpu
 def test_gpu_arm_prints_one_json_line():
     r = _run("--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--other-batch", "256", "--mpc-streams", "64", "--mpc-resolves", "5",
-             "--cpu-sample-other", "16")
+             "--cpu-sample-other", "16", "--quad-batch", "8")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
@@ -55,7 +55,7 @@ def test_gpu_arm_prints_one_json_line():
     assert d["roofline"]["bound"] == "fp64-issue" and d["roofline"]["unit"] == "TFLOP/s" and d["roofline"]["peak"] > 10.0
     assert 0.0 < d["roofline"]["hbm"]["frac"] < 0.05          # real DRAM traffic: a fraction of a per cent of the HBM peak
     oc = d["other_configs"]
-    assert isinstance(oc, list) and [o["workload"][0] for o in oc] == ["E", "D", "C"], oc
+    assert isinstance(oc, list) and [o["workload"][0] for o in oc] == ["E", "D", "C", "Q"], oc
     for o in oc:
         assert o["value"] > 0 and o["e2e"]["value"] > 0 and 0.5 < o["converged_fraction"] <= 1.0
         assert o["cpu_baseline"]["value"] > 0 and o["cpu_baseline"]["kind"] == "port"

@@ -389,3 +389,12 @@ def test_band_bulk_vs_c_oracle(capsys):
 
 def test_singular_fallback(monkeypatch):
     parity.check_singular_fallback(LIB, monkeypatch)
+
+
+def test_local_gather_two_devices():
+    """Single-process multi-GPU path of the C ABI (agb_peer_init / agb_peer_connect_local / agb_allgather): uneven shards on
+    two devices, every gather buffer holds every shard's results.  Needs two GPUs (skipped on a one-GPU box)."""
+    import torch
+    if os.environ.get("AGB_GPU_TESTS_ON_EMULATOR") or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    parity.check_local_gather(LIB, ndev=2, total=37)
