@@ -55,9 +55,10 @@ constexpr int kMaxNi = 12, kMaxMi = 4;
 // per-player continuous dynamics ẋ_i = f(x_i, u_i) (all models are separable per player)
 template <class T> __device__ void dyn_f(const DevDesc* d, const T* s, const T* u, T* f) {
   switch (d->model) {
-    case AGB_MODEL_DOUBLE_INTEGRATOR:                      // dynamics/double_integrator.jl:27-31
-      f[0] = s[2]; f[1] = s[3]; f[2] = u[0]; f[3] = u[1];
-      break;
+    case AGB_MODEL_DOUBLE_INTEGRATOR: {                    // dynamics/double_integrator.jl:27-31, any dimension d = mi
+      const int dd = d->mi;
+      for (int c = 0; c < dd; c++) { f[c] = s[dd + c]; f[dd + c] = u[c]; }
+    } break;
     case AGB_MODEL_UNICYCLE:                               // dynamics/unicycle.jl:27-32
       f[0] = cos_(s[2]) * s[3]; f[1] = sin_(s[2]) * s[3]; f[2] = u[0]; f[3] = u[1];
       break;

@@ -156,16 +156,17 @@ static int build_dev_desc(const agb_problem_desc* d, DevDesc* o, std::string* wh
   if (d->p < 1 || d->p > AGB_MAX_P) { *why = "p must be in 1..4"; return AGB_EINVAL; }
   if (d->model < 0 || d->model > 3) { *why = "unknown model"; return AGB_EINVAL; }
   if (d->solver != AGB_SOLVER_AUTO && d->solver != AGB_SOLVER_BAND) { *why = "unknown solver"; return AGB_EINVAL; }
-  if (d->model == AGB_MODEL_DOUBLE_INTEGRATOR && d->d != 2) { *why = "DoubleIntegratorGame: only d = 2 is supported"; return AGB_EUNSUPPORTED; }
+  if (d->model == AGB_MODEL_DOUBLE_INTEGRATOR && d->d != 2 && d->d != 3) { *why = "DoubleIntegratorGame: d must be 2 or 3"; return AGB_EUNSUPPORTED; }
   if (d->N < 2) { *why = "N must be >= 2"; return AGB_EINVAL; }
   if (!(d->dt > 0)) { *why = "dt must be positive"; return AGB_EINVAL; }
-  const int ni = d->model == AGB_MODEL_QUADROTOR ? 12 : 4, mi = d->model == AGB_MODEL_QUADROTOR ? 4 : 2;
+  const bool di3 = d->model == AGB_MODEL_DOUBLE_INTEGRATOR && d->d == 3;          // 3-D double integrator: band solver
+  const int ni = d->model == AGB_MODEL_QUADROTOR ? 12 : (di3 ? 6 : 4), mi = d->model == AGB_MODEL_QUADROTOR ? 4 : (di3 ? 3 : 2);
   const int p = d->p, n = ni * p, m = mi * p;
   o->ni = ni; o->mi = mi;
   o->model = d->model; o->p = p; o->n = n; o->m = m; o->N = d->N; o->K = d->N - 1;
   o->quad_mass = d->quad_mass; o->spherical = d->spherical_collision ? 1 : 0;
   if (d->model == AGB_MODEL_QUADROTOR && !(d->quad_mass > 0)) { *why = "QuadrotorGame: mass must be positive"; return AGB_EINVAL; }
-  o->use_band = (d->model == AGB_MODEL_QUADROTOR || d->spherical_collision || d->solver == AGB_SOLVER_BAND) ? 1 : 0;
+  o->use_band = (d->model == AGB_MODEL_QUADROTOR || di3 || d->spherical_collision || d->solver == AGB_SOLVER_BAND) ? 1 : 0;
   for (int i = 0; i < p; i++) if (d->n_walls3d[i] > 0 || d->n_cylinders[i] > 0) o->use_band = 1;
   o->kl = (2 * n - 1 > n + m) ? 2 * n - 1 : n + m;
   o->ku = (p * n + n - 1 > p * n + m) ? p * n + n - 1 : p * n + m;

@@ -100,15 +100,25 @@ def pack_host_results(out):
 
 def solve_sharded(make_batch, x0, xf, Z0, L0, opts, rank, world, gather=True):
     """Shard a batch contiguously across `world` ranks, solve the local shard, all-gather the results.
-    `make_batch(local_B)` returns a GameBatch on this rank's device."""
-    lo, hi = shard_bounds(x0.shape[0], world, rank)
+    `make_batch(local_B)` returns a GameBatch on this rank's device.  Shards may be uneven (total % world != 0): every rank
+    pads its slab to the largest shard for the collective and the padding is trimmed afterwards."""
+    total = x0.shape[0]
+    if world > total:
+        raise ValueError(f"cannot shard {total} instances over {world} ranks: every rank needs at least one instance")
+    lo, hi = shard_bounds(total, world, rank)
     gb = make_batch(hi - lo)
     gb.set_instance_params(x0=x0[lo:hi], xf=None if xf is None else xf[lo:hi])
     gb.set_initial(Z0[lo:hi], L0[lo:hi])
     out = gb.newton_solve(opts)
     slab = pack_host_results(out)
     if gather and world > 1:
-        slab = all_gather_results(slab)
+        import torch
+        sizes = [shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world)]
+        pad = max(sizes)
+        if slab.shape[0] < pad:
+            slab = torch.cat([slab, torch.zeros((pad - slab.shape[0], slab.shape[1]), dtype=slab.dtype)], dim=0)
+        full = all_gather_results(slab).view(world, pad, -1)
+        slab = torch.cat([full[r, :sizes[r]] for r in range(world)], dim=0)
     res = unpack_results(slab, gb.N, gb.n, gb.m, gb.p)
     gb.close()
     return res

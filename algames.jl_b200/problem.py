@@ -45,13 +45,13 @@ class _GameModel:
 
 
 class DoubleIntegratorGame(_GameModel):
-    """dynamics/double_integrator.jl:2-33 (only d = 2 is supported by the CUDA path)."""
+    """dynamics/double_integrator.jl:2-33: d = 2 (structured kernels) or d = 3 (band solver)."""
     name = "double_integrator"
 
     def __init__(self, p: int = 2, d: int = 2):
-        if d != 2:
-            raise NotImplementedError("DoubleIntegratorGame: only d = 2 is supported")
-        super().__init__(p)
+        if d not in (2, 3):
+            raise NotImplementedError("DoubleIntegratorGame: d must be 2 or 3")
+        super().__init__(p, 2 * d, d)
         self.d = d
 
 

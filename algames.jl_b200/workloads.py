@@ -227,6 +227,25 @@ def config_q(batch=8, seed=7890, N=12, p=2, constraints=True):
     return model, N, dt, obj, con, Options(), x0, None
 
 
-CONFIGS = {"Q": config_q, "S": config_s, "V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}
+def config_b3(batch=8, seed=8901, N=10):
+    """3-player DoubleIntegratorGame(d = 3) with spherical collision avoidance: the game of the reference's
+    test/constraints/constraints_methods.jl:30-57 given an objective (band solver)."""
+    p, dt = 3, 0.1
+    model = DoubleIntegratorGame(p=p, d=3)
+    obj = GameObjective([10 * np.ones(6)] * p, [0.1 * np.ones(3)] * p, [np.zeros(6)] * p, [np.zeros(3)] * p, N, model)
+    add_collision_cost(obj, 1.0 * np.ones(p), 2.0 * np.ones(p))
+    con = GameConstraintValues(ProblemSize(N, model))
+    add_spherical_collision_avoidance(con, 0.2)
+    add_control_bound(con, 3 * np.ones(model.m), -3 * np.ones(model.m))
+    rng = np.random.default_rng(seed)
+    th = 2 * math.pi * np.arange(p) / p
+    x0 = np.zeros((batch, model.n))
+    x0[:, 0:p] = 0.6 * np.cos(th) + rng.uniform(-0.05, 0.05, (batch, p))
+    x0[:, p:2 * p] = 0.6 * np.sin(th) + rng.uniform(-0.05, 0.05, (batch, p))
+    x0[:, 2 * p:3 * p] = rng.uniform(-0.2, 0.2, (batch, p))
+    return model, N, dt, obj, con, Options(), x0, None
+
+
+CONFIGS = {"B3": config_b3, "Q": config_q, "S": config_s, "V": config_v, "A": config_a, "A'": config_a_prime, "B": config_b, "C": config_c, "D": config_d, "E": config_e}
 for _ls in range(1, 5):                                   # "S1" … "S4": random StateBound layouts
     CONFIGS["S%d" % _ls] = (lambda ls: (lambda batch=4, N=8: config_s_random(ls, batch=batch, N=N)))(_ls)

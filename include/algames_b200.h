@@ -85,7 +85,7 @@ enum { AGB_OK = 0, AGB_EINVAL = -1, AGB_ECUDA = -2, AGB_ENOMEM = -3, AGB_EUNSUPP
 typedef struct agb_problem_desc {
   int model;                 /* AGB_MODEL_*                                              */
   int p;                     /* players (1..4); n = ni·p, m = mi·p (ni, mi = 4, 2; quadrotor 12, 4) */
-  int d;                     /* DoubleIntegratorGame dimension — only d = 2 is supported */
+  int d;                     /* DoubleIntegratorGame dimension: 2 (structured kernels) or 3 (band solver)      */
   int N;                     /* knots                                                    */
   double dt;
   double lf, lr;             /* BicycleGame (dynamics/bicycle.jl:15)                     */

@@ -16,9 +16,9 @@ import algames_b200 as ab
 from algames_b200 import distributed as D
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
-model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=4, N=10)
+model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=5, N=10)
 rng = np.random.default_rng(5)
-Z0 = 1e-8 * rng.random((4, N, model.n + model.m)); L0 = 1e-8 * rng.random((4, model.p, N - 1, model.n))
+Z0 = 1e-8 * rng.random((5, N, model.n + model.m)); L0 = 1e-8 * rng.random((5, model.p, N - 1, model.n))
 mk = lambda B: ab.GameBatch(model, N, dt, obj, con, B, lib_path=%(emu)r)
 res = D.solve_sharded(mk, x0, xf, Z0, L0, opts, rank, world)
 if rank == 0:
@@ -43,10 +43,13 @@ def test_sharded_solve_two_gloo_ranks(tmp_path):
     import algames_b200 as ab
     from algames_b200 import distributed as D
     assert D.shard_bounds(5, 2, 0) == (0, 3) and D.shard_bounds(5, 2, 1) == (3, 5)
-    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=4, N=10)
+    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=5, N=10)          # 5 instances on 2 ranks: uneven shards (3 + 2)
     rng = np.random.default_rng(5)
-    Z0 = 1e-8 * rng.random((4, N, model.n + model.m)); L0 = 1e-8 * rng.random((4, model.p, N - 1, model.n))
+    Z0 = 1e-8 * rng.random((5, N, model.n + model.m)); L0 = 1e-8 * rng.random((5, model.p, N - 1, model.n))
     ref = D.solve_sharded(lambda B: ab.GameBatch(model, N, dt, obj, con, B, lib_path=emu), x0, xf, Z0, L0, opts, 0, 1)
     for k in ("Z", "L", "stats", "status"):
         assert np.array_equal(got[k], ref[k]), k
-    assert (ref["status"] == 0).all()
+    assert (ref["status"] == 0).all() and ref["Z"].shape[0] == 5
+    import pytest
+    with pytest.raises(ValueError):
+        D.solve_sharded(None, x0[:1], None, Z0[:1], L0[:1], opts, 0, 2)

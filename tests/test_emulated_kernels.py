@@ -251,6 +251,12 @@ def test_band_per_function_parity_emulated(emu_lib, name, N, kw):
         parity.check_band_per_function(emu_lib, name, seed=3, N=N, **kw)
 
 
+def test_band_double_integrator_3d_emulated(emu_lib):
+    # DoubleIntegratorGame(d = 3) + add_spherical_collision_avoidance! (test/constraints/constraints_methods.jl:30-57)
+    parity.check_band_per_function(emu_lib, "B3", seed=2, N=5)
+    parity.check_band_solve_vs_oracle(emu_lib, "B3", B=1, N=6)
+
+
 def test_band_quadrotor_solve_emulated(emu_lib):
     parity.check_band_solve_vs_oracle(emu_lib, "Q", B=1, N=5, p=1)
     parity.check_band_solve_vs_oracle(emu_lib, "Q", B=1, N=4, p=2)

@@ -329,6 +329,12 @@ def test_band_per_function_parity(name, N, kw):
     parity.check_band_per_function(LIB, name, seed=4, N=N, **kw)
 
 
+def test_band_double_integrator_3d():
+    """DoubleIntegratorGame(d = 3) with spherical collision avoidance (test/constraints/constraints_methods.jl:30-57)."""
+    parity.check_band_per_function(LIB, "B3", seed=2, N=8)
+    parity.check_band_solve_vs_oracle(LIB, "B3", B=4, N=10, which=[0, 3])
+
+
 def test_band_quadrotor_solves_vs_oracle():
     """QuadrotorGame on the device: 1 and 2 players, spherical collision avoidance, rotor bounds, a 3-D wall and
     a cylinder — full newton_solve! vs the NumPy oracle: trajectories, duals, multipliers, the whole Statistics history."""
