@@ -1155,6 +1155,27 @@ struct Inst {
 #pragma unroll
           for (int r = 0; r < m; r++) kc[r] = ku[r * W + col];
           double pn[4];
+#ifdef AGB_P3_PREFETCH
+          // all four row groups are fetched before the first product, so that one shared-memory latency is exposed instead of four
+          double2 wv[4][m / 2]; double bs[4];
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int a = c * P + i2;
+            const double2* w = reinterpret_cast<const double2*>(Wm + (i * n + a) * m);
+            bs[c] = Base[(i * n + a) * n1 + col];
+#pragma unroll
+            for (int r = 0; r < m / 2; r++) wv[c][r] = w[r];
+          }
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int a = c * P + i2;
+            double v0 = bs[c], v1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < m; r += 2) { v0 -= wv[c][r / 2].x * kc[r]; v1 -= wv[c][r / 2].y * kc[r + 1]; }
+            pn[c] = v0 + v1;
+            if (col < n) Pm[(i * n + a) * n + col] = pn[c]; else Sv[i * n + a] = pn[c];
+          }
+#else
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const int a = c * P + i2;
@@ -1165,6 +1186,7 @@ struct Inst {
             pn[c] = v0 + v1;
             if (col < n) Pm[(i * n + a) * n + col] = pn[c]; else Sv[i * n + a] = pn[c];
           }
+#endif
           if (i2 == i) {                                    // Y for the next stage (s-1)
             double At[8], Bt[8]; loadAB(s - 1, i, At, Bt);
             Ym[(0 * P + i) * n1 + col] = bt_dot<0>(Bt, pn[0], pn[1], pn[2], pn[3]);

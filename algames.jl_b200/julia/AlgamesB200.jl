@@ -352,7 +352,37 @@ gather buffer over NVLink peer memory (the path's single collective, SURVEY §8e
 """
 mutable struct ShardedBatch
     handles::Vector{Ptr{Cvoid}}
-    shards::Vector{Batch}
+    bounds::Vector{UnitRange{Int}}          # problems of shard r (contiguous split, ranks < B % ndev get one more)
+    probs::Vector
+end
+
+function ShardedBatch(probs::AbstractVector{<:GameProblem}; devices::Union{Nothing,Vector{Cint}}=nothing)
+    B = length(probs); desc = Ref(make_desc(probs[1]))
+    ndev = Ref{Cint}(0); hs = Vector{Ptr{Cvoid}}(undef, 64)
+    rc = ccall((:agb_create_sharded, LIB), Cint, (Ref{AgbProblemDesc}, Cint, Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Ref{Cint}),
+               desc, B, devices === nothing ? 0 : length(devices), devices === nothing ? C_NULL : pointer(devices), hs, ndev)
+    rc == 0 || error("agb_create_sharded ($rc): " * unsafe_string(ccall((:agb_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    nd = Int(ndev[]); resize!(hs, nd)
+    bounds = UnitRange{Int}[]; lo = 1
+    for r in 0:nd-1
+        cnt = div(B, nd) + (r < B % nd ? 1 : 0); push!(bounds, lo:lo+cnt-1); lo += cnt
+    end
+    return ShardedBatch(hs, bounds, collect(probs))
+end
+
+"""
+    newton_solve!(sb::ShardedBatch)
+
+Every shard solved on its own GPU (asynchronously, no communication), then ONE all-gather: afterwards every GPU's gather
+buffer holds every shard's trajectories, duals, stats and status (`agb_gathered_view` / `agb_unpack_gathered`).
+"""
+function newton_solve!(sb::ShardedBatch)
+    o = Ref(AgbOptions(sb.probs[1].opts))
+    for (h, rng) in zip(sb.handles, sb.bounds)          # (initial iterates are pushed per shard with agb_set_instance_params /
+        check(ccall((:agb_newton_solve_async, LIB), Cint, (Ptr{Cvoid}, Ref{AgbOptions}, Ptr{Cvoid}), h, o, ccall((:agb_get_stream, LIB), Ptr{Cvoid}, (Ptr{Cvoid},), h)), h)
+    end                                                 #  agb_set_initial exactly as Batch does for one device)
+    allgather!(sb.handles)
+    return nothing
 end
 
 function allgather!(hs::Vector{Ptr{Cvoid}})

@@ -10,7 +10,7 @@ from .problem import GameBatch, Options
 
 
 def mpc_run(batch: GameBatch, opts: Options, x0, n_resolves: int, xf=None, disturbance_std: float = 0.0, seed: int = 0,
-            stream: int = 0, collect: bool = True):
+            stream: int = 0, collect: bool = True, disturbances=None):
     """Run `n_resolves` warm-started re-solves for every stream of the batch.  Returns per-step stats
     [n_resolves, B, 10], status [n_resolves, B] and the executed closed-loop states [n_resolves + 1, B, n]."""
     rng = np.random.default_rng(seed)
@@ -26,7 +26,10 @@ def mpc_run(batch: GameBatch, opts: Options, x0, n_resolves: int, xf=None, distu
             stats.append(out["stats"]); status.append(out["status"])
         else:
             batch.newton_solve(first if t == 0 else warm, want=())      # same stream as mpc_advance; no D2H copies
-        d = disturbance_std * rng.standard_normal((B, n)) if disturbance_std > 0 else None
+        if disturbances is not None:
+            d = np.ascontiguousarray(disturbances[t])              # caller-supplied [n_resolves, B, n]
+        else:
+            d = disturbance_std * rng.standard_normal((B, n)) if disturbance_std > 0 else None
         if collect:
             xs.append(out["Z"][:, 1, :n] + (0.0 if d is None else d))
         batch.mpc_advance(1, d)

@@ -404,3 +404,40 @@ def test_local_gather_two_devices():
     if os.environ.get("AGB_GPU_TESTS_ON_EMULATOR") or torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
     parity.check_local_gather(LIB, ndev=2, total=37)
+
+
+def test_handles_of_different_footprints_coexist():
+    """The dynamic-shared-memory opt-in limit is a per-kernel attribute shared by every handle of the same template instance: a
+    later, smaller handle must not lower it under an earlier, larger one (config B at N = 40 needs 56 KB, above the 48 KB default)."""
+    import algames_b200 as ab
+    big = ab.workloads.config_b(batch=4, N=40)
+    small = ab.workloads.config_b(batch=4, N=6)
+    g1 = ab.GameBatch(big[0], big[1], big[2], big[3], big[4], 4, lib_path=LIB)
+    g2 = ab.GameBatch(small[0], small[1], small[2], small[3], small[4], 4, lib_path=LIB)
+    g2.set_instance_params(x0=small[6]); g2.random_initial()
+    assert (g2.newton_solve(small[5])["status"] == 0).all()
+    g1.set_instance_params(x0=big[6]); g1.random_initial()
+    assert (g1.newton_solve(big[5])["status"] == 0).all()          # launches of the earlier, larger handle still fit
+    g1.close(); g2.close()
+
+
+def test_async_solve_is_ordered_with_the_handle_stream():
+    """agb_newton_solve_async on a caller stream, then calls that run on the handle's own stream (get_state, mpc_advance,
+    residual): they must see the finished solve — same results as the synchronous call, without any host synchronisation in
+    between."""
+    if os.environ.get("AGB_GPU_TESTS_ON_EMULATOR"):
+        pytest.skip("streams are not emulated")
+    import torch
+    import algames_b200 as ab
+    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=256, N=40)
+    gb = ab.GameBatch(model, N, dt, obj, con, 256, lib_path=LIB)
+    gb.set_instance_params(x0=x0)
+    Z0, L0 = gb.random_initial()
+    ref = gb.newton_solve(opts)
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        gb.set_initial(Z0, L0)
+        gb.newton_solve_async(opts, side.cuda_stream)
+        Z, L, cl, cm = gb.get_state()                                # runs on the handle's stream, right behind the launch
+        assert np.array_equal(Z, ref["Z"]) and np.array_equal(L, ref["L"]) and np.array_equal(cl, ref["conlam"])
+    gb.close()
