@@ -84,6 +84,8 @@ SYMBOLS = {
     "agb_shift_initial": (C.c_int, [_H, C.c_int, _DP, _DP]),
     "agb_mpc_advance": (C.c_int, [_H, C.c_int, _DP, _DP, _DP]),
     "agb_mpc_advance_async": (C.c_int, [_H, C.c_int, C.c_void_p]),
+    "agb_mpc_run_async": (C.c_int, [_H, C.POINTER(OptionsC), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agb_mpc_run": (C.c_int, [_H, C.POINTER(OptionsC), C.c_int, C.c_int, _DP, _DP, _IP, _DP]),
     "agb_get_stream": (C.c_void_p, [_H]),
     "agb_join_stream": (C.c_int, [_H, C.c_void_p]),
     "agb_rollout": (C.c_int, [_H]),

@@ -124,6 +124,7 @@ struct agb_handle {
   double* stage = nullptr; size_t stage_bytes = 0;     // scratch for exported outputs
   double* stage2 = nullptr; size_t stage2_bytes = 0;
   double* stage3 = nullptr;                            // disturbance staging of agb_mpc_advance
+  double* stage_mpc = nullptr; size_t stage_mpc_bytes = 0;   // agb_mpc_run: disturbances in, per-re-solve records out
   long long launches = 0;
   size_t smem_bytes = 0;
   cudaEvent_t ev_async = nullptr;                      // orders agb_newton_solve_async (caller stream) against h->stream
@@ -348,7 +349,7 @@ void agb_destroy(agb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->hist, h->hist_count, h->Hpg, h->band, h->conlam0, h->conmu0};
+  void* ptrs[] = {h->dd, h->x0, h->xf, h->Q, h->R, h->uf, h->Z0, h->L0, h->results, h->conlam, h->conmu, h->D, h->KUg, h->stage, h->stage2, h->stage3, h->stage_mpc, h->hist, h->hist_count, h->Hpg, h->band, h->conlam0, h->conmu0};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int r = 0; r < h->nranks; r++) if (h->peer_ipc_opened[r]) cudaIpcCloseMemHandle(h->peer_gather[r]);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -571,6 +572,80 @@ int agb_mpc_advance_async(agb_handle* h, int s, const double* disturbance_dev) {
   return AGB_OK;
 }
 
+static int launch_solve_range(agb_handle* h, const agb_options* o, cudaStream_t st, int lo, int hi, int slot0, int nslots, const MpcArgs* mp = nullptr);
+static int launch_solve(agb_handle* h, const agb_options* o, cudaStream_t st);
+static int finish(agb_handle* h);
+
+// The whole receding-horizon loop in ONE launch of the solve kernel (MpcArgs, agb_kernels.cuh): stream b's CTA runs its `resolves`
+// re-solves back to back, so a stream that needs 140 Newton steps at one re-solve delays nobody else — the step-wise loop pays the
+// slowest stream at every step.  The last advance goes through agb_mpc_advance_async, which leaves the handle (Z, L, Z0, L0, x0)
+// exactly as the step-wise loop does.  Band-solver schemas run the step-wise loop here, with the same outputs.
+int agb_mpc_run_async(agb_handle* h, const agb_options* o, int resolves, int s, const double* disturbance_dev, double* stats_dev,
+                      int* status_dev, double* xs_dev, void* stream) {
+  if (!h || !o || !stats_dev || !status_dev) return AGB_EINVAL;
+  if (resolves < 1) return fail(h, AGB_EINVAL, "resolves must be >= 1");
+  if (s < 1 || s >= h->hd.N) return fail(h, AGB_EINVAL, "shift must be in 1..N-1");
+  if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1) return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter must be >= 1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const size_t B = h->batch, n = h->hd.n;
+  if (st != h->stream) {
+    AGB_CUDA(h, cudaEventRecord(h->ev_async, h->stream));
+    AGB_CUDA(h, cudaStreamWaitEvent(st, h->ev_async, 0));
+  }
+  if (h->hd.use_band) {
+    if (st != h->stream) return fail(h, AGB_EUNSUPPORTED, "band-solver schemas run the receding-horizon loop on the handle's own stream");
+    agb_options ow = *o;
+    for (int t = 0; t < resolves; t++) {
+      AGB_TRY(launch_solve(h, t == 0 ? o : &ow, st));
+      ow.dual_reset = 0;
+      AGB_CUDA(h, cudaMemcpyAsync(stats_dev + (size_t)t * B * AGB_NSTATS, h->stats, B * AGB_NSTATS * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      AGB_CUDA(h, cudaMemcpyAsync(status_dev + (size_t)t * B, h->status, B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+      if (t + 1 < resolves) {
+        AGB_TRY(agb_mpc_advance_async(h, s, disturbance_dev ? disturbance_dev + (size_t)t * B * n : nullptr));
+        if (xs_dev) AGB_CUDA(h, cudaMemcpyAsync(xs_dev + (size_t)t * B * n, h->x0, B * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      }
+    }
+  } else {
+    MpcArgs mp;
+    mp.resolves = resolves; mp.shift = s; mp.dist = disturbance_dev; mp.stats = stats_dev; mp.status = status_dev; mp.xs = xs_dev;
+    AGB_TRY(launch_solve_range(h, o, st, 0, h->batch, 0, h->band_slots, &mp));
+  }
+  if (st != h->stream) {
+    AGB_CUDA(h, cudaEventRecord(h->ev_async, st));
+    AGB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_async, 0));
+  }
+  AGB_TRY(agb_mpc_advance_async(h, s, disturbance_dev ? disturbance_dev + (size_t)(resolves - 1) * B * n : nullptr));   // on the handle's stream
+  if (h->hd.use_band && xs_dev)
+    AGB_CUDA(h, cudaMemcpyAsync(xs_dev + (size_t)(resolves - 1) * B * n, h->x0, B * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return AGB_OK;
+}
+
+// Host-buffer form: disturbance [resolves][B][n] (or NULL) in, per-re-solve stats / status / executed states out.
+int agb_mpc_run(agb_handle* h, const agb_options* o, int resolves, int s, const double* disturbance, double* stats_out,
+                int* status_out, double* xs_out) {
+  if (!h || !o) return AGB_EINVAL;
+  if (resolves < 1) return fail(h, AGB_EINVAL, "resolves must be >= 1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = h->batch, n = h->hd.n, R = (size_t)resolves;
+  const size_t nd = disturbance ? R * B * n : 0, ns = R * B * AGB_NSTATS, nx = xs_out ? R * B * n : 0;
+  const size_t status_doubles = (R * B * sizeof(int) + sizeof(double) - 1) / sizeof(double);
+  AGB_TRY(ensure_stage(h, &h->stage_mpc, &h->stage_mpc_bytes, (nd + ns + nx + status_doubles) * sizeof(double)));
+  double* dd = disturbance ? h->stage_mpc : nullptr;
+  double* sd = h->stage_mpc + nd;
+  double* xd = xs_out ? sd + ns : nullptr;
+  int* td = (int*)(sd + ns + nx);
+  AGB_TRY(h2d(h, dd, disturbance, nd));
+  AGB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  AGB_TRY(agb_mpc_run_async(h, o, resolves, s, dd, sd, td, xd, h->stream));
+  AGB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  AGB_TRY(d2h(h, stats_out, sd, ns));
+  AGB_TRY(d2h(h, xs_out, xd, nx));
+  if (status_out) AGB_CUDA(h, cudaMemcpyAsync(status_out, td, R * B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
 void* agb_get_stream(agb_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int agb_join_stream(agb_handle* h, void* stream) {
@@ -752,7 +827,7 @@ int agb_debug_gain_solve(agb_handle* h, const double* aug, double* aug_out, int*
 // newton_solve! of instances [lo, hi) on stream st: the band solver for band-only schemas; otherwise the structured kernel,
 // followed (fallback) by a band-solver launch that re-solves, from the same initial iterate, the instances it left
 // AGB_SINGULAR.  `slot0 / nslots`: the band scratch slots this launch may use (concurrent chunks get disjoint slots).
-static int launch_solve_range(agb_handle* h, const agb_options* o, cudaStream_t st, int lo, int hi, int slot0, int nslots) {
+static int launch_solve_range(agb_handle* h, const agb_options* o, cudaStream_t st, int lo, int hi, int slot0, int nslots, const MpcArgs* mp) {
   Buffers g = buffers_of(h);
   if (h->hd.use_band) {
     const int grid = (hi - lo) < nslots ? (hi - lo) : nslots;
@@ -772,10 +847,12 @@ static int launch_solve_range(agb_handle* h, const agb_options* o, cudaStream_t 
   L.model = h->hd.model; L.grid = hi - lo; L.smem = h->smem_bytes; L.stream = st; L.dd = h->dd; L.o = *o;
   memset(&L.io, 0, sizeof L.io);
   L.g = g; memset(&L.a, 0, sizeof L.a); L.batch = hi; L.inst0 = lo;
+  memset(&L.mp, 0, sizeof L.mp);
+  if (mp) L.mp = *mp;
   agb::launch_solve(h->hd.p, h->hd.big, L);
   h->launches++;
   AGB_CUDA(h, cudaGetLastError());
-  if (fb) {
+  if (fb && !mp) {
     g.band = h->band + (size_t)slot0 * h->band_stride; g.band_slots = nslots;
     if (!o->dual_reset && cs) { g.conlam0 = h->conlam0; g.conmu0 = h->conmu0; }
     const int grid = (hi - lo) < nslots ? (hi - lo) : nslots;

@@ -97,6 +97,16 @@ struct Buffers {
   int hpg_stride;
 };
 
+// Receding-horizon loop run inside the solve kernel (agb_mpc_run): every stream's CTA does `resolves` × (newton_solve!, advance by
+// `shift` knots) on its own.  All pointers are device memory; resolves == 0 means one plain solve and nothing else here is read.
+struct MpcArgs {
+  int resolves, shift;
+  const double* dist;   // [resolves][B][n] disturbance added to the executed state, or nullptr
+  double* stats;        // [resolves][B][AGB_NSTATS]
+  int* status;          // [resolves][B]
+  double* xs;           // [resolves][B][n] executed states (x0 of the next re-solve), or nullptr
+};
+
 enum Op {
   OP_ROLLOUT = 0, OP_RESIDUAL, OP_JAC_DENSE, OP_KKT_SOLVE, OP_LINE_SEARCH, OP_UPDATE,
   OP_DUAL_UPDATE, OP_PENALTY_UPDATE, OP_RESET, OP_EVAL_CON, OP_ACTIVE_SET, OP_GAIN_SOLVE, OP_VIOLATIONS

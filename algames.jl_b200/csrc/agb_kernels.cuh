@@ -17,7 +17,7 @@ namespace agb {
 // =============================================================================================================
 // newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
 template <int P, int MODEL, int LAY>
-__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 : 4))) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch) {
+__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 : 4))) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch, MpcArgs mp) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;
   I.bind(dd, sm);
@@ -35,9 +35,13 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     I.load_iterate(g.Z0, g.L0, inst, &g);
     __syncthreads();
     for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];     // x_1 ← x0 (primal_dual_traj.jl:42)
+    // Receding horizon (mp.resolves > 0): this CTA runs ALL re-solves of its stream back to back — solve, apply the first
+    // control (x0 ← x_{1+s} + disturbance), shift the iterate by s knots in shared memory, re-solve keeping multipliers and
+    // penalties (Options.shift / dual_reset = false, options.jl:16-17) — with no launch boundary and no other stream to wait for.
+    for (int t_mpc = 0;; t_mpc++) {
     __syncthreads();
     I.rollout();                                                                        // :17
-    if (o.dual_reset) I.reset_duals_penalties(o);                                       // :25
+    if (o.dual_reset && t_mpc == 0) I.reset_duals_penalties(o);                         // :25
 #ifdef AGB_PHASE_TIMING
 #define AGB_PROFK(k) do { const long long t_ = clock64(); I.prof[k] += t_ - I.prof_t; I.prof_t = t_; } while (0)
 #else
@@ -101,6 +105,22 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     if (g.hist != nullptr && I.tid == 0) g.hist_count[inst] = n_rec;
     const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
     const bool conv = finite && rec.dyn < o.eps_dyn && rec.con < o.eps_con && rec.sta < o.eps_sta && rec.opt < o.eps_opt;
+    if (mp.resolves > 0) {
+      if (I.tid == 0) {                                                                 // this re-solve's record: [resolves][batch][…]
+        double* st = mp.stats + ((size_t)t_mpc * batch + inst) * AGB_NSTATS;
+        st[0] = rec.sum / S; st[1] = rec.dyn; st[2] = rec.con; st[3] = rec.sta; st[4] = rec.opt;
+        st[5] = delta; st[6] = (double)n_newton; st[7] = (double)outer_done; st[8] = (double)n_eval; st[9] = (double)(failed != 0);
+        mp.status[(size_t)t_mpc * batch + inst] = conv ? AGB_CONVERGED : (failed ? failed : (!finite ? AGB_NONFINITE : last_exit));
+      }
+      if (mp.xs != nullptr)                                                             // executed state x_{1+s} + disturbance
+        for (int a = I.tid; a < n; a += kThreads)
+          mp.xs[((size_t)t_mpc * batch + inst) * n + a] = I.X[mp.shift * n + a] + (mp.dist ? mp.dist[((size_t)t_mpc * batch + inst) * n + a] : 0.0);
+      if (t_mpc + 1 < mp.resolves) {                                                    // (the host applies the last advance)
+        __syncthreads();
+        I.mpc_shift(mp.shift, mp.dist ? mp.dist + ((size_t)t_mpc * batch + inst) * n : nullptr);
+        continue;
+      }
+    }
     I.store_iterate(g.Z, g.L, inst);
     I.store_duals(g, inst);
     AGB_PROFK(11);
@@ -114,6 +134,8 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
       st[5] = delta; st[6] = (double)n_newton; st[7] = (double)outer_done; st[8] = (double)n_eval; st[9] = (double)(failed != 0);
       g.status[inst] = conv ? AGB_CONVERGED : (failed ? failed : (!finite ? AGB_NONFINITE : last_exit));
     }
+    break;
+    }   // re-solves of this stream
   }
 }
 
@@ -392,6 +414,7 @@ struct LaunchArgs {
   OpArgs a;
   int batch;
   int inst0;             // first instance of the launch (newton_solve only; chunked host pipeline)
+  MpcArgs mp;            // receding-horizon loop inside the solve kernel (resolves <= 1: one plain solve)
 };
 
 template <int P, int MODEL, int LAY> inline cudaError_t set_attr_pm(size_t smem) {
@@ -410,7 +433,7 @@ template <int P, int LAY> inline cudaError_t set_attr_p(int model, size_t smem) 
 }
 template <int P, int MODEL, int LAY> inline void launch_solve_pm(const LaunchArgs& L) {
   auto kfn = agb_newton_solve_kernel<P, MODEL, LAY>;
-  AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.inst0, L.batch);
+  AGB_LAUNCH(kfn, L.grid, threads_for(P), L.smem, L.stream, L.dd, L.o, L.g, L.inst0, L.batch, L.mp);
 }
 template <int P, int MODEL, int LAY> inline void launch_ibr_pm(const LaunchArgs& L) {
   auto kfn = agb_ibr_solve_kernel<P, MODEL, LAY>;

@@ -1593,6 +1593,22 @@ struct Inst {
     if (bulk) { if (tid == 0) bulk_commit_wait(); }          // (Λ's shared copy is not rewritten before the next block barrier)
     else for (int item = tid; item < P * K * n; item += kThreads) l[item] = L[item];
   }
+  // Receding-horizon advance inside the CTA (the in-kernel form of agb_advance_kernel + agb_shift_kernel, agb_capi.cu): the iterate
+  // moves s knots forward — z_k ← z_{k+s}, λ_k ← λ_{k+s}, zero tail (init_traj! with s, primal_dual_traj.jl:34-41) — and
+  // x_1 ← x_{1+s} + disturbance.  One thread per component walks its column in ascending k, so the shift is in place.
+  __device__ void mpc_shift(int s, const double* __restrict__ dist) {
+    if (tid < n) {
+      const double x0n = X[s * n + tid] + (dist ? dist[tid] : 0.0);
+      for (int k = 0; k < N; k++) X[k * n + tid] = (k + s < N) ? X[(k + s) * n + tid] : 0.0;
+      X[tid] = x0n;
+    } else if (tid < n + m) {
+      const int e = tid - n;
+      for (int k = 0; k < N; k++) U[k * m + e] = (k + s < N) ? U[(k + s) * m + e] : 0.0;
+    } else if (tid < n + m + P * n) {
+      const int r = tid - n - m, i = r / n, e = r - i * n;
+      for (int k = 0; k < K; k++) L[(i * K + k) * n + e] = (k + s < K) ? L[(i * K + k + s) * n + e] : 0.0;
+    }
+  }
   __device__ void load_duals(const Buffers& g, int inst) {
     const size_t o = (size_t)inst * K * nrow;
     for (int item = tid; item < K * nrow; item += kThreads) { CL[item] = g.conlam[o + item]; CM[item] = g.conmu[o + item]; }

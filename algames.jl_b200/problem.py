@@ -545,6 +545,26 @@ class GameBatch:
         """agb_mpc_advance_async: the same step with a DEVICE pointer for the disturbance (0 = none) and no host sync."""
         self._ck(self.lib.agb_mpc_advance_async(self.h, int(s), C.c_void_p(disturbance_dev) if disturbance_dev else None))
 
+    def mpc_run(self, opts: "Options", resolves: int, s: int = 1, disturbances=None, want_xs: bool = True):
+        """agb_mpc_run: the whole receding-horizon loop of every stream in one launch.  disturbances [resolves, B, n] or None.
+        Returns per-re-solve stats [resolves, B, 10], status [resolves, B] and the executed states [resolves, B, n]."""
+        R, B = int(resolves), self.batch
+        d = self._arr(disturbances, (R, B, self.n))
+        stats = np.empty((R, B, _capi.NSTATS)); status = np.empty((R, B), dtype=np.int32)
+        xs = np.empty((R, B, self.n)) if want_xs else None
+        o = opts.to_c()
+        self._ck(self.lib.agb_mpc_run(self.h, C.byref(o), R, int(s), _capi.dptr(d), _capi.dptr(stats),
+                                      status.ctypes.data_as(C.POINTER(C.c_int)), _capi.dptr(xs)))
+        return stats, status, xs
+
+    def mpc_run_async(self, opts: "Options", resolves: int, s: int, disturbance_dev: int, stats_dev: int, status_dev: int,
+                      xs_dev: int = 0, stream: int = 0):
+        """agb_mpc_run_async: device pointers (integers) in and out, nothing synchronises."""
+        o = opts.to_c()
+        vp = lambda a: C.c_void_p(a) if a else None
+        self._ck(self.lib.agb_mpc_run_async(self.h, C.byref(o), int(resolves), int(s), vp(disturbance_dev), vp(stats_dev),
+                                            vp(status_dev), vp(xs_dev), vp(stream)))
+
     def stream(self) -> int:
         """agb_get_stream: the handle's own cudaStream_t (as an integer)."""
         return int(self.lib.agb_get_stream(self.h) or 0)

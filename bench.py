@@ -551,26 +551,62 @@ def run_mpc_config(ctx, streams, resolves, cpu_streams, cpu_resolves):
         torch.cuda.synchronize(ctx.dev)
         return a.elapsed_time(b), float(conv.item()), float(newton.item())
 
-    loop(False)                                      # warm-up pass (same work)
+    # (1) the fused loop: agb_mpc_run_async — every stream's CTA runs all its re-solves inside ONE launch of the solve kernel
+    stats_dev = torch.empty((resolves, streams, 10), dtype=torch.float64, device=ctx.dev)
+    status_dev = torch.empty((resolves, streams), dtype=torch.int32, device=ctx.dev)
+    xs_dev = torch.empty((resolves, streams, n), dtype=torch.float64, device=ctx.dev)
+
+    def fused():
+        gb.set_instance_params(x0=x0, xf=xf)
+        gb.random_initial(opts.amplitude_init, opts.seed + rank)
+        torch.cuda.synchronize(ctx.dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hs = torch.cuda.ExternalStream(gb.stream(), device=ctx.dev)
+        with torch.cuda.stream(hs):
+            a.record(hs)
+            gb.mpc_run_async(first, resolves, 1, dist_dev.data_ptr(), stats_dev.data_ptr(), status_dev.data_ptr(), xs_dev.data_ptr(), hs.cuda_stream)
+            b.record(hs)
+        torch.cuda.synchronize(ctx.dev)
+        return a.elapsed_time(b), float((status_dev == 0).sum().item()), float(stats_dev[:, :, 6].sum().item()), float(stats_dev[:, :, 6].max().item())
+
+    fused()                                          # warm-up pass (same work)
+    ms_f, conv_f, newton_f, newton_max = fused()
+    ms_f_max = ctx.allreduce([ms_f], "max")[0]
+    conv_fa, newton_fa = ctx.allreduce([conv_f, newton_f])
+    newton_max = ctx.allreduce([newton_max], "max")[0]
+    # (2) the step-wise loop (one launch per re-solve; a step lasts as long as its slowest stream), for comparison
+    loop(False)
     ms, conv_l, newton_l = loop(True)
     ms_max = ctx.allreduce([ms], "max")[0]
     conv, newton = ctx.allreduce([conv_l, newton_l])
-    # e2e: every re-solve's trajectories, stats and status copied to the host, disturbance supplied from the host
+    # e2e: disturbances supplied from the host, every re-solve's stats, status and executed state copied back (agb_mpc_run)
+    gb.set_instance_params(x0=x0, xf=xf)
+    gb.random_initial(opts.amplitude_init, opts.seed + rank)
+    ctx.sync_all()
     t0 = time.perf_counter()
-    e2e_n = resolves
-    stats, status, xs = ab.mpc.mpc_run(gb, opts, x0, e2e_n, xf=xf, disturbances=dist_np)
+    stats, status, xs = gb.mpc_run(first, resolves, 1, dist_np)
     ctx.sync_all()
     e2e_t = ctx.allreduce([time.perf_counter() - t0], "max")[0]
     e2e_conv = ctx.allreduce([float((status == 0).sum())])[0]
+    same = bool(np.array_equal(status, status_dev.cpu().numpy()) and np.array_equal(stats, stats_dev.cpu().numpy()))
+    # e2e of the step-wise host loop (trajectories, stats and status to the host after every re-solve)
+    t0 = time.perf_counter()
+    stats_s, status_s, xs_s = ab.mpc.mpc_run(gb, opts, x0, resolves, xf=xf, disturbances=dist_np)
+    ctx.sync_all()
+    e2e_step_t = ctx.allreduce([time.perf_counter() - t0], "max")[0]
+    same_step = bool(np.array_equal(status_s, status) and np.array_equal(stats_s, stats))
     rec = {"workload": "D: MPC ramp merge, 3-player UnicycleGame N=40, shift=1, dual_reset=false, x0 <- x_2 + N(0,1e-3) after every solve",
            "streams": int(total), "streams_per_gpu": int(streams), "resolves": int(resolves), "n_gpus": world,
-           "value": conv / (ms_max / 1e3), "unit": "converged re-solves/s", "ms_per_resolve": ms_max / resolves,
-           "converged_fraction": conv / (total * resolves), "newton_steps_per_resolve": newton / (total * resolves),
-           "loop": "device-resident: agb_newton_solve_async + agb_mpc_advance_async per re-solve on the handle's stream, no host synchronisation; timed with CUDA events. "
-                   "A step lasts as long as its slowest stream: the rare re-solve that runs to outer_iter (up to 140 Newton steps) holds the whole batch",
-           "newton_steps_max_per_resolve": None,
-           "e2e": {"value": e2e_conv / e2e_t, "unit": "converged re-solves/s", "resolves": int(e2e_n),
-                   "what": "agb_newton_solve_batch + agb_mpc_advance with host disturbances; trajectories, stats and status copied to the host after every re-solve"}}
+           "value": conv_fa / (ms_f_max / 1e3), "unit": "converged re-solves/s", "ms_per_resolve": ms_f_max / resolves,
+           "converged_fraction": conv_fa / (total * resolves), "newton_steps_per_resolve": newton_fa / (total * resolves),
+           "newton_steps_max_per_resolve": newton_max,
+           "loop": "agb_mpc_run_async: ONE launch of the solve kernel, every stream's CTA runs its re-solves back to back in shared memory "
+                   "(solve, x0 <- x_2 + disturbance, shift, re-solve) — no stream waits for another; timed with CUDA events",
+           "stepwise": {"value": conv / (ms_max / 1e3), "ms_per_resolve": ms_max / resolves,
+                        "loop": "agb_newton_solve_async + agb_mpc_advance_async per re-solve (5 launches each), no host sync: a step lasts as long as its slowest stream",
+                        "e2e_value": e2e_conv / e2e_step_t, "identical_to_fused": same_step},
+           "e2e": {"value": e2e_conv / e2e_t, "unit": "converged re-solves/s", "resolves": int(resolves), "identical_to_device_loop": same,
+                   "what": "agb_mpc_run: disturbances from host memory, per-re-solve stats, status and executed states copied back"}}
     gb.close()
     if rank == 0 and world == 1 and cpu_streams > 0:
         # CPU arm on the same kind of loop: C oracle, cpu_streams streams × cpu_resolves re-solves

@@ -208,6 +208,21 @@ int agb_mpc_advance(agb_handle* h, int s, const double* disturbance, const doubl
  * zero, nothing synchronises.  agb_newton_solve_async + agb_mpc_advance_async, repeated, is one uninterrupted stream of
  * kernels (the ordering rules of agb_newton_solve_async apply). */
 int agb_mpc_advance_async(agb_handle* h, int s, const double* disturbance_dev);
+/* The whole receding-horizon loop of every stream in ONE kernel launch (config D: Options.shift = s, dual_reset = false after
+ * the first solve; struct/options.jl:16-17, :114-115; init_traj! with s, primal_dual_traj.jl:34-41).  Stream b's CTA runs
+ * `resolves` x (newton_solve!, x0 <- x_{1+s} + disturbance[t][b], shift by s knots, multipliers and penalties carried) back to
+ * back in shared memory: no launch boundary, and a stream whose re-solve runs long holds nobody else.  Bit for bit the same
+ * results as `resolves` x (agb_newton_solve_async, agb_mpc_advance_async); afterwards the handle holds the last solution advanced
+ * once, exactly as that loop leaves it.  o->dual_reset applies to the first re-solve only.  A re-solve the structured kernel
+ * reports AGB_SINGULAR is recorded as such and the stream carries on from it (the step-wise loop would re-solve it with the band
+ * solver).  All pointers are DEVICE memory: disturbance_dev [resolves][B][n] or NULL; stats_dev [resolves][B][AGB_NSTATS];
+ * status_dev [resolves][B]; xs_dev [resolves][B][n] executed states (the x0 of re-solve t+1), or NULL.  stream: a cudaStream_t, or
+ * NULL for the handle's own.  QuadrotorGame / 3-D schemas (band solver) run the step-wise loop behind the same call. */
+int agb_mpc_run_async(agb_handle* h, const agb_options* o, int resolves, int s, const double* disturbance_dev, double* stats_dev,
+                      int* status_dev, double* xs_dev, void* stream);
+/* The same with HOST buffers (disturbance may be NULL; stats_out / status_out / xs_out may be NULL), synchronous. */
+int agb_mpc_run(agb_handle* h, const agb_options* o, int resolves, int s, const double* disturbance, double* stats_out,
+                int* status_out, double* xs_out);
 /* The handle's own stream (a cudaStream_t): pass it to agb_newton_solve_async to keep a device-resident loop on ONE stream. */
 void* agb_get_stream(agb_handle* h);
 /* Makes `stream` (a cudaStream_t) wait, on the device, for everything enqueued so far on the handle's own stream. */

@@ -700,3 +700,35 @@ def check_singular_fallback(lib_path, monkeypatch):
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     assert np.array_equal(b["stats"][:, 9] >= 2, np.arange(6) % 3 == 0), b["stats"][:, 9]
     assert np.abs(a["Z"] - b["Z"]).max() < TOL_SOLVE and np.array_equal(a["stats"][:, 6], b["stats"][:, 6])
+
+
+def check_mpc_fused_equals_stepwise(lib_path, name="D", B=8, N=None, resolves=6, disturbance_std=1e-3, seed=5, force_layout=None):
+    """agb_mpc_run (every stream's whole receding-horizon loop inside ONE launch of the solve kernel) against the step-wise loop
+    agb_newton_solve_batch + agb_mpc_advance: per-re-solve stats and status, executed states, and the handle's final state
+    (Z, L, multipliers, penalties) must be IDENTICAL bit for bit — the streams are independent and the arithmetic is the same."""
+    import os
+    cfg = small_config(name, B, N)
+    model, N_, dt, obj, con, opts, x0, xf = cfg
+    rng = np.random.default_rng(seed)
+    dist = disturbance_std * rng.standard_normal((resolves, B, model.n))
+    if force_layout is not None:
+        os.environ["AGB_FORCE_BIG_LAYOUT"] = str(force_layout)
+    try:
+        g1 = ab.GameBatch(model, N_, dt, obj, con, B, lib_path=lib_path)
+        g2 = ab.GameBatch(model, N_, dt, obj, con, B, lib_path=lib_path)
+    finally:
+        os.environ.pop("AGB_FORCE_BIG_LAYOUT", None)
+    stats1, status1, xs1 = ab.mpc.mpc_run(g1, opts, x0, resolves, xf=xf, disturbances=dist)
+    g2.set_instance_params(x0=x0, xf=xf)
+    g2.random_initial(opts.amplitude_init, opts.seed)
+    first = ab.Options(**{**opts.to_dict(), "dual_reset": True})
+    stats2, status2, xs2 = g2.mpc_run(first, resolves, 1, dist)
+    assert np.array_equal(status1, status2), (status1, status2)
+    assert np.array_equal(stats1, stats2), np.abs(stats1 - stats2).max()
+    assert np.array_equal(xs1[1:], xs2)
+    for a, b in zip(g1.get_state(), g2.get_state()):
+        assert np.array_equal(a, b)
+    v1, v2 = g1.newton_solve(ab.Options(**{**opts.to_dict(), "dual_reset": False})), g2.newton_solve(ab.Options(**{**opts.to_dict(), "dual_reset": False}))
+    assert np.array_equal(v1["Z"], v2["Z"]) and np.array_equal(v1["stats"], v2["stats"])      # x0 and the warm start carried over too
+    g1.close(); g2.close()
+    return stats2, status2

@@ -269,3 +269,9 @@ def test_band_equals_structured_emulated(emu_lib):
 
 def test_singular_fallback_emulated(emu_lib, monkeypatch):
     parity.check_singular_fallback(emu_lib, monkeypatch)
+
+
+def test_mpc_fused_loop_equals_stepwise_emulated(emu_lib):
+    """agb_mpc_run (the receding-horizon loop inside the solve kernel) == the step-wise loop, bit for bit, on the CTA emulator."""
+    parity.check_mpc_fused_equals_stepwise(emu_lib, "D", B=3, N=10, resolves=4)
+    parity.check_mpc_fused_equals_stepwise(emu_lib, "D", B=2, N=8, resolves=3, force_layout=2)

@@ -441,3 +441,10 @@ def test_async_solve_is_ordered_with_the_handle_stream():
         Z, L, cl, cm = gb.get_state()                                # runs on the handle's stream, right behind the launch
         assert np.array_equal(Z, ref["Z"]) and np.array_equal(L, ref["L"]) and np.array_equal(cl, ref["conlam"])
     gb.close()
+
+
+@pytest.mark.parametrize("name,B,N,resolves,layout", [("D", 16, 40, 8, None), ("D", 6, 16, 5, 2), ("B", 8, 12, 4, None), ("E", 4, 12, 4, None), ("C", 3, 10, 3, None)])
+def test_mpc_fused_loop_equals_stepwise(name, B, N, resolves, layout):
+    """agb_mpc_run: all re-solves of a stream inside one launch == the step-wise solve/advance loop, bit for bit (small and big
+    layouts, 2 / 3 / 4 players)."""
+    parity.check_mpc_fused_equals_stepwise(LIB, name, B=B, N=N, resolves=resolves, force_layout=layout)
