@@ -8,6 +8,7 @@
 #include <stddef.h>
 #include <string>
 #include "agb_kernels.cuh"
+#include "agb_active_set.cuh"
 
 using namespace agb;
 
@@ -807,6 +808,139 @@ int agb_active_set(agb_handle* h, double tol, unsigned char* active_out) {
   a.tol = tol; a.bout = (unsigned char*)h->stage;
   AGB_TRY(launch_op(h, nullptr, a));
   AGB_CUDA(h, cudaMemcpyAsync(active_out, h->stage, cnt, cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+// ---- active-set analysis (src/active_set/*.jl): bordered residual / Jacobian, active masks, null space -------------------------
+struct DevBuf {                       // scratch of one call (an analysis entry point, not the solve path): freed on return
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+static int as_check(agb_handle* h, int* Sv, int* Sh) {
+  if (h->hd.use_band) return fail(h, AGB_EUNSUPPORTED, "the active-set analysis covers the planar models (collision avoidance between position pairs)");
+  const int npo = h->hd.p * (h->hd.p - 1);
+  *Sv = h->hd.S + h->hd.K * npo / 2; *Sh = h->hd.S + h->hd.K * npo;            // active_set_core.jl:81-82
+  return AGB_OK;
+}
+
+int agb_active_set_sizes(agb_handle* h, int* Sv_out, int* Sh_out) {
+  if (!h || !Sv_out || !Sh_out) return AGB_EINVAL;
+  return as_check(h, Sv_out, Sh_out);
+}
+
+// device-side assembly shared by the entry points below: res [B][Sv], jac [B][Sv][Sh], vmask [B][Sv], hmask [B][Sh]
+// (any of them may be null); masked = 0 marks every pair active
+static int as_assemble(agb_handle* h, double tol, int masked, double* res, double* jac, unsigned char* vmask, unsigned char* hmask) {
+  int Sv, Sh;
+  AGB_TRY(as_check(h, &Sv, &Sh));
+  const size_t B = h->batch, S = h->hd.S;
+  DevBuf act;
+  if (masked && (vmask || hmask)) {
+    const size_t cnt = B * h->hd.K * h->hd.nrow;
+    if (act.alloc(cnt) != cudaSuccess) return fail(h, AGB_ENOMEM, "cudaMalloc (active flags)");
+    OpArgs a = op_args(OP_ACTIVE_SET);
+    a.tol = tol; a.bout = (unsigned char*)act.p;
+    AGB_TRY(launch_op(h, nullptr, a));
+  }
+  if (res) {
+    AGB_CUDA(h, cudaMemsetAsync(res, 0, B * Sv * sizeof(double), h->stream));
+    AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, (B * S + B * 5) * sizeof(double)));
+    AGB_TRY(ensure_stage(h, &h->stage2, &h->stage2_bytes, B * S * sizeof(double)));
+    OpArgs a = op_args(OP_RESIDUAL);
+    a.out0 = h->stage; a.out1 = h->stage + B * S;
+    AGB_TRY(launch_op(h, nullptr, a));
+    AGB_LAUNCH(agb_export_kernel, grid_for(B * S), 256, 0, h->stream, h->stage, h->stage2, h->batch, h->hd.p, h->hd.K, 0);
+    h->launches++;
+    AGB_CUDA(h, cudaMemcpy2DAsync(res, Sv * sizeof(double), h->stage2, S * sizeof(double), S * sizeof(double), B, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (jac) {
+    AGB_CUDA(h, cudaMemsetAsync(jac, 0, B * Sv * Sh * sizeof(double), h->stream));
+    AGB_TRY(ensure_stage(h, &h->stage, &h->stage_bytes, B * S * S * sizeof(double)));
+    AGB_CUDA(h, cudaMemsetAsync(h->stage, 0, B * S * S * sizeof(double), h->stream));
+    OpArgs a = op_args(OP_JAC_DENSE);                       // residual_jacobian!(prob, pdtraj), unregularised (:141-142)
+    a.out0 = h->stage;
+    AGB_TRY(launch_op(h, nullptr, a));
+    for (size_t b = 0; b < B; b++)
+      AGB_CUDA(h, cudaMemcpy2DAsync(jac + b * Sv * Sh, Sh * sizeof(double), h->stage + b * S * S, S * sizeof(double), S * sizeof(double), S,
+                                    cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (vmask) AGB_CUDA(h, cudaMemsetAsync(vmask, 1, B * Sv, h->stream));
+  if (hmask) AGB_CUDA(h, cudaMemsetAsync(hmask, 1, B * Sh, h->stream));
+  AGB_LAUNCH(agb_as_border_kernel, grid_for(B * h->hd.K * h->hd.p * (h->hd.p - 1)), 256, 0, h->stream, h->dd, h->Z,
+             (const unsigned char*)act.p, h->batch, jac, res, vmask, hmask);
+  h->launches++;
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));            // `act` is released on return
+  AGB_CUDA(h, cudaGetLastError());
+  return AGB_OK;
+}
+
+static int as_too_big(agb_handle* h, int Sv, int Sh) {
+  if ((size_t)h->batch * Sv * Sh * sizeof(double) > ((size_t)8 << 30))
+    return fail(h, AGB_EUNSUPPORTED, "dense active-set Jacobian is for small cases only (> 8 GiB requested)");
+  return AGB_OK;
+}
+
+int agb_active_set_residual(agb_handle* h, double* res_out) {
+  if (!h || !res_out) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  int Sv, Sh;
+  AGB_TRY(as_check(h, &Sv, &Sh));
+  DevBuf res;
+  if (res.alloc((size_t)h->batch * Sv * sizeof(double)) != cudaSuccess) return fail(h, AGB_ENOMEM, "cudaMalloc (active-set residual)");
+  AGB_TRY(as_assemble(h, 0.0, 0, (double*)res.p, nullptr, nullptr, nullptr));
+  AGB_TRY(d2h(h, res_out, (double*)res.p, (size_t)h->batch * Sv));
+  return finish(h);
+}
+
+int agb_active_set_jacobian_dense(agb_handle* h, double* jac_out) {
+  if (!h || !jac_out) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  int Sv, Sh;
+  AGB_TRY(as_check(h, &Sv, &Sh));
+  AGB_TRY(as_too_big(h, Sv, Sh));
+  DevBuf jac;
+  if (jac.alloc((size_t)h->batch * Sv * Sh * sizeof(double)) != cudaSuccess) return fail(h, AGB_ENOMEM, "cudaMalloc (active-set Jacobian)");
+  AGB_TRY(as_assemble(h, 0.0, 0, nullptr, (double*)jac.p, nullptr, nullptr));
+  AGB_TRY(d2h(h, jac_out, (double*)jac.p, (size_t)h->batch * Sv * Sh));
+  return finish(h);
+}
+
+int agb_active_set_masks(agb_handle* h, double tol, unsigned char* vmask_out, unsigned char* hmask_out) {
+  if (!h || !vmask_out || !hmask_out) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  int Sv, Sh;
+  AGB_TRY(as_check(h, &Sv, &Sh));
+  const size_t B = h->batch;
+  DevBuf mk;
+  if (mk.alloc(B * (Sv + Sh)) != cudaSuccess) return fail(h, AGB_ENOMEM, "cudaMalloc (active-set masks)");
+  unsigned char* vm = (unsigned char*)mk.p; unsigned char* hm = vm + B * Sv;
+  AGB_TRY(as_assemble(h, tol, 1, nullptr, nullptr, vm, hm));
+  AGB_CUDA(h, cudaMemcpyAsync(vmask_out, vm, B * Sv, cudaMemcpyDeviceToHost, h->stream));
+  AGB_CUDA(h, cudaMemcpyAsync(hmask_out, hm, B * Sh, cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+int agb_update_nullspace(agb_handle* h, double tol, double atol, int max_dim, double* null_out, int* dim_out) {
+  if (!h || !dim_out || max_dim < 0 || (max_dim > 0 && !null_out)) return AGB_EINVAL;
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  int Sv, Sh;
+  AGB_TRY(as_check(h, &Sv, &Sh));
+  AGB_TRY(as_too_big(h, Sv, Sh));
+  const size_t B = h->batch;
+  DevBuf jac, work, iwork, mk, nul, dim;
+  if (jac.alloc(B * Sv * Sh * sizeof(double)) != cudaSuccess || work.alloc(B * ((size_t)Sv * Sh + Sv) * sizeof(double)) != cudaSuccess ||
+      iwork.alloc(B * (Sv + 2 * (size_t)Sh) * sizeof(int)) != cudaSuccess || mk.alloc(B * (Sv + Sh)) != cudaSuccess ||
+      nul.alloc(B * (size_t)max_dim * Sh * sizeof(double)) != cudaSuccess || dim.alloc(B * sizeof(int)) != cudaSuccess)
+    return fail(h, AGB_ENOMEM, "cudaMalloc (null-space workspace)");
+  unsigned char* vm = (unsigned char*)mk.p; unsigned char* hm = vm + B * Sv;
+  AGB_TRY(as_assemble(h, tol, 1, nullptr, (double*)jac.p, vm, hm));
+  AGB_LAUNCH(agb_as_nullspace_kernel, (int)(B < 148 * 4 ? B : 148 * 4), kAsThreads, 0, h->stream, h->batch, Sv, Sh, (const double*)jac.p,
+             (const unsigned char*)vm, (const unsigned char*)hm, (double*)work.p, (int*)iwork.p, atol, max_dim, (double*)nul.p, (int*)dim.p);
+  h->launches++;
+  AGB_TRY(d2h(h, null_out, (double*)nul.p, B * (size_t)max_dim * Sh));
+  AGB_CUDA(h, cudaMemcpyAsync(dim_out, dim.p, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   return finish(h);
 }
 

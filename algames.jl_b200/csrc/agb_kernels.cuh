@@ -12,12 +12,18 @@ namespace agb {
 #define AGB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// resident CTAs per SM the register allocation is capped for, per layout (DevDesc::big; see the table above the launchers)
+#ifndef AGB_LAY2_CTAS
+#define AGB_LAY2_CTAS 4
+#endif
+#define AGB_MIN_CTAS(LAY) ((LAY) == 1 ? 2 : ((LAY) == 3 ? 3 : ((LAY) == 2 ? AGB_LAY2_CTAS : 4)))
+
 // =============================================================================================================
 // Kernels
 // =============================================================================================================
 // newton_solve!(prob) for every instance of the batch (solver_methods.jl:5-65); one CTA per instance.
 template <int P, int MODEL, int LAY>
-__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 : 4))) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch, MpcArgs mp) {
+__global__ void __launch_bounds__(threads_for(P), AGB_MIN_CTAS(LAY)) agb_newton_solve_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch, MpcArgs mp) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;
   I.bind(dd, sm);
@@ -35,18 +41,20 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     I.load_iterate(g.Z0, g.L0, inst, &g);
     __syncthreads();
     for (int a = I.tid; a < n; a += kThreads) I.X[a] = g.x0[(size_t)inst * n + a];     // x_1 ← x0 (primal_dual_traj.jl:42)
-    // Receding horizon (mp.resolves > 0): this CTA runs ALL re-solves of its stream back to back — solve, apply the first
-    // control (x0 ← x_{1+s} + disturbance), shift the iterate by s knots in shared memory, re-solve keeping multipliers and
-    // penalties (Options.shift / dual_reset = false, options.jl:16-17) — with no launch boundary and no other stream to wait for.
-    for (int t_mpc = 0;; t_mpc++) {
-    __syncthreads();
-    I.rollout();                                                                        // :17
-    if (o.dual_reset && t_mpc == 0) I.reset_duals_penalties(o);                         // :25
 #ifdef AGB_PHASE_TIMING
 #define AGB_PROFK(k) do { const long long t_ = clock64(); I.prof[k] += t_ - I.prof_t; I.prof_t = t_; } while (0)
 #else
 #define AGB_PROFK(k) do { } while (0)
 #endif
+    // Receding horizon (mp.resolves > 0): this CTA runs ALL re-solves of its stream back to back — solve, apply the first
+    // control (x0 ← x_{1+s} + disturbance), shift the iterate by s knots in shared memory, re-solve keeping multipliers and
+    // penalties (Options.shift / dual_reset = false, options.jl:16-17) — with no launch boundary and no other stream to wait for.
+    for (int t_mpc = 0;; t_mpc++) {
+    __syncthreads();
+    AGB_PROFK(11);
+    I.rollout();                                                                        // :17
+    AGB_PROFK(15);
+    if (o.dual_reset && t_mpc == 0) I.reset_duals_penalties(o);                         // :25
     AGB_PROFK(11);
     int n_newton = 0, n_eval = 0, outer_done = 0, failed = 0, n_rec = 0;
     // record!(stats, …) (statistics.jl:44-57): optional per-instance log of every record of the solve
@@ -64,6 +72,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
     Acc kept_rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double delta = 0.0;
     Acc rec = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    bool rec_current = false;        // rec was evaluated at the resident iterate with the resident multipliers (nothing moved since)
     int last_exit = AGB_MAX_OUTER;   // how the last inner loop ended (status of a non-converged instance)
     for (int kout = 1; kout <= o.outer_iter; kout++) {                                  // :30
       outer_done = kout;
@@ -75,6 +84,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         // ---- inner_iteration (:67-103)
         if (kept) { I.load_kept_residual(); rec = kept_rec; kept = false; AGB_PROFK(10); }   // accepted trial point: already evaluated
         else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; AGB_PROFK(0); }   // :73-75 (the reg terms vanish at Z)
+        rec_current = true;
         const double res_norm = rec.sum / S;                                            // :76
         log_record(rec, delta, kout, l);                                                // :75
         delta = 0.0;
@@ -87,6 +97,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         AGB_PROFK(1);
         ls_count = (j == o.ls_iter) ? ls_count + 1 : 0;                                 // :92-93
         delta = I.update_traj(alpha);                                                   // :94-95 (taken even when the search failed)
+        rec_current = false;
         AGB_PROFK(9);
         if (delta < o.delta_min) { last_exit = AGB_STALLED; break; }                    // :96-98
         if (ls_count >= 1) { last_exit = AGB_LINE_SEARCH_FAILED; break; }               // :43
@@ -97,10 +108,13 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
         break;                                                                          // :49-55
       I.dual_update(o);                                                                 // :57-58
       I.penalty_update(o);                                                              // :61
-      kept = false;                                                                     // multipliers changed
+      kept = false; rec_current = false;                                                // multipliers changed
     }
-    if (kept) { I.load_kept_residual(); rec = kept_rec; }                               // :63 final record
+    AGB_PROFK(11);
+    if (rec_current) { }                                                                // :63 final record — the inner loop left on its ϵ_opt test: same point, same numbers
+    else if (kept) { I.load_kept_residual(); rec = kept_rec; }
     else { rec = I.template residual<false>(0.0, 0.0, 0.0, I.R); n_eval++; }
+    AGB_PROFK(13);
     log_record(rec, delta, outer_done, 0);                                              // :63
     if (g.hist != nullptr && I.tid == 0) g.hist_count[inst] = n_rec;
     const bool finite = (rec.sum == rec.sum) && !isinf(rec.sum);
@@ -117,7 +131,9 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
           mp.xs[((size_t)t_mpc * batch + inst) * n + a] = I.X[mp.shift * n + a] + (mp.dist ? mp.dist[((size_t)t_mpc * batch + inst) * n + a] : 0.0);
       if (t_mpc + 1 < mp.resolves) {                                                    // (the host applies the last advance)
         __syncthreads();
+        AGB_PROFK(11);
         I.mpc_shift(mp.shift, mp.dist ? mp.dist + ((size_t)t_mpc * batch + inst) * n : nullptr);
+        AGB_PROFK(14);
         continue;
       }
     }
@@ -141,7 +157,7 @@ __global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 
 
 // ibr_newton_solve!(prob; ibr_opts) for every instance (solver_methods.jl:133-224); one CTA per instance.
 template <int P, int MODEL, int LAY>
-__global__ void __launch_bounds__(threads_for(P), (LAY == 1 ? 2 : (LAY == 3 ? 3 : 4))) agb_ibr_solve_kernel(const DevDesc* __restrict__ dd, agb_options o,
+__global__ void __launch_bounds__(threads_for(P), AGB_MIN_CTAS(LAY)) agb_ibr_solve_kernel(const DevDesc* __restrict__ dd, agb_options o,
                                                                                           agb_ibr_options io, Buffers g, int batch) {
   AGB_DYN_SMEM(sm);
   Inst<P, MODEL, (LAY != 0)> I;

@@ -1453,6 +1453,48 @@ struct Inst {
 
   // rollout!(RK3, model, traj): independent per player (separable dynamics)
   __device__ void rollout() {
+    if constexpr (MODEL == AGB_MODEL_UNICYCLE) {
+      // Unicycle: (θ, v) evolve from the controls alone and the position derivative depends on (θ, v) only, so the serial chain
+      // of rk3_step splits into three passes with the same arithmetic (same operations in the same order per component):
+      //   A  2P threads   θ_k, v_k for every knot            (a chain of additions, no trigonometry)
+      //   B  P·K threads  the position increment of stage k   (the three sincos of the RK3 stages, all stages in parallel)
+      //   C  2P threads   x_{k+1} = x_k + increment           (a chain of additions)
+      if (tid < 2 * P) {
+        const int i = tid % P, c = 2 + tid / P, j = tid / P;
+        double st = X[c * P + i];
+        for (int s = 0; s < K; s++) {
+          const double u = U[s * m + j * P + i];
+          const double k1 = u * dt, k2 = u * dt, k3 = u * dt;
+          st = st + (k1 + 4 * k2 + k3) / 6;
+          X[(s + 1) * n + c * P + i] = st;
+        }
+      }
+      __syncthreads();
+      for (int item = tid; item < P * K; item += kThreads) {
+        const int i = item % P, s = item / P;
+        const double th = X[s * n + 2 * P + i], v = X[s * n + 3 * P + i], w = U[s * m + i], a = U[s * m + P + i];
+        const double k1t = w * dt, k1v = a * dt;
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        const double k1x = (cs * v) * dt, k1y = (sn * v) * dt;
+        const double tb = th + k1t / 2, vb = v + k1v / 2;
+        sincos(tb, &sn, &cs);
+        const double k2x = (cs * vb) * dt, k2y = (sn * vb) * dt, k2t = w * dt, k2v = a * dt;
+        const double tc = th - k1t + 2 * k2t, vc = v - k1v + 2 * k2v;
+        sincos(tc, &sn, &cs);
+        const double k3x = (cs * vc) * dt, k3y = (sn * vc) * dt;
+        X[(s + 1) * n + 0 * P + i] = (k1x + 4 * k2x + k3x) / 6;          // increments, summed by pass C
+        X[(s + 1) * n + 1 * P + i] = (k1y + 4 * k2y + k3y) / 6;
+      }
+      __syncthreads();
+      if (tid < 2 * P) {
+        const int i = tid % P, c = tid / P;
+        double st = X[c * P + i];
+        for (int s = 0; s < K; s++) { st = st + X[(s + 1) * n + c * P + i]; X[(s + 1) * n + c * P + i] = st; }
+      }
+      __syncthreads();
+      return;
+    }
     if (tid < P) {
       const int i = tid;
       double st[4], u[2], xn[4];
@@ -1597,16 +1639,22 @@ struct Inst {
   // moves s knots forward — z_k ← z_{k+s}, λ_k ← λ_{k+s}, zero tail (init_traj! with s, primal_dual_traj.jl:34-41) — and
   // x_1 ← x_{1+s} + disturbance.  One thread per component walks its column in ascending k, so the shift is in place.
   __device__ void mpc_shift(int s, const double* __restrict__ dist) {
-    if (tid < n) {
-      const double x0n = X[s * n + tid] + (dist ? dist[tid] : 0.0);
-      for (int k = 0; k < N; k++) X[k * n + tid] = (k + s < N) ? X[(k + s) * n + tid] : 0.0;
-      X[tid] = x0n;
-    } else if (tid < n + m) {
-      const int e = tid - n;
-      for (int k = 0; k < N; k++) U[k * m + e] = (k + s < N) ? U[(k + s) * m + e] : 0.0;
-    } else if (tid < n + m + P * n) {
-      const int r = tid - n - m, i = r / n, e = r - i * n;
-      for (int k = 0; k < K; k++) L[(i * K + k) * n + e] = (k + s < K) ? L[(i * K + k + s) * n + e] : 0.0;
+    const double x0n = (tid < n) ? X[s * n + tid] + (dist ? dist[tid] : 0.0) : 0.0;
+    shift_array((double*)X, N * n, s * n);
+    shift_array((double*)U, N * m, s * m);
+    for (int i = 0; i < P; i++) shift_array((double*)L + i * K * n, K * n, s * n);
+    if (tid < n) X[tid] = x0n;
+  }
+  // a[item] ← a[item + by] (zero past the end), in ascending chunks of 4·kThreads elements: every thread reads its elements of the
+  // chunk into registers, block barrier, writes.  A later chunk reads only elements no earlier chunk wrote (by ≥ 1).
+  __device__ __forceinline__ void shift_array(double* a, int len, int by) {
+    for (int c0 = 0; c0 < len; c0 += 4 * kThreads) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const int item = c0 + tid + q * kThreads; v[q] = (item + by < len) ? a[item + by] : 0.0; }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const int item = c0 + tid + q * kThreads; if (item < len) a[item] = v[q]; }
     }
   }
   __device__ void load_duals(const Buffers& g, int inst) {

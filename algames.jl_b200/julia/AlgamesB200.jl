@@ -344,6 +344,25 @@ function mpc_step!(b::Batch; disturbance::Union{Nothing,Matrix{Float64}}=nothing
 end
 
 """
+    mpc_run!(batch::Batch, resolves; shift=1, disturbances=nothing) -> (stats, status, xs)
+
+The whole receding-horizon loop of every stream in ONE kernel launch (`agb_mpc_run`): stream b's CTA runs `resolves` ×
+(newton_solve!, x0 ← x_{1+shift} + disturbances[:, b, t], shift the iterate, carry multipliers and penalties) back to back on
+the device; bit for bit the results of `resolves` × (`newton_solve!`, `mpc_step!`).  `disturbances` is n × B × resolves.
+Returns per-re-solve `stats` (NSTATS × B × resolves), `status` (B × resolves) and the executed states `xs` (n × B × resolves).
+`opts.dual_reset` applies to the first re-solve only.
+"""
+function mpc_run!(b::Batch, resolves::Integer; shift::Integer=1, disturbances::Union{Nothing,Array{Float64,3}}=nothing)
+    B = length(b.probs)
+    stats = zeros(NSTATS, B, resolves); status = zeros(Cint, B, resolves); xs = zeros(b.n, B, resolves)
+    o = Ref(AgbOptions(b.probs[1].opts))
+    check(ccall((:agb_mpc_run, LIB), Cint,
+        (Ptr{Cvoid}, Ref{AgbOptions}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}, Ptr{Float64}),
+        b.h, o, resolves, shift, disturbances === nothing ? C_NULL : pointer(disturbances), stats, status, xs), b.h)
+    return stats, status, xs
+end
+
+"""
     ShardedBatch(probs; devices=nothing)
 
 Single-process multi-GPU form (agb_create_sharded): the problems are split contiguously over the visible GPUs, every shard

@@ -25,6 +25,7 @@ __all__ = [
     "add_circle_constraint", "add_wall_constraint", "Wall", "GameProblem", "GameBatch", "newton_solve",
     "residual", "residual_jacobian", "kkt_solve", "line_search", "update_traj", "rollout", "dual_update",
     "penalty_update", "reset", "evaluate", "active_set", "Statistics", "spec_of", "IBROptions", "ibr_newton_solve",
+    "ActiveSetCore", "NullSpace", "active_set_residual", "active_set_residual_jacobian", "active_masks", "update_nullspace",
 ]
 
 
@@ -634,6 +635,44 @@ class GameBatch:
         self._ck(self.lib.agb_active_set(self.h, float(tol), a.ctypes.data_as(C.POINTER(C.c_ubyte))))
         return a.astype(bool)
 
+    # ---- active-set analysis (src/active_set/*.jl) --------------------------------------------------------------
+    def active_set_sizes(self):
+        """(Sv, Sh) of ActiveSetCore (active_set_core.jl:81-82)."""
+        sv, sh = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.agb_active_set_sizes(self.h, C.byref(sv), C.byref(sh)))
+        return sv.value, sh.value
+
+    def active_set_residual(self):
+        sv, _ = self.active_set_sizes()
+        r = np.empty((self.batch, sv))
+        self._ck(self.lib.agb_active_set_residual(self.h, _capi.dptr(r)))
+        return r
+
+    def active_set_jacobian(self):
+        sv, sh = self.active_set_sizes()
+        J = np.empty((self.batch, sv, sh))
+        self._ck(self.lib.agb_active_set_jacobian_dense(self.h, _capi.dptr(J)))
+        return J
+
+    def active_set_masks(self, tol):
+        sv, sh = self.active_set_sizes()
+        vm, hm = np.empty((self.batch, sv), dtype=np.uint8), np.empty((self.batch, sh), dtype=np.uint8)
+        ub = C.POINTER(C.c_ubyte)
+        self._ck(self.lib.agb_active_set_masks(self.h, float(tol), vm.ctypes.data_as(ub), hm.ctypes.data_as(ub)))
+        return vm.astype(bool), hm.astype(bool)
+
+    def update_nullspace(self, tol, atol=1e-20, max_dim=None):
+        """agb_update_nullspace: per instance an orthonormal basis [dim, Sh] of nullspace(jac[vmask, hmask]) (rows of the inactive
+        columns are zero).  Returns a list of arrays, one per instance."""
+        sv, sh = self.active_set_sizes()
+        if max_dim is None:
+            max_dim = sh - self.S + (self.sizes.N - 1) * self.p          # every pair active gives Sh − Sv; leave room for rank deficiency
+        out = np.zeros((self.batch, max_dim, sh)); dim = np.zeros(self.batch, dtype=np.int32)
+        self._ck(self.lib.agb_update_nullspace(self.h, float(tol), float(atol), int(max_dim), _capi.dptr(out), _capi.iptr(dim)))
+        if (dim > max_dim).any():
+            raise AlgamesError(f"null space of dimension {int(dim.max())} exceeds max_dim = {max_dim}")
+        return [out[b, :dim[b]].copy() for b in range(self.batch)]
+
     def debug_gain_solve(self, aug):
         """agb_debug_gain_solve: the kernel's Gauss-Jordan on aug [B, m, m+n+1]; returns (reduced systems, ok flags)."""
         aug = self._arr(aug, (self.batch, self.m, self.m + self.n + 1))
@@ -1062,6 +1101,56 @@ def reset(prob: GameProblem):
 
 def evaluate(prob: GameProblem):
     return prob._push().evaluate()[0]
+
+
+class NullSpace:
+    """NullSpace (active_set_core.jl:5-27): `mat` Sh x dim, `vec` its columns."""
+
+    def __init__(self, sh):
+        self.mat = np.zeros((sh, 0)); self.vec = []
+
+
+class ActiveSetCore:
+    """ActiveSetCore(probsize) (active_set_core.jl:57-160): the Newton system bordered by the collision rows (pairs i < j) and
+    columns (ordered pairs); `vmask` / `hmask` are 0-based index arrays here."""
+
+    def __init__(self, probsize: "ProblemSize"):
+        self.probsize = probsize
+        N, p, S = probsize.N, probsize.p, probsize.S
+        self.Sv, self.Sh = S + p * (p - 1) * (N - 1) // 2, S + p * (p - 1) * (N - 1)
+        self.res = np.zeros(self.Sv); self.jac = np.zeros((self.Sv, self.Sh))
+        self.vmask = np.arange(self.Sv); self.hmask = np.arange(self.Sh)
+        self.null = NullSpace(self.Sh)
+
+
+def active_set_residual(ascore: ActiveSetCore, prob: "GameProblem"):
+    """residual!(ascore, prob, pdtraj) (active_set_methods.jl:96-124)."""
+    ascore.res[:] = prob._push().active_set_residual()[0]
+    return ascore.res
+
+
+def active_set_residual_jacobian(ascore: ActiveSetCore, prob: "GameProblem"):
+    """residual_jacobian!(ascore, prob, pdtraj) (active_set_methods.jl:131-170)."""
+    ascore.jac[:] = prob._push().active_set_jacobian()[0]
+    return ascore.jac
+
+
+def active_masks(ascore: ActiveSetCore, prob: "GameProblem", tol: Optional[float] = None):
+    """active_vertical_mask! + active_horizontal_mask! (active_set_methods.jl:28-74) at the problem's iterate and multipliers."""
+    vm, hm = prob._push().active_set_masks(prob.opts.active_set_tolerance if tol is None else tol)
+    ascore.vmask, ascore.hmask = np.flatnonzero(vm[0]), np.flatnonzero(hm[0])
+    return ascore.vmask, ascore.hmask
+
+
+def update_nullspace(ascore: ActiveSetCore, prob: "GameProblem", atol: float = 1e-20, tol: Optional[float] = None):
+    """update_nullspace!(ascore, prob, pdtraj; atol) (active_set_methods.jl:173-184)."""
+    tol = prob.opts.active_set_tolerance if tol is None else tol
+    b = prob._push()
+    vm, hm = b.active_set_masks(tol)
+    ascore.vmask, ascore.hmask = np.flatnonzero(vm[0]), np.flatnonzero(hm[0])
+    basis = b.update_nullspace(tol, atol)[0]
+    ascore.null.mat = basis.T.copy(); ascore.null.vec = [basis[d].copy() for d in range(basis.shape[0])]
+    return ascore.null
 
 
 def active_set(prob: GameProblem, tol: Optional[float] = None):

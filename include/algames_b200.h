@@ -254,6 +254,27 @@ int agb_reset_duals_penalties(agb_handle* h, const agb_options* o);
 int agb_evaluate_constraints(agb_handle* h, double* c_out);
 int agb_active_set(agb_handle* h, double tol, unsigned char* active_out);
 
+/* ---- Active-set analysis of the resident iterate (src/active_set/*.jl; off the solve path, planar models) ----------------------
+ * ActiveSetCore (active_set_core.jl:57-160) borders the Newton system with one ROW per unordered collision pair i<j and knot
+ * k = 2..N — stamp (:v,:col,i,j,k), row S + (k-2)·p(p-1)/2 + index of (i,j) — and one COLUMN per ordered pair i!=j and knot —
+ * stamp (:h,:col,i,j,k), column S + (k-2)·p(p-1) + index of (i,j).  Sv = S + p(p-1)(N-1)/2 rows, Sh = S + p(p-1)(N-1) columns
+ * (:81-82); the first S rows / columns are residual! / residual_jacobian! in the reference's order. */
+int agb_active_set_sizes(agb_handle* h, int* Sv_out, int* Sh_out);
+/* residual!(ascore, prob, pdtraj) (active_set_methods.jl:96-124): [KKT residual ; c_ij(x_k) of the pairs i<j].  res_out [B][Sv]. */
+int agb_active_set_residual(agb_handle* h, double* res_out);
+/* residual_jacobian!(ascore, prob, pdtraj) (:131-170): the unregularised KKT Jacobian bordered by grad c_ij' in column (h,i,j,k) on
+ * the rows (opt_i, x_k), and by grad c_ij in row (v,i,j,k), i<j, on the columns x_k.  Dense, row-major: jac_out [B][Sv][Sh]. */
+int agb_active_set_jacobian_dense(agb_handle* h, double* jac_out);
+/* active_vertical_mask! / active_horizontal_mask! (:28-74): 1 for the Newton rows / columns and for the pairs whose collision row
+ * is active — c >= -tol or lambda > 0 (active(game_con, stamp), :5-26).  vmask_out [B][Sv], hmask_out [B][Sh]. */
+int agb_active_set_masks(agb_handle* h, double tol, unsigned char* vmask_out, unsigned char* hmask_out);
+/* update_nullspace!(ascore, prob, pdtraj) (:173-184): an orthonormal basis of nullspace(jac[vmask, hmask]), scattered to the hmask
+ * rows (add_matrix!, active_set_core.jl:29-42).  One CTA per instance: Gauss-Jordan with complete pivoting on the dense masked
+ * matrix, rank = number of pivots > atol (the reference passes atol = 1e-20 to LinearAlgebra.nullspace), modified Gram-Schmidt.
+ * The basis is unique only up to rotation: compare subspaces.  null_out [B][max_dim][Sh] (vector d of instance b at
+ * null_out + (b*max_dim + d)*Sh), dim_out [B] = the dimension found (vectors beyond max_dim are not written). */
+int agb_update_nullspace(agb_handle* h, double tol, double atol, int max_dim, double* null_out, int* dim_out);
+
 /* Diagnostic: runs the kernel's m x (m+n+1) gain-system solver (threshold-pivoted Gauss-Jordan with partial-pivoting
  * fallback) on caller-supplied systems aug [B][m][m+n+1]; the reduced systems come back in place of the
  * input layout in aug_out, ok_out[B] = 0 when a pivot was zero / non-finite.  Unit-test hook for the pivoting logic. */

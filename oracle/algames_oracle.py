@@ -1812,7 +1812,7 @@ def as_residual_jacobian(ascore, prob, pd=None):
     ps, core = ascore.ps, prob.core
     ascore.jac[:] = 0.0
     residual(prob, pd)
-    ascore.jac[:ps.S, :ps.S] = residual_jacobian(prob, pd)
+    ascore.jac[:ps.S, :ps.S] = residual_jacobian(prob, pd, regularize=False)     # :141 residual_jacobian! only — no regularize_residual_jacobian!
     prob.game_con.jacobian(pd.X, pd.U)
     for i in range(1, ps.p + 1):
         for j in range(1, ps.p + 1):

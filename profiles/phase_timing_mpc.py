@@ -22,8 +22,8 @@ for _ in range(2):
 hist, _ = gb.get_history()
 prof = hist.reshape(B, -1)[:, :16]
 names = ["residual", "line-search evals", "kkt terminal setup", "phase 1 (Aug)", "phase 2 (GJ | rows | H)", "phase 3 (P update)", "forward sweep",
-         "costate pre-pass", "costate recursion", "update_traj", "load kept residual", "load / rollout / shift / store / AL update", "(GJ alone, inside phase 2)"]
-tot = prof[:, :12].sum(axis=1)
+         "costate pre-pass", "costate recursion", "update_traj", "load kept residual", "load / store / records / AL update", "(GJ alone, inside phase 2)", "final record", "shift + advance", "rollout"]
+tot = prof[:, :12].sum(axis=1) + prof[:, 13:16].sum(axis=1)
 newton = stats[:, :, 6].sum()
 evals = stats[:, :, 8].sum()
 rep = {"config": "D (fused MPC loop)", "streams": B, "resolves": R, "loop_ms": ms, "cycles_per_resolve": float(tot.sum() / (B * R)),

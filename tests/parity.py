@@ -732,3 +732,68 @@ def check_mpc_fused_equals_stepwise(lib_path, name="D", B=8, N=None, resolves=6,
     assert np.array_equal(v1["Z"], v2["Z"]) and np.array_equal(v1["stats"], v2["stats"])      # x0 and the warm start carried over too
     g1.close(); g2.close()
     return stats2, status2
+
+
+def check_active_set_analysis(lib_path, name="B", N=8, seed=3, partial=True):
+    """src/active_set/*.jl on the device (agb_active_set_* / agb_update_nullspace) against the oracle's restatement at a random
+    iterate: bordered residual and Jacobian entry by entry, the active masks, and the null space of the masked Jacobian as a
+    SUBSPACE (dimension, J·v = 0, and the two orthonormal bases span each other — a basis is unique only up to rotation).
+    With `partial` the multipliers and positions are arranged so that only some collision pairs are active."""
+    cfg = small_config(name, 1, N)
+    model, N_, dt, obj, con, opts, x0, xf = cfg
+    x0 = np.asarray(x0).reshape(-1, model.n)[0]
+    xfj = None if xf is None else np.asarray(xf).reshape(-1, model.n)[0]
+    op = oracle_problem(model, N_, dt, obj, con, opts, x0, xfj)
+    rng = np.random.default_rng(seed)
+    Z, L, lam, mu = random_state(op, x0, rng)
+    if partial:                                   # players on top of each other at the early knots (active pairs), far apart later
+        p = model.p
+        for k in range(1, N_):
+            for i in range(p):
+                if k < N_ // 2:
+                    Z[k, i], Z[k, p + i] = 0.01 * rng.normal(), 0.01 * rng.normal()
+                else:
+                    Z[k, i], Z[k, p + i] = 10.0 * (i + 1) + rng.normal(), -7.0 * (i + 1) + rng.normal()
+        lam = np.zeros_like(lam)
+    op.pdtraj.X[:], op.pdtraj.U[:], op.pdtraj.du[:] = Z[:, :model.n], Z[:, model.n:], L
+    O.unpack_multipliers(op, lam, mu)
+    gb = ab.GameBatch(model, N_, dt, obj, con, 1, lib_path=lib_path)
+    gb.set_instance_params(x0=x0[None], xf=None if xfj is None else xfj[None])
+    gb.set_initial(Z[None], L[None], lam[None], mu[None])
+    asc = O.ActiveSetCore(op.probsize)
+    assert gb.active_set_sizes() == (asc.Sv, asc.Sh)
+    r_ref = O.as_residual(asc, op).copy()
+    r_dev = gb.active_set_residual()[0]
+    scale = max(1.0, np.abs(r_ref).max())
+    assert np.abs(r_dev - r_ref).max() <= TOL_FUNC * scale, np.abs(r_dev - r_ref).max()
+    J_ref = O.as_residual_jacobian(asc, op).copy()
+    J_dev = gb.active_set_jacobian()[0]
+    assert np.abs(J_dev - J_ref).max() <= TOL_FUNC * max(1.0, np.abs(J_ref).max()), np.abs(J_dev - J_ref).max()
+    tol = opts.active_set_tolerance
+    op.game_con.active_set_tolerance = tol
+    N_ref = O.update_nullspace(asc, op)
+    vm, hm = gb.active_set_masks(tol)
+    assert np.array_equal(np.flatnonzero(vm[0]), asc.vmask) and np.array_equal(np.flatnonzero(hm[0]), asc.hmask)
+    if partial:
+        assert op.probsize.S < len(asc.vmask) < asc.Sv          # the case really is a partial active set
+    basis = gb.update_nullspace(tol)[0]                          # [dim, Sh]
+    assert basis.shape == (N_ref.shape[1], asc.Sh), (basis.shape, N_ref.shape)
+    inactive = np.setdiff1d(np.arange(asc.Sh), asc.hmask)
+    assert not basis[:, inactive].any()
+    Bm = basis[:, asc.hmask]                                     # rows: orthonormal vectors in the masked column space
+    assert np.abs(Bm @ Bm.T - np.eye(Bm.shape[0])).max() < 1e-10
+    dj = J_ref[np.ix_(asc.vmask, asc.hmask)]
+    assert np.abs(dj @ Bm.T).max() <= 1e-9 * max(1.0, np.abs(dj).max())
+    sv = np.linalg.svd(dj, compute_uv=False)
+    if sv[-1] > 1e-10 * sv[0]:
+        # full numerical row rank — the null space is well defined: projecting the oracle's basis onto the device's loses nothing
+        assert np.abs(N_ref - Bm.T @ (Bm @ N_ref)).max() < 1e-8
+    else:
+        # a singular value at round-off level (> atol = 1e-20, so nullspace() still counts it as rank): the reference's basis is then
+        # ANY n - m of the n - m + 1 numerically null directions; the device's must lie inside that numerical null space
+        Vt = np.linalg.svd(dj, full_matrices=True)[2]
+        NN = Vt[int((sv > 1e-10 * sv[0]).sum()):].T
+        gap = sv[sv > 1e-10 * sv[0]][-1]
+        assert np.abs(Bm.T - NN @ (NN.T @ Bm.T)).max() <= 1e3 * np.abs(dj @ Bm.T).max() / gap + 1e-12
+    gb.close()
+    return basis.shape[0]

@@ -275,3 +275,9 @@ def test_mpc_fused_loop_equals_stepwise_emulated(emu_lib):
     """agb_mpc_run (the receding-horizon loop inside the solve kernel) == the step-wise loop, bit for bit, on the CTA emulator."""
     parity.check_mpc_fused_equals_stepwise(emu_lib, "D", B=3, N=10, resolves=4)
     parity.check_mpc_fused_equals_stepwise(emu_lib, "D", B=2, N=8, resolves=3, force_layout=2)
+
+
+@pytest.mark.parametrize("name,N,partial", [("B", 6, True), ("C", 5, False)])
+def test_active_set_analysis_emulated(emu_lib, name, N, partial):
+    """src/active_set/*.jl on the device kernels (CTA emulator) vs the oracle: bordered residual / Jacobian, masks, null space."""
+    parity.check_active_set_analysis(emu_lib, name, N=N, partial=partial)

@@ -448,3 +448,30 @@ def test_mpc_fused_loop_equals_stepwise(name, B, N, resolves, layout):
     """agb_mpc_run: all re-solves of a stream inside one launch == the step-wise solve/advance loop, bit for bit (small and big
     layouts, 2 / 3 / 4 players)."""
     parity.check_mpc_fused_equals_stepwise(LIB, name, B=B, N=N, resolves=resolves, force_layout=layout)
+
+
+@pytest.mark.parametrize("name,N,partial", [("B", 10, True), ("B", 8, False), ("C", 6, True), ("D", 8, True), ("E", 10, False)])
+def test_active_set_analysis_vs_oracle(name, N, partial):
+    """SURVEY §8 f4 on the device: ActiveSetCore residual / Jacobian, active masks and update_nullspace! (src/active_set/*.jl) vs the
+    oracle — the null space compared as a subspace."""
+    parity.check_active_set_analysis(LIB, name, N=N, partial=partial)
+
+
+def test_active_set_reference_nullspace_test():
+    """test/active_set/active_set_methods.jl:96-127 through the host mirror: 3-player unicycle, N = 10, collision radius 1.0 at the
+    initial iterate — null.mat is (S + (N−1)p(p−1)) x (N−1)p."""
+    import algames_b200 as ab
+    rng = np.random.default_rng(0)
+    N, dt, p = 10, 0.1, 3
+    model = ab.UnicycleGame(p=p)
+    ps = ab.ProblemSize(N, model)
+    obj = ab.GameObjective([rng.random(4) for _ in range(p)], [rng.random(2) for _ in range(p)],
+                           [(i + 1) * np.ones(4) for i in range(p)], [2 * (i + 1) * np.ones(2) for i in range(p)], N, model)
+    con = ab.GameConstraintValues(ps)
+    ab.add_collision_avoidance(con, 1.0)
+    prob = ab.GameProblem(N, dt, rng.random(model.n), model, ab.Options(), obj, con, lib_path=LIB)
+    asc = ab.ActiveSetCore(ps)
+    ab.active_set_residual(asc, prob); ab.active_set_residual_jacobian(asc, prob)
+    null = ab.update_nullspace(asc, prob)
+    assert null.mat.shape == (ps.S + (N - 1) * p * (p - 1), (N - 1) * p)
+    assert len(null.vec) == (N - 1) * p and len(null.vec[0]) == ps.S + (N - 1) * p * (p - 1)
