@@ -104,6 +104,7 @@ SYMBOLS = {
     "agb_active_set_jacobian_dense": (C.c_int, [_H, _DP]),
     "agb_active_set_masks": (C.c_int, [_H, C.c_double, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]),
     "agb_update_nullspace": (C.c_int, [_H, C.c_double, C.c_double, C.c_int, _DP, _IP]),
+    "agb_band_info": (C.c_int, [_H, _IP, _IP]),
     "agb_debug_gain_solve": (C.c_int, [_H, _DP, _DP, _IP]),
     "agb_newton_solve_batch": (C.c_int, [_H, C.POINTER(OptionsC), _DP, _DP, _DP, _DP, _DP, _IP]),
     "agb_ibr_newton_solve_batch": (C.c_int, [_H, C.POINTER(OptionsC), C.POINTER(IBROptionsC), _DP, _DP, _DP, _DP, _DP, _IP]),

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kAsThreads) agb_as_nullspace_kernel(int batch,
       }
     }
     int rank = 0;
+    double amax = 0.0;
     const int tmax = r < c ? r : c;
     for (int t = 0;; t++) {
       // block arg-max of (lmax, li, lj)
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kAsThreads) agb_as_nullspace_kernel(int batch,
         const double ov = s_pmax[w]; const int oi = s_pi[w], oj = s_pj[w];
         if (ov > pmax || (ov == pmax && (oi < pi || (oi == pi && oj < pj)))) { pmax = ov; pi = oi; pj = oj; }
       }
+      if (t == 0) amax = pmax;
       if (t >= tmax || !(pmax > atol)) { rank = t; break; }
       if (pi != t) for (int q = tid; q < c; q += nt) { const double v = M[(size_t)t * c + q]; M[(size_t)t * c + q] = M[(size_t)pi * c + q]; M[(size_t)pi * c + q] = v; }
       __syncthreads();
@@ -154,7 +156,11 @@ __global__ void __launch_bounds__(kAsThreads) agb_as_nullspace_kernel(int batch,
       }
       __syncthreads();
     }
-    const int dim = c - rank;
+    // An EXACT rank deficiency (structurally zero border rows: coincident players have grad c = 0) leaves exact zeros here, while the
+    // reference's SVD returns those singular values at round-off level, eps * sigma_max > atol = 1e-20, and counts them as rank: its
+    // null.mat then has c - min(r, c) columns (test/active_set/active_set_methods.jl:123 expects exactly that).  Same count here —
+    // the first c - min(r, c) of the c - rank null vectors — whenever atol is below what an SVD can resolve.
+    const int dim = (rank < tmax && atol < 2.220446049250313e-16 * amax) ? c - tmax : c - rank;
     if (tid == 0) dim_out[inst] = dim;
     const int nd = dim < max_dim ? dim : max_dim;
     double* NV = null_out + (size_t)inst * max_dim * Sh;

@@ -1,5 +1,6 @@
 // agb_band.cu — kernels and launchers of the band solver (agb_band.cuh): the general newton_solve! for every schema, and
 // the fallback for instances the structured kernels return as AGB_SINGULAR.
+#include <cstdio>
 #include "agb_band.cuh"
 #include "agb_kernels.cuh"
 
@@ -7,6 +8,7 @@ namespace agb {
 
 using band::Ctx;
 using band::Norms;
+constexpr int kBandThreads = 128;     // band_solve_window reproduces the 128 partial sums of the global path's back substitution
 
 // time-major band numbering → the reference's vertical (row) / horizontal (column) order (core/newton_core.jl:40-89)
 __device__ __forceinline__ int ref_row(const Ctx& C, int r) {
@@ -51,13 +53,18 @@ __device__ void band_store(Ctx& C, const Buffers& g, int inst) {
 
 // newton_solve!(prob) (solver_methods.jl:5-65) for every instance — or, with only_status >= 0, for the instances a previous
 // kernel left with that status (the structured solver's AGB_SINGULAR ones), from the same initial iterate.
-__global__ void __launch_bounds__(128) agb_band_newton_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch, int only_status) {
+__global__ void __launch_bounds__(kBandThreads, 3) agb_band_newton_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, int inst0, int batch, int only_status) {
   __shared__ double red[64];
+  AGB_DYN_SMEM(sm);
   if ((int)blockIdx.x >= g.band_slots) return;
   Ctx C;
   C.bind(dd, g.band + (size_t)blockIdx.x * g.band_stride, red);
+  C.win = g.band_win > 0 ? sm : nullptr;
   const int K = C.K, n = C.n, m = C.m;
   const double Sd = (double)C.S;
+#ifdef AGB_BAND_TIMING
+  const long long bt_k0 = clock64();
+#endif
   for (int inst = inst0 + blockIdx.x; inst < batch; inst += gridDim.x) {   // instances [inst0, batch)
     __syncthreads();
     if (only_status >= 0 && g.status[inst] != only_status) continue;
@@ -131,14 +138,24 @@ __global__ void __launch_bounds__(128) agb_band_newton_kernel(const DevDesc* __r
       g.status[inst] = conv ? AGB_CONVERGED : (failed ? failed : (!finite ? AGB_NONFINITE : last_exit));
     }
   }
+#ifdef AGB_BAND_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    band::g_bt[15] += clock64() - bt_k0;
+    printf("BAND_TIMING pass1 %lld zero %lld pass2 %lld norms %lld elim %lld backsub %lld total %lld\n", band::g_bt[0], band::g_bt[1], band::g_bt[2],
+           band::g_bt[3], band::g_bt[4], band::g_bt[5], band::g_bt[15]);
+    printf("BAND_TIMING_ELIM search %lld setup %lld update %lld tail+barrier %lld\n", band::g_bt[6], band::g_bt[7], band::g_bt[8], band::g_bt[9]);
+  }
+#endif
 }
 
 // per-function entry points of the band solver on the resident batch (parity tests; outputs in the reference's orders)
-__global__ void __launch_bounds__(128) agb_band_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
+__global__ void __launch_bounds__(kBandThreads) agb_band_op_kernel(const DevDesc* __restrict__ dd, agb_options o, Buffers g, OpArgs a, int batch) {
   __shared__ double red[64];
+  AGB_DYN_SMEM(sm);
   if ((int)blockIdx.x >= g.band_slots) return;
   Ctx C;
   C.bind(dd, g.band + (size_t)blockIdx.x * g.band_stride, red);
+  C.win = g.band_win > 0 ? sm : nullptr;
   const int Sz = C.S;
   for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
     __syncthreads();
@@ -188,10 +205,32 @@ __global__ void __launch_bounds__(128) agb_band_op_kernel(const DevDesc* __restr
 }
 
 void launch_band_solve(const DevDesc* dd, const agb_options& o, const Buffers& g, int inst0, int batch, int only_status, int grid, cudaStream_t st) {
-  AGB_LAUNCH(agb_band_newton_kernel, grid, 128, 0, st, dd, o, g, inst0, batch, only_status);
+  AGB_LAUNCH(agb_band_newton_kernel, grid, kBandThreads, g.band_win, st, dd, o, g, inst0, batch, only_status);
 }
 void launch_band_op(const DevDesc* dd, const agb_options& o, const Buffers& g, const OpArgs& a, int batch, int grid, cudaStream_t st) {
-  AGB_LAUNCH(agb_band_op_kernel, grid, 128, 0, st, dd, o, g, a, batch);
+  AGB_LAUNCH(agb_band_op_kernel, grid, kBandThreads, g.band_win, st, dd, o, g, a, batch);
+}
+// Shared-memory bytes of band_solve_window's window: (kl+2) row slots of (kl+ku+2 | 1) doubles + the two slot maps; 0 when a row
+// does not fit the per-lane register cache (8 x 32 entries) or the window exceeds `limit` (then the band is eliminated in global memory).
+size_t band_window_bytes(const DevDesc& d, size_t limit) {
+  const size_t CW = (size_t)d.kl + d.ku + 1, WR = (size_t)d.kl + 2, WS = (CW + 2) | 1;
+  if (CW + 1 > 256) return 0;
+  size_t RW = 32; while (RW < CW + 1) RW <<= 1;
+  const size_t bytes = (WR * WS + WR + RW + 4 * (kBandThreads / 32 + 1)) * sizeof(double) + 16;   // window | slot maps | x ring | pivot candidates
+  return bytes <= limit ? bytes : 0;
+}
+// Opt the two band kernels in to `bytes` of dynamic shared memory (once per device: the attribute is only ever raised) and return
+// how many CTAs of the solve kernel fit one SM.
+int band_prepare(size_t bytes, int device) {
+  static size_t raised[64] = {0};
+  if (device >= 0 && device < 64 && bytes > raised[device]) {
+    cudaFuncSetAttribute((const void*)agb_band_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncSetAttribute((const void*)agb_band_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    raised[device] = bytes;
+  }
+  int occ = 2;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agb_band_newton_kernel, kBandThreads, bytes);
+  return occ > 0 ? occ : 1;
 }
 size_t band_scratch_doubles(const DevDesc& d) {
   const size_t N = d.N, K = d.K, n = d.n, m = d.m, p = d.p, S = d.S;

@@ -116,6 +116,16 @@ __device__ inline void rk3(const DevDesc* d, const double* s, const double* u, d
 
 struct Norms { double sum, opt, dyn, con, sta; };
 
+// -DAGB_BAND_TIMING (profiling builds of agb_band.cu only): thread 0 of CTA 0 accumulates clock64() per phase, printed at kernel end
+#ifdef AGB_BAND_TIMING
+__device__ long long g_bt[16];
+#define BT_MARK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_bt[slot] += t_ - bt_t0; bt_t0 = t_; } } while (0)
+#define BT_START() long long bt_t0 = clock64()
+#else
+#define BT_MARK(slot) do { } while (0)
+#define BT_START() do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------------------
 // one instance
 // ------------------------------------------------------------------------------------------------------------
@@ -128,6 +138,7 @@ struct Ctx {
   double *X, *U, *L, *Xt, *Ut, *Lt, *dX, *dU, *dL, *res, *rhs, *AB, *XN, *bandm;
   double *lam, *mu;                                   // [K][nrow], this instance's slice of the result buffers
   double* red;                                        // shared: 8 doubles per warp + broadcast slots
+  double* win = nullptr;                              // shared-memory elimination window (band_solve_window), nullptr: global path
 
   __device__ void bind(const DevDesc* dd, double* scratch, double* red_) {
     d = dd; p = dd->p; n = dd->n; m = dd->m; ni = dd->ni; mi = dd->mi; N = dd->N; K = dd->K; b = dd->b; S = dd->S; nrow = dd->nrow;
@@ -238,6 +249,7 @@ struct Ctx {
   __device__ Norms assemble(const double* Xa, const double* Ua, const double* La, const double* Xref, const double* Uref,
                             double reg_res, bool jac, double reg_jac) {
     // pass 1: RK2 values and forward-mode Jacobians [A | B] per (stage, player); zero the band
+    BT_START();
     const int ncol = ni + mi;
     for (int item = tid; item < K * p * (ncol + 1); item += nt) {
       const int c = item % (ncol + 1), sp = item / (ncol + 1), i = sp % p, s = sp / p;
@@ -256,38 +268,69 @@ struct Ctx {
         for (int q = 0; q < ni; q++) ab[q * ncol + c] = xn[q].d;
       }
     }
+    BT_MARK(0);
     if (jac) for (size_t q = tid; q < (size_t)S * wd; q += nt) bandm[q] = 0.0;
     __syncthreads();
-    // pass 2: one work item per (stage, row group): group 0 = dynamics rows + u rows, group 1+i = x rows of player i
+    BT_MARK(1);
+    // pass 2a: one work item per band row — the smooth part of the row (dynamics defect, LQR gradient, costate terms) and its
+    // Jacobian entries; rows are disjoint, so the order of the additions into every entry is the order of the serial form
     Norms nm = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int r = tid; r < S; r += nt) {
+      const int s = r / b, e = r - s * b, k = s + 1;
+      const double* x = Xa + k * n;
+      const double* u = Ua + s * m;
+      if (e < n) {                                                              // dyn_s: f_RK2(x_s, u_s) − x_{s+1}
+        const int a = e, ia = a % p, ca = a / p;
+        res[r] = XN[s * n + a] - x[a];
+        if (jac) {
+          const double* ab = AB + (size_t)(s * p + ia) * nab + ca * ncol;
+          if (s >= 1) for (int q = 0; q < ni; q++) be(r, col_x(s - 1, q * p + ia)) += ab[q];
+          for (int q = 0; q < mi; q++) be(r, col_u(s, q * p + ia)) += ab[ni + q];
+          be(r, col_x(s, a)) += -1.0;
+        }
+      } else if (e < n + m) {                                                   // opt_i u_{i,s}: own control components
+        const int idx = e - n, i = idx % p, j = idx / p;
+        const double* ab = AB + (size_t)(s * p + i) * nab;
+        const double* lamd = La + (size_t)(i * K + s) * n;
+        double v = dt * R[idx] * (u[idx] - uf[idx]);
+        for (int q = 0; q < ni; q++) v += ab[q * ncol + ni + j] * lamd[q * p + i];
+        if (reg_res != 0.0) v += reg_res * (u[idx] - Uref[s * m + idx]);
+        res[r] = v;
+        if (jac) {
+          be(r, col_u(s, idx)) += dt * R[idx] + reg_jac;
+          for (int q = 0; q < ni; q++) be(r, col_l(s, i, q * p + i)) += ab[q * ncol + ni + j];
+        }
+      } else {                                                                  // opt_i x_{k}: row a of player i
+        const int t = e - n - m, i = t / n, a = t - i * n;
+        const double dtx = (k < K) ? dt : 1.0;                                  // the terminal knot is not dt-scaled
+        const int ia = a % p, ca = a / p;
+        double v = -La[(size_t)(i * K + s) * n + a];                            // −λ_{i,s}
+        if (ia == i) v += dtx * Q[a] * (x[a] - xf[a]);                          // LQR gradient (objective.jl:24-32)
+        if (s + 1 < K) {                                                        // + A_{s+1}ᵀ λ_{i,s+1}
+          const double* ab = AB + (size_t)((s + 1) * p + ia) * nab;
+          const double* lamn = La + (size_t)(i * K + s + 1) * n;
+          for (int q = 0; q < ni; q++) v += ab[q * ncol + ca] * lamn[q * p + ia];
+        }
+        if (reg_res != 0.0) v += reg_res * (x[a] - Xref[k * n + a]);
+        res[r] = v;
+        if (jac) {
+          be(r, col_l(s, i, a)) += -1.0;
+          if (s + 1 < K) {
+            const double* ab = AB + (size_t)((s + 1) * p + ia) * nab;
+            for (int q = 0; q < ni; q++) be(r, col_l(s + 1, i, q * p + ia)) += ab[q * ncol + ca];
+          }
+          be(r, col_x(s, a)) += (ia == i ? dtx * Q[a] : 0.0) + reg_jac;
+        }
+      }
+    }
+    __syncthreads();
+    // pass 2b: one work item per (stage, row group) — collision cost and augmented-Lagrangian terms, which add into several rows of
+    // their own group: group 0 = control rows of stage s, group 1+i = state rows of player i at knot s+1
     for (int item = tid; item < K * (1 + p); item += nt) {
       const int grp = item % (1 + p), s = item / (1 + p), k = s + 1;
       const double* x = Xa + k * n;
       const double* u = Ua + s * m;
       if (grp == 0) {
-        for (int a = 0; a < n; a++) {                                           // dyn_s: f_RK2(x_s, u_s) − x_{s+1}
-          const int ia = a % p, ca = a / p, r = row_dyn(s, a);
-          res[r] = XN[s * n + a] - x[a];
-          if (jac) {
-            const double* ab = AB + (size_t)(s * p + ia) * nab + ca * ncol;
-            if (s >= 1) for (int q = 0; q < ni; q++) be(r, col_x(s - 1, q * p + ia)) += ab[q];
-            for (int q = 0; q < mi; q++) be(r, col_u(s, q * p + ia)) += ab[ni + q];
-            be(r, col_x(s, a)) += -1.0;
-          }
-        }
-        for (int idx = 0; idx < m; idx++) {                                     // opt_i u_{i,s}: own control components
-          const int i = idx % p, j = idx / p, r = row_u(s, idx);
-          const double* ab = AB + (size_t)(s * p + i) * nab;
-          const double* lamd = La + (size_t)(i * K + s) * n;
-          double v = dt * R[idx] * (u[idx] - uf[idx]);
-          for (int q = 0; q < ni; q++) v += ab[q * ncol + ni + j] * lamd[q * p + i];
-          if (reg_res != 0.0) v += reg_res * (u[idx] - Uref[s * m + idx]);
-          res[r] = v;
-          if (jac) {
-            be(r, col_u(s, idx)) += dt * R[idx] + reg_jac;
-            for (int q = 0; q < ni; q++) be(r, col_l(s, i, q * p + i)) += ab[q * ncol + ni + j];
-          }
-        }
         control_rows(u, [&](int row, double c, int nnz, const int* ix, const double* g) {
           const double lm = lam[s * nrow + row], mm = mu[s * nrow + row];
           const double w = ((c >= 0.0) || (lm > 0.0)) ? mm : 0.0, gl = lm + w * c;
@@ -299,26 +342,6 @@ struct Ctx {
       } else {
         const int i = grp - 1;
         const double dtx = (k < K) ? dt : 1.0;                                  // the terminal knot is not dt-scaled
-        for (int a = 0; a < n; a++) {
-          const int ia = a % p, ca = a / p, r = row_x(s, i, a);
-          double v = -La[(size_t)(i * K + s) * n + a];                          // −λ_{i,s}
-          if (ia == i) v += dtx * Q[a] * (x[a] - xf[a]);                        // LQR gradient (objective.jl:24-32)
-          if (s + 1 < K) {                                                      // + A_{s+1}ᵀ λ_{i,s+1}
-            const double* ab = AB + (size_t)((s + 1) * p + ia) * nab;
-            const double* lamn = La + (size_t)(i * K + s + 1) * n;
-            for (int q = 0; q < ni; q++) v += ab[q * ncol + ca] * lamn[q * p + ia];
-          }
-          if (reg_res != 0.0) v += reg_res * (x[a] - Xref[k * n + a]);
-          res[r] = v;
-          if (jac) {
-            be(r, col_l(s, i, a)) += -1.0;
-            if (s + 1 < K) {
-              const double* ab = AB + (size_t)((s + 1) * p + ia) * nab;
-              for (int q = 0; q < ni; q++) be(r, col_l(s + 1, i, q * p + ia)) += ab[q * ncol + ca];
-            }
-            be(r, col_x(s, a)) += (ia == i ? dtx * Q[a] : 0.0) + reg_jac;
-          }
-        }
         if (d->has_cc) {                                                        // soft collision cost on px (objective.jl:134-173)
           for (int j = 0; j < p; j++) {
             if (j == i) continue;
@@ -352,16 +375,235 @@ struct Ctx {
       }
     }
     __syncthreads();
+    BT_MARK(2);
     for (int q = tid; q < S; q += nt) {
       const double v = fabs(res[q]);
       nm.sum += v;
       if (q % b < n) nm.dyn = fmax(nm.dyn, v); else nm.opt = fmax(nm.opt, v);
     }
-    return reduce(nm);
+    nm = reduce(nm);
+    BT_MARK(3);
+    return nm;
   }
 
   // ---- Δtraj = −(lu(jac) \ res): band LU with partial pivoting, in place; rhs ← solution.  false: singular ------------
   __device__ bool band_solve() {
+    if (win == nullptr) return band_solve_global();
+    switch ((kl + ku + 2 + 31) / 32) {                                          // 32-column chunks of a window row (+ right-hand side) per lane
+      case 1: return band_solve_window<1>();
+      case 2: return band_solve_window<2>();
+      case 3: return band_solve_window<3>();
+      case 4: return band_solve_window<4>();
+      case 5: return band_solve_window<5>();
+      case 6: return band_solve_window<6>();
+      case 7: return band_solve_window<7>();
+      default: return band_solve_window<8>();
+    }
+  }
+
+  // The same elimination, operation for operation (identical pivots, identical roundings), with the active rows held in shared
+  // memory.  At column j the live part of the matrix is rows j..j+kl, columns j..j+kl+ku: a window of WR = kl+2 physical row slots
+  // (kl+1 live rows + the slot the next row streams into) of CW = kl+ku+1 entries addressed by ABSOLUTE column modulo CW, plus the
+  // right-hand side in position CW.  Absolute columns make a row interchange a swap of two entries of the logical-row -> slot map
+  // (double buffered by the parity of j) instead of a data move.  A column costs ONE block barrier:
+  //   [rank-1 update, two rows per warp pass with all loads issued before the FMAs, the pivot row cached in registers; the lane that
+  //    owns column j+1 keeps the arg-max of its warp's updated rows | pivot row retired to the global band (U, for the back
+  //    substitution) | row j+kl+1 streamed into the spare slot | next map written]  barrier  [pivot of column j+1 = arg-max of the
+  //    per-warp candidates and of the streamed row, first row on ties — the global path's choice].
+  // The position of column j is zeroed as each row is updated: it is column j+CW of the next step.
+  // Back substitution: warps 1.. stream the retired U rows back from the global band into two shared buffers of RB rows each while
+  // warp 0 substitutes out of the other buffer (the last CW solution entries in a shared ring), reproducing the 128 partial sums of
+  // the global path's reduction four per lane.
+  template <int NCH> __device__ bool band_solve_window() {
+    BT_START();
+    const int CW = kl + ku + 1, WR = kl + 2, WS = (CW + 2) | 1;                  // row: CW columns | right-hand side | dummy (lanes past the row's end)
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    int* lp = reinterpret_cast<int*>(win + (size_t)WR * WS);                    // lp[2][WR]
+    int RW = 32; while (RW < CW + 1) RW <<= 1;
+    double* xr = win + (size_t)WR * WS + WR;                                    // x ring [RW] (behind the maps: 2 WR ints = WR doubles)
+    double* cand0 = xr + RW;                                                    // pivot candidates [2][value [nw+1] | row (as double) [nw+1]], by parity of j
+    auto load_row = [&](int r, int c0, int q) -> double {                       // entry q of row r for the window whose first column is c0
+      if (q == CW) return -res[r];
+      const int c = c0 + q;
+      return (c >= r - kl && c <= r + ku && c < S) ? bandm[(size_t)r * wd + (c - r + kl)] : 0.0;
+    };
+    const int r0 = (kl + 1 < S) ? kl + 1 : S;                                   // rows 0..r0-1 start in the window, slot = row
+    for (int r = warp; r < r0; r += nw) {
+      double* dst = win + (size_t)r * WS;
+      for (int q = lane; q <= CW; q += 32) dst[q] = load_row(r, 0, q);          // columns 0..CW-1 sit at positions 0..CW-1
+    }
+    for (int q = tid; q < WR; q += nt) lp[q] = q;
+    __syncthreads();
+    // pivot of column 0: first row of maximal |a_r0| (every warp, same data, same answer)
+    double best = -1.0; int pr = 0;
+    for (int r = lane; r < r0; r += 32) { const double v = fabs(win[(size_t)r * WS]); if (v > best) { best = v; pr = r; } }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int orr = __shfl_xor_sync(0xffffffffu, pr, o);
+      if (ob > best || (ob == best && orr < pr)) { best = ob; pr = orr; }
+    }
+    int spare = WR - 1;                                                         // free physical slot (uniform)
+    int posj = 0, lrj = 0;                                                      // j % CW, j % WR
+    for (int j = 0; j < S; j++) {
+      if (!(best > 0.0)) { __syncthreads(); return false; }                     // (uniform)
+      const int rmax = (j + kl < S - 1) ? j + kl : S - 1, cmax = (j + ku + kl < S - 1) ? j + ku + kl : S - 1;
+      const int* M = lp + (j & 1) * WR;
+      int* Mn = lp + ((j & 1) ^ 1) * WR;
+      int lrp = lrj + (pr - j); if (lrp >= WR) lrp -= WR;
+      const int Pj = M[lrj], P = M[lrp];                                        // slots of logical row j and of the pivot row
+      const double* prow = win + (size_t)P * WS;
+      const double inv = 1.0 / prow[posj];
+      const int nr = rmax - j, nc = cmax - j;
+      int pos1 = posj + 1; if (pos1 >= CW) pos1 -= CW;                          // position of column j+1
+      // this lane's columns j+1+cc, cc = lane + 32 t (cc == nc: the right-hand side), pivot row values in registers
+      double pv[NCH]; int pp[NCH];
+#pragma unroll
+      for (int t = 0; t < NCH; t++) {
+        const int cc = lane + 32 * t;
+        int q = pos1 + cc; if (q >= CW) q -= CW;
+        pp[t] = (cc < nc) ? q : (cc == nc ? CW : CW + 1);                       // past the end: the row's dummy entry, factor 0
+        pv[t] = (cc <= nc) ? prow[pp[t]] : 0.0;
+      }
+      // retire the pivot row: U row j and its right-hand side go to the global band
+      for (int cc = tid; cc <= nc + 1; cc += nt) {
+        if (cc == nc + 1) rhs[j] = prow[CW];
+        else { int q = posj + cc; if (q >= CW) q -= CW; bandm[(size_t)j * wd + kl + cc] = prow[q]; }
+      }
+      // the row that enters the window at step j+1 (values held in registers until the update is done)
+      const int rn = j + kl + 1;
+      double nv0 = 0.0, nv1 = 0.0;
+      if (rn < S) {
+        if (tid <= CW) nv0 = load_row(rn, j + 1, tid);
+        if (tid + nt <= CW) nv1 = load_row(rn, j + 1, tid + nt);
+      }
+      BT_MARK(7);
+      // rank-1 update, rows j+1+ri: two rows per pass; lane 0 holds column j+1 (cc = 0) and tracks this warp's pivot candidate
+      double cbest = -1.0; int crow = 0;
+      const bool track = (lane == 0) && (nc >= 1);
+      int ri = warp;
+      for (; ri + nw < nr; ri += 2 * nw) {                                      // two rows per pass
+        const int ri2 = ri + nw;
+        int lra = lrj + 1 + ri; if (lra >= WR) lra -= WR;
+        int lrb = lrj + 1 + ri2; if (lrb >= WR) lrb -= WR;
+        const int ra = j + 1 + ri, rb = j + 1 + ri2;
+        double* rowa = win + (size_t)((ra == pr) ? Pj : M[lra]) * WS;
+        double* rowb = win + (size_t)((rb == pr) ? Pj : M[lrb]) * WS;
+        const double fa = rowa[posj] * inv, fb = rowb[posj] * inv;
+        double va[NCH], vb[NCH];
+#pragma unroll
+        for (int t = 0; t < NCH; t++) { va[t] = rowa[pp[t]]; vb[t] = rowb[pp[t]]; }
+#pragma unroll
+        for (int t = 0; t < NCH; t++) { va[t] -= fa * pv[t]; vb[t] -= fb * pv[t]; }
+#pragma unroll
+        for (int t = 0; t < NCH; t++) { rowa[pp[t]] = va[t]; rowb[pp[t]] = vb[t]; }
+        if (track) {
+          const double aa = fabs(va[0]); if (aa > cbest) { cbest = aa; crow = ra; }
+          const double ab = fabs(vb[0]); if (ab > cbest) { cbest = ab; crow = rb; }
+        }
+        __syncwarp();
+        if (lane == 0) { rowa[posj] = 0.0; rowb[posj] = 0.0; }                  // becomes column j + CW
+      }
+      if (ri < nr) {                                                            // odd row out
+        int lra = lrj + 1 + ri; if (lra >= WR) lra -= WR;
+        const int ra = j + 1 + ri;
+        double* rowa = win + (size_t)((ra == pr) ? Pj : M[lra]) * WS;
+        const double fa = rowa[posj] * inv;
+        double va[NCH];
+#pragma unroll
+        for (int t = 0; t < NCH; t++) va[t] = rowa[pp[t]];
+#pragma unroll
+        for (int t = 0; t < NCH; t++) va[t] -= fa * pv[t];
+#pragma unroll
+        for (int t = 0; t < NCH; t++) rowa[pp[t]] = va[t];
+        if (track) { const double aa = fabs(va[0]); if (aa > cbest) { cbest = aa; crow = ra; } }
+        __syncwarp();
+        if (lane == 0) rowa[posj] = 0.0;
+      }
+      BT_MARK(8);
+      // next step's map, the candidates and the new row
+      int lrn = lrj + kl + 1; if (lrn >= WR) lrn -= WR;                           // logical position of row j+kl+1 (that of row j-1)
+      for (int q = tid; q < WR; q += nt) {
+        int v = M[q];
+        if (q == lrp) v = Pj;
+        if (q == lrn) v = spare;
+        Mn[q] = v;
+      }
+      double* cand = cand0 + (j & 1) * 2 * (nw + 1);                             // (a fast warp may write step j+1's while a slow one still reads step j's)
+      if (lane == 0) { cand[warp] = cbest; cand[nw + 1 + warp] = (double)crow; }
+      if (tid == 0) { cand[nw] = (rn < S) ? fabs(nv0) : -1.0; cand[2 * nw + 1] = (double)rn; }   // entry 0 of the new row is column j+1
+      if (rn < S) {
+        double* dst = win + (size_t)spare * WS;
+        // columns j+1 .. j+CW: position of column j+1+q is (pos1 + q) mod CW
+        if (tid <= CW) { int q = pos1 + tid; if (q >= CW) q -= CW; dst[tid == CW ? CW : q] = nv0; }
+        if (tid + nt <= CW) { int q = pos1 + tid + nt; if (q >= CW) q -= CW; dst[tid + nt == CW ? CW : q] = nv1; }
+      }
+      spare = P;
+      posj = pos1; lrj = (lrj + 1 == WR) ? 0 : lrj + 1;
+      __syncthreads();
+      // pivot of column j+1: first row of maximal |a| among the candidates (rows of one warp ascend, strict > keeps the first)
+      best = -1.0; pr = j + 1;
+      if (j + 1 < S) {
+        for (int w = 0; w <= nw; w++) {
+          const double v = cand[w]; const int rr = (int)cand[nw + 1 + w];
+          if (v > best || (v == best && v >= 0.0 && rr < pr)) { best = v; pr = rr; }
+        }
+        if (nc < 1) best = -1.0;                                                // (cannot happen for j + 1 < S: column j+1 exists)
+      } else best = 1.0;
+      BT_MARK(9);
+    }
+    BT_MARK(4);
+    // ---- back substitution ----
+    {
+      const int RB = (int)(((size_t)WR * WS / 2) / (size_t)(CW + 1));            // U rows per buffer (>= 1)
+      double* buf[2] = {win, win + (size_t)RB * (CW + 1)};
+      // chunk g holds rows hi_g-1 down to lo_g (hi_0 = S); row j of a chunk at buf + (hi_g-1-j)*(CW+1): entries c = j..j+CW-1, then rhs
+      auto load_chunk = [&](int hi, double* dst, int first, int step) {
+        const int lo = hi - RB > 0 ? hi - RB : 0;
+        for (int item = first; item < (hi - lo) * (CW + 1); item += step) {
+          const int jr = item / (CW + 1), q = item - jr * (CW + 1), j = hi - 1 - jr;
+          double v;
+          if (q == CW) v = rhs[j];
+          else { const int c = j + q; v = (c < S && q <= kl + ku) ? bandm[(size_t)j * wd + kl + q] : 0.0; }
+          dst[item] = v;
+        }
+      };
+      load_chunk(S, buf[0], tid, nt);
+      __syncthreads();
+      int cur = 0;
+      for (int hi = S; hi > 0; hi -= RB, cur ^= 1) {
+        const int lo = hi - RB > 0 ? hi - RB : 0;
+        if (warp == 0) {
+          const double* bsrc = buf[cur];
+          for (int j = hi - 1; j >= lo; j--) {
+            const double* urow = bsrc + (size_t)(hi - 1 - j) * (CW + 1);
+            const int cmax = (j + ku + kl < S - 1) ? j + ku + kl : S - 1;
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+              for (int c = j + 1 + lane + 32 * w; c <= cmax; c += 128) a[w] += urow[c - j] * xr[c & (RW - 1)];
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+              for (int w = 0; w < 4; w++) a[w] += __shfl_xor_sync(0xffffffffu, a[w], o);
+            }
+            if (lane == 0) {
+              double t = 0.0;
+#pragma unroll
+              for (int w = 0; w < 4; w++) t += a[w];
+              const double x = (urow[CW] - t) / urow[0];
+              xr[j & (RW - 1)] = x; rhs[j] = x;
+            }
+            __syncwarp();
+          }
+        } else if (lo > 0) {
+          load_chunk(lo, buf[cur ^ 1], tid - 32, nt - 32);
+        }
+        __syncthreads();
+      }
+    }
+    BT_MARK(5);
+    return true;
+  }
+
+  __device__ bool band_solve_global() {
     for (int q = tid; q < S; q += nt) rhs[q] = -res[q];
     __syncthreads();
     int* ired = reinterpret_cast<int*>(red + 48);

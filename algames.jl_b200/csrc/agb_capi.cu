@@ -16,6 +16,8 @@ namespace agb {   // agb_band.cu
 void launch_band_solve(const DevDesc* dd, const agb_options& o, const Buffers& g, int inst0, int batch, int only_status, int grid, cudaStream_t st);
 void launch_band_op(const DevDesc* dd, const agb_options& o, const Buffers& g, const OpArgs& a, int batch, int grid, cudaStream_t st);
 size_t band_scratch_doubles(const DevDesc& d);
+size_t band_window_bytes(const DevDesc& d, size_t limit);
+int band_prepare(size_t bytes, int device);
 }
 
 // internal stage-major layout → reference row ("vertical", mode 0) or column ("horizontal", mode 1) order
@@ -118,7 +120,7 @@ struct agb_handle {
   double* results = nullptr; size_t results_doubles = 0;   // owns Z, L, stats, status
   // band solver (agb_band.cuh): scratch slots (one per resident CTA); conlam0 / conmu0 keep the multipliers a warm-started
   // solve began with, for the fallback re-solve of AGB_SINGULAR instances
-  double* band = nullptr; size_t band_stride = 0; int band_slots = 0;
+  double* band = nullptr; size_t band_stride = 0; int band_slots = 0; int band_win = 0;
   double *conlam0 = nullptr, *conmu0 = nullptr;
   bool fallback = true;
   int force_singular = 0;
@@ -426,7 +428,10 @@ int agb_create(const agb_problem_desc* desc, int batch, int device, agb_handle**
     if (t.use_band || h->fallback) {
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-      const int want = t.use_band ? 2 * sms : 32;
+      const char* w = getenv("AGB_BAND_WINDOW");           // "0": eliminate in the global band (the first form of the solver; A/B and tests)
+      h->band_win = (w && w[0] == '0') ? 0 : (int)agb::band_window_bytes(t, (size_t)max_smem - 1024);
+      const int occ = agb::band_prepare((size_t)h->band_win, device);
+      const int want = t.use_band ? occ * sms : 32;
       h->band_slots = batch < want ? batch : want;
       h->band_stride = (agb::band_scratch_doubles(t) + 1) & ~(size_t)1;
       CK(alloc_d(h, &h->band, (size_t)h->band_slots * h->band_stride));
@@ -468,7 +473,7 @@ static Buffers buffers_of(agb_handle* h) {
   g.conlam = h->conlam; g.conmu = h->conmu; g.D = h->D; g.KUg = h->KUg; g.stats = h->stats; g.status = h->status;
   g.hist = h->hist; g.hist_count = h->hist_count; g.hist_max = h->hist_max;
   g.Hpg = h->Hpg; g.hpg_stride = h->hpg_stride;
-  g.band = h->band; g.band_stride = h->band_stride; g.band_slots = h->band_slots; g.conlam0 = nullptr; g.conmu0 = nullptr;
+  g.band = h->band; g.band_stride = h->band_stride; g.band_slots = h->band_slots; g.band_win = h->band_win; g.conlam0 = nullptr; g.conmu0 = nullptr;
   g.force_singular = h->force_singular;
   return g;
 }
@@ -942,6 +947,13 @@ int agb_update_nullspace(agb_handle* h, double tol, double atol, int max_dim, do
   AGB_TRY(d2h(h, null_out, (double*)nul.p, B * (size_t)max_dim * Sh));
   AGB_CUDA(h, cudaMemcpyAsync(dim_out, dim.p, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   return finish(h);
+}
+
+int agb_band_info(const agb_handle* h, int* window_bytes_out, int* slots_out) {
+  if (!h) return AGB_EINVAL;
+  if (window_bytes_out) *window_bytes_out = h->band_win;
+  if (slots_out) *slots_out = h->band_slots;
+  return AGB_OK;
 }
 
 int agb_debug_gain_solve(agb_handle* h, const double* aug, double* aug_out, int* ok_out) {

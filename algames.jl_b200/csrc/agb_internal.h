@@ -90,6 +90,7 @@ struct Buffers {
   double* band;       // band solver scratch: [slots][band_stride]
   size_t band_stride;
   int band_slots;
+  int band_win;       // bytes of the shared-memory elimination window per CTA (band_window_bytes), 0: eliminate in the global band
   const double* conlam0;   // multipliers / penalties the solve started from (fallback re-solves with dual_reset = 0), or nullptr
   const double* conmu0;
   int force_singular; // test hook (AGB_TEST_FORCE_SINGULAR=k): the structured solve kernel reports every k-th instance as AGB_SINGULAR

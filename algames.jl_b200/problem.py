@@ -673,6 +673,12 @@ class GameBatch:
             raise AlgamesError(f"null space of dimension {int(dim.max())} exceeds max_dim = {max_dim}")
         return [out[b, :dim[b]].copy() for b in range(self.batch)]
 
+    def band_info(self):
+        """agb_band_info: (bytes of the band solver's shared-memory elimination window per CTA, band scratch slots)."""
+        w = C.c_int(0); sl = C.c_int(0)
+        self._ck(self.lib.agb_band_info(self.h, C.byref(w), C.byref(sl)))
+        return w.value, sl.value
+
     def debug_gain_solve(self, aug):
         """agb_debug_gain_solve: the kernel's Gauss-Jordan on aug [B, m, m+n+1]; returns (reduced systems, ok flags)."""
         aug = self._arr(aug, (self.batch, self.m, self.m + self.n + 1))
@@ -1104,10 +1110,11 @@ def evaluate(prob: GameProblem):
 
 
 class NullSpace:
-    """NullSpace (active_set_core.jl:5-27): `mat` Sh x dim, `vec` its columns."""
+    """NullSpace (active_set_core.jl:5-27): `mat` len(hmask) x dim, `vec` its columns scattered to Sh entries and scaled to unit
+    mean absolute value, `dtraj` / `dlam` their first S / remaining entries (the reference's Δtraj, Δλ)."""
 
     def __init__(self, sh):
-        self.mat = np.zeros((sh, 0)); self.vec = []
+        self.mat = np.zeros((sh, 0)); self.vec = []; self.dtraj = []; self.dlam = []
 
 
 class ActiveSetCore:
@@ -1149,7 +1156,11 @@ def update_nullspace(ascore: ActiveSetCore, prob: "GameProblem", atol: float = 1
     vm, hm = b.active_set_masks(tol)
     ascore.vmask, ascore.hmask = np.flatnonzero(vm[0]), np.flatnonzero(hm[0])
     basis = b.update_nullspace(tol, atol)[0]
-    ascore.null.mat = basis.T.copy(); ascore.null.vec = [basis[d].copy() for d in range(basis.shape[0])]
+    # add_matrix! (active_set_core.jl:29-52): mat keeps the masked rows, vec the scattered vectors scaled to unit mean |.|
+    ascore.null.mat = basis[:, ascore.hmask].T.copy()
+    ascore.null.vec = [basis[d] / np.mean(np.abs(basis[d])) for d in range(basis.shape[0])]
+    S = prob.probsize.S
+    ascore.null.dtraj = [v[:S] for v in ascore.null.vec]; ascore.null.dlam = [v[S:] for v in ascore.null.vec]
     return ascore.null
 
 

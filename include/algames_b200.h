@@ -36,6 +36,7 @@
  *   AGB_HOST_CHUNKS=1..32       agb_solve_from_host: number of copy/solve pipeline chunks (default 8 for batch >= 1024)
  *   AGB_BAND_FALLBACK=0         agb_create: do not re-solve AGB_SINGULAR instances of the structured kernels with the band solver
  *   AGB_TEST_FORCE_SINGULAR=k   agb_create: the structured solve reports every k-th instance as AGB_SINGULAR (fallback tests)
+ *   AGB_BAND_WINDOW=0           agb_create: the band solver eliminates in the global-memory band, not in its shared-memory window
  */
 #ifndef ALGAMES_B200_H
 #define ALGAMES_B200_H
@@ -271,9 +272,16 @@ int agb_active_set_masks(agb_handle* h, double tol, unsigned char* vmask_out, un
 /* update_nullspace!(ascore, prob, pdtraj) (:173-184): an orthonormal basis of nullspace(jac[vmask, hmask]), scattered to the hmask
  * rows (add_matrix!, active_set_core.jl:29-42).  One CTA per instance: Gauss-Jordan with complete pivoting on the dense masked
  * matrix, rank = number of pivots > atol (the reference passes atol = 1e-20 to LinearAlgebra.nullspace), modified Gram-Schmidt.
- * The basis is unique only up to rotation: compare subspaces.  null_out [B][max_dim][Sh] (vector d of instance b at
+ * The basis is unique only up to rotation: compare subspaces.  With atol below eps * max|jac| an exactly rank-deficient matrix
+ * yields n_cols - min(n_rows, n_cols) vectors, the count the reference's SVD produces (round-off-level singular values pass its
+ * atol test).  null_out [B][max_dim][Sh] (vector d of instance b at
  * null_out + (b*max_dim + d)*Sh), dim_out [B] = the dimension found (vectors beyond max_dim are not written). */
 int agb_update_nullspace(agb_handle* h, double tol, double atol, int max_dim, double* null_out, int* dim_out);
+
+/* Diagnostic: how this handle runs the band solver (lu(jac) \ res on the explicit KKT band, solver_methods.jl:87) — bytes of the
+ * shared-memory elimination window per CTA (0: the window does not fit or AGB_BAND_WINDOW=0, the band is eliminated in global
+ * memory) and the number of resident CTA slots with band scratch (0: structured kernels only, no fallback). */
+int agb_band_info(const agb_handle* h, int* window_bytes_out, int* slots_out);
 
 /* Diagnostic: runs the kernel's m x (m+n+1) gain-system solver (threshold-pivoted Gauss-Jordan with partial-pivoting
  * fallback) on caller-supplied systems aug [B][m][m+n+1]; the reduced systems come back in place of the

@@ -103,6 +103,7 @@ inline cudaError_t cudaStreamWaitEvent(void*, void*, unsigned) { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 232448; return 0; }
 inline cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }

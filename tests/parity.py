@@ -682,6 +682,39 @@ def check_band_equals_structured(lib_path, name, B=4, N=None):
     return a
 
 
+def check_band_window_equals_global(lib_path, monkeypatch, name, B=2, N=None, **kw):
+    """band_solve_window (elimination window in shared memory, one barrier per column, slot map instead of row swaps) against
+    band_solve_global (the first form, selected with AGB_BAND_WINDOW=0): the same operations in the same order — every result,
+    the whole Statistics history and the Newton step of a random iterate must agree BIT FOR BIT."""
+    W = ab.workloads
+    model, N, dt, obj, con, opts, x0, xf = W.CONFIGS[name](batch=B, **({"N": N} if N else {}), **kw)
+    res = {}
+    for win in ("0", "1"):
+        monkeypatch.setenv("AGB_BAND_WINDOW", win)
+        gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=lib_path, solver=ab._capi.SOLVER_BAND)
+        assert (gb.band_info()[0] > 0) == (win == "1")               # the window path really is the one that runs
+        gb.set_instance_params(x0=x0, xf=xf)
+        gb.random_initial(opts.amplitude_init, opts.seed)
+        gb.set_history(opts.outer_iter * opts.inner_iter + 1)
+        out = gb.newton_solve(opts)
+        out["hist"], out["count"] = gb.get_history()
+        rng = np.random.default_rng(11)
+        Z = rng.normal(size=out["Z"].shape); L = rng.normal(size=out["L"].shape)
+        gb.set_initial(Z, L)
+        out["dtraj"] = gb.kkt_solve(1e-3, 1e-3)
+        res[win] = out
+        gb.close()
+    monkeypatch.delenv("AGB_BAND_WINDOW")
+    a, b = res["0"], res["1"]
+    assert a["stats"][:, 6].min() >= 1                                   # the solves did factorise
+    for k in ("status", "Z", "L", "conlam", "conmu", "stats", "count"):
+        assert np.array_equal(a[k], b[k]), k
+    for i in range(B):
+        assert np.array_equal(a["hist"][i, :a["count"][i]], b["hist"][i, :b["count"][i]])
+    assert np.array_equal(a["dtraj"], b["dtraj"])
+    return a
+
+
 def check_singular_fallback(lib_path, monkeypatch):
     """Plumbing of the fallback: with the test hook AGB_TEST_FORCE_SINGULAR=k the structured kernel reports every k-th
     instance as AGB_SINGULAR after its first factorisation; the band solver must re-solve exactly those, from the same

@@ -281,3 +281,29 @@ def test_mpc_fused_loop_equals_stepwise_emulated(emu_lib):
 def test_active_set_analysis_emulated(emu_lib, name, N, partial):
     """src/active_set/*.jl on the device kernels (CTA emulator) vs the oracle: bordered residual / Jacobian, masks, null space."""
     parity.check_active_set_analysis(emu_lib, name, N=N, partial=partial)
+
+
+def test_active_set_reference_nullspace_test_emulated(emu_lib):
+    """test/active_set/active_set_methods.jl:96-127 through the host mirror on the CTA emulator: at the zero initial iterate every
+    collision gradient vanishes (exactly zero border rows) and null.mat still has the reference's (N−1)p columns."""
+    import algames_b200 as ab
+    rng = np.random.default_rng(0)
+    N, dt, p = 6, 0.1, 3
+    model = ab.UnicycleGame(p=p)
+    ps = ab.ProblemSize(N, model)
+    obj = ab.GameObjective([rng.random(4) for _ in range(p)], [rng.random(2) for _ in range(p)],
+                           [(i + 1) * np.ones(4) for i in range(p)], [2 * (i + 1) * np.ones(2) for i in range(p)], N, model)
+    con = ab.GameConstraintValues(ps)
+    ab.add_collision_avoidance(con, 1.0)
+    prob = ab.GameProblem(N, dt, rng.random(model.n), model, ab.Options(), obj, con, lib_path=emu_lib)
+    asc = ab.ActiveSetCore(ps)
+    null = ab.update_nullspace(asc, prob)
+    assert null.mat.shape == (ps.S + (N - 1) * p * (p - 1), (N - 1) * p)
+    assert len(null.vec) == (N - 1) * p and len(null.vec[0]) == ps.S + (N - 1) * p * (p - 1)
+    assert all(abs(np.mean(np.abs(v)) - 1.0) < 1e-12 for v in null.vec)
+
+
+@pytest.mark.parametrize("name,B,N,kw", [("Q", 1, 4, {"p": 2}), ("Q", 1, 5, {"p": 1}), ("B", 2, 8, {}), ("C", 1, 6, {}), ("B3", 1, 5, {})])
+def test_band_window_equals_global_emulated(emu_lib, monkeypatch, name, B, N, kw):
+    """The shared-memory elimination window of the band solver == the global-memory elimination, bit for bit (CTA emulator)."""
+    parity.check_band_window_equals_global(emu_lib, monkeypatch, name, B=B, N=N, **kw)

@@ -475,3 +475,10 @@ def test_active_set_reference_nullspace_test():
     null = ab.update_nullspace(asc, prob)
     assert null.mat.shape == (ps.S + (N - 1) * p * (p - 1), (N - 1) * p)
     assert len(null.vec) == (N - 1) * p and len(null.vec[0]) == ps.S + (N - 1) * p * (p - 1)
+
+
+@pytest.mark.parametrize("name,B,N,kw", [("Q", 3, 8, {"p": 2}), ("Q", 2, 6, {"p": 3}), ("B", 8, 20, {}), ("C", 4, 12, {}), ("B3", 4, 10, {})])
+def test_band_window_equals_global(monkeypatch, name, B, N, kw):
+    """Band solver: elimination in the shared-memory window (slot map, one barrier per column, pivot search fused into the update,
+    double-buffered back substitution) == elimination in the global band, bit for bit — results, histories and a Newton step."""
+    parity.check_band_window_equals_global(LIB, monkeypatch, name, B=B, N=N, **kw)
