@@ -740,16 +740,61 @@ struct Inst {
 #endif
   }
 
+  static __device__ __forceinline__ int imax(int x, int y) { return x > y ? x : y; }
+
   // Gauss-Jordan on the m x W augmented gain system, one column per lane (warp 0).  Threshold pivoting like the
   // reference's UMFPACK: the diagonal pivot is kept while |a_tt| >= 2^-7·max_r |a_rt| (no row exchange, no index
   // shuffles); only if some step violates the threshold is the system re-solved from shared memory with full partial
   // pivoting.  Returns false on a zero / non-finite pivot.
+  //
+  // Default form: 2 x 2 BLOCK pivots (m = 2P is even): the two pivot columns of a block step travel through shared memory in one
+  // round trip and the block [p00 p01; p10 p11] is inverted explicitly (one determinant, one reciprocal), so the m-pivot chain of
+  // [store column -> load -> reciprocal -> scale -> eliminate] becomes m/2 links of barely longer length, with fewer instructions
+  // on this warp (the stage loop's critical path).  The threshold test bounds the same quantity as the scalar form,
+  // the size of the elimination multipliers: max|inverse entry| * max|entry below the block| <= 2^7, on the integer pipe; a zero /
+  // non-finite determinant or a violated bound sends the system to the partial-pivoting fallback.  -DAGB_GJ_SCALAR keeps the
+  // scalar-pivot form (A/B measurements).
   __device__ bool gj_warp(double* aug, double* kg = nullptr) {
     double a[m];
     const bool act = lane < W;
 #pragma unroll
     for (int r = 0; r < m; r++) a[r] = act ? aug[r * W + lane] : 0.0;
     bool weak = false;                                   // warp-uniform: evaluated on the broadcast pivot column
+#ifndef AGB_GJ_SCALAR
+#pragma unroll
+    for (int t = 0; t < m; t += 2) {
+      double2* piv = reinterpret_cast<double2*>(Ym + t * m);                // columns t, t+1 (Ym is free between phases 1 and 3)
+      if (lane == t || lane == t + 1) {
+        double2* dst = piv + (lane - t) * (m / 2);
+#pragma unroll
+        for (int r = 0; r < m; r += 2) dst[r / 2] = make_double2(a[r], a[r + 1]);
+      }
+      __syncwarp();
+      double f0[m], f1[m];
+#pragma unroll
+      for (int r = 0; r < m; r += 2) {
+        const double2 v = piv[r / 2], w = piv[m / 2 + r / 2];
+        f0[r] = v.x; f0[r + 1] = v.y; f1[r] = w.x; f1[r + 1] = w.y;
+      }
+      const double p00 = f0[t], p10 = f0[t + 1], p01 = f1[t], p11 = f1[t + 1];
+      const double det = fma(p00, p11, -(p01 * p10));
+      const int hd = abs_hi(det);
+      if ((unsigned)(hd - 0x00100000) >= 0x7fe00000u) weak = true;          // zero / subnormal / inf / NaN determinant
+      const double rd = fast_rcp(det);
+      const double i00 = p11 * rd, i01 = -(p01 * rd), i10 = -(p10 * rd), i11 = p00 * rd;
+      if (t + 2 < m) {                                                       // multipliers of the rows below the block stay <= 2^7
+        int hi_i = imax(imax(abs_hi(i00), abs_hi(i01)), imax(abs_hi(i10), abs_hi(i11)));
+        int hi_f = 0;
+#pragma unroll
+        for (int r = t + 2; r < m; r++) hi_f = imax(hi_f, imax(abs_hi(f0[r]), abs_hi(f1[r])));
+        if (hi_f > 0 && hi_i + hi_f - (1023 << 20) > ((1023 + 7) << 20)) weak = true;
+      }
+      const double at0 = fma(i01, a[t + 1], i00 * a[t]), at1 = fma(i11, a[t + 1], i10 * a[t]);
+#pragma unroll
+      for (int r = 0; r < m; r++) if (r != t && r != t + 1) a[r] = fma(-f1[r], at1, fma(-f0[r], at0, a[r]));
+      a[t] = at0; a[t + 1] = at1;
+    }
+#else
 #pragma unroll
     for (int t = 0; t < m; t++) {
       // pivot column t → every lane, through shared memory (Ym is free between phases 1 and 3; one slot per step)
@@ -774,6 +819,7 @@ struct Inst {
       for (int r = 0; r < m; r++) if (r != t) a[r] = fma(-f[r], at, a[r]);
       a[t] = at;
     }
+#endif
     if (!weak) {
       if (act) {
 #pragma unroll
