@@ -432,7 +432,7 @@ struct Ctx {
       double* dst = win + (size_t)r * WS;
       for (int q = lane; q <= CW; q += 32) dst[q] = load_row(r, 0, q);          // columns 0..CW-1 sit at positions 0..CW-1
     }
-    for (int q = tid; q < WR; q += nt) lp[q] = q;
+    for (int q = tid; q < WR; q += nt) { lp[q] = q; win[(size_t)q * WS + CW + 1] = 0.0; }   // slot map; dummy entries (read by lanes past a row's end)
     __syncthreads();
     // pivot of column 0: first row of maximal |a_r0| (every warp, same data, same answer)
     double best = -1.0; int pr = 0;
@@ -494,7 +494,7 @@ struct Ctx {
 #pragma unroll
         for (int t = 0; t < NCH; t++) { va[t] -= fa * pv[t]; vb[t] -= fb * pv[t]; }
 #pragma unroll
-        for (int t = 0; t < NCH; t++) { rowa[pp[t]] = va[t]; rowb[pp[t]] = vb[t]; }
+        for (int t = 0; t < NCH; t++) if (pp[t] <= CW) { rowa[pp[t]] = va[t]; rowb[pp[t]] = vb[t]; }   // (the dummy entry is only ever read)
         if (track) {
           const double aa = fabs(va[0]); if (aa > cbest) { cbest = aa; crow = ra; }
           const double ab = fabs(vb[0]); if (ab > cbest) { cbest = ab; crow = rb; }
@@ -513,7 +513,7 @@ struct Ctx {
 #pragma unroll
         for (int t = 0; t < NCH; t++) va[t] -= fa * pv[t];
 #pragma unroll
-        for (int t = 0; t < NCH; t++) rowa[pp[t]] = va[t];
+        for (int t = 0; t < NCH; t++) if (pp[t] <= CW) rowa[pp[t]] = va[t];
         if (track) { const double aa = fabs(va[0]); if (aa > cbest) { cbest = aa; crow = ra; } }
         __syncwarp();
         if (lane == 0) rowa[posj] = 0.0;
