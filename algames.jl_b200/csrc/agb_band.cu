@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(kBandThreads, 3) agb_band_newton_kernel(const 
   __shared__ double red[64];
   AGB_DYN_SMEM(sm);
   if ((int)blockIdx.x >= g.band_slots) return;
+  if (only_status >= 0) {                              // fallback launch: normally nothing to do — one coalesced scan of the range's statuses
+    int none = 1;
+    for (int i = inst0 + (int)threadIdx.x; i < batch; i += (int)blockDim.x) none &= (g.status[i] != only_status);
+    if (__syncthreads_and(none)) return;
+  }
   Ctx C;
   C.bind(dd, g.band + (size_t)blockIdx.x * g.band_stride, red);
   C.win = g.band_win > 0 ? sm : nullptr;

@@ -109,6 +109,16 @@ struct agb_handle {
   cudaStream_t stream = nullptr;
   static constexpr int kMaxChunks = 32;
   cudaStream_t chunk_stream[kMaxChunks] = {};   // agb_solve_from_host pipeline
+#ifndef AGB_EMULATE
+  // agb_solve_from_host as a CUDA graph: the ~11 copies / launches per chunk are captured once per (buffers, options, chunking)
+  // and replayed with one cudaGraphLaunch, which takes the host's API time off the step and lets the pipeline run finer chunks
+  struct HostKey { const void* ptr[9]; agb_options o; int chunks; int epoch; };
+  HostKey fh_key{}, fh_seen{};
+  bool fh_valid = false, fh_seen_valid = false;
+  cudaGraphExec_t fh_exec = nullptr;
+  cudaEvent_t fh_fork = nullptr, fh_join[kMaxChunks] = {};
+  int fh_launches = 0, fh_epoch = 0;
+#endif
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // device buffers
@@ -362,6 +372,11 @@ void agb_destroy(agb_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaStream_t cs : h->chunk_stream) if (cs) cudaStreamDestroy(cs);
+#ifndef AGB_EMULATE
+  if (h->fh_exec) cudaGraphExecDestroy(h->fh_exec);
+  if (h->fh_fork) cudaEventDestroy(h->fh_fork);
+  for (cudaEvent_t e : h->fh_join) if (e) cudaEventDestroy(e);
+#endif
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1098,24 +1113,12 @@ int agb_ibr_kkt_solve(agb_handle* h, int player, double reg_x, double reg_u, dou
   return finish(h);
 }
 
-int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, const double* Z0, const double* L0,
-                        double* Z_out, double* L_out, double* conlam_out, double* conmu_out, double* stats_out, int* status_out) {
-  if (!h || !o || !x0 || !Z0 || !L0) return AGB_EINVAL;
-  if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1) return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter must be >= 1");
-  AGB_CUDA(h, cudaSetDevice(h->device));
-  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+// the chunk pipeline of agb_solve_from_host: chunk c = [H2D inputs -> solve -> D2H results] on its own stream
+static int enqueue_host_chunks(agb_handle* h, const agb_options* o, int chunks, const double* x0, const double* Z0, const double* L0,
+                               double* Z_out, double* L_out, double* conlam_out, double* conmu_out, double* stats_out, int* status_out) {
   const int B = h->batch, n = h->hd.n;
   const size_t zs = (size_t)h->hd.N * (h->hd.n + h->hd.m), ls = (size_t)h->hd.p * h->hd.K * h->hd.n, cs = (size_t)h->hd.K * h->hd.nrow;
-  int chunks = B >= 1024 ? 8 : (B >= 512 ? 4 : 1);   // each chunk: H2D -> solve -> D2H on its own stream
-  if (h->hd.use_band) chunks = 1;                     // band-only schemas: a solve takes ~100 ms, the copies microseconds, and splitting
-                                                      // the scratch slots over chunks only adds waves (measured: 4 chunks = 3.5 x slower)
-  if (const char* e = getenv("AGB_HOST_CHUNKS")) {    // tuning hook
-    const int v = atoi(e);
-    if (v >= 1 && v <= agb_handle::kMaxChunks) chunks = v < B ? v : B;
-  }
-  if (h->band_slots > 0 && chunks > h->band_slots) chunks = h->band_slots;           // every chunk needs its own band scratch slot
   for (int c = 0; c < chunks; c++) {
-    if (!h->chunk_stream[c]) AGB_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
     cudaStream_t st = h->chunk_stream[c];
     const int lo = (int)((long long)B * c / chunks), hi = (int)((long long)B * (c + 1) / chunks), cnt = hi - lo;
     if (cnt <= 0) continue;
@@ -1133,6 +1136,95 @@ int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, c
     if (stats_out) AGB_CUDA(h, cudaMemcpyAsync(stats_out + (size_t)lo * AGB_NSTATS, h->stats + (size_t)lo * AGB_NSTATS, (size_t)cnt * AGB_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (status_out) AGB_CUDA(h, cudaMemcpyAsync(status_out + lo, h->status + lo, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
+  return AGB_OK;
+}
+
+#ifndef AGB_EMULATE
+static bool host_pinned(const void* p) {                 // page-locked (or managed) host memory: async copies of it can be captured
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+#endif
+
+int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, const double* Z0, const double* L0,
+                        double* Z_out, double* L_out, double* conlam_out, double* conmu_out, double* stats_out, int* status_out) {
+  if (!h || !o || !x0 || !Z0 || !L0) return AGB_EINVAL;
+  if (o->ls_iter < 1 || o->outer_iter < 1 || o->inner_iter < 1) return fail(h, AGB_EINVAL, "outer_iter, inner_iter, ls_iter must be >= 1");
+  AGB_CUDA(h, cudaSetDevice(h->device));
+  AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int B = h->batch;
+  bool graph_ok = false;
+#ifndef AGB_EMULATE
+  {
+    const char* e = getenv("AGB_HOST_GRAPH");          // "0": always enqueue call by call
+    graph_ok = !(e && e[0] == '0') && !h->hd.use_band && host_pinned(x0) && host_pinned(Z0) && host_pinned(L0) && host_pinned(Z_out) &&
+               host_pinned(L_out) && host_pinned(conlam_out) && host_pinned(conmu_out) && host_pinned(stats_out) && host_pinned(status_out);
+  }
+#endif
+  // each chunk: H2D -> solve -> D2H on its own stream.  Measured on config B, batch 1024 (converged instances/s end to end): call by
+  // call 1 / 2 / 4 / 6 / 8 / 12 chunks = 296 / 332 / 339 / 346 / 345 / 325 k; replayed as a graph 8 / 12 / 16 / 24 / 32 chunks =
+  // 348 / 346 / 345 / 342 / 334 k — finer chunks lose on the device side (small kernels and copies), not on the host's API time
+  int chunks = B >= 1024 ? 8 : (B >= 512 ? 4 : 1);
+  if (h->hd.use_band) chunks = 1;                     // band-only schemas: a solve takes ~100 ms, the copies microseconds, and splitting
+                                                      // the scratch slots over chunks only adds waves (measured: 4 chunks = 3.5 x slower)
+  if (const char* e = getenv("AGB_HOST_CHUNKS")) {    // tuning hook
+    const int v = atoi(e);
+    if (v >= 1 && v <= agb_handle::kMaxChunks) chunks = v < B ? v : B;
+  }
+  if (h->band_slots > 0 && chunks > h->band_slots) chunks = h->band_slots;           // every chunk needs its own band scratch slot
+  for (int c = 0; c < chunks; c++)
+    if (!h->chunk_stream[c]) AGB_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
+#ifndef AGB_EMULATE
+  if (graph_ok) {
+    agb_handle::HostKey key;
+    memset(&key, 0, sizeof key);
+    const void* ptrs[9] = {x0, Z0, L0, Z_out, L_out, conlam_out, conmu_out, stats_out, status_out};
+    memcpy(key.ptr, ptrs, sizeof ptrs); key.o = *o; key.chunks = chunks; key.epoch = h->fh_epoch;
+    if (h->fh_valid && memcmp(&key, &h->fh_key, sizeof key) == 0) {                    // the captured pipeline, one launch
+      AGB_CUDA(h, cudaGraphLaunch(h->fh_exec, h->stream));
+      h->launches += h->fh_launches;
+      AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+      return AGB_OK;
+    }
+    if (h->fh_seen_valid && memcmp(&key, &h->fh_seen, sizeof key) == 0) {              // second call with these buffers: capture it
+      if (!h->fh_fork) AGB_CUDA(h, cudaEventCreateWithFlags(&h->fh_fork, cudaEventDisableTiming));
+      for (int c = 0; c < chunks; c++) if (!h->fh_join[c]) AGB_CUDA(h, cudaEventCreateWithFlags(&h->fh_join[c], cudaEventDisableTiming));
+      if (h->fh_exec) { cudaGraphExecDestroy(h->fh_exec); h->fh_exec = nullptr; }
+      h->fh_valid = false;
+      cudaGraph_t graph = nullptr;
+      const int launches0 = h->launches;
+      AGB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+      int rc = AGB_OK;
+      cudaError_t ce = cudaEventRecord(h->fh_fork, h->stream);
+      for (int c = 0; c < chunks && ce == cudaSuccess; c++) ce = cudaStreamWaitEvent(h->chunk_stream[c], h->fh_fork, 0);
+      if (ce == cudaSuccess) rc = enqueue_host_chunks(h, o, chunks, x0, Z0, L0, Z_out, L_out, conlam_out, conmu_out, stats_out, status_out);
+      for (int c = 0; c < chunks && ce == cudaSuccess; c++) {
+        ce = cudaEventRecord(h->fh_join[c], h->chunk_stream[c]);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->stream, h->fh_join[c], 0);
+      }
+      const cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);                  // always ends the capture, also after an error
+      h->fh_launches = h->launches - launches0;
+      h->launches = launches0;
+      if (rc == AGB_OK && ce == cudaSuccess && ee == cudaSuccess && graph &&
+          cudaGraphInstantiate(&h->fh_exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        h->fh_key = key; h->fh_valid = true;
+        AGB_CUDA(h, cudaGraphLaunch(h->fh_exec, h->stream));
+        h->launches += h->fh_launches;
+        AGB_CUDA(h, cudaStreamSynchronize(h->stream));
+        return AGB_OK;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();                                                              // capture failed: fall through to the call-by-call path
+      h->fh_seen_valid = false;
+    } else {
+      h->fh_seen = key; h->fh_seen_valid = true;
+    }
+  }
+#endif
+  AGB_TRY(enqueue_host_chunks(h, o, chunks, x0, Z0, L0, Z_out, L_out, conlam_out, conmu_out, stats_out, status_out));
   for (int c = 0; c < chunks; c++) if (h->chunk_stream[c]) AGB_CUDA(h, cudaStreamSynchronize(h->chunk_stream[c]));
   AGB_CUDA(h, cudaGetLastError());
   return AGB_OK;
@@ -1149,6 +1241,9 @@ int agb_get_device_view(agb_handle* h, agb_device_view* out) {
 int agb_set_history(agb_handle* h, int max_records) {
   if (!h || max_records < 0) return AGB_EINVAL;
   AGB_CUDA(h, cudaSetDevice(h->device));
+#ifndef AGB_EMULATE
+  h->fh_epoch++;                                       // the history buffers are kernel arguments of a captured pipeline
+#endif
   AGB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->hist) { cudaFree(h->hist); h->hist = nullptr; }
   if (h->hist_count) { cudaFree(h->hist_count); h->hist_count = nullptr; }

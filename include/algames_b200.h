@@ -34,6 +34,8 @@
  *   AGB_FORCE_BIG_LAYOUT=1|2|3  agb_create: force a big-storage shared-memory layout on 3-player instances (parity tests
  *                               run every layout on small games with it)
  *   AGB_HOST_CHUNKS=1..32       agb_solve_from_host: number of copy/solve pipeline chunks (default 8 for batch >= 1024)
+ *   AGB_HOST_GRAPH=0            agb_solve_from_host: never replay the pipeline as a CUDA graph (default: captured on the second call
+ *                               with the same page-locked buffers and options, replayed afterwards)
  *   AGB_BAND_FALLBACK=0         agb_create: do not re-solve AGB_SINGULAR instances of the structured kernels with the band solver
  *   AGB_TEST_FORCE_SINGULAR=k   agb_create: the structured solve reports every k-th instance as AGB_SINGULAR (fallback tests)
  *   AGB_BAND_WINDOW=0           agb_create: the band solver eliminates in the global-memory band, not in its shared-memory window
@@ -317,7 +319,9 @@ int agb_ibr_kkt_solve(agb_handle* h, int player, double reg_x, double reg_u, dou
  * batch cut into chunks whose host->device copy, solve and device->host copy are pipelined on separate streams (pass
  * page-locked buffers for the copies to overlap).  Equivalent to agb_set_instance_params(x0) + agb_set_initial(Z0, L0) +
  * agb_newton_solve_batch, except that the per-function "resident iterate" is the result, and o->dual_reset should be 1
- * (the multipliers start from the handle's resident values otherwise).  Outputs may be NULL. */
+ * (the multipliers start from the handle's resident values otherwise).  Outputs may be NULL.  With page-locked buffers the
+ * second call with the same buffer addresses and options captures the whole pipeline as a CUDA graph and later calls replay it
+ * with one launch (an MPC or Monte-Carlo loop refills the same buffers); agb_set_history invalidates the capture. */
 int agb_solve_from_host(agb_handle* h, const agb_options* o, const double* x0, const double* Z0, const double* L0,
                         double* Z_out, double* L_out, double* conlam_out, double* conmu_out,
                         double* stats_out, int* status_out);

@@ -482,3 +482,53 @@ def test_band_window_equals_global(monkeypatch, name, B, N, kw):
     """Band solver: elimination in the shared-memory window (slot map, one barrier per column, pivot search fused into the update,
     double-buffered back substitution) == elimination in the global band, bit for bit — results, histories and a Newton step."""
     parity.check_band_window_equals_global(LIB, monkeypatch, name, B=B, N=N, **kw)
+
+
+def test_solve_from_host_graph_replay():
+    """agb_solve_from_host with page-locked buffers: the second call with the same buffers captures the chunk pipeline as a CUDA graph,
+    later calls replay it.  Every call must equal the staged solve bit for bit — also after the CONTENTS of the input buffers changed
+    (the graph copies from the same addresses), after agb_set_history (a new capture) and with pageable buffers (call by call)."""
+    import torch
+    import algames_b200 as ab
+    B = 1100
+    model, N, dt, obj, con, opts, x0, xf = ab.workloads.config_b(batch=B, N=12)
+    gb = ab.GameBatch(model, N, dt, obj, con, B, lib_path=LIB)
+    gb.set_instance_params(x0=x0)
+    Z0, L0 = gb.random_initial()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hx, hZ, hL = pin(x0), pin(Z0), pin(L0)
+    keys = ("Z", "L", "conlam", "conmu", "stats", "status")
+    nrow = gb.sizes.nrow
+    out = {"Z": pin(np.empty_like(Z0)), "L": pin(np.empty_like(L0)), "conlam": pin(np.empty((B, N - 1, nrow))), "conmu": pin(np.empty((B, N - 1, nrow))),
+           "stats": pin(np.empty((B, 10))), "status": pin(np.empty(B, dtype=np.int32))}
+    def staged():
+        gb.set_instance_params(x0=hx); gb.set_initial(hZ, hL)
+        return gb.newton_solve(opts)
+    ref = staged()
+    launches = []
+    for call in range(4):                                   # call by call, capture + launch, replay, replay
+        for k in keys: out[k][...] = 0
+        l0 = gb.launch_count()
+        gb.solve_from_host(opts, hx, hZ, hL, out=out)
+        launches.append(gb.launch_count() - l0)
+        for k in keys:
+            assert np.array_equal(ref[k], out[k]), (call, k)
+    assert launches[1] == launches[2] == launches[3] and launches[1] > 0
+    hx[:, :3] += 0.05; hZ *= 0.5                            # new problem data at the same addresses
+    ref2 = staged()
+    assert not np.array_equal(ref2["Z"], ref["Z"])
+    gb.solve_from_host(opts, hx, hZ, hL, out=out)
+    for k in keys:
+        assert np.array_equal(ref2[k], out[k]), ("new contents", k)
+    gb.set_history(8)                                       # kernel arguments change: the old graph must not be replayed
+    ref3 = staged()
+    for _ in range(3):
+        gb.solve_from_host(opts, hx, hZ, hL, out=out)
+        for k in keys:
+            assert np.array_equal(ref3[k], out[k]), ("after set_history", k)
+    hist, cnt = gb.get_history()
+    assert (cnt > 0).all()
+    got = gb.solve_from_host(opts, hx.copy(), hZ.copy(), hL.copy())       # pageable buffers
+    for k in keys:
+        assert np.array_equal(ref3[k], got[k]), ("pageable", k)
+    gb.close()
