@@ -304,6 +304,31 @@ function violations(b::Batch)
     return dyn, con, sta, opt
 end
 
+"""
+    update_nullspace!(ascore::ActiveSetCore, batch::Batch, k::Integer=1; atol=1e-20)
+
+`Algames.update_nullspace!` (src/active_set/active_set_methods.jl:173-184) for instance `k` of a resident batch, on the device:
+active masks (`agb_active_set_masks`), null space of the masked bordered Jacobian (`agb_update_nullspace`), then the reference's own
+`add_matrix!` (active_set_core.jl:29-52) fills `ascore.null`.  The basis is orthonormal; it is unique only up to a rotation.
+"""
+function update_nullspace!(ascore, b::Batch, k::Integer=1; atol::Float64=1e-20)
+    B = length(b.probs)
+    sv = Ref{Cint}(0); sh = Ref{Cint}(0)
+    check(ccall((:agb_active_set_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cint}), b.h, sv, sh), b.h)
+    Sv, Sh = Int(sv[]), Int(sh[])
+    tol = b.probs[1].opts.active_set_tolerance
+    vmask = zeros(UInt8, Sv, B); hmask = zeros(UInt8, Sh, B)
+    check(ccall((:agb_active_set_masks, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ptr{UInt8}, Ptr{UInt8}), b.h, tol, vmask, hmask), b.h)
+    maxdim = Sh - Sv + (b.N - 1) * b.p
+    null = zeros(Sh, maxdim, B); dim = zeros(Cint, B)
+    check(ccall((:agb_update_nullspace, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cint, Ptr{Float64}, Ptr{Cint}),
+        b.h, tol, atol, maxdim, null, dim), b.h)
+    ascore.vmask = findall(!iszero, view(vmask, :, k)); ascore.hmask = findall(!iszero, view(hmask, :, k))
+    Algames.reset!(ascore.null)
+    Algames.add_matrix!(ascore.null, null[ascore.hmask, 1:dim[k], k], ascore.hmask)
+    return nothing
+end
+
 function scatter_results!(b::Batch)
     n, m, p, N = b.n, b.m, b.p, b.N
     dyn, con, sta, opt = violations(b)
