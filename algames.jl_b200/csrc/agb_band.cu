@@ -218,7 +218,7 @@ void launch_band_op(const DevDesc* dd, const agb_options& o, const Buffers& g, c
 // Shared-memory bytes of band_solve_window's window: (kl+2) row slots of (kl+ku+2 | 1) doubles + the two slot maps; 0 when a row
 // does not fit the per-lane register cache (8 x 32 entries) or the window exceeds `limit` (then the band is eliminated in global memory).
 size_t band_window_bytes(const DevDesc& d, size_t limit) {
-  const size_t CW = (size_t)d.kl + d.ku + 1, WR = (size_t)d.kl + 2, WS = (CW + 2) | 1;
+  const size_t CW = (size_t)d.kl + d.ku + 1, WR = (size_t)d.kl + 2, WS = ((CW + 1 + 31) / 32) * 32 + 1;   // as band_solve_window<NCH>
   if (CW + 1 > 256) return 0;
   size_t RW = 32; while (RW < CW + 1) RW <<= 1;
   const size_t bytes = (WR * WS + WR + RW + 4 * (kBandThreads / 32 + 1)) * sizeof(double) + 16;   // window | slot maps | x ring | pivot candidates

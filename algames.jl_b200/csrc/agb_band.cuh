@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <type_traits>
 #include "agb_internal.h"
 
 namespace agb {
@@ -416,7 +417,7 @@ struct Ctx {
   // the global path's reduction four per lane.
   template <int NCH> __device__ bool band_solve_window() {
     BT_START();
-    const int CW = kl + ku + 1, WR = kl + 2, WS = (CW + 2) | 1;                  // row: CW columns | right-hand side | dummy (lanes past the row's end)
+    const int CW = kl + ku + 1, WR = kl + 2, WS = NCH * 32 + 1;                  // row: CW columns | right-hand side | padding to NCH chunks of 32 (+1: odd stride)
     const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     int* lp = reinterpret_cast<int*>(win + (size_t)WR * WS);                    // lp[2][WR]
     int RW = 32; while (RW < CW + 1) RW <<= 1;
@@ -432,7 +433,8 @@ struct Ctx {
       double* dst = win + (size_t)r * WS;
       for (int q = lane; q <= CW; q += 32) dst[q] = load_row(r, 0, q);          // columns 0..CW-1 sit at positions 0..CW-1
     }
-    for (int q = tid; q < WR; q += nt) { lp[q] = q; win[(size_t)q * WS + CW + 1] = 0.0; }   // slot map; dummy entries (read by lanes past a row's end)
+    for (int q = tid; q < WR; q += nt) lp[q] = q;                               // slot map
+    for (int q = tid; q < WR * (WS - CW - 1); q += nt) win[(size_t)(q / (WS - CW - 1)) * WS + CW + 1 + q % (WS - CW - 1)] = 0.0;   // row padding
     __syncthreads();
     // pivot of column 0: first row of maximal |a_r0| (every warp, same data, same answer)
     double best = -1.0; int pr = 0;
@@ -454,15 +456,14 @@ struct Ctx {
       const double inv = 1.0 / prow[posj];
       const int nr = rmax - j, nc = cmax - j;
       int pos1 = posj + 1; if (pos1 >= CW) pos1 -= CW;                          // position of column j+1
-      // this lane's columns j+1+cc, cc = lane + 32 t (cc == nc: the right-hand side), pivot row values in registers
-      double pv[NCH]; int pp[NCH];
+      // every lane owns the same POSITIONS lane + 32 t of a window row for the whole elimination (position = column mod CW, position
+      // CW = right-hand side), so the update addresses a row with compile-time offsets and no per-column index arithmetic.  At
+      // column j the positions other than posj hold the live columns j+1 .. j+CW-1; a pivot row is zero beyond its fill, so
+      // updating all of them performs the global path's operations plus subtractions of f * 0
+      double pv[NCH];
 #pragma unroll
-      for (int t = 0; t < NCH; t++) {
-        const int cc = lane + 32 * t;
-        int q = pos1 + cc; if (q >= CW) q -= CW;
-        pp[t] = (cc < nc) ? q : (cc == nc ? CW : CW + 1);                       // past the end: the row's dummy entry, factor 0
-        pv[t] = (cc <= nc) ? prow[pp[t]] : 0.0;
-      }
+      for (int t = 0; t < NCH; t++) pv[t] = prow[lane + 32 * t];
+      const int lj = posj & 31;                                                 // the lane that owns the pivot column's position
       // retire the pivot row: U row j and its right-hand side go to the global band
       for (int cc = tid; cc <= nc + 1; cc += nt) {
         if (cc == nc + 1) rhs[j] = prow[CW];
@@ -476,47 +477,53 @@ struct Ctx {
         if (tid + nt <= CW) nv1 = load_row(rn, j + 1, tid + nt);
       }
       BT_MARK(7);
-      // rank-1 update, rows j+1+ri: two rows per pass; lane 0 holds column j+1 (cc = 0) and tracks this warp's pivot candidate
+      // rank-1 update, rows j+1+ri, two rows per pass with the loads issued before the FMAs; the lane that owns the position of
+      // column j+1 tracks this warp's pivot candidate (rows ascend: strict > keeps the first maximum)
       double cbest = -1.0; int crow = 0;
-      const bool track = (lane == 0) && (nc >= 1);
-      int ri = warp;
-      for (; ri + nw < nr; ri += 2 * nw) {                                      // two rows per pass
-        const int ri2 = ri + nw;
-        int lra = lrj + 1 + ri; if (lra >= WR) lra -= WR;
-        int lrb = lrj + 1 + ri2; if (lrb >= WR) lrb -= WR;
-        const int ra = j + 1 + ri, rb = j + 1 + ri2;
-        double* rowa = win + (size_t)((ra == pr) ? Pj : M[lra]) * WS;
-        double* rowb = win + (size_t)((rb == pr) ? Pj : M[lrb]) * WS;
-        const double fa = rowa[posj] * inv, fb = rowb[posj] * inv;
-        double va[NCH], vb[NCH];
+      const int l1 = pos1 & 31, t1 = pos1 >> 5;
+      const bool track = (lane == l1) && (nc >= 1);
+      auto pass = [&](auto rc, int ri0) {
+        constexpr int R = decltype(rc)::value;
+        double* row[R]; double f[R]; double v[R][NCH];
 #pragma unroll
-        for (int t = 0; t < NCH; t++) { va[t] = rowa[pp[t]]; vb[t] = rowb[pp[t]]; }
-#pragma unroll
-        for (int t = 0; t < NCH; t++) { va[t] -= fa * pv[t]; vb[t] -= fb * pv[t]; }
-#pragma unroll
-        for (int t = 0; t < NCH; t++) if (pp[t] <= CW) { rowa[pp[t]] = va[t]; rowb[pp[t]] = vb[t]; }   // (the dummy entry is only ever read)
-        if (track) {
-          const double aa = fabs(va[0]); if (aa > cbest) { cbest = aa; crow = ra; }
-          const double ab = fabs(vb[0]); if (ab > cbest) { cbest = ab; crow = rb; }
+        for (int q = 0; q < R; q++) {
+          const int ri = ri0 + q * nw, r = j + 1 + ri;
+          int lr = lrj + 1 + ri; if (lr >= WR) lr -= WR;
+          row[q] = win + (size_t)((r == pr) ? Pj : M[lr]) * WS;
         }
-        __syncwarp();
-        if (lane == 0) { rowa[posj] = 0.0; rowb[posj] = 0.0; }                  // becomes column j + CW
-      }
-      if (ri < nr) {                                                            // odd row out
-        int lra = lrj + 1 + ri; if (lra >= WR) lra -= WR;
-        const int ra = j + 1 + ri;
-        double* rowa = win + (size_t)((ra == pr) ? Pj : M[lra]) * WS;
-        const double fa = rowa[posj] * inv;
-        double va[NCH];
 #pragma unroll
-        for (int t = 0; t < NCH; t++) va[t] = rowa[pp[t]];
+        for (int q = 0; q < R; q++) f[q] = row[q][posj] * inv;
 #pragma unroll
-        for (int t = 0; t < NCH; t++) va[t] -= fa * pv[t];
+        for (int q = 0; q < R; q++)
 #pragma unroll
-        for (int t = 0; t < NCH; t++) if (pp[t] <= CW) rowa[pp[t]] = va[t];
-        if (track) { const double aa = fabs(va[0]); if (aa > cbest) { cbest = aa; crow = ra; } }
-        __syncwarp();
-        if (lane == 0) rowa[posj] = 0.0;
+          for (int t = 0; t < NCH; t++) v[q][t] = row[q][lane + 32 * t];
+#pragma unroll
+        for (int q = 0; q < R; q++)
+#pragma unroll
+          for (int t = 0; t < NCH; t++) v[q][t] -= f[q] * pv[t];
+        __syncwarp();                                                           // every lane has read its factors from position posj
+#pragma unroll
+        for (int q = 0; q < R; q++)
+#pragma unroll
+          for (int t = 0; t < NCH; t++) row[q][lane + 32 * t] = v[q][t];
+        if (lane == lj) {
+#pragma unroll
+          for (int q = 0; q < R; q++) row[q][posj] = 0.0;                           // eliminated; the position becomes column j + CW
+        }
+        if (track) {
+#pragma unroll
+          for (int q = 0; q < R; q++) {
+            double av = 0.0;
+#pragma unroll
+            for (int t = 0; t < NCH; t++) if (t == t1) av = fabs(v[q][t]);
+            if (av > cbest) { cbest = av; crow = j + 1 + ri0 + q * nw; }
+          }
+        }
+      };
+      {
+        int ri = warp;
+        for (; ri + nw < nr; ri += 2 * nw) pass(std::integral_constant<int, 2>(), ri);
+        for (; ri < nr; ri += nw) pass(std::integral_constant<int, 1>(), ri);
       }
       BT_MARK(8);
       // next step's map, the candidates and the new row
@@ -528,7 +535,7 @@ struct Ctx {
         Mn[q] = v;
       }
       double* cand = cand0 + (j & 1) * 2 * (nw + 1);                             // (a fast warp may write step j+1's while a slow one still reads step j's)
-      if (lane == 0) { cand[warp] = cbest; cand[nw + 1 + warp] = (double)crow; }
+      if (lane == l1) { cand[warp] = cbest; cand[nw + 1 + warp] = (double)crow; }
       if (tid == 0) { cand[nw] = (rn < S) ? fabs(nv0) : -1.0; cand[2 * nw + 1] = (double)rn; }   // entry 0 of the new row is column j+1
       if (rn < S) {
         double* dst = win + (size_t)spare * WS;
