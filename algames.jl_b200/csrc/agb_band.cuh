@@ -433,7 +433,7 @@ struct Ctx {
       double* dst = win + (size_t)r * WS;
       for (int q = lane; q <= CW; q += 32) dst[q] = load_row(r, 0, q);          // columns 0..CW-1 sit at positions 0..CW-1
     }
-    for (int q = tid; q < WR; q += nt) lp[q] = q;                               // slot map
+    for (int q = tid; q < WR; q += nt) lp[q] = q * WS;                          // logical row -> element offset of its slot
     for (int q = tid; q < WR * (WS - CW - 1); q += nt) win[(size_t)(q / (WS - CW - 1)) * WS + CW + 1 + q % (WS - CW - 1)] = 0.0;   // row padding
     __syncthreads();
     // pivot of column 0: first row of maximal |a_r0| (every warp, same data, same answer)
@@ -443,7 +443,7 @@ struct Ctx {
       const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int orr = __shfl_xor_sync(0xffffffffu, pr, o);
       if (ob > best || (ob == best && orr < pr)) { best = ob; pr = orr; }
     }
-    int spare = WR - 1;                                                         // free physical slot (uniform)
+    int spare = (WR - 1) * WS;                                                  // element offset of the free physical slot (uniform)
     int posj = 0, lrj = 0;                                                      // j % CW, j % WR
     for (int j = 0; j < S; j++) {
       if (!(best > 0.0)) { __syncthreads(); return false; }                     // (uniform)
@@ -452,7 +452,7 @@ struct Ctx {
       int* Mn = lp + ((j & 1) ^ 1) * WR;
       int lrp = lrj + (pr - j); if (lrp >= WR) lrp -= WR;
       const int Pj = M[lrj], P = M[lrp];                                        // slots of logical row j and of the pivot row
-      const double* prow = win + (size_t)P * WS;
+      const double* prow = win + P;
       const double inv = 1.0 / prow[posj];
       const int nr = rmax - j, nc = cmax - j;
       int pos1 = posj + 1; if (pos1 >= CW) pos1 -= CW;                          // position of column j+1
@@ -480,7 +480,7 @@ struct Ctx {
       // rank-1 update, rows j+1+ri, two rows per pass with the loads issued before the FMAs; the lane that owns the position of
       // column j+1 tracks this warp's pivot candidate (rows ascend: strict > keeps the first maximum)
       double cbest = -1.0; int crow = 0;
-      const int l1 = pos1 & 31, t1 = pos1 >> 5;
+      const int l1 = pos1 & 31;
       const bool track = (lane == l1) && (nc >= 1);
       auto pass = [&](auto rc, int ri0) {
         constexpr int R = decltype(rc)::value;
@@ -489,7 +489,7 @@ struct Ctx {
         for (int q = 0; q < R; q++) {
           const int ri = ri0 + q * nw, r = j + 1 + ri;
           int lr = lrj + 1 + ri; if (lr >= WR) lr -= WR;
-          row[q] = win + (size_t)((r == pr) ? Pj : M[lr]) * WS;
+          row[q] = win + ((r == pr) ? Pj : M[lr]);
         }
 #pragma unroll
         for (int q = 0; q < R; q++) f[q] = row[q][posj] * inv;
@@ -510,14 +510,9 @@ struct Ctx {
 #pragma unroll
           for (int q = 0; q < R; q++) row[q][posj] = 0.0;                           // eliminated; the position becomes column j + CW
         }
-        if (track) {
+        if (track) {                                                            // (this lane stored position pos1 itself, just above)
 #pragma unroll
-          for (int q = 0; q < R; q++) {
-            double av = 0.0;
-#pragma unroll
-            for (int t = 0; t < NCH; t++) if (t == t1) av = fabs(v[q][t]);
-            if (av > cbest) { cbest = av; crow = j + 1 + ri0 + q * nw; }
-          }
+          for (int q = 0; q < R; q++) { const double av = fabs(row[q][pos1]); if (av > cbest) { cbest = av; crow = j + 1 + ri0 + q * nw; } }
         }
       };
       {
@@ -538,7 +533,7 @@ struct Ctx {
       if (lane == l1) { cand[warp] = cbest; cand[nw + 1 + warp] = (double)crow; }
       if (tid == 0) { cand[nw] = (rn < S) ? fabs(nv0) : -1.0; cand[2 * nw + 1] = (double)rn; }   // entry 0 of the new row is column j+1
       if (rn < S) {
-        double* dst = win + (size_t)spare * WS;
+        double* dst = win + spare;
         // columns j+1 .. j+CW: position of column j+1+q is (pos1 + q) mod CW
         if (tid <= CW) { int q = pos1 + tid; if (q >= CW) q -= CW; dst[tid == CW ? CW : q] = nv0; }
         if (tid + nt <= CW) { int q = pos1 + tid + nt; if (q >= CW) q -= CW; dst[tid + nt == CW ? CW : q] = nv1; }
